@@ -12,7 +12,7 @@ CC        ?= gcc
 LIBDIR    := bam_parallel_b200/lib
 CSRC      := bam_parallel_b200/csrc
 NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
-             -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude -I$(CSRC)
+             -Xcompiler -fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas -Wno-deprecated-gpu-targets -Iinclude -I$(CSRC)
 CXXFLAGS  := -O2 -std=c++17 -fPIC -Wall -pthread
 
 CU_SRCS   := $(wildcard $(CSRC)/*.cu)
@@ -33,7 +33,7 @@ build/%.cpp.o: $(CSRC)/%.cpp $(HDRS)
 
 $(LIBDIR)/libbamgpu.so: $(CU_OBJS) $(CPP_OBJS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) -shared -o $@ $^ -lcudart -lpthread
+	$(NVCC) -Wno-deprecated-gpu-targets -shared -o $@ $^ -lpthread
 
 $(LIBDIR)/libbamgen.so: tools/bamgen.cpp
 	@mkdir -p $(LIBDIR)

@@ -1,0 +1,136 @@
+"""ctypes binding of libbamgpu.so (include/bamgpu.h).  Fails loudly when the CUDA library is missing:
+there is no CPU fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_ROOT, "bam_parallel_b200", "lib", "libbamgpu.so")
+
+OK, EOF = 0, 1
+ERR_NAMES = {
+    -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_NOMEM", -4: "ERR_IO", -10: "ERR_BLOCK_TOO_SMALL", -11: "ERR_TRUNCATED_BLOCK",
+    -12: "ERR_INFLATE", -13: "ERR_ISIZE", -14: "ERR_CRC", -20: "ERR_BAD_MAGIC", -21: "ERR_SHORT_HEADER",
+    -22: "ERR_SHORT_RECORD", -23: "ERR_BUFFER_TOO_SMALL", -24: "ERR_STATE",
+}
+COPY_DATA, COPY_COLUMNS, WANT_HI, NO_CRC, NO_RECORDS = 1, 2, 4, 8, 16
+
+
+class BamGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str = ""):
+        super().__init__(f"bamgpu {ERR_NAMES.get(code, code)} ({code}): {msg}")
+        self.code = code
+
+
+class Block(C.Structure):
+    _fields_ = [("in_off", C.c_uint64), ("out_off", C.c_uint64), ("in_len", C.c_uint32), ("isize", C.c_uint32),
+                ("crc32", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+COLUMN_FIELDS = [
+    ("rec_off", C.c_uint64), ("rec_len", C.c_uint32), ("ref_id", C.c_int32), ("pos", C.c_int32),
+    ("l_read_name", C.c_uint8), ("mapq", C.c_uint8), ("bin", C.c_uint16), ("n_cigar_op", C.c_uint16),
+    ("flag", C.c_uint16), ("l_seq", C.c_uint32), ("next_ref_id", C.c_int32), ("next_pos", C.c_int32),
+    ("tlen", C.c_int32), ("cigar_off", C.c_uint32), ("seq_off", C.c_uint32), ("qual_off", C.c_uint32),
+    ("tags_off", C.c_uint32), ("coord_key", C.c_uint64), ("strand", C.c_uint8), ("hi_present", C.c_uint8),
+    ("hi_value", C.c_int32),
+]
+
+
+class Columns(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n, _ in COLUMN_FIELDS]
+
+
+class Batch(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("data_len", C.c_uint64), ("data", C.c_void_p), ("h_data", C.c_void_p),
+                ("dev", Columns), ("host", Columns), ("first_record_index", C.c_uint64), ("bad_flag_records", C.c_uint64)]
+
+
+class Opts(C.Structure):
+    _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("batch_bytes", C.c_uint64), ("inflate_impl", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("blocks", "bytes_in", "bytes_out", "records", "batches", "kernel_launches")] + \
+               [(n, C.c_double) for n in ("ms_h2d", "ms_inflate", "ms_crc", "ms_records", "ms_d2h", "ms_total")]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+READ_FN = C.CFUNCTYPE(C.c_long, C.c_void_p, C.POINTER(C.c_uint8), C.c_size_t)
+REFSEQ_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p)
+
+# every symbol include/bamgpu.h declares
+EXPORTS = [
+    "bamgpu_scan_blocks", "bamgpu_engine_new", "bamgpu_engine_free", "bamgpu_engine_last_error", "bamgpu_device_alloc",
+    "bamgpu_device_free", "bamgpu_pinned_alloc", "bamgpu_pinned_free", "bamgpu_memcpy_h2d", "bamgpu_memcpy_d2h",
+    "bamgpu_engine_decode", "bamgpu_engine_stats", "bamgpu_engine_reset_stats", "bamgpu_reader_new",
+    "bamgpu_reader_from_memory", "bamgpu_reader_free", "bamgpu_last_error", "bamgpu_read_header", "bamgpu_next_rec",
+    "bamgpu_append_record", "bamgpu_read", "bamgpu_next_batch", "bamgpu_reader_stats",
+    "bamgpu_parse_reference_sequences", "bamgpu_status_str", "bamgpu_build_info",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads libbamgpu.so. Raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `make` (nvcc, sm_100a). "
+                          "bam_parallel_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, u64p = C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)
+    L.bamgpu_scan_blocks.restype = C.c_int
+    L.bamgpu_scan_blocks.argtypes = [vp, sz, C.c_int, vp, sz, C.POINTER(sz), C.POINTER(sz), u64p]
+    L.bamgpu_engine_new.restype = vp
+    L.bamgpu_engine_new.argtypes = [C.POINTER(Opts)]
+    L.bamgpu_engine_free.argtypes = [vp]
+    L.bamgpu_engine_last_error.restype = C.c_char_p
+    L.bamgpu_engine_last_error.argtypes = [vp]
+    L.bamgpu_device_alloc.restype = vp
+    L.bamgpu_device_alloc.argtypes = [vp, sz]
+    L.bamgpu_device_free.argtypes = [vp, vp]
+    L.bamgpu_pinned_alloc.restype = vp
+    L.bamgpu_pinned_alloc.argtypes = [sz]
+    L.bamgpu_pinned_free.argtypes = [vp]
+    L.bamgpu_memcpy_h2d.restype = C.c_int
+    L.bamgpu_memcpy_h2d.argtypes = [vp, vp, vp, sz]
+    L.bamgpu_memcpy_d2h.restype = C.c_int
+    L.bamgpu_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+    L.bamgpu_engine_decode.restype = C.c_int
+    L.bamgpu_engine_decode.argtypes = [vp, vp, vp, sz, C.c_uint64, C.c_int, C.c_uint32, vp, C.POINTER(Batch), u64p]
+    L.bamgpu_engine_stats.restype = C.c_int
+    L.bamgpu_engine_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.bamgpu_engine_reset_stats.argtypes = [vp]
+    L.bamgpu_reader_new.restype = vp
+    L.bamgpu_reader_new.argtypes = [READ_FN, vp, sz, u64p, C.POINTER(Opts)]
+    L.bamgpu_reader_from_memory.restype = vp
+    L.bamgpu_reader_from_memory.argtypes = [vp, sz, sz, C.POINTER(Opts)]
+    L.bamgpu_reader_free.argtypes = [vp]
+    L.bamgpu_last_error.restype = C.c_char_p
+    L.bamgpu_last_error.argtypes = [vp]
+    L.bamgpu_read_header.restype = C.c_int
+    L.bamgpu_read_header.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
+    L.bamgpu_next_rec.restype = C.c_int
+    L.bamgpu_next_rec.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
+    L.bamgpu_append_record.restype = C.c_int
+    L.bamgpu_append_record.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.bamgpu_read.restype = C.c_long
+    L.bamgpu_read.argtypes = [vp, vp, sz]
+    L.bamgpu_next_batch.restype = C.c_int
+    L.bamgpu_next_batch.argtypes = [vp, C.POINTER(Batch)]
+    L.bamgpu_reader_stats.restype = C.c_int
+    L.bamgpu_reader_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.bamgpu_parse_reference_sequences.restype = C.c_int
+    L.bamgpu_parse_reference_sequences.argtypes = [vp, sz, REFSEQ_CB, vp]
+    L.bamgpu_status_str.restype = C.c_char_p
+    L.bamgpu_status_str.argtypes = [C.c_int]
+    L.bamgpu_build_info.restype = C.c_char_p
+    _lib = L
+    return L

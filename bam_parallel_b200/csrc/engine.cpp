@@ -1,0 +1,932 @@
+// engine.cpp — host side of libbamgpu.so: BGZF scan, the per-batch engine (K1 -> K2 -> K3) and the
+// streaming Reader that mirrors bam_tools::Reader.  Compiled by nvcc as CUDA C++ (no kernels here).
+//
+// Reference code paths replaced (all relative to /root/reference/bam_tools/src):
+//   util.rs:18-71          fetch_block / read_block_size / consume_trailer  -> bamgpu_scan_blocks
+//   reader/readahead.rs    reader thread + rayon inflate tasks + ordering   -> feeder thread + pinned slots + streams
+//   reader.rs:28-55        Reader::new                                      -> bamgpu_reader_new
+//   reader.rs:87-98,154-200 read_header                                     -> bamgpu_read_header
+//   reader.rs:57-81        read_record / append_record                      -> bamgpu_next_rec / bamgpu_append_record
+//   reader.rs:114-152      impl Read                                        -> bamgpu_read
+//   reader.rs:101-112      parse_reference_sequences                        -> bamgpu_parse_reference_sequences
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "bamgpu.h"
+#include "inflate_core.cuh"
+#include "kernels.h"
+
+using namespace bamgpu;
+
+namespace {
+
+constexpr size_t OUT_LEAD_PAD = 64;   // readable bytes before the inflated stream (K1 window loads)
+constexpr size_t OUT_TAIL_PAD = 64;   // readable bytes after it (unaligned field loads)
+constexpr size_t IN_TAIL_PAD = 64;
+
+inline uint16_t rd16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+inline uint32_t rd32(const uint8_t* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+// Growable device / pinned buffers ---------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+}  // namespace
+
+// =================================================================================================
+// Engine
+// =================================================================================================
+struct bamgpu_engine {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint32_t default_flags = 0;
+
+  // block table (SoA) staging + device
+  PinBuf h_tab;
+  DevBuf d_tab;
+  DevBuf d_status, d_misc;  // d_misc: work counter (u32 @0), first_bad (u64 @8), ChainResult @64
+  DevBuf d_crc_tables;
+  bool crc_ready = false;
+  // inflated data
+  DevBuf d_out;
+  uint64_t data_len = 0;    // bytes valid in d_out (after lead pad), carry included
+  uint64_t carry_len = 0;   // bytes at the front of the next batch kept from this one
+  uint64_t keep_from = 0;   // where those bytes currently sit
+  int32_t n_ref = -1;
+  // tiles
+  DevBuf d_tiles;
+  // columns
+  DevBuf d_cols;
+  uint64_t cols_cap = 0;
+  ColumnsDev cols{};
+  // host mirrors
+  PinBuf h_data, h_cols, h_res;
+  uint64_t first_record_index = 0;
+  // timing
+  cudaEvent_t ev[8]{};
+  bamgpu_stats stats{};
+
+  uint8_t* out_ptr() const { return d_out.as<uint8_t>() + OUT_LEAD_PAD; }
+};
+
+#define ECK(call)                                                                                   \
+  do {                                                                                              \
+    cudaError_t _e = (call);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      E->err = std::string(#call) + ": " + cudaGetErrorString(_e);                                  \
+      return BAMGPU_ERR_CUDA;                                                                       \
+    }                                                                                               \
+  } while (0)
+
+extern "C" const char* bamgpu_status_str(int s) {
+  switch (s) {
+    case BAMGPU_OK: return "ok";
+    case BAMGPU_EOF: return "eof";
+    case BAMGPU_ERR_ARG: return "bad argument";
+    case BAMGPU_ERR_CUDA: return "CUDA error";
+    case BAMGPU_ERR_NOMEM: return "out of memory";
+    case BAMGPU_ERR_IO: return "read callback failed";
+    case BAMGPU_ERR_BLOCK_TOO_SMALL: return "BGZF block smaller than 26 bytes";
+    case BAMGPU_ERR_TRUNCATED_BLOCK: return "truncated BGZF block";
+    case BAMGPU_ERR_INFLATE: return "corrupt DEFLATE stream";
+    case BAMGPU_ERR_ISIZE: return "inflated size differs from ISIZE";
+    case BAMGPU_ERR_CRC: return "CRC32 mismatch";
+    case BAMGPU_ERR_BAD_MAGIC: return "invalid BAM header";
+    case BAMGPU_ERR_SHORT_HEADER: return "short BAM header";
+    case BAMGPU_ERR_SHORT_RECORD: return "record runs past end of stream";
+    case BAMGPU_ERR_BUFFER_TOO_SMALL: return "destination buffer too small";
+    case BAMGPU_ERR_STATE: return "call out of order";
+    default: return "unknown";
+  }
+}
+
+extern "C" const char* bamgpu_build_info(void) { return "sm_100a;libbamgpu " __DATE__ " " __TIME__; }
+
+// -------------------------------------------------------------------------------------------------
+// util.rs:18-71 restated for a memory buffer; keeps ISIZE + CRC32 instead of discarding them.
+// -------------------------------------------------------------------------------------------------
+extern "C" int bamgpu_scan_blocks(const uint8_t* buf, size_t len, int final, bamgpu_block* blocks, size_t cap,
+                                  size_t* n_blocks, size_t* consumed, uint64_t* total_isize) {
+  size_t pos = 0, n = 0;
+  uint64_t o = 0;
+  int rc = BAMGPU_OK;
+  for (;;) {
+    if (len - pos < 18) {                       // util.rs:58-60: short header read => Ok(0) => EOF
+      if (final) rc = BAMGPU_EOF;
+      break;
+    }
+    uint16_t bs = (uint16_t)(rd16(buf + pos + 16) + 1);  // util.rs:65, u16 wrap in release
+    if (bs == 0) { rc = BAMGPU_EOF; break; }
+    if (bs < 26) { rc = BAMGPU_ERR_BLOCK_TOO_SMALL; break; }  // util.rs:29-38
+    if (len - pos < bs) {
+      if (final) rc = BAMGPU_ERR_TRUNCATED_BLOCK;  // util.rs:42/44 read_exact fails
+      break;
+    }
+    if (blocks && n < cap) {
+      bamgpu_block& b = blocks[n];
+      b.in_off = pos + 18;
+      b.in_len = (uint32_t)bs - 26;
+      b.out_off = o;
+      b.isize = rd32(buf + pos + bs - 4);
+      b.crc32 = rd32(buf + pos + bs - 8);
+      b.reserved = 0;
+    } else if (blocks) {
+      break;  // table full: caller rescans the rest
+    }
+    o += rd32(buf + pos + bs - 4);
+    ++n;
+    pos += bs;
+  }
+  if (n_blocks) *n_blocks = n;
+  if (consumed) *consumed = pos;
+  if (total_isize) *total_isize = o;
+  return rc;
+}
+
+extern "C" bamgpu_engine* bamgpu_engine_new(const bamgpu_opts* opts) {
+  bamgpu_engine* E = new bamgpu_engine();
+  int dev = opts ? opts->device : -1;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    fprintf(stderr, "bamgpu: no CUDA device available; this library has no CPU fallback\n");
+    delete E;
+    return nullptr;
+  }
+  if (dev < 0) cudaGetDevice(&dev);
+  if (cudaSetDevice(dev) != cudaSuccess) { delete E; return nullptr; }
+  E->device = dev;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) E->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking) != cudaSuccess) { delete E; return nullptr; }
+  for (auto& e : E->ev) cudaEventCreate(&e);
+  E->default_flags = opts ? opts->flags : 0;
+  if (E->d_misc.reserve(4096) != cudaSuccess || E->d_crc_tables.reserve(CRC_TABLE_WORDS * 4) != cudaSuccess ||
+      E->h_res.reserve(4096) != cudaSuccess) {
+    bamgpu_engine_free(E);
+    return nullptr;
+  }
+  crc32_init_tables(E->d_crc_tables.as<uint32_t>(), E->stream);
+  if (cudaStreamSynchronize(E->stream) != cudaSuccess) { bamgpu_engine_free(E); return nullptr; }
+  E->crc_ready = true;
+  return E;
+}
+
+extern "C" void bamgpu_engine_free(bamgpu_engine* E) {
+  if (!E) return;
+  cudaSetDevice(E->device);
+  if (E->stream) { cudaStreamSynchronize(E->stream); cudaStreamDestroy(E->stream); }
+  for (auto& e : E->ev) if (e) cudaEventDestroy(e);
+  E->h_tab.release(); E->d_tab.release(); E->d_status.release(); E->d_misc.release(); E->d_crc_tables.release();
+  E->d_out.release(); E->d_tiles.release(); E->d_cols.release(); E->h_data.release(); E->h_cols.release(); E->h_res.release();
+  delete E;
+}
+
+extern "C" const char* bamgpu_engine_last_error(const bamgpu_engine* E) { return E ? E->err.c_str() : "null engine"; }
+
+extern "C" void* bamgpu_device_alloc(bamgpu_engine* E, size_t bytes) {
+  if (!E) return nullptr;
+  cudaSetDevice(E->device);
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes + IN_TAIL_PAD) != cudaSuccess) return nullptr;
+  cudaMemset((uint8_t*)p + bytes, 0, IN_TAIL_PAD);
+  return p;
+}
+extern "C" void bamgpu_device_free(bamgpu_engine* E, void* p) { if (E) cudaSetDevice(E->device); if (p) cudaFree(p); }
+extern "C" void* bamgpu_pinned_alloc(size_t bytes) { void* p = nullptr; return cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess ? p : nullptr; }
+extern "C" void bamgpu_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+extern "C" int bamgpu_memcpy_h2d(bamgpu_engine* E, void* dst, const void* src, size_t bytes) {
+  if (!E) return BAMGPU_ERR_ARG;
+  ECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, E->stream));
+  ECK(cudaStreamSynchronize(E->stream));
+  return BAMGPU_OK;
+}
+extern "C" int bamgpu_memcpy_d2h(bamgpu_engine* E, void* dst, const void* src, size_t bytes) {
+  if (!E) return BAMGPU_ERR_ARG;
+  ECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, E->stream));
+  ECK(cudaStreamSynchronize(E->stream));
+  return BAMGPU_OK;
+}
+
+namespace {
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Carves the SoA columns out of one allocation.
+void carve_columns(uint8_t* base, uint64_t cap, ColumnsDev& c) {
+  size_t o = 0;
+  auto take = [&](size_t elem) { void* p = base + o; o += align_up(elem * cap, 256); return p; };
+  c.rec_off = (uint64_t*)take(8); c.coord_key = (uint64_t*)take(8);
+  c.rec_len = (uint32_t*)take(4); c.ref_id = (int32_t*)take(4); c.pos = (int32_t*)take(4); c.l_seq = (uint32_t*)take(4);
+  c.next_ref_id = (int32_t*)take(4); c.next_pos = (int32_t*)take(4); c.tlen = (int32_t*)take(4);
+  c.cigar_off = (uint32_t*)take(4); c.seq_off = (uint32_t*)take(4); c.qual_off = (uint32_t*)take(4); c.tags_off = (uint32_t*)take(4);
+  c.hi_value = (int32_t*)take(4);
+  c.bin = (uint16_t*)take(2); c.n_cigar_op = (uint16_t*)take(2); c.flag = (uint16_t*)take(2);
+  c.l_read_name = (uint8_t*)take(1); c.mapq = (uint8_t*)take(1); c.strand = (uint8_t*)take(1); c.hi_present = (uint8_t*)take(1);
+}
+size_t columns_bytes(uint64_t cap) {
+  // 2x8 + 12x4 + 3x2 + 4x1 = 74 bytes per record, each column padded to 256 B
+  return (size_t)(74 * cap) + 21 * 256;
+}
+
+void fill_public_columns(const ColumnsDev& c, bamgpu_columns& o) {
+  o.rec_off = c.rec_off; o.rec_len = c.rec_len; o.ref_id = c.ref_id; o.pos = c.pos; o.l_read_name = c.l_read_name;
+  o.mapq = c.mapq; o.bin = c.bin; o.n_cigar_op = c.n_cigar_op; o.flag = c.flag; o.l_seq = c.l_seq;
+  o.next_ref_id = c.next_ref_id; o.next_pos = c.next_pos; o.tlen = c.tlen; o.cigar_off = c.cigar_off; o.seq_off = c.seq_off;
+  o.qual_off = c.qual_off; o.tags_off = c.tags_off; o.coord_key = c.coord_key; o.strand = c.strand;
+  o.hi_present = c.hi_present; o.hi_value = c.hi_value;
+}
+
+int map_block_status(uint32_t st) {
+  if (st == IST_CRC_MISMATCH) return BAMGPU_ERR_CRC;
+  if (st == IST_OUTPUT_OVERRUN || st == IST_SIZE_MISMATCH) return BAMGPU_ERR_ISIZE;
+  return BAMGPU_ERR_INFLATE;
+}
+
+}  // namespace
+
+// Stage 1: inflate (+CRC) `n_blocks` blocks into d_out after the carried-over bytes.
+static int engine_inflate(bamgpu_engine* E, const uint8_t* d_comp, const bamgpu_block* blocks, size_t n_blocks,
+                          uint32_t flags, cudaStream_t s) {
+  ECK(cudaSetDevice(E->device));
+  // 1. move the carry to the front
+  uint64_t carry = E->carry_len;
+  uint64_t total = 0;
+  for (size_t i = 0; i < n_blocks; ++i) total += blocks[i].isize;
+  uint64_t new_len = carry + total;
+  if (E->d_out.cap < OUT_LEAD_PAD + new_len + OUT_TAIL_PAD) {
+    DevBuf nb;
+    ECK(nb.reserve(OUT_LEAD_PAD + new_len + OUT_TAIL_PAD));
+    ECK(cudaMemsetAsync(nb.p, 0, OUT_LEAD_PAD, s));
+    if (carry) ECK(cudaMemcpyAsync((uint8_t*)nb.p + OUT_LEAD_PAD, E->out_ptr() + E->keep_from, carry, cudaMemcpyDeviceToDevice, s));
+    ECK(cudaStreamSynchronize(s));
+    E->d_out.release();
+    E->d_out = nb;
+  } else if (carry && E->keep_from != 0) {
+    // ranges may overlap only if carry > keep_from; stage through the tile buffer in that rare case
+    if (carry <= E->keep_from) {
+      ECK(cudaMemcpyAsync(E->out_ptr(), E->out_ptr() + E->keep_from, carry, cudaMemcpyDeviceToDevice, s));
+    } else {
+      DevBuf tmp;
+      ECK(tmp.reserve(carry));
+      ECK(cudaMemcpyAsync(tmp.p, E->out_ptr() + E->keep_from, carry, cudaMemcpyDeviceToDevice, s));
+      ECK(cudaMemcpyAsync(E->out_ptr(), tmp.p, carry, cudaMemcpyDeviceToDevice, s));
+      ECK(cudaStreamSynchronize(s));
+      tmp.release();
+    }
+  }
+  E->carry_len = 0;
+  E->keep_from = 0;
+  E->data_len = new_len;
+  ECK(cudaMemsetAsync(E->out_ptr() + new_len, 0, OUT_TAIL_PAD, s));
+  if (n_blocks == 0) return BAMGPU_OK;
+  if (n_blocks > 0xfffffff0ull) { E->err = "too many blocks in one batch"; return BAMGPU_ERR_ARG; }
+
+  // 2. block table -> SoA in pinned memory -> device
+  const size_t nb = n_blocks;
+  const size_t o_in_off = 0, o_out_off = align_up(o_in_off + 8 * nb, 256), o_in_len = align_up(o_out_off + 8 * nb, 256),
+               o_isize = align_up(o_in_len + 4 * nb, 256), o_crc = align_up(o_isize + 4 * nb, 256),
+               tab_bytes = align_up(o_crc + 4 * nb, 256);
+  ECK(E->h_tab.reserve(tab_bytes));
+  ECK(E->d_tab.reserve(tab_bytes));
+  ECK(E->d_status.reserve(4 * nb));
+  {
+    uint8_t* h = E->h_tab.as<uint8_t>();
+    uint64_t* in_off = (uint64_t*)(h + o_in_off);
+    uint64_t* out_off = (uint64_t*)(h + o_out_off);
+    uint32_t* in_len = (uint32_t*)(h + o_in_len);
+    uint32_t* isize = (uint32_t*)(h + o_isize);
+    uint32_t* crc = (uint32_t*)(h + o_crc);
+    uint64_t o = carry;
+    for (size_t i = 0; i < nb; ++i) {
+      in_off[i] = blocks[i].in_off; in_len[i] = blocks[i].in_len; out_off[i] = o; isize[i] = blocks[i].isize; crc[i] = blocks[i].crc32;
+      o += blocks[i].isize;
+    }
+  }
+  ECK(cudaMemcpyAsync(E->d_tab.p, E->h_tab.p, tab_bytes, cudaMemcpyHostToDevice, s));
+  uint8_t* d = E->d_tab.as<uint8_t>();
+  BlockTableDev t{(const uint64_t*)(d + o_in_off), (const uint32_t*)(d + o_in_len), (const uint64_t*)(d + o_out_off),
+                  (const uint32_t*)(d + o_isize), (const uint32_t*)(d + o_crc), (uint32_t)nb};
+  uint32_t* counter = E->d_misc.as<uint32_t>();
+  unsigned long long* first_bad = (unsigned long long*)(E->d_misc.as<uint8_t>() + 8);
+  ECK(cudaMemsetAsync(counter, 0, 4, s));
+  ECK(cudaMemsetAsync(E->d_status.p, 0xff, 4 * nb, s));
+  ECK(cudaEventRecord(E->ev[0], s));
+  launch_inflate(d_comp, t, E->out_ptr(), E->d_status.as<uint32_t>(), counter, E->num_sms, s);
+  ECK(cudaEventRecord(E->ev[1], s));
+  E->stats.kernel_launches += 1;
+  if (!(flags & BAMGPU_NO_CRC)) {
+    launch_crc32(E->out_ptr(), t, E->d_crc_tables.as<uint32_t>(), E->d_status.as<uint32_t>(), s);
+    E->stats.kernel_launches += 1;
+  }
+  ECK(cudaEventRecord(E->ev[2], s));
+  launch_status_reduce(E->d_status.as<uint32_t>(), (uint32_t)nb, first_bad, s);
+  E->stats.kernel_launches += 1;
+  unsigned long long* h_bad = E->h_res.as<unsigned long long>();
+  ECK(cudaMemcpyAsync(h_bad, first_bad, 8, cudaMemcpyDeviceToHost, s));
+  ECK(cudaStreamSynchronize(s));
+  ECK(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, E->ev[0], E->ev[1]); E->stats.ms_inflate += ms;
+  cudaEventElapsedTime(&ms, E->ev[1], E->ev[2]); E->stats.ms_crc += ms;
+  E->stats.blocks += nb;
+  E->stats.bytes_out += total;
+  for (size_t i = 0; i < nb; ++i) E->stats.bytes_in += blocks[i].in_len + 26;
+  if (*h_bad != ~0ull) {
+    uint32_t idx = (uint32_t)(*h_bad >> 32), st = (uint32_t)*h_bad;
+    char msg[160];
+    snprintf(msg, sizeof msg, "BGZF block %u of this batch failed (device status %u): %s", idx, st,
+             bamgpu_status_str(map_block_status(st)));
+    E->err = msg;
+    return map_block_status(st);
+  }
+  return BAMGPU_OK;
+}
+
+// Stage 2: record chain + columns over d_out[0 .. data_len).
+static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t flags, cudaStream_t s,
+                          bamgpu_batch* out, uint64_t* tail_off_out) {
+  ECK(cudaSetDevice(E->device));
+  memset(out, 0, sizeof *out);
+  out->data = E->out_ptr();
+  out->data_len = E->data_len;
+  out->first_record_index = E->first_record_index;
+  ChainResult* d_res = (ChainResult*)(E->d_misc.as<uint8_t>() + 64);
+  ChainResult* h_res = (ChainResult*)(E->h_res.as<uint8_t>() + 64);
+  uint64_t n_rec = 0, tail_off = start;
+  uint32_t tail_kind = EXIT_TAIL;
+  uint64_t bad_flags = 0;
+  ECK(cudaEventRecord(E->ev[3], s));
+  if (!(flags & BAMGPU_NO_RECORDS) && start < E->data_len) {
+    RecordParams p{E->out_ptr(), E->data_len, start, E->n_ref};
+    uint32_t n_tiles = (uint32_t)((E->data_len + TILE_BYTES - 1) / TILE_BYTES);
+    // tile arrays: entry u64, exit u64, base u64, count u32, kind u32, nxt u32, jump u32, jump2 u32, reach u8
+    size_t nt = n_tiles;
+    size_t o_entry = 0, o_exit = align_up(o_entry + 8 * nt, 256), o_base = align_up(o_exit + 8 * nt, 256),
+           o_count = align_up(o_base + 8 * nt, 256), o_kind = align_up(o_count + 4 * nt, 256),
+           o_nxt = align_up(o_kind + 4 * nt, 256), o_jump = align_up(o_nxt + 4 * nt, 256),
+           o_jump2 = align_up(o_jump + 4 * nt, 256), o_reach = align_up(o_jump2 + 4 * nt, 256),
+           tiles_bytes = align_up(o_reach + nt, 256);
+    ECK(E->d_tiles.reserve(tiles_bytes));
+    uint8_t* tb = E->d_tiles.as<uint8_t>();
+    TileArrays t{(uint64_t*)(tb + o_entry), (uint64_t*)(tb + o_exit), (uint32_t*)(tb + o_count), (uint32_t*)(tb + o_kind),
+                 (uint32_t*)(tb + o_nxt), (uint32_t*)(tb + o_jump), (uint32_t*)(tb + o_jump2), (uint8_t*)(tb + o_reach),
+                 (uint64_t*)(tb + o_base), n_tiles};
+    launch_tile_walk(p, t, s);
+    E->stats.kernel_launches += 1;
+    for (int iter = 0;; ++iter) {
+      launch_chain_resolve(p, t, d_res, s);
+      E->stats.kernel_launches += 3;
+      ECK(cudaMemcpyAsync(h_res, d_res, sizeof(ChainResult), cudaMemcpyDeviceToHost, s));
+      ECK(cudaStreamSynchronize(s));
+      ECK(cudaGetLastError());
+      if (h_res->broken_tile == 0xffffffffu) break;
+      if (h_res->broken_tile >= n_tiles) { E->err = "internal: chain left the buffer"; return BAMGPU_ERR_STATE; }
+      launch_tile_repair(p, t, h_res->broken_tile, h_res->broken_entry, s);
+      E->stats.kernel_launches += 1;
+      if (iter > 1000000) { E->err = "internal: chain repair did not converge"; return BAMGPU_ERR_STATE; }
+    }
+    n_rec = h_res->n_records;
+    tail_off = h_res->tail_off;
+    tail_kind = h_res->tail_kind;
+    if (n_rec) {
+      if (n_rec > E->cols_cap) {
+        uint64_t cap = n_rec + n_rec / 8 + 1024;
+        ECK(E->d_cols.reserve(columns_bytes(cap)));
+        E->cols_cap = cap;
+        carve_columns(E->d_cols.as<uint8_t>(), cap, E->cols);
+      }
+      launch_tile_emit(p, t, E->cols.rec_off, E->cols.rec_len, s);
+      launch_extract(p, E->cols, n_rec, (flags & BAMGPU_WANT_HI) != 0, d_res, s);
+      E->stats.kernel_launches += 2;
+      ECK(cudaMemcpyAsync(h_res, d_res, sizeof(ChainResult), cudaMemcpyDeviceToHost, s));
+      ECK(cudaStreamSynchronize(s));
+      ECK(cudaGetLastError());
+      bad_flags = h_res->bad_flags;
+    }
+  } else if (flags & BAMGPU_NO_RECORDS) {
+    tail_off = E->data_len;
+  }
+  ECK(cudaEventRecord(E->ev[4], s));
+  // End-of-chain semantics (reader.rs:63-81).
+  int rc = BAMGPU_OK;
+  if (!(flags & BAMGPU_NO_RECORDS)) {
+    if (tail_kind == EXIT_INCOMPLETE && final) {
+      E->err = "Failed to read. (record body runs past the end of the stream, reader.rs:69-70)";
+      rc = BAMGPU_ERR_SHORT_RECORD;
+    }
+    if (tail_kind == EXIT_ZERO) rc = BAMGPU_EOF;             // block_size == 0 ends iteration even mid-stream
+    if (tail_kind == EXIT_TAIL && final) rc = BAMGPU_EOF;    // 0..3 trailing bytes: silent EOF
+  }
+  out->n_records = n_rec;
+  out->bad_flag_records = bad_flags;
+  fill_public_columns(E->cols, out->dev);
+  // host mirrors
+  if (flags & BAMGPU_COPY_DATA) {
+    ECK(E->h_data.reserve(E->data_len + 64));
+    if (E->data_len) ECK(cudaMemcpyAsync(E->h_data.p, E->out_ptr(), E->data_len, cudaMemcpyDeviceToHost, s));
+    out->h_data = E->h_data.as<uint8_t>();
+  }
+  if ((flags & BAMGPU_COPY_COLUMNS) && n_rec) {
+    size_t bytes = columns_bytes(E->cols_cap);
+    ECK(E->h_cols.reserve(bytes));
+    // copy only the used prefix of every column
+    ColumnsDev hc;
+    carve_columns(E->h_cols.as<uint8_t>(), E->cols_cap, hc);
+    auto cp = [&](void* dst, const void* src, size_t elem) {
+      return cudaMemcpyAsync(dst, src, elem * n_rec, cudaMemcpyDeviceToHost, s);
+    };
+    ECK(cp(hc.rec_off, E->cols.rec_off, 8)); ECK(cp(hc.coord_key, E->cols.coord_key, 8));
+    ECK(cp(hc.rec_len, E->cols.rec_len, 4)); ECK(cp(hc.ref_id, E->cols.ref_id, 4)); ECK(cp(hc.pos, E->cols.pos, 4));
+    ECK(cp(hc.l_seq, E->cols.l_seq, 4)); ECK(cp(hc.next_ref_id, E->cols.next_ref_id, 4)); ECK(cp(hc.next_pos, E->cols.next_pos, 4));
+    ECK(cp(hc.tlen, E->cols.tlen, 4)); ECK(cp(hc.cigar_off, E->cols.cigar_off, 4)); ECK(cp(hc.seq_off, E->cols.seq_off, 4));
+    ECK(cp(hc.qual_off, E->cols.qual_off, 4)); ECK(cp(hc.tags_off, E->cols.tags_off, 4)); ECK(cp(hc.hi_value, E->cols.hi_value, 4));
+    ECK(cp(hc.bin, E->cols.bin, 2)); ECK(cp(hc.n_cigar_op, E->cols.n_cigar_op, 2)); ECK(cp(hc.flag, E->cols.flag, 2));
+    ECK(cp(hc.l_read_name, E->cols.l_read_name, 1)); ECK(cp(hc.mapq, E->cols.mapq, 1)); ECK(cp(hc.strand, E->cols.strand, 1));
+    ECK(cp(hc.hi_present, E->cols.hi_present, 1));
+    fill_public_columns(hc, out->host);
+  }
+  ECK(cudaEventRecord(E->ev[5], s));
+  ECK(cudaStreamSynchronize(s));
+  ECK(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, E->ev[3], E->ev[4]); E->stats.ms_records += ms;
+  cudaEventElapsedTime(&ms, E->ev[4], E->ev[5]); E->stats.ms_d2h += ms;
+  E->stats.records += n_rec;
+  E->stats.batches += 1;
+  E->first_record_index += n_rec;
+  if (tail_off_out) *tail_off_out = tail_off;
+  // what the next batch must see in front of its own bytes
+  if (!final && rc == BAMGPU_OK && !(flags & BAMGPU_NO_RECORDS)) {
+    E->keep_from = tail_off;
+    E->carry_len = E->data_len - tail_off;
+  } else {
+    E->keep_from = 0;
+    E->carry_len = 0;
+  }
+  return rc;
+}
+
+extern "C" int bamgpu_engine_decode(bamgpu_engine* E, const uint8_t* d_comp, const bamgpu_block* blocks, size_t n_blocks,
+                                    uint64_t stream_start, int final, uint32_t flags, void* cuda_stream,
+                                    bamgpu_batch* out, uint64_t* tail_off) {
+  if (!E || !out || (n_blocks && (!blocks || !d_comp))) return BAMGPU_ERR_ARG;
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : E->stream;
+  flags |= E->default_flags;
+  int rc = engine_inflate(E, d_comp, blocks, n_blocks, flags, s);
+  if (rc != BAMGPU_OK) return rc;
+  return engine_records(E, stream_start, final, flags, s, out, tail_off);
+}
+
+extern "C" int bamgpu_engine_stats(const bamgpu_engine* E, bamgpu_stats* out) {
+  if (!E || !out) return BAMGPU_ERR_ARG;
+  *out = E->stats;
+  out->ms_total = out->ms_h2d + out->ms_inflate + out->ms_crc + out->ms_records + out->ms_d2h;
+  return BAMGPU_OK;
+}
+extern "C" void bamgpu_engine_reset_stats(bamgpu_engine* E) { if (E) E->stats = bamgpu_stats{}; }
+
+// Internal hooks used by the Reader (same translation unit keeps them out of the public ABI).
+static void engine_set_n_ref(bamgpu_engine* E, int32_t n) { E->n_ref = n; }
+
+// =================================================================================================
+// Reader
+// =================================================================================================
+namespace {
+
+struct Slot {
+  PinBuf host;               // compressed bytes as read from the source
+  DevBuf dev;                // same bytes on the device
+  size_t len = 0;            // bytes covered by whole blocks
+  std::vector<bamgpu_block> blocks;
+  bool final = false;        // no more input after this slot
+  int status = BAMGPU_OK;    // scan / io status for this slot
+  cudaEvent_t copied = nullptr;
+};
+
+}  // namespace
+
+struct bamgpu_reader {
+  bamgpu_engine* E = nullptr;
+  bamgpu_read_fn read = nullptr;
+  void* ctx = nullptr;
+  size_t thread_num = 3;
+  uint64_t track_total = 0;
+  uint64_t bytes_fed = 0;
+  uint32_t flags = 0;
+  size_t batch_bytes = 256u << 20;
+  std::string err;
+  // memory source
+  const uint8_t* mem = nullptr;
+  size_t mem_len = 0, mem_pos = 0;
+  // feeder
+  static constexpr int N_SLOTS = 3;
+  Slot slots[N_SLOTS];
+  std::thread feeder;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<int> ready, freeq;
+  bool stop = false;
+  cudaStream_t copy_stream = nullptr;
+  // consumer state
+  int cur_slot = -1;
+  bool header_done = false, eof = false, raw_mode = false, inflated_pending = false, input_done = false;
+  int sticky = BAMGPU_OK;
+  std::vector<uint8_t> header;      // without magic
+  size_t off_to_refs = 0;
+  uint64_t next_start = 0;          // chain start inside the next engine_records call
+  bamgpu_batch batch{};
+  bool batch_valid = false;
+  uint64_t rec_cursor = 0;          // next record of `batch` to hand out
+  uint64_t byte_cursor = 0;         // raw mode: next byte of batch.h_data
+  bool pending_final = false;
+};
+
+static long mem_read(void* ctx, uint8_t* dst, size_t cap) {
+  bamgpu_reader* R = (bamgpu_reader*)ctx;
+  size_t n = std::min(cap, R->mem_len - R->mem_pos);
+  memcpy(dst, R->mem + R->mem_pos, n);
+  R->mem_pos += n;
+  return (long)n;
+}
+
+// Feeder thread: readahead.rs:88-118's reading thread, but it batches whole blocks into a pinned slot,
+// scans their headers AND footers, and starts the H2D copy on its own stream.
+static void feeder_main(bamgpu_reader* R) {
+  cudaSetDevice(R->E->device);
+  std::vector<uint8_t> carry;  // partial block left over from the previous slot
+  bool src_eof = false;
+  for (;;) {
+    int si;
+    {
+      std::unique_lock<std::mutex> lk(R->mu);
+      R->cv.wait(lk, [&] { return R->stop || !R->freeq.empty(); });
+      if (R->stop) return;
+      si = R->freeq.front();
+      R->freeq.pop_front();
+    }
+    Slot& S = R->slots[si];
+    S.blocks.clear();
+    S.status = BAMGPU_OK;
+    S.final = false;
+    size_t cap = R->batch_bytes + 65536 + 64;
+    if (S.host.reserve(cap + IN_TAIL_PAD) != cudaSuccess || S.dev.reserve(cap + IN_TAIL_PAD) != cudaSuccess) {
+      S.status = BAMGPU_ERR_NOMEM; S.final = true;
+    } else {
+      uint8_t* h = S.host.as<uint8_t>();
+      size_t fill = carry.size();
+      if (fill) memcpy(h, carry.data(), fill);
+      carry.clear();
+      while (!src_eof && fill < R->batch_bytes) {
+        long n = R->read(R->ctx, h + fill, std::min<size_t>(cap - fill, 8u << 20));
+        if (n < 0) { S.status = BAMGPU_ERR_IO; src_eof = true; break; }
+        if (n == 0) { src_eof = true; break; }
+        fill += (size_t)n;
+        R->bytes_fed += (uint64_t)n;
+      }
+      if (S.status == BAMGPU_OK) {
+        size_t nb = 0, consumed = 0;
+        uint64_t tot = 0;
+        // count, then fill
+        int rc = bamgpu_scan_blocks(h, fill, src_eof ? 1 : 0, nullptr, 0, &nb, &consumed, &tot);
+        S.blocks.resize(nb);
+        if (nb) bamgpu_scan_blocks(h, fill, src_eof ? 1 : 0, S.blocks.data(), nb, &nb, &consumed, &tot);
+        S.len = consumed;
+        if (rc < 0) { S.status = rc; S.final = true; }
+        else if (rc == BAMGPU_EOF || src_eof) S.final = true;   // silent EOF (short header / BSIZE wrap) ends the stream
+        else carry.assign(h + consumed, h + fill);
+        if (S.len) {
+          memset(h + S.len, 0, IN_TAIL_PAD);
+          cudaMemcpyAsync(S.dev.p, h, S.len + IN_TAIL_PAD, cudaMemcpyHostToDevice, R->copy_stream);
+        }
+        cudaEventRecord(S.copied, R->copy_stream);
+      } else {
+        S.final = true;
+      }
+    }
+    bool fin = S.final;
+    {
+      std::lock_guard<std::mutex> lk(R->mu);
+      R->ready.push_back(si);
+    }
+    R->cv.notify_all();
+    if (fin) return;
+  }
+}
+
+static bamgpu_reader* reader_create(bamgpu_read_fn read, void* ctx, size_t thread_num, const uint64_t* track_progress,
+                                    const bamgpu_opts* opts) {
+  bamgpu_engine* E = bamgpu_engine_new(opts);
+  if (!E) return nullptr;
+  bamgpu_reader* R = new bamgpu_reader();
+  R->E = E;
+  R->read = read;
+  R->ctx = ctx;
+  unsigned hc = std::thread::hardware_concurrency();
+  if (hc && thread_num > hc) thread_num = hc;      // reader.rs:33-35
+  R->thread_num = std::max<size_t>(thread_num, 3);  // readahead.rs:53
+  R->track_total = track_progress ? *track_progress : 0;
+  R->flags = opts ? opts->flags : 0;
+  if (opts && opts->batch_bytes) R->batch_bytes = (size_t)opts->batch_bytes;
+  if (R->batch_bytes < 65536) R->batch_bytes = 65536;
+  cudaStreamCreateWithFlags(&R->copy_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < bamgpu_reader::N_SLOTS; ++i) {
+    cudaEventCreateWithFlags(&R->slots[i].copied, cudaEventDisableTiming);
+    R->freeq.push_back(i);
+  }
+  return R;
+}
+
+extern "C" bamgpu_reader* bamgpu_reader_new(bamgpu_read_fn read, void* ctx, size_t thread_num, const uint64_t* track_progress,
+                                            const bamgpu_opts* opts) {
+  if (!read) return nullptr;
+  bamgpu_reader* R = reader_create(read, ctx, thread_num, track_progress, opts);
+  if (R) R->feeder = std::thread(feeder_main, R);
+  return R;
+}
+
+extern "C" bamgpu_reader* bamgpu_reader_from_memory(const uint8_t* buf, size_t len, size_t thread_num, const bamgpu_opts* opts) {
+  if (!buf && len) return nullptr;
+  bamgpu_reader* R = reader_create(mem_read, nullptr, thread_num, nullptr, opts);
+  if (!R) return nullptr;
+  R->ctx = R;
+  R->mem = buf;
+  R->mem_len = len;
+  R->feeder = std::thread(feeder_main, R);
+  return R;
+}
+
+extern "C" void bamgpu_reader_free(bamgpu_reader* R) {
+  if (!R) return;
+  {
+    std::lock_guard<std::mutex> lk(R->mu);
+    R->stop = true;
+  }
+  R->cv.notify_all();
+  if (R->feeder.joinable()) R->feeder.join();
+  cudaSetDevice(R->E->device);
+  if (R->copy_stream) { cudaStreamSynchronize(R->copy_stream); cudaStreamDestroy(R->copy_stream); }
+  for (auto& s : R->slots) { if (s.copied) cudaEventDestroy(s.copied); s.host.release(); s.dev.release(); }
+  bamgpu_engine_free(R->E);
+  delete R;
+}
+
+extern "C" const char* bamgpu_last_error(const bamgpu_reader* R) {
+  if (!R) return "null reader (no CUDA device? this library has no CPU fallback)";
+  return R->err.empty() ? R->E->err.c_str() : R->err.c_str();
+}
+
+// Returns the current slot to the feeder and takes the next one; inflates it. BAMGPU_EOF when input is exhausted.
+static int reader_inflate_next(bamgpu_reader* R, uint32_t flags) {
+  if (R->input_done) return BAMGPU_EOF;
+  if (R->cur_slot >= 0) {
+    {
+      std::lock_guard<std::mutex> lk(R->mu);
+      R->freeq.push_back(R->cur_slot);
+    }
+    R->cv.notify_all();
+    R->cur_slot = -1;
+  }
+  int si;
+  {
+    std::unique_lock<std::mutex> lk(R->mu);
+    R->cv.wait(lk, [&] { return !R->ready.empty(); });
+    si = R->ready.front();
+    R->ready.pop_front();
+  }
+  R->cur_slot = si;
+  Slot& S = R->slots[si];
+  if (S.final) R->input_done = true;
+  R->pending_final = S.final;
+  if (S.status < 0) {
+    R->err = std::string("input: ") + bamgpu_status_str(S.status);
+    return S.status;
+  }
+  bamgpu_engine* E = R->E;
+  cudaSetDevice(E->device);
+  if (cudaStreamWaitEvent(E->stream, S.copied, 0) != cudaSuccess) { R->err = "cudaStreamWaitEvent failed"; return BAMGPU_ERR_CUDA; }
+  int rc = engine_inflate(E, S.dev.as<uint8_t>(), S.blocks.data(), S.blocks.size(), flags, E->stream);
+  if (rc != BAMGPU_OK) return rc;
+  R->inflated_pending = true;
+  return BAMGPU_OK;
+}
+
+extern "C" int bamgpu_read_header(bamgpu_reader* R, const uint8_t** bytes, size_t* len, size_t* offset_to_ref_seqs) {
+  if (!R) return BAMGPU_ERR_ARG;
+  if (R->sticky < 0) return R->sticky;
+  if (R->header_done || R->raw_mode) { R->err = "read_header called twice or after read()"; return BAMGPU_ERR_STATE; }
+  bamgpu_engine* E = R->E;
+  // Inflate batches until the whole header is on the device (normally the first batch).
+  std::vector<uint8_t> hb;
+  auto fetch = [&](uint64_t need) -> int {  // make hb hold the first `need` inflated bytes
+    while (E->data_len < need) {
+      if (R->input_done) return BAMGPU_ERR_SHORT_HEADER;
+      // keep everything inflated so far as carry for the next inflate
+      E->carry_len = E->data_len; E->keep_from = 0;
+      int rc = reader_inflate_next(R, R->flags);
+      if (rc == BAMGPU_EOF) return BAMGPU_ERR_SHORT_HEADER;
+      if (rc < 0) return rc;
+    }
+    if (hb.size() < need) {
+      size_t old = hb.size();
+      hb.resize(need);
+      int rc = bamgpu_memcpy_d2h(E, hb.data() + old, E->out_ptr() + old, need - old);
+      if (rc < 0) return rc;
+    }
+    return BAMGPU_OK;
+  };
+  int rc = reader_inflate_next(R, R->flags);
+  if (rc < 0) { R->sticky = rc; return rc; }
+  auto fail = [&](int code, const char* what) { R->err = what; R->sticky = code; return code; };
+  if ((rc = fetch(4)) < 0) return fail(rc == BAMGPU_ERR_SHORT_HEADER ? BAMGPU_ERR_SHORT_HEADER : rc, "short BAM header");
+  if (memcmp(hb.data(), "BAM\1", 4) != 0) return fail(BAMGPU_ERR_BAD_MAGIC, "invalid BAM header");   // reader.rs:90-95
+  if ((rc = fetch(8)) < 0) return fail(rc, "short BAM header");
+  uint64_t p = 4;
+  uint64_t l_text = rd32(hb.data() + p); p += 4;
+  if ((rc = fetch(p + l_text + 4)) < 0) return fail(rc, "short BAM header");
+  p += l_text;
+  R->off_to_refs = (size_t)(p - 4);
+  uint32_t n_ref = rd32(hb.data() + p); p += 4;
+  for (uint32_t i = 0; i < n_ref; ++i) {
+    if ((rc = fetch(p + 4)) < 0) return fail(rc, "short BAM header");
+    uint64_t l_name = rd32(hb.data() + p); p += 4;
+    if ((rc = fetch(p + l_name + 4)) < 0) return fail(rc, "short BAM header");
+    p += l_name + 4;
+  }
+  R->header.assign(hb.begin() + 4, hb.begin() + p);
+  R->header_done = true;
+  R->next_start = p;
+  engine_set_n_ref(E, n_ref > 0x7fffffffu ? -1 : (int32_t)n_ref);
+  if (bytes) *bytes = R->header.data();
+  if (len) *len = R->header.size();
+  if (offset_to_ref_seqs) *offset_to_ref_seqs = R->off_to_refs;
+  return BAMGPU_OK;
+}
+
+// Produces the next non-empty batch (or EOF). Uses the inflated-but-unparsed batch left by read_header first.
+static int reader_next_batch(bamgpu_reader* R, uint32_t extra_flags) {
+  if (R->sticky < 0) return R->sticky;
+  if (R->eof) return BAMGPU_EOF;
+  if (!R->header_done) { R->err = "records requested before read_header()"; return BAMGPU_ERR_STATE; }
+  bamgpu_engine* E = R->E;
+  uint32_t flags = R->flags | extra_flags;
+  for (;;) {
+    if (!R->inflated_pending) {
+      int rc = reader_inflate_next(R, flags);
+      if (rc == BAMGPU_EOF) {
+        // input exhausted and nothing pending: whatever carry is left was already judged with final=1
+        R->eof = true;
+        return BAMGPU_EOF;
+      }
+      if (rc < 0) { R->sticky = rc; return rc; }
+    }
+    R->inflated_pending = false;
+    uint64_t tail = 0;
+    int rc = engine_records(E, R->next_start, R->pending_final ? 1 : 0, flags, E->stream, &R->batch, &tail);
+    R->next_start = 0;
+    if (rc < 0) { R->sticky = rc; return rc; }
+    R->batch_valid = true;
+    R->rec_cursor = 0;
+    if (rc == BAMGPU_EOF || R->pending_final) R->eof = true;
+    if (R->batch.n_records) return BAMGPU_OK;
+    if (R->eof) return BAMGPU_EOF;
+  }
+}
+
+extern "C" int bamgpu_next_batch(bamgpu_reader* R, bamgpu_batch* out) {
+  if (!R || !out) return BAMGPU_ERR_ARG;
+  if (R->raw_mode) { R->err = "next_batch after read()"; return BAMGPU_ERR_STATE; }
+  if (R->eof) return R->sticky < 0 ? R->sticky : BAMGPU_EOF;
+  int rc = reader_next_batch(R, 0);
+  if (rc != BAMGPU_OK) return rc;
+  *out = R->batch;
+  R->rec_cursor = R->batch.n_records;  // the batch is handed out whole
+  return BAMGPU_OK;
+}
+
+extern "C" int bamgpu_next_rec(bamgpu_reader* R, const uint8_t** body, size_t* len) {
+  if (!R || !body || !len) return BAMGPU_ERR_ARG;
+  if (R->raw_mode) { R->err = "next_rec after read()"; return BAMGPU_ERR_STATE; }
+  while (!R->batch_valid || R->rec_cursor >= R->batch.n_records) {
+    if (R->eof) { *body = nullptr; *len = 0; return R->sticky < 0 ? R->sticky : BAMGPU_EOF; }
+    int rc = reader_next_batch(R, BAMGPU_COPY_DATA | BAMGPU_COPY_COLUMNS);
+    if (rc != BAMGPU_OK) { *body = nullptr; *len = 0; return rc; }
+  }
+  if (!R->batch.h_data || !R->batch.host.rec_off) { R->err = "internal: batch has no host mirror"; return BAMGPU_ERR_STATE; }
+  uint64_t i = R->rec_cursor++;
+  *body = R->batch.h_data + R->batch.host.rec_off[i];
+  *len = R->batch.host.rec_len[i];
+  return BAMGPU_OK;
+}
+
+extern "C" int bamgpu_append_record(bamgpu_reader* R, uint8_t* dst, size_t cap, size_t* len) {
+  if (!R || !len) return BAMGPU_ERR_ARG;
+  const uint8_t* b;
+  size_t n;
+  uint64_t save = R->rec_cursor;
+  int rc = bamgpu_next_rec(R, &b, &n);
+  if (rc == BAMGPU_EOF) { *len = 0; return BAMGPU_OK; }   // reader.rs:63-73 returns Ok(0) at EOF
+  if (rc < 0) return rc;
+  if (n > cap || !dst) {
+    R->rec_cursor = R->rec_cursor - 1;  // un-consume (same batch by construction)
+    (void)save;
+    *len = n;
+    return BAMGPU_ERR_BUFFER_TOO_SMALL;
+  }
+  memcpy(dst, b, n);
+  *len = n;
+  return BAMGPU_OK;
+}
+
+extern "C" long bamgpu_read(bamgpu_reader* R, uint8_t* dst, size_t cap) {
+  if (!R || (!dst && cap)) return BAMGPU_ERR_ARG;
+  if (R->sticky < 0) return R->sticky;
+  if (R->header_done && !R->raw_mode) { R->err = "read() after read_header(): use the record calls"; return BAMGPU_ERR_STATE; }
+  R->raw_mode = true;
+  size_t got = 0;
+  while (got < cap) {
+    if (R->batch_valid && R->byte_cursor < R->batch.data_len) {
+      size_t n = (size_t)std::min<uint64_t>(cap - got, R->batch.data_len - R->byte_cursor);
+      memcpy(dst + got, R->batch.h_data + R->byte_cursor, n);
+      R->byte_cursor += n;
+      got += n;
+      continue;
+    }
+    if (R->eof) break;
+    int rc = reader_inflate_next(R, R->flags | BAMGPU_NO_RECORDS);
+    if (rc == BAMGPU_EOF) { R->eof = true; break; }
+    if (rc < 0) { R->sticky = rc; return got ? (long)got : rc; }
+    uint64_t tail;
+    rc = engine_records(R->E, 0, R->pending_final, R->flags | BAMGPU_NO_RECORDS | BAMGPU_COPY_DATA, R->E->stream, &R->batch, &tail);
+    if (rc < 0) { R->sticky = rc; return got ? (long)got : rc; }
+    R->inflated_pending = false;
+    R->batch_valid = true;
+    R->byte_cursor = 0;
+    if (R->pending_final) R->eof = true;
+  }
+  return (long)got;
+}
+
+extern "C" int bamgpu_reader_stats(const bamgpu_reader* R, bamgpu_stats* out) {
+  if (!R) return BAMGPU_ERR_ARG;
+  return bamgpu_engine_stats(R->E, out);
+}
+
+extern "C" int bamgpu_parse_reference_sequences(const uint8_t* b, size_t len, bamgpu_refseq_cb cb, void* user) {
+  if (!b || len < 4) return BAMGPU_ERR_SHORT_HEADER;
+  uint32_t n = rd32(b);
+  size_t p = 4;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (len - p < 4) return BAMGPU_ERR_SHORT_HEADER;
+    size_t l = rd32(b + p); p += 4;
+    if (len - p < l) return BAMGPU_ERR_SHORT_HEADER;
+    // CStr::from_bytes_with_nul (reader.rs:202-211): exactly one NUL, at the end
+    if (l == 0 || b[p + l - 1] != 0 || memchr(b + p, 0, l - 1) != nullptr) return BAMGPU_ERR_SHORT_HEADER;
+    const char* name = (const char*)(b + p);
+    p += l;
+    if (len - p < 4) return BAMGPU_ERR_SHORT_HEADER;
+    uint32_t l_ref = rd32(b + p); p += 4;
+    if (cb) cb(name, l - 1, l_ref, user);
+  }
+  return BAMGPU_OK;
+}

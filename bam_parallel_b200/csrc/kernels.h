@@ -1,0 +1,100 @@
+// kernels.h — internal launch interface between the host engine (engine.cpp) and the CUDA kernels.
+// Not part of the public ABI (that is include/bamgpu.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bamgpu {
+
+// Device-side view of the BGZF block table of one batch (structure of arrays).
+struct BlockTableDev {
+  const uint64_t* in_off;   // payload offset in the compressed buffer
+  const uint32_t* in_len;   // payload bytes
+  const uint64_t* out_off;  // offset in the inflated buffer (exclusive scan of ISIZE, + carry)
+  const uint32_t* isize;    // ISIZE footer
+  const uint32_t* crc;      // CRC32 footer
+  uint32_t n_blocks;
+};
+
+// ---- K1: DEFLATE inflate, one BGZF block per lane (inflate.cu) -------------------------------
+// status[b] = IST_* (inflate_core.cuh).  work_counter: one zeroed u32 in device memory.
+void launch_inflate(const uint8_t* comp, const BlockTableDev& t, uint8_t* out, uint32_t* status,
+                    uint32_t* work_counter, int num_sms, cudaStream_t s);
+size_t inflate_smem_bytes();
+
+// ---- K2: CRC32 of every inflated block vs its footer (crc32.cu) ------------------------------
+// Sets status[b] = IST_CRC_MISMATCH where status[b]==0 and the CRC differs.
+constexpr uint32_t IST_CRC_MISMATCH = 100;
+void crc32_init_tables(uint32_t* d_tables /* CRC_TABLE_WORDS words */, cudaStream_t s);
+constexpr int CRC_TABLE_WORDS = 2 * 4 * 256;
+void launch_crc32(const uint8_t* out, const BlockTableDev& t, const uint32_t* d_tables, uint32_t* status,
+                  cudaStream_t s);
+
+// first_bad[0] = min over blocks with status != 0 of (block index << 32 | status); ~0ull if none.
+void launch_status_reduce(const uint32_t* status, uint32_t n_blocks, unsigned long long* first_bad, cudaStream_t s);
+
+// ---- K3: record boundaries, fixed fields, sort keys (records.cu) -----------------------------
+constexpr uint32_t TILE_BYTES = 1u << 16;
+
+// exit_kind values
+enum : uint32_t {
+  EXIT_NORMAL = 0,      // exit offset is the start of the first record beginning at/after the tile end
+  EXIT_TAIL = 1,        // fewer than 4 bytes left at exit offset (reader.rs:78 UnexpectedEof => 0)
+  EXIT_ZERO = 2,        // block_size == 0 at exit offset (reader.rs:64-72: iteration ends)
+  EXIT_INCOMPLETE = 3,  // record at exit offset runs past the data (needs more bytes / SHORT_RECORD)
+  EXIT_NONE = 4,        // tile has no candidate entry
+};
+
+struct TileArrays {
+  uint64_t* entry;      // speculated (or known) first record start in the tile; ~0ull if none
+  uint64_t* exit_off;   // where the walk stopped
+  uint32_t* count;      // records STARTING in this tile when entered at entry
+  uint32_t* exit_kind;
+  uint32_t* nxt;        // pointer-jumping: successor tile (self if terminal/broken)
+  uint32_t* jump;       // doubling scratch
+  uint32_t* jump2;
+  uint8_t* reach;       // on the true chain
+  uint64_t* base;       // exclusive scan of count over reachable tiles
+  uint32_t n_tiles;
+};
+
+struct RecordParams {
+  const uint8_t* data;  // inflated bytes (carry + new); readable 16 bytes before and after
+  uint64_t data_len;
+  uint64_t start;       // chain start (absolute offset in data)
+  int32_t n_ref;        // number of reference sequences (plausibility filter); <0 = unknown
+};
+
+// Output columns (device pointers, capacity >= n_records). Mirrors bamgpu_columns.
+struct ColumnsDev {
+  uint64_t* rec_off; uint32_t* rec_len;
+  int32_t* ref_id; int32_t* pos; uint8_t* l_read_name; uint8_t* mapq; uint16_t* bin; uint16_t* n_cigar_op;
+  uint16_t* flag; uint32_t* l_seq; int32_t* next_ref_id; int32_t* next_pos; int32_t* tlen;
+  uint32_t* cigar_off; uint32_t* seq_off; uint32_t* qual_off; uint32_t* tags_off;
+  uint64_t* coord_key; uint8_t* strand; uint8_t* hi_present; int32_t* hi_value;
+};
+
+// Result block written by the chain kernels (device), copied to the host once per batch.
+struct ChainResult {
+  unsigned long long n_records;
+  unsigned long long tail_off;     // first byte not covered by a complete record
+  uint32_t tail_kind;              // EXIT_* at the end of the true chain
+  uint32_t broken_tile;            // first reachable tile whose successor's speculation mismatched; ~0u if none
+  unsigned long long broken_entry; // the true entry for that successor tile
+  unsigned long long bad_flags;    // records with flag bits >= 0x1000
+  uint32_t rounds;
+  uint32_t pad;
+};
+
+void launch_tile_walk(const RecordParams& p, const TileArrays& t, cudaStream_t s);
+// Re-walks from `entry` at tile `tile` sequentially until the walk re-synchronises with a tile's speculation.
+void launch_tile_repair(const RecordParams& p, const TileArrays& t, uint32_t tile, uint64_t entry, cudaStream_t s);
+// Link + pointer-doubling reachability + masked scan of counts + result summary.
+void launch_chain_resolve(const RecordParams& p, const TileArrays& t, ChainResult* d_result, cudaStream_t s);
+// Second walk: writes rec_off / rec_len for reachable tiles.
+void launch_tile_emit(const RecordParams& p, const TileArrays& t, uint64_t* rec_off, uint32_t* rec_len, cudaStream_t s);
+// Per-record fixed fields, variable offsets, keys (and HI when want_hi).
+void launch_extract(const RecordParams& p, const ColumnsDev& c, uint64_t n_records, bool want_hi,
+                    ChainResult* d_result, cudaStream_t s);
+
+}  // namespace bamgpu

@@ -1,0 +1,341 @@
+// records.cu — K3: BAM record boundaries, fixed fields, variable-field offsets and sort keys.
+//
+// Replaces the single-threaded consumer loop of the reference:
+//   Reader::read_block_size / append_record        bam_tools/src/reader.rs:57-81
+//   Records::next_rec                              reader/records.rs:23-29
+// and materialises what the sort later pulls lazily out of every record:
+//   fixed-field offsets                            record/bamrawrecord.rs:86-97
+//   variable-field offsets (usize form)            record/bamrawrecord.rs:61-77
+//   KeyTuple::CoordinatesAndStrand / Name / HI     sorting/comparators.rs:41-59, record/tags.rs:113-129
+//
+// The chain  next = p + 4 + u32[p]  is serial by definition and the reference walks it blindly
+// (no validation).  We get the identical chain in parallel:
+//   1. k3_tile_walk: the inflated stream is cut into 64 KiB tiles; one thread per tile guesses the
+//      first record start in its tile with a plausibility filter (spec invariants only, so a real
+//      record start of a valid BAM always passes) and walks the chain to the tile end
+//      -> (entry, exit, count).  Tile 0 starts from the KNOWN start (end of the header).
+//   2. k3_link + k3_jump: tile k points at the tile holding its exit iff that tile's guess equals
+//      the exit; pointer DOUBLING from tile 0 marks the tiles on the true chain in log2(n) rounds.
+//   3. a guess that does not match (or a tile jumped over by a long record) is never trusted: the
+//      chain stops there, the host launches k3_tile_repair (serial re-walk from the true entry
+//      until it re-synchronises) and resolves again.  The result is therefore exactly the blind
+//      walk, never the filter's opinion.
+//   4. k3_scan gives every tile its first record index, k3_tile_emit re-walks and writes
+//      rec_off / rec_len, k3_extract (one thread per record) writes the SoA columns + keys.
+#include "kernels.h"
+
+namespace bamgpu {
+namespace {
+
+constexpr uint64_t NONE64 = ~0ull;
+
+__device__ __forceinline__ uint32_t ld32(const uint8_t* data, uint64_t off) {
+  const uint32_t* a = (const uint32_t*)(data + (off & ~3ull));
+  uint32_t sh = (uint32_t)(off & 3) * 8;
+  uint32_t lo = a[0];
+  return sh ? __funnelshift_r(lo, a[1], sh) : lo;
+}
+
+// Spec invariants of a record start (SAM spec §4.2).  Used ONLY to guess; never to decide.
+__device__ bool plausible(const RecordParams& p, uint64_t q) {
+  if (p.data_len - q < 36) return false;
+  uint32_t bs = ld32(p.data, q);
+  if (bs < 33u || bs > (1u << 28)) return false;
+  int32_t ref = (int32_t)ld32(p.data, q + 4);
+  if (ref < -1 || (p.n_ref >= 0 && ref >= p.n_ref)) return false;
+  if ((int32_t)ld32(p.data, q + 8) < -1) return false;
+  uint32_t w = ld32(p.data, q + 12);
+  uint32_t l_name = w & 0xff;
+  if (l_name == 0) return false;
+  uint32_t n_cig = ld32(p.data, q + 16) & 0xffff;
+  uint32_t l_seq = ld32(p.data, q + 20);
+  if (l_seq > bs) return false;
+  int32_t nref = (int32_t)ld32(p.data, q + 24);
+  if (nref < -1 || (p.n_ref >= 0 && nref >= p.n_ref)) return false;
+  if ((int32_t)ld32(p.data, q + 28) < -1) return false;
+  uint64_t need = 32ull + l_name + 4ull * n_cig + (uint64_t)((l_seq + 1u) >> 1) + l_seq;
+  if (need > bs) return false;
+  uint64_t nul = q + 4 + 32 + l_name - 1;
+  if (nul < p.data_len && p.data[nul] != 0) return false;
+  return true;
+}
+
+struct WalkOut { uint64_t exit_off; uint32_t count; uint32_t kind; };
+
+// reader.rs:57-81 restricted to records STARTING before tile_end.  When EMIT, writes offsets.
+template <bool EMIT>
+__device__ WalkOut walk(const RecordParams& p, uint64_t q, uint64_t tile_end, uint64_t* rec_off, uint32_t* rec_len,
+                        uint64_t base) {
+  WalkOut o;
+  uint32_t cnt = 0;
+  for (;;) {
+    if (p.data_len - q < 4) { o.kind = EXIT_TAIL; break; }           // :78 UnexpectedEof => 0
+    if (q >= tile_end) { o.kind = EXIT_NORMAL; break; }
+    uint32_t bs = ld32(p.data, q);
+    if (bs == 0) { o.kind = EXIT_ZERO; break; }                       // :64-72, records.rs:25
+    if (p.data_len - (q + 4) < bs) { o.kind = EXIT_INCOMPLETE; break; }  // :69-70 would panic if final
+    if (EMIT) { rec_off[base + cnt] = q + 4; rec_len[base + cnt] = bs; }
+    ++cnt;
+    q += 4ull + bs;
+  }
+  o.exit_off = q;
+  o.count = cnt;
+  return o;
+}
+
+__global__ void k3_tile_walk(RecordParams p, TileArrays t) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= t.n_tiles) return;
+  const uint64_t tb = (uint64_t)k * TILE_BYTES;
+  uint64_t te = tb + TILE_BYTES;
+  if (te > p.data_len) te = p.data_len;
+  const uint32_t k0 = (uint32_t)(p.start / TILE_BYTES);
+  uint64_t e = NONE64;
+  if (k == k0) e = p.start;
+  else if (k > k0) {
+    for (uint64_t q = tb; q < te; ++q)
+      if (plausible(p, q)) { e = q; break; }
+  }
+  t.entry[k] = e;
+  if (e == NONE64) { t.exit_off[k] = 0; t.count[k] = 0; t.exit_kind[k] = EXIT_NONE; return; }
+  WalkOut o = walk<false>(p, e, te, nullptr, nullptr, 0);
+  t.exit_off[k] = o.exit_off;
+  t.count[k] = o.count;
+  t.exit_kind[k] = o.kind;
+}
+
+// Serial repair: the true chain enters tile `tile` at `entry` but the tile guessed otherwise.
+__global__ void k3_tile_repair(RecordParams p, TileArrays t, uint32_t tile, uint64_t entry) {
+  if (blockIdx.x || threadIdx.x) return;
+  for (;;) {
+    uint64_t te = (uint64_t)(tile + 1) * TILE_BYTES;
+    if (te > p.data_len) te = p.data_len;
+    WalkOut o = walk<false>(p, entry, te, nullptr, nullptr, 0);
+    t.entry[tile] = entry;
+    t.exit_off[tile] = o.exit_off;
+    t.count[tile] = o.count;
+    t.exit_kind[tile] = o.kind;
+    if (o.kind != EXIT_NORMAL) return;
+    uint32_t j = (uint32_t)(o.exit_off / TILE_BYTES);
+    if (t.entry[j] == o.exit_off) return;  // re-synchronised with the guess
+    tile = j;
+    entry = o.exit_off;
+  }
+}
+
+__global__ void k3_link(RecordParams p, TileArrays t) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= t.n_tiles) return;
+  uint32_t nx = k;
+  if (t.entry[k] != NONE64 && t.exit_kind[k] == EXIT_NORMAL) {
+    uint32_t j = (uint32_t)(t.exit_off[k] / TILE_BYTES);
+    if (j < t.n_tiles && t.entry[j] == t.exit_off[k]) nx = j;
+  }
+  t.nxt[k] = nx;
+  t.jump[k] = nx;
+  t.reach[k] = (k == (uint32_t)(p.start / TILE_BYTES)) ? 1 : 0;
+}
+
+__global__ void k3_jump(TileArrays t, const uint32_t* __restrict__ jin, uint32_t* __restrict__ jout) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= t.n_tiles) return;
+  uint32_t j = jin[k];
+  if (t.reach[k]) t.reach[j] = 1;
+  jout[k] = jin[j];
+}
+
+// Exclusive scan of (reach ? count : 0) over all tiles + chain summary.  Single CTA.
+__global__ void __launch_bounds__(1024) k3_scan(RecordParams p, TileArrays t, ChainResult* res) {
+  __shared__ unsigned long long warp_sums[32];
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) {
+    carry = 0;
+    res->broken_tile = 0xffffffffu;
+    res->tail_off = p.start;
+    res->tail_kind = EXIT_TAIL;
+    res->bad_flags = 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < t.n_tiles; base += 1024) {
+    uint32_t k = base + threadIdx.x;
+    bool in = k < t.n_tiles;
+    bool rc = in && t.reach[k];
+    unsigned long long v = rc ? t.count[k] : 0;
+    // the chain's last tile: reachable and its own successor
+    if (rc && t.nxt[k] == k) {
+      if (t.exit_kind[k] == EXIT_NORMAL) {  // successor's guess mismatched (or successor out of range)
+        res->broken_tile = (uint32_t)(t.exit_off[k] / TILE_BYTES);
+        res->broken_entry = t.exit_off[k];
+      } else {
+        res->tail_off = t.exit_off[k];
+        res->tail_kind = t.exit_kind[k];
+      }
+    }
+    unsigned long long x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned long long s = warp_sums[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long y = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += y;
+      }
+      warp_sums[lane] = s;  // inclusive
+    }
+    __syncthreads();
+    unsigned long long off = carry + (wid ? warp_sums[wid - 1] : 0) + (x - v);
+    if (in) t.base[k] = off;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = off + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) res->n_records = carry;
+}
+
+__global__ void k3_tile_emit(RecordParams p, TileArrays t, uint64_t* rec_off, uint32_t* rec_len) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= t.n_tiles || !t.reach[k]) return;
+  uint64_t te = (uint64_t)(k + 1) * TILE_BYTES;
+  if (te > p.data_len) te = p.data_len;
+  walk<true>(p, t.entry[k], te, rec_off, rec_len, t.base[k]);
+}
+
+// ---- HI tag: record/tags.rs:62-129 through bamrawrecord.rs:80-104 (u8-wrapping offset) -------------
+__device__ __forceinline__ int tag_size(uint8_t c) {
+  switch (c) {
+    case 'C': case 'c': case 'A': return 1;
+    case 'S': case 's': return 2;
+    case 'I': case 'i': case 'f': return 4;
+    default: return -1;
+  }
+}
+__device__ __forceinline__ bool tag_type_ok(uint8_t c) {
+  switch (c) {
+    case 'A': case 'B': case 'C': case 'c': case 'f': case 'H': case 'i': case 'I': case 'S': case 's': case 'Z': return true;
+    default: return false;
+  }
+}
+
+// returns 0 none, 1 found (value in *val), 2 = the reference would panic
+__device__ int hit_count(const uint8_t* body, uint32_t len, int32_t* val) {
+  uint32_t l_name = body[8];
+  uint32_t cig = (32u + l_name) & 0xffu;  // bamrawrecord.rs:81 `32 + self.l_read_name()` in u8 (release wrap)
+  uint32_t n_cig = body[12] | (body[13] << 8);
+  uint32_t l_seq = body[16] | (body[17] << 8) | (body[18] << 16) | ((uint32_t)body[19] << 24);
+  uint64_t tags = (uint64_t)cig + 4ull * n_cig + (uint64_t)((l_seq + 1u) / 2u) + l_seq;
+  if (tags > len) return 2;
+  const uint8_t* data = body + tags;
+  uint64_t n = len - tags, idx = 0;
+  while (idx < n) {
+    if (idx + 2 > n) return 2;
+    const uint8_t* d = data + idx + 2;
+    uint64_t dl = n - idx - 2;
+    if (dl < 1) return 2;
+    uint8_t ty = d[0];
+    if (!tag_type_ok(ty)) return 2;
+    const uint8_t* v;
+    uint64_t used;
+    if (ty == 'B') {
+      if (dl < 2 || !tag_type_ok(d[1])) return 2;
+      int isz = tag_size(d[1]);
+      if (isz < 0 || dl < 6) return 2;
+      uint64_t cnt = d[2] | (d[3] << 8) | (d[4] << 16) | ((uint64_t)d[5] << 24);
+      uint64_t bytes = cnt * (uint64_t)isz;
+      if (dl < 6 + bytes) return 2;
+      v = d + 6; used = 6 + bytes;
+    } else if (ty == 'Z' || ty == 'H') {
+      uint64_t i = 1;
+      for (;;) { if (i >= dl) return 2; if (d[i] == 0) break; ++i; }
+      v = d + 1; used = i + 1;
+    } else {
+      int isz = tag_size(ty);
+      if (dl < 1 + (uint64_t)isz) return 2;
+      v = d + 1; used = 1 + isz;
+    }
+    if (data[idx] == 'H' && data[idx + 1] == 'I') {
+      switch (ty) {
+        case 'A': case 'C': *val = (int32_t)v[0]; return 1;
+        case 'c': *val = (int32_t)(int8_t)v[0]; return 1;
+        case 's': *val = (int32_t)(int16_t)(v[0] | (v[1] << 8)); return 1;
+        case 'S': *val = (int32_t)(v[0] | (v[1] << 8)); return 1;
+        case 'i': case 'I': *val = (int32_t)(v[0] | (v[1] << 8) | (v[2] << 16) | ((uint32_t)v[3] << 24)); return 1;
+        default: return 2;  // tags.rs:127 panic
+      }
+    }
+    idx += 2 + used;
+  }
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) k3_extract(RecordParams p, ColumnsDev c, uint64_t n, bool want_hi, ChainResult* res) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool bad = false;
+  if (i < n) {
+    const uint64_t off = c.rec_off[i];
+    const uint32_t len = c.rec_len[i];
+    // a body shorter than 32 bytes makes the reference's get_slice panic; the columns then hold
+    // whatever bytes follow (still inside the buffer padding) — callers see rec_len < 32.
+    uint32_t w0 = ld32(p.data, off), w1 = ld32(p.data, off + 4), w2 = ld32(p.data, off + 8), w3 = ld32(p.data, off + 12);
+    uint32_t w4 = ld32(p.data, off + 16), w5 = ld32(p.data, off + 20), w6 = ld32(p.data, off + 24), w7 = ld32(p.data, off + 28);
+    int32_t ref = (int32_t)w0, pos = (int32_t)w1;
+    uint32_t l_name = w2 & 0xff, n_cig = w3 & 0xffff, flag = w3 >> 16, l_seq = w4;
+    c.ref_id[i] = ref; c.pos[i] = pos;
+    c.l_read_name[i] = (uint8_t)l_name; c.mapq[i] = (uint8_t)(w2 >> 8); c.bin[i] = (uint16_t)(w2 >> 16);
+    c.n_cigar_op[i] = (uint16_t)n_cig; c.flag[i] = (uint16_t)flag; c.l_seq[i] = l_seq;
+    c.next_ref_id[i] = (int32_t)w5; c.next_pos[i] = (int32_t)w6; c.tlen[i] = (int32_t)w7;
+    uint32_t cig = 32u + l_name, seq = cig + 4u * n_cig, qual = seq + (l_seq + 1u) / 2u, tags = qual + l_seq;
+    c.cigar_off[i] = cig; c.seq_off[i] = seq; c.qual_off[i] = qual; c.tags_off[i] = tags;
+    uint32_t r = (ref == -1) ? 0x7fffffffu : (uint32_t)ref;               // comparators.rs:51-54
+    c.coord_key[i] = ((uint64_t)(r ^ 0x80000000u) << 32) | (uint64_t)((uint32_t)pos ^ 0x80000000u);
+    c.strand[i] = (flag & 0x10u) ? 1 : 0;                                  // comparators.rs:173-180
+    bad = (flag & 0xF000u) != 0;                                           // Flags::from_bits(..).unwrap()
+    uint8_t hp = 0; int32_t hv = 0;
+    if (want_hi && len >= 20) { int rc = hit_count(p.data + off, len, &hv); hp = (uint8_t)rc; if (rc != 1) hv = 0; }
+    c.hi_present[i] = hp; c.hi_value[i] = hv;
+  }
+  unsigned m = __ballot_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&res->bad_flags, (unsigned long long)__popc(m));
+}
+
+}  // namespace
+
+static inline uint32_t grid_for(uint64_t n, uint32_t block) { return (uint32_t)((n + block - 1) / block); }
+
+void launch_tile_walk(const RecordParams& p, const TileArrays& t, cudaStream_t s) {
+  if (t.n_tiles) k3_tile_walk<<<grid_for(t.n_tiles, 128), 128, 0, s>>>(p, t);
+}
+
+void launch_tile_repair(const RecordParams& p, const TileArrays& t, uint32_t tile, uint64_t entry, cudaStream_t s) {
+  k3_tile_repair<<<1, 32, 0, s>>>(p, t, tile, entry);
+}
+
+void launch_chain_resolve(const RecordParams& p, const TileArrays& t, ChainResult* d_result, cudaStream_t s) {
+  if (t.n_tiles == 0) return;
+  uint32_t g = grid_for(t.n_tiles, 256);
+  k3_link<<<g, 256, 0, s>>>(p, t);
+  uint32_t* a = t.jump;
+  uint32_t* b = t.jump2;
+  uint32_t rounds = 1;
+  for (uint64_t span = 1; span < t.n_tiles; span <<= 1) ++rounds;
+  for (uint32_t r = 0; r < rounds; ++r) {
+    k3_jump<<<g, 256, 0, s>>>(t, a, b);
+    uint32_t* tmp = a; a = b; b = tmp;
+  }
+  k3_scan<<<1, 1024, 0, s>>>(p, t, d_result);
+}
+
+void launch_tile_emit(const RecordParams& p, const TileArrays& t, uint64_t* rec_off, uint32_t* rec_len, cudaStream_t s) {
+  if (t.n_tiles) k3_tile_emit<<<grid_for(t.n_tiles, 128), 128, 0, s>>>(p, t, rec_off, rec_len);
+}
+
+void launch_extract(const RecordParams& p, const ColumnsDev& c, uint64_t n_records, bool want_hi, ChainResult* d_result,
+                    cudaStream_t s) {
+  if (n_records) k3_extract<<<grid_for(n_records, 256), 256, 0, s>>>(p, c, n_records, want_hi, d_result);
+}
+
+}  // namespace bamgpu

@@ -1,0 +1,286 @@
+"""Host-side mirror of the reference's reader API over the C ABI (include/bamgpu.h).
+
+Names, argument meaning and error behaviour follow ``bam_tools::Reader``
+(/root/reference/bam_tools/src/reader.rs, reader/records.rs):
+
+    reader = Reader.new(inner, thread_num, track_progress=None)   # reader.rs:28-55
+    header_bytes, offset_to_ref_seqs = reader.read_header()       # reader.rs:87-98
+    records = reader.records()                                    # reader.rs:83
+    rec = records.next_rec()            # Option<&Vec<u8>> -> memoryview | None   records.rs:23-29
+    for rec in reader.records(): ...    # cloning iterator -> bytes               records.rs:32-42
+    n = reader.read_record(buf)         # clears then appends; 0 = EOF            reader.rs:57-61
+    n = reader.append_record(buf)       # reader.rs:63-73
+    data = reader.read(n)               # impl Read                               reader.rs:114-152
+    parse_reference_sequences(header_bytes[offset_to_ref_seqs:])  # reader.rs:101-112
+
+Where the reference panics (corrupt block, short record body) this raises BamGpuError; where it
+ends silently (short tail, block_size 0, BSIZE wrap) this ends silently too.
+
+The record bytes, the columns and the keys all come from the CUDA kernels in libbamgpu.so.
+There is no CPU decode path here; importing works without a GPU but constructing a Reader does not.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import (COLUMN_FIELDS, COPY_COLUMNS, COPY_DATA, NO_CRC, NO_RECORDS, WANT_HI, BamGpuError, Batch, Block, Opts,
+                   Stats)
+
+_NP = {C.c_uint64: np.uint64, C.c_uint32: np.uint32, C.c_int32: np.int32, C.c_uint16: np.uint16, C.c_uint8: np.uint8}
+
+
+def _view(ptr, n, ctype):
+    if not ptr or n == 0:
+        return np.zeros(0, dtype=_NP[ctype])
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,))
+
+
+class RecordBatch:
+    """All records of one pipeline batch: device pointers plus (when copied) host numpy views.
+    Views are valid until the next batch is requested from the same Reader / Engine."""
+
+    def __init__(self, b: Batch):
+        self.n_records = int(b.n_records)
+        self.data_len = int(b.data_len)
+        self.first_record_index = int(b.first_record_index)
+        self.bad_flag_records = int(b.bad_flag_records)
+        self.dev_data = b.data
+        self.dev = {n: getattr(b.dev, n) for n, _ in COLUMN_FIELDS}
+        self.data = _view(b.h_data, self.data_len, C.c_uint8) if b.h_data else None
+        self.columns = None
+        if b.host.rec_off:
+            self.columns = {n: _view(getattr(b.host, n), self.n_records, ct) for n, ct in COLUMN_FIELDS}
+
+    def body(self, i: int) -> memoryview:
+        o = int(self.columns["rec_off"][i])
+        return memoryview(self.data)[o:o + int(self.columns["rec_len"][i])]
+
+
+class Records:
+    """reader/records.rs:10-42."""
+
+    def __init__(self, reader: "Reader"):
+        self._r = reader
+
+    def next_rec(self) -> Optional[memoryview]:
+        """Lends the next record body (valid until the next call); None at EOF."""
+        L, r = self._r._L, self._r
+        body, n = C.c_void_p(), C.c_size_t()
+        rc = L.bamgpu_next_rec(r._h, C.byref(body), C.byref(n))
+        if rc == _lib.EOF:
+            return None
+        if rc < 0:
+            raise BamGpuError(rc, L.bamgpu_last_error(r._h).decode())
+        return memoryview((C.c_uint8 * n.value).from_address(body.value))
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> bytes:
+        rec = self.next_rec()
+        if rec is None:
+            raise StopIteration
+        return bytes(rec)
+
+
+class Reader:
+    def __init__(self, inner, thread_num: int = 4, track_progress: Optional[int] = None, *, flags: int = 0,
+                 batch_bytes: int = 0, device: int = -1):
+        self._L = L = _lib.load()
+        self._inner = inner
+        opts = Opts(device, flags, batch_bytes, 0, 0)
+        tp = C.c_uint64(track_progress) if track_progress is not None else None
+        self._keep = None
+        if isinstance(inner, (bytes, bytearray, memoryview, np.ndarray)):
+            arr = np.frombuffer(inner, dtype=np.uint8) if not isinstance(inner, np.ndarray) else inner
+            self._keep = arr
+            self._h = L.bamgpu_reader_from_memory(arr.ctypes.data, arr.size, thread_num, C.byref(opts))
+        else:
+            readinto = getattr(inner, "readinto", None)
+
+            def _read(_ctx, dst, cap):
+                try:
+                    if readinto is not None:
+                        buf = (C.c_uint8 * cap).from_address(C.addressof(dst.contents))
+                        n = readinto(buf)
+                        return int(n or 0)
+                    chunk = inner.read(cap)
+                    C.memmove(dst, chunk, len(chunk))
+                    return len(chunk)
+                except Exception:
+                    return -1
+
+            self._cb = _lib.READ_FN(_read)
+            self._h = L.bamgpu_reader_new(self._cb, None, thread_num, C.byref(tp) if tp is not None else None, C.byref(opts))
+        if not self._h:
+            raise BamGpuError(-2, "could not create reader: no usable CUDA device (there is no CPU fallback)")
+
+    # Reader::new(inner, thread_num, track_progress)
+    @classmethod
+    def new(cls, inner, thread_num: int = 4, track_progress: Optional[int] = None, **kw) -> "Reader":
+        return cls(inner, thread_num, track_progress, **kw)
+
+    def _check(self, rc):
+        if rc < 0:
+            raise BamGpuError(rc, self._L.bamgpu_last_error(self._h).decode())
+        return rc
+
+    def read_header(self):
+        p, n, off = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        self._check(self._L.bamgpu_read_header(self._h, C.byref(p), C.byref(n), C.byref(off)))
+        return C.string_at(p.value, n.value), off.value
+
+    def records(self) -> Records:
+        return Records(self)
+
+    def append_record(self, buf: bytearray) -> int:
+        need = C.c_size_t()
+        rc = self._L.bamgpu_append_record(self._h, None, 0, C.byref(need))
+        if rc == _lib.OK and need.value == 0:
+            return 0
+        if rc != -23:
+            self._check(rc)
+        n = need.value
+        tmp = (C.c_uint8 * n)()
+        self._check(self._L.bamgpu_append_record(self._h, tmp, n, C.byref(need)))
+        buf += bytes(tmp)
+        return n
+
+    def read_record(self, buf: bytearray) -> int:
+        del buf[:]
+        return self.append_record(buf)
+
+    def read(self, n: int = -1) -> bytes:
+        out = bytearray()
+        chunk = 1 << 20 if n < 0 else n
+        tmp = (C.c_uint8 * chunk)()
+        while n < 0 or len(out) < n:
+            want = chunk if n < 0 else min(chunk, n - len(out))
+            got = self._L.bamgpu_read(self._h, tmp, want)
+            if got < 0:
+                raise BamGpuError(got, self._L.bamgpu_last_error(self._h).decode())
+            if got == 0:
+                break
+            out += bytes(tmp[:got]) if got < chunk else bytes(tmp)
+        return bytes(out)
+
+    def next_batch(self) -> Optional[RecordBatch]:
+        """GPU-native interface: every record of the next batch as structure-of-arrays columns."""
+        b = Batch()
+        rc = self._L.bamgpu_next_batch(self._h, C.byref(b))
+        if rc == _lib.EOF:
+            return None
+        self._check(rc)
+        return RecordBatch(b)
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._L.bamgpu_reader_stats(self._h, C.byref(s))
+        return s.asdict()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.bamgpu_reader_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def parse_reference_sequences(b: bytes):
+    """reader.rs:101-112: [(name without NUL, l_ref)] from header bytes starting at n_ref."""
+    L = _lib.load()
+    out = []
+
+    @_lib.REFSEQ_CB
+    def cb(name, n, l_ref, _u):
+        out.append((C.string_at(name, n).decode("utf-8"), l_ref))
+
+    buf = (C.c_uint8 * len(b)).from_buffer_copy(b) if len(b) else None
+    rc = L.bamgpu_parse_reference_sequences(buf, len(b), cb, None)
+    if rc < 0:
+        raise BamGpuError(rc, "parse_reference_sequences")
+    return out
+
+
+def scan_blocks(data, final: bool = True):
+    """bamgpu_scan_blocks over a bytes-like object -> (ctypes Block array, n, consumed, total_isize, rc)."""
+    L = _lib.load()
+    arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    n, consumed, tot = C.c_size_t(), C.c_size_t(), C.c_uint64()
+    rc = L.bamgpu_scan_blocks(arr.ctypes.data, arr.size, int(final), None, 0, C.byref(n), C.byref(consumed), C.byref(tot))
+    blocks = (Block * max(n.value, 1))()
+    if n.value:
+        L.bamgpu_scan_blocks(arr.ctypes.data, arr.size, int(final), blocks, n.value, C.byref(n), C.byref(consumed), C.byref(tot))
+    return blocks, n.value, consumed.value, tot.value, rc
+
+
+class Engine:
+    """Device-resident decode (bamgpu_engine_*): what Reader runs per batch and what bench.py times."""
+
+    def __init__(self, device: int = -1, flags: int = 0):
+        self._L = L = _lib.load()
+        opts = Opts(device, flags, 0, 0, 0)
+        self._h = L.bamgpu_engine_new(C.byref(opts))
+        if not self._h:
+            raise BamGpuError(-2, "could not create engine: no usable CUDA device (there is no CPU fallback)")
+        self._dev_bufs = []
+
+    def upload(self, data) -> int:
+        arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        d = self._L.bamgpu_device_alloc(self._h, max(arr.size, 1))
+        if not d:
+            raise BamGpuError(-3, "device alloc")
+        self._dev_bufs.append(d)
+        if arr.size:
+            rc = self._L.bamgpu_memcpy_h2d(self._h, d, arr.ctypes.data, arr.size)
+            if rc < 0:
+                raise BamGpuError(rc, self._L.bamgpu_engine_last_error(self._h).decode())
+        return d
+
+    def free(self, d):
+        self._dev_bufs.remove(d)
+        self._L.bamgpu_device_free(self._h, d)
+
+    def decode(self, d_comp, blocks, n_blocks, stream_start, final=True, flags=COPY_DATA | COPY_COLUMNS, cuda_stream=None):
+        b, tail = Batch(), C.c_uint64()
+        rc = self._L.bamgpu_engine_decode(self._h, d_comp, blocks, n_blocks, stream_start, int(final), flags,
+                                          cuda_stream, C.byref(b), C.byref(tail))
+        if rc < 0:
+            raise BamGpuError(rc, self._L.bamgpu_engine_last_error(self._h).decode())
+        return RecordBatch(b), tail.value, rc
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._L.bamgpu_engine_stats(self._h, C.byref(s))
+        return s.asdict()
+
+    def reset_stats(self):
+        self._L.bamgpu_engine_reset_stats(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for d in self._dev_bufs:
+                self._L.bamgpu_device_free(self._h, d)
+            self._dev_bufs = []
+            self._L.bamgpu_engine_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

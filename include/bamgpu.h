@@ -1,0 +1,226 @@
+/*
+ * bamgpu.h — C ABI of the B200-native BAM decode path (libbamgpu.so).
+ *
+ * This is the drop-in boundary for ONE path of NickRoz1/bam_parallel: the
+ * multi-threaded BGZF inflater + BAM record parser behind
+ *     bam_tools::Reader::new(reader, n, track_progress)      bam_tools/src/reader.rs:28-55
+ *     Reader::read_header()                                  reader.rs:87-98
+ *     Reader::records().next_rec()                           reader/records.rs:23-29
+ *     Reader::read_record / append_record                    reader.rs:57-73
+ *     impl Read for Reader                                   reader.rs:114-152
+ *     parse_reference_sequences()                            reader.rs:101-112
+ * plus the key-extraction slice of the sort that consumes it
+ *     create_key_tuple / KeyTuple                            sorting/comparators.rs:15-59
+ *     BAMRawRecord fixed/variable field offsets              record/bamrawrecord.rs:49-105
+ *     get_hit_count (HI tag)                                 record/tags.rs:113-129
+ *
+ * The reference has no FFI of its own (pure Rust); these entry points are what a Rust
+ * `bam_tools` shim binds (rust/bamgpu-sys).  Plain C types only: no
+ * CUDA, torch or C++ types cross this boundary.  No exceptions or panics cross it
+ * either: every call returns 0 / a negative bamgpu_status, and bamgpu_last_error()
+ * gives the text.  One consumer thread per reader (the reference takes &mut self).
+ *
+ * There is NO CPU fallback: if no CUDA device is usable, constructors fail with
+ * BAMGPU_ERR_CUDA.
+ */
+#ifndef BAMGPU_H
+#define BAMGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum bamgpu_status {
+  BAMGPU_OK = 0,
+  BAMGPU_EOF = 1,                   /* clean end of stream (reference: Ok(0) / None) */
+  BAMGPU_ERR_ARG = -1,
+  BAMGPU_ERR_CUDA = -2,             /* CUDA runtime failure or no device */
+  BAMGPU_ERR_NOMEM = -3,
+  BAMGPU_ERR_IO = -4,               /* the caller's read callback returned < 0 */
+  BAMGPU_ERR_BLOCK_TOO_SMALL = -10, /* util.rs:29-38  InvalidData "expected clen >= 26" */
+  BAMGPU_ERR_TRUNCATED_BLOCK = -11, /* util.rs:42,44  read_exact fails -> readahead.rs:92 unwrap panic */
+  BAMGPU_ERR_INFLATE = -12,         /* readahead.rs:148 expect("Decompression failed.") */
+  BAMGPU_ERR_ISIZE = -13,           /* stricter than the reference: inflated size != ISIZE footer */
+  BAMGPU_ERR_CRC = -14,             /* stricter than the reference: CRC32 footer mismatch (util.rs:68-71 discards it) */
+  BAMGPU_ERR_BAD_MAGIC = -20,       /* reader.rs:90-95 "invalid BAM header" */
+  BAMGPU_ERR_SHORT_HEADER = -21,    /* reader.rs:172-190 unwrap()/? on a short header */
+  BAMGPU_ERR_SHORT_RECORD = -22,    /* reader.rs:69-70 expect("Failed to read.") */
+  BAMGPU_ERR_BUFFER_TOO_SMALL = -23,
+  BAMGPU_ERR_STATE = -24            /* call out of order (e.g. records before read_header) */
+} bamgpu_status;
+
+/* ------------------------------------------------------------------------------------------
+ * Host-side BGZF scan (replaces util.rs:18-71 fetch_block/read_block_size/consume_trailer).
+ * Unlike the reference we KEEP the trailer: ISIZE places each block's output by exclusive
+ * scan, CRC32 is verified on the GPU.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct bamgpu_block {
+  uint64_t in_off;   /* offset of the DEFLATE payload (after the 18-byte header) in the scanned buffer */
+  uint64_t out_off;  /* exclusive scan of ISIZE: where this block's bytes land in the inflated stream */
+  uint32_t in_len;   /* DEFLATE payload length = BSIZE+1-26 */
+  uint32_t isize;    /* ISIZE footer */
+  uint32_t crc32;    /* CRC32 footer */
+  uint32_t reserved;
+} bamgpu_block;
+
+/* Scans `len` bytes of a BGZF stream.  Writes up to `cap` block descriptors; *n_blocks gets the
+ * number found; *consumed the bytes covered by whole blocks; *total_isize the sum of ISIZE.
+ * `final` != 0 means no more bytes will follow: a trailing partial header (<18 bytes) or a
+ * BSIZE of 0xFFFF ends the stream silently (util.rs:58-60,65), a partial block body is
+ * BAMGPU_ERR_TRUNCATED_BLOCK.  With final == 0 a partial tail is simply left unconsumed.
+ * Returns BAMGPU_OK, BAMGPU_EOF (silent end seen) or an error. */
+int bamgpu_scan_blocks(const uint8_t* buf, size_t len, int final, bamgpu_block* blocks, size_t cap,
+                       size_t* n_blocks, size_t* consumed, uint64_t* total_isize);
+
+/* ------------------------------------------------------------------------------------------
+ * Decoded batch: structure-of-arrays view of consecutive records (K3 output).
+ * Every pointer is a DEVICE pointer unless the name starts with h_ (pinned host mirror, only
+ * filled when the corresponding BAMGPU_COPY_* bit is set).  Valid until the next
+ * bamgpu_next_batch / bamgpu_engine_decode call on the same object.
+ * Field meanings: record/bamrawrecord.rs:86-97 (fixed), :61-77 (variable offsets, usize form),
+ * sorting/comparators.rs:41-59 (keys), record/tags.rs:113-129 (HI).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct bamgpu_columns {
+  const uint64_t* rec_off;      /* offset of the record BODY (after block_size) in `data` */
+  const uint32_t* rec_len;      /* block_size */
+  const int32_t* ref_id;
+  const int32_t* pos;
+  const uint8_t* l_read_name;
+  const uint8_t* mapq;
+  const uint16_t* bin;
+  const uint16_t* n_cigar_op;
+  const uint16_t* flag;
+  const uint32_t* l_seq;
+  const int32_t* next_ref_id;
+  const int32_t* next_pos;
+  const int32_t* tlen;
+  const uint32_t* cigar_off;    /* body-relative: 32 + l_read_name */
+  const uint32_t* seq_off;      /* + 4*n_cigar_op */
+  const uint32_t* qual_off;     /* + (l_seq+1)/2 */
+  const uint32_t* tags_off;     /* + l_seq */
+  const uint64_t* coord_key;    /* ((refID==-1 ? i32::MAX : refID) ^ 2^31) << 32 | (pos ^ 2^31); order = (coord_key, strand) */
+  const uint8_t* strand;        /* (flag & 0x10) != 0 : comparators.rs:173-180 */
+  const uint8_t* hi_present;    /* HI tag found (get_hit_count -> Some) ; 2 = reference would panic walking the tags */
+  const int32_t* hi_value;
+} bamgpu_columns;
+
+typedef struct bamgpu_batch {
+  uint64_t n_records;
+  uint64_t data_len;            /* bytes of inflated stream held in `data` */
+  const uint8_t* data;          /* device: inflated bytes; record i's body = data[rec_off[i] .. +rec_len[i]] */
+  const uint8_t* h_data;        /* pinned host mirror of data (BAMGPU_COPY_DATA) */
+  bamgpu_columns dev;           /* device columns */
+  bamgpu_columns host;          /* pinned host mirrors (BAMGPU_COPY_COLUMNS), else NULLs */
+  uint64_t first_record_index;  /* index of record 0 of this batch in the whole stream */
+  uint64_t bad_flag_records;    /* records with flag bits >= 0x1000 (reference coord sort would panic) */
+} bamgpu_batch;
+
+enum {
+  BAMGPU_COPY_DATA = 1,         /* D2H the inflated bytes (needed by next_rec/read/append_record) */
+  BAMGPU_COPY_COLUMNS = 2,      /* D2H the SoA columns */
+  BAMGPU_WANT_HI = 4,           /* walk aux tags for HI (only the -n -M sort needs it) */
+  BAMGPU_NO_CRC = 8,            /* skip the CRC32 check (default: verify) */
+  BAMGPU_NO_RECORDS = 16        /* inflate (+CRC) only: no record kernel (impl Read consumers) */
+};
+
+typedef struct bamgpu_opts {
+  int32_t device;               /* CUDA device ordinal; -1 = current */
+  uint32_t flags;               /* BAMGPU_* bits */
+  uint64_t batch_bytes;         /* compressed bytes per pipeline batch (0 = default 256 MiB) */
+  int32_t inflate_impl;         /* 0 = default; see DESIGN.md "K1 variants" */
+  int32_t reserved;
+} bamgpu_opts;
+
+/* Per-stage device times (CUDA events on the engine's stream) and counters, cumulative. */
+typedef struct bamgpu_stats {
+  uint64_t blocks, bytes_in, bytes_out, records, batches, kernel_launches;
+  double ms_h2d, ms_inflate, ms_crc, ms_records, ms_d2h, ms_total;
+} bamgpu_stats;
+
+/* ------------------------------------------------------------------------------------------
+ * Engine: runs the kernels over a compressed buffer that is ALREADY in device memory.
+ * This is what Reader uses per batch, and what bench.py times for the device-resident
+ * `value` line.  One engine = one CUDA device + one stream.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct bamgpu_engine bamgpu_engine;
+
+bamgpu_engine* bamgpu_engine_new(const bamgpu_opts* opts /*nullable*/);
+void bamgpu_engine_free(bamgpu_engine*);
+const char* bamgpu_engine_last_error(const bamgpu_engine*);
+
+/* Device allocation helpers so callers without a CUDA binding (ctypes tests) can stage data. */
+void* bamgpu_device_alloc(bamgpu_engine*, size_t bytes);
+void bamgpu_device_free(bamgpu_engine*, void* dptr);
+void* bamgpu_pinned_alloc(size_t bytes);
+void bamgpu_pinned_free(void* p);
+int bamgpu_memcpy_h2d(bamgpu_engine*, void* dst, const void* src, size_t bytes);
+int bamgpu_memcpy_d2h(bamgpu_engine*, void* dst, const void* src, size_t bytes);
+
+/* Decode `n_blocks` BGZF blocks whose payloads live in device buffer d_comp (in_off relative to it;
+ * the buffer must be readable for 16 bytes past the last payload).  `stream_start` is the offset in
+ * the inflated stream where the record chain starts (reader.rs:63: right after the BAM header for the
+ * first batch, the carry-over position for later ones).  If `cuda_stream` is non-NULL the work is
+ * enqueued on that cudaStream_t instead of the engine's own (lets a caller time it with its own
+ * events).  Synchronises before returning.  *tail_off gets the offset of the first byte not covered
+ * by a complete record (== data_len when the chain ends exactly at the end or on a 0..3-byte tail /
+ * block_size 0 with `final`), so a streaming caller can carry the partial record over. */
+int bamgpu_engine_decode(bamgpu_engine*, const uint8_t* d_comp, const bamgpu_block* blocks, size_t n_blocks,
+                         uint64_t stream_start, int final, uint32_t flags, void* cuda_stream,
+                         bamgpu_batch* out, uint64_t* tail_off);
+
+int bamgpu_engine_stats(const bamgpu_engine*, bamgpu_stats* out);
+void bamgpu_engine_reset_stats(bamgpu_engine*);
+
+/* ------------------------------------------------------------------------------------------
+ * Reader: streaming drop-in for bam_tools::Reader over a caller-supplied byte source.
+ * ---------------------------------------------------------------------------------------- */
+/* std::io::Read::read: return n > 0 bytes written to dst, 0 at EOF, < 0 on error. May be called from
+ * an internal thread (the reference moves `inner` to its reading thread too: readahead.rs:88). */
+typedef long (*bamgpu_read_fn)(void* ctx, uint8_t* dst, size_t cap);
+
+typedef struct bamgpu_reader bamgpu_reader;
+
+/* Reader::new (reader.rs:28-55).  thread_num is accepted for signature parity and clamped like the
+ * reference ([3, num_cpus]); the GPU path needs one host feeder thread regardless.  track_progress
+ * (nullable) = total compressed size, kept as a byte counter (no progress bar). */
+bamgpu_reader* bamgpu_reader_new(bamgpu_read_fn read, void* ctx, size_t thread_num, const uint64_t* track_progress,
+                                 const bamgpu_opts* opts /*nullable*/);
+/* Convenience: reader over an in-memory BGZF buffer (not copied; must outlive the reader). */
+bamgpu_reader* bamgpu_reader_from_memory(const uint8_t* buf, size_t len, size_t thread_num, const bamgpu_opts* opts);
+void bamgpu_reader_free(bamgpu_reader*);
+const char* bamgpu_last_error(const bamgpu_reader*);
+
+/* Reader::read_header (reader.rs:87-98): *bytes = l_text|text|n_ref|(l_name|name|l_ref)* WITHOUT the
+ * 4 magic bytes, owned by the reader; *offset_to_ref_seqs = 4 + l_text. */
+int bamgpu_read_header(bamgpu_reader*, const uint8_t** bytes, size_t* len, size_t* offset_to_ref_seqs);
+
+/* Records::next_rec (records.rs:23-29): lends the next record body; valid until the next call.
+ * Returns BAMGPU_OK, BAMGPU_EOF (None) or an error. */
+int bamgpu_next_rec(bamgpu_reader*, const uint8_t** body, size_t* len);
+/* Reader::append_record (reader.rs:63-73): copies the next body to dst[0..cap); *len = block_size,
+ * 0 at EOF. BAMGPU_ERR_BUFFER_TOO_SMALL leaves the record unconsumed and sets *len to the size needed. */
+int bamgpu_append_record(bamgpu_reader*, uint8_t* dst, size_t cap, size_t* len);
+/* impl Read for Reader (reader.rs:114-152): inflated byte stream; returns bytes read, 0 at EOF, <0 error.
+ * Unlike the reference it never returns a short "Interrupted" read at block switches. */
+long bamgpu_read(bamgpu_reader*, uint8_t* dst, size_t cap);
+/* GPU-native batch interface (no reference counterpart): all records of the next pipeline batch. */
+int bamgpu_next_batch(bamgpu_reader*, bamgpu_batch* out);
+int bamgpu_reader_stats(const bamgpu_reader*, bamgpu_stats* out);
+
+/* parse_reference_sequences (reader.rs:101-112,213-228) over header bytes starting at n_ref.
+ * Calls cb(name_without_nul, name_len, l_ref, user) per reference; returns BAMGPU_OK or
+ * BAMGPU_ERR_SHORT_HEADER (short input / name not NUL-terminated or with an interior NUL). */
+typedef void (*bamgpu_refseq_cb)(const char* name, size_t name_len, uint32_t l_ref, void* user);
+int bamgpu_parse_reference_sequences(const uint8_t* bytes, size_t len, bamgpu_refseq_cb cb, void* user);
+
+const char* bamgpu_status_str(int status);
+/* "sm_100a;<build id>" — lets callers assert the CUDA library (not a fallback) is loaded. */
+const char* bamgpu_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAMGPU_H */

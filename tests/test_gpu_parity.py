@@ -1,0 +1,323 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the oracle on the same seeded inputs.
+Bit-exact everywhere (byte / integer / index work): inflated bytes, record boundaries, the 11 fixed
+fields, the 4 variable-field offsets, the coordinate key + strand, HI, and the md5 of record bodies
+(main.rs:83-99).  Run with `pytest -m gpu` on the B200 box."""
+import hashlib
+import io
+import json
+import os
+import random
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+import bam_parallel_b200 as bp
+from bam_parallel_b200 import synth
+from oracle import oracle as orc
+from tests import bamcraft as bc
+
+pytestmark = pytest.mark.gpu
+
+COLS = [n for n in orc.COLUMN_DTYPES]
+
+
+@pytest.fixture(scope="module")
+def engine():
+    e = bp.Engine()
+    yield e
+    e.close()
+
+
+def _oracle_decode(oracle, data, want_hi=True):
+    u, sizes = oracle.inflate_all(data)
+    hdr, off_refs, consumed = oracle.read_header(u)
+    off, ln = oracle.walk_records(u, consumed)
+    cols, bf, bt = oracle.extract(u, off, ln, want_hi)
+    return u, hdr, off_refs, consumed, off, ln, cols, bf, bt
+
+
+def _engine_decode(engine, data, start, flags=bp.COPY_DATA | bp.COPY_COLUMNS | bp.WANT_HI, final=True):
+    blocks, nb, consumed, total, rc = bp.scan_blocks(data)
+    d = engine.upload(data)
+    try:
+        batch, tail, rc = engine.decode(d, blocks, nb, start, final, flags)
+        # copy out of the pinned mirrors before the next call reuses them
+        out = dict(n=batch.n_records, data=batch.data.copy() if batch.data is not None else None,
+                   cols={k: v.copy() for k, v in batch.columns.items()} if batch.columns else None,
+                   tail=tail, rc=rc, bad_flags=batch.bad_flag_records)
+    finally:
+        engine.free(d)
+    return out
+
+
+def _assert_parity(oracle, engine, data, want_hi=True):
+    u, hdr, off_refs, consumed, off, ln, cols, bf, bt = _oracle_decode(oracle, data, want_hi)
+    g = _engine_decode(engine, data, consumed)
+    assert g["data"].tobytes() == u.tobytes()
+    assert g["n"] == off.size
+    assert np.array_equal(g["cols"]["rec_off"], off) and np.array_equal(g["cols"]["rec_len"], ln)
+    for k in COLS:
+        if k == "hi_present":
+            assert np.array_equal(g["cols"][k] == 1, cols[k] == 1), k
+            assert int((g["cols"][k] == 2).sum()) == bt
+        else:
+            assert np.array_equal(g["cols"][k], cols[k]), k
+    assert np.array_equal(g["cols"]["strand"], cols["strand"])
+    assert g["bad_flags"] == bf
+    return u, off, ln, g
+
+
+@pytest.mark.parametrize("shape,n,payload", [("se150", 20000, 0xFF00), ("pe150", 20000, 0xFF00), ("longname", 8000, 0xFF00),
+                                             ("long10k", 300, 4096), ("long10k", 300, 0xFF00), ("pe150", 1500, 300)])
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_engine_parity_synth(oracle, engine, shape, n, payload, level):
+    data = synth.generate(shape, n, level=level, payload=payload).tobytes()
+    _assert_parity(oracle, engine, data)
+
+
+def test_engine_matches_self_golden_md5(oracle, engine):
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "selfgolden.json")))
+    for shape, n, level, payload, tag in [("pe150", 5000, 6, 0xFF00, "pe150_5000_L6"), ("se150", 5000, 6, 0xFF00, "se150_5000_L6"),
+                                          ("longname", 3000, 1, 0xFF00, "longname_3000_L1"),
+                                          ("long10k", 100, 9, 4096, "long10k_100_L9_p4096")]:
+        data = synth.generate(shape, n, level=level, payload=payload, threads=1).tobytes()
+        assert hashlib.md5(data).hexdigest() == g[tag + "_md5_file"]
+        u = oracle.inflate_all(data)[0]
+        _, _, consumed = oracle.read_header(u)
+        r = _engine_decode(engine, data, consumed)
+        h = hashlib.md5()
+        db = r["data"].tobytes()
+        for o, l in zip(r["cols"]["rec_off"].tolist(), r["cols"]["rec_len"].tolist()):
+            h.update(db[o:o + l])
+        assert h.hexdigest() == g[tag + "_md5_bodies"]
+
+
+def test_one_million_record_config1(oracle, engine):
+    """BASELINE.json configs[0]: 1M-record 150bp single-end BAM, level 6."""
+    data = synth.generate("se150", 1_000_000, level=6).tobytes()
+    _assert_parity(oracle, engine, data, want_hi=False)
+
+
+def test_deflate_block_kinds_and_overlaps(oracle, engine):
+    rnd = random.Random(1)
+    noise = bytes(rnd.randrange(256) for _ in range(40000))
+    text = b"".join(b"read%05d\tACGTACGTTTGA\t!!!!FFFFFFFF\n" % i for i in range(1500))
+    payloads = []
+    for period in [1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 258, 259, 32768]:
+        pat = bytes(rnd.randrange(1, 256) for _ in range(period))
+        for lead in range(4):
+            payloads.append(bytes(rnd.randrange(256) for _ in range(lead)) + (pat * (65000 // period + 1))[: 65000 - lead])
+    blk = lambda ps, **kw: b"".join(bc.bgzf_block(p, **kw) for p in ps)
+    data = (blk([noise], level=0) + blk([noise], level=6) + blk([b"abcabcabcabc" * 3, b"a", b"", b"xyz"], level=6)
+            + blk([text[:60000]], level=9) + blk([text[:50000]], level=6, strategy=zlib.Z_FIXED)
+            + blk([text[:50000]], level=6, strategy=zlib.Z_HUFFMAN_ONLY)
+            + blk([b"\0" * 65000, b"ab" * 30000], level=6, strategy=zlib.Z_RLE) + blk(payloads, level=6)
+            + blk([bytes(rnd.randrange(256) for _ in range(0xFF00))]) + blk([b"Q" * 65535], level=9) + bc.BGZF_EOF)
+    u, _ = oracle.inflate_all(data)
+    r = _engine_decode(engine, data, 0, flags=bp.COPY_DATA | bp.NO_RECORDS)
+    assert r["data"].tobytes() == u.tobytes()
+
+
+def test_many_small_unaligned_blocks(oracle, engine):
+    rnd = random.Random(3)
+    payloads = [bytes(rnd.choice(b"ACGTN!F#") for _ in range(rnd.randrange(0, 700))) for _ in range(3000)]
+    data = b"".join(bc.bgzf_block(p, level=rnd.choice([1, 6, 9])) for p in payloads) + bc.BGZF_EOF
+    u, _ = oracle.inflate_all(data)
+    r = _engine_decode(engine, data, 0, flags=bp.COPY_DATA | bp.NO_RECORDS)
+    assert r["data"].tobytes() == u.tobytes()
+
+
+def test_corrupt_blocks_are_reported(engine):
+    rnd = random.Random(11)
+    good = bytes(rnd.choice(b"ACGT") for _ in range(30000))
+    ok = bc.bgzf_block(good)
+    bad_crc = bc.bgzf_block(good, crc=0x12345678)
+    with pytest.raises(bp.BamGpuError) as e:
+        _engine_decode(engine, ok + bad_crc + ok + bc.BGZF_EOF, 0, flags=bp.COPY_DATA | bp.NO_RECORDS)
+    assert e.value.code == -14 and "block 1" in str(e.value)
+    # the reference never looks at the CRC (util.rs:68-71): NO_CRC reproduces that
+    r = _engine_decode(engine, ok + bad_crc + bc.BGZF_EOF, 0, flags=bp.COPY_DATA | bp.NO_RECORDS | bp.NO_CRC)
+    assert r["data"].tobytes() == good + good
+    with pytest.raises(bp.BamGpuError) as e:
+        _engine_decode(engine, bc.bgzf_block(good, isize=len(good) - 1) + bc.BGZF_EOF, 0, flags=bp.NO_RECORDS)
+    assert e.value.code == -13
+    b2 = bytearray(ok); b2[18] |= 0x06
+    with pytest.raises(bp.BamGpuError) as e:
+        _engine_decode(engine, bytes(b2) + bc.BGZF_EOF, 0, flags=bp.NO_RECORDS)
+    assert e.value.code == -12
+    for trial in range(40):                       # random corruption: an error or (rarely) same bytes; never a crash
+        b3 = bytearray(ok)
+        for _ in range(rnd.randrange(1, 4)):
+            b3[rnd.randrange(18, len(b3) - 8)] ^= 1 << rnd.randrange(8)
+        try:
+            _engine_decode(engine, ok + bytes(b3) + ok + bc.BGZF_EOF, 0, flags=bp.NO_RECORDS)
+        except bp.BamGpuError as ex:
+            assert ex.code in (-12, -13, -14)
+
+
+def test_record_chain_edge_cases(oracle, engine):
+    hdr = bc.bam_header()
+    cases = {
+        "header only": hdr,
+        "one record": hdr + bc.bam_record(),
+        "tail 3 bytes": hdr + bc.bam_record() + b"\x07\x07\x07",
+        "zero block_size stops": hdr + bc.bam_record(name=b"a") + struct.pack("<I", 0) + bc.bam_record(name=b"ghost") * 50,
+        "default record": hdr + struct.pack("<I", 34) + bytes.fromhex("ffffffffffffffff02ff481200000400" "00000000ffffffffffffffff000000002a00"),
+        "long names": hdr + b"".join(bc.bam_record(name=b"N" * k, tags=b"HIi" + struct.pack("<i", k)) for k in (1, 100, 222, 223, 229, 254)),
+        "bad flags": hdr + bc.bam_record(flag=0x1010) + bc.bam_record(flag=0xFFFF),
+    }
+    for name, stream in cases.items():
+        for payload in (0xFF00, 61):
+            _assert_parity(oracle, engine, bc.bgzf(stream, payload=payload))
+
+
+def test_adversarial_bodies_do_not_fool_the_chain(oracle, engine):
+    """Record payloads that contain byte patterns looking exactly like record starts: the speculative tile
+    entry may be fooled, the verified chain must not be (it has to equal the blind walk of reader.rs:63-81)."""
+    hdr = bc.bam_header()
+    fake = bc.bam_record(name=b"fake", seq_len=20)
+    rnd = random.Random(9)
+    recs = []
+    for i in range(3000):
+        # qualities made of whole fake records, at random phase, so every tile boundary lands in look-alike data
+        q = (fake * 40)[rnd.randrange(len(fake)):][:2000]
+        recs.append(bc.bam_record(name=b"r%d" % i, pos=i, seq_len=2000, qual=q, cigar=((2000, 0),)))
+    stream = hdr + b"".join(recs)
+    _assert_parity(oracle, engine, bc.bgzf(stream, level=1))
+
+
+def test_huge_record_spanning_many_tiles(oracle, engine):
+    hdr = bc.bam_header()
+    big = bc.bam_record(name=b"big", seq_len=400000, cigar=((400000, 0),))     # ~600 KB: jumps over 9 tiles
+    stream = hdr + bc.bam_record(name=b"a") + big + bc.bam_record(name=b"b") * 300 + big + bc.bam_record(name=b"c")
+    _assert_parity(oracle, engine, bc.bgzf(stream, level=1))
+
+
+def test_short_record_is_an_error_like_the_reference_panic(oracle, engine):
+    stream = bc.bam_header() + bc.bam_record() + bc.bam_record()[:-5]
+    data = bc.bgzf(stream)
+    u = oracle.inflate_all(data)[0]
+    _, _, consumed = oracle.read_header(u)
+    with pytest.raises(orc.OracleError):
+        oracle.walk_records(u, consumed)
+    with pytest.raises(bp.BamGpuError) as e:
+        _engine_decode(engine, data, consumed)
+    assert e.value.code == -22                                           # reader.rs:69-70
+
+
+# ---- the Reader API (reader.rs) through the C ABI -----------------------------------------------------
+
+def _reader_md5(reader):
+    h = hashlib.md5()
+    n = 0
+    recs = reader.records()
+    while True:
+        r = recs.next_rec()
+        if r is None:
+            break
+        h.update(r)
+        n += 1
+    return h.hexdigest(), n
+
+
+@pytest.mark.parametrize("batch_bytes", [0, 1 << 20, 70000])
+@pytest.mark.parametrize("shape,n,payload", [("pe150", 30000, 0xFF00), ("long10k", 400, 4096), ("longname", 5000, 0xFF00)])
+def test_reader_api_matches_oracle(oracle, shape, n, payload, batch_bytes):
+    data = synth.generate(shape, n, payload=payload).tobytes()
+    u, hdr, off_refs, consumed, off, ln, cols, bf, bt = _oracle_decode(oracle, data)
+    ub = u.tobytes()
+    want = hashlib.md5(b"".join(ub[o:o + l] for o, l in zip(off.tolist(), ln.tolist()))).hexdigest()
+    # in-memory source
+    with bp.Reader.new(data, 5, batch_bytes=batch_bytes) as r:
+        hb, ho = r.read_header()
+        assert (hb, ho) == (hdr, off_refs)
+        assert bp.parse_reference_sequences(hb[ho:])[0] == ("chr1", 249250621)
+        assert _reader_md5(r) == (want, n)
+    # file-like source through the read callback, small reads
+    class Dribble(io.BytesIO):
+        def readinto(self, b):
+            return super().readinto(memoryview(b)[: 100000])
+    with bp.Reader.new(Dribble(data), 20, len(data), batch_bytes=batch_bytes) as r:
+        r.read_header()
+        assert _reader_md5(r) == (want, n)
+
+
+def test_reader_batches_columns_and_iterator(oracle):
+    data = synth.generate("pe150", 50000).tobytes()
+    u, hdr, off_refs, consumed, off, ln, cols, bf, bt = _oracle_decode(oracle, data)
+    with bp.Reader.new(data, 4, batch_bytes=1 << 20, flags=bp.COPY_COLUMNS | bp.COPY_DATA | bp.WANT_HI) as r:
+        r.read_header()
+        got = {k: [] for k in COLS if k != "hi_present"}
+        bodies = hashlib.md5()
+        total = 0
+        nb = 0
+        while True:
+            b = r.next_batch()
+            if b is None:
+                break
+            assert b.first_record_index == total
+            total += b.n_records
+            nb += 1
+            for k in got:
+                got[k].append(b.columns[k].copy() if k != "rec_off" else b.columns[k].copy())
+            db = b.data.tobytes()
+            for o, l in zip(b.columns["rec_off"].tolist(), b.columns["rec_len"].tolist()):
+                bodies.update(db[o:o + l])
+        assert total == off.size and nb > 3
+        for k in got:
+            if k == "rec_off":
+                continue                       # batch-relative
+            assert np.array_equal(np.concatenate(got[k]), cols[k]), k
+        ub = u.tobytes()
+        assert bodies.hexdigest() == hashlib.md5(b"".join(ub[o:o + l] for o, l in zip(off.tolist(), ln.tolist()))).hexdigest()
+    with bp.Reader.new(data, 4) as r:
+        r.read_header()
+        recs = list(r.records())
+        assert len(recs) == off.size and recs[7] == ub[int(off[7]): int(off[7]) + int(ln[7])]
+    with bp.Reader.new(data, 4) as r:
+        r.read_header()
+        buf = bytearray()
+        assert r.read_record(buf) == int(ln[0]) and bytes(buf) == ub[int(off[0]): int(off[0]) + int(ln[0])]
+        assert r.append_record(buf) == int(ln[1]) and len(buf) == int(ln[0]) + int(ln[1])
+
+
+def test_reader_impl_read_raw_stream(oracle):
+    data = synth.generate("pe150", 20000).tobytes()
+    u, _ = oracle.inflate_all(data)
+    with bp.Reader.new(data, 4, batch_bytes=300000) as r:
+        got = r.read(1000) + r.read(123457) + r.read()
+        assert got == u.tobytes()
+        assert r.read(10) == b""
+
+
+def test_reader_errors_and_quirks(oracle):
+    with bp.Reader.new(bc.bgzf(b"BAX\x01" + b"\0" * 40), 4) as r:
+        with pytest.raises(bp.BamGpuError) as e:
+            r.read_header()
+        assert e.value.code == -20
+    with bp.Reader.new(bc.bgzf(bc.bam_header()[:-3]), 4) as r:
+        with pytest.raises(bp.BamGpuError) as e:
+            r.read_header()
+        assert e.value.code == -21
+    with bp.Reader.new(b"", 4) as r:
+        with pytest.raises(bp.BamGpuError):
+            r.read_header()
+    s = bc.bam_header() + bc.bam_record(name=b"a") + bc.bam_record(name=b"b")
+    cut = len(bc.bam_header()) + 20
+    data = bc.bgzf_block(s[:cut]) + bc.BGZF_EOF + bc.bgzf_block(s[cut:]) + bc.BGZF_EOF   # EOF marker mid-stream
+    with bp.Reader.new(data, 4) as r:
+        r.read_header()
+        assert len(list(r.records())) == 2
+    trunc = bc.bgzf(bc.bam_header() + bc.bam_record() + bc.bam_record()[:-5])
+    with bp.Reader.new(trunc, 4) as r:
+        r.read_header()
+        with pytest.raises(bp.BamGpuError) as e:
+            list(r.records())
+        assert e.value.code == -22
+    with bp.Reader.new(bc.bgzf(bc.bam_header() + bc.bam_record())[:-40], 4) as r:   # truncated last BGZF block
+        with pytest.raises(bp.BamGpuError) as e:
+            r.read_header()
+            list(r.records())
+        assert e.value.code == -11
