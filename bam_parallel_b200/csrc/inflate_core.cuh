@@ -25,8 +25,14 @@
 
 #if defined(__CUDACC__)
 #define BG_HD __host__ __device__ __forceinline__
+#if defined(BG_INLINE_HEADER)
+#define BG_HD_COLD __host__ __device__ __forceinline__
+#else
+#define BG_HD_COLD __host__ __device__ __noinline__
+#endif
 #else
 #define BG_HD inline
+#define BG_HD_COLD inline
 #endif
 
 namespace bamgpu {
@@ -245,7 +251,7 @@ struct Lane {
   }
 
   // Parses one DEFLATE block header (and its code tables).  Sets state.
-  BG_HD void do_header(uint8_t* lens /* >= 320 bytes of private scratch */) {
+  BG_HD_COLD void do_header(uint8_t* lens /* >= 320 bytes of private scratch */) {
     refill();
     if (bits_consumed() + 3 > in_bits) { err = IST_INPUT_OVERRUN; state = ST_NEXT; return; }
     bfinal = (uint32_t)bb & 1u;
