@@ -14,7 +14,7 @@ ERR_NAMES = {
     -12: "ERR_INFLATE", -13: "ERR_ISIZE", -14: "ERR_CRC", -20: "ERR_BAD_MAGIC", -21: "ERR_SHORT_HEADER",
     -22: "ERR_SHORT_RECORD", -23: "ERR_BUFFER_TOO_SMALL", -24: "ERR_STATE",
 }
-COPY_DATA, COPY_COLUMNS, WANT_HI, NO_CRC, NO_RECORDS = 1, 2, 4, 8, 16
+COPY_DATA, COPY_COLUMNS, WANT_HI, NO_CRC, NO_RECORDS, SPECULATIVE_START = 1, 2, 4, 8, 16, 32
 
 
 class BamGpuError(RuntimeError):
@@ -44,7 +44,8 @@ class Columns(C.Structure):
 
 class Batch(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("data_len", C.c_uint64), ("data", C.c_void_p), ("h_data", C.c_void_p),
-                ("dev", Columns), ("host", Columns), ("first_record_index", C.c_uint64), ("bad_flag_records", C.c_uint64)]
+                ("dev", Columns), ("host", Columns), ("first_record_index", C.c_uint64), ("bad_flag_records", C.c_uint64),
+                ("chain_start", C.c_uint64), ("chain_repairs", C.c_uint64)]
 
 
 class Opts(C.Structure):

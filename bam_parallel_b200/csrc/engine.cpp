@@ -391,6 +391,7 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
   out->data = E->out_ptr();
   out->data_len = E->data_len;
   out->first_record_index = E->first_record_index;
+  out->chain_start = start;
   ChainResult* d_res = (ChainResult*)(E->d_misc.as<uint8_t>() + 64);
   ChainResult* h_res = (ChainResult*)(E->h_res.as<uint8_t>() + 64);
   uint64_t n_rec = 0, tail_off = start;
@@ -398,7 +399,7 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
   uint64_t bad_flags = 0;
   ECK(cudaEventRecord(E->ev[3], s));
   if (!(flags & BAMGPU_NO_RECORDS) && start < E->data_len) {
-    RecordParams p{E->out_ptr(), E->data_len, start, E->n_ref};
+    RecordParams p{E->out_ptr(), E->data_len, start, E->n_ref, (flags & BAMGPU_SPECULATIVE_START) ? 0 : 1};
     uint32_t n_tiles = (uint32_t)((E->data_len + TILE_BYTES - 1) / TILE_BYTES);
     // tile arrays: entry u64, exit u64, base u64, count u32, kind u32, nxt u32, jump u32, jump2 u32, reach u8
     size_t nt = n_tiles;
@@ -413,19 +414,14 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
                  (uint32_t*)(tb + o_nxt), (uint32_t*)(tb + o_jump), (uint32_t*)(tb + o_jump2), (uint8_t*)(tb + o_reach),
                  (uint64_t*)(tb + o_base), n_tiles};
     launch_tile_walk(p, t, s);
-    E->stats.kernel_launches += 1;
-    for (int iter = 0;; ++iter) {
-      launch_chain_resolve(p, t, d_res, s);
-      E->stats.kernel_launches += 3;
-      ECK(cudaMemcpyAsync(h_res, d_res, sizeof(ChainResult), cudaMemcpyDeviceToHost, s));
-      ECK(cudaStreamSynchronize(s));
-      ECK(cudaGetLastError());
-      if (h_res->broken_tile == 0xffffffffu) break;
-      if (h_res->broken_tile >= n_tiles) { E->err = "internal: chain left the buffer"; return BAMGPU_ERR_STATE; }
-      launch_tile_repair(p, t, h_res->broken_tile, h_res->broken_entry, s);
-      E->stats.kernel_launches += 1;
-      if (iter > 1000000) { E->err = "internal: chain repair did not converge"; return BAMGPU_ERR_STATE; }
-    }
+    launch_chain_resolve(p, t, d_res, s);
+    E->stats.kernel_launches += 2;
+    ECK(cudaMemcpyAsync(h_res, d_res, sizeof(ChainResult), cudaMemcpyDeviceToHost, s));
+    ECK(cudaStreamSynchronize(s));
+    ECK(cudaGetLastError());
+    if (h_res->broken_tile != 0xffffffffu) { E->err = "internal: record chain left the buffer"; return BAMGPU_ERR_STATE; }
+    out->chain_start = h_res->chain_start;
+    out->chain_repairs = h_res->rounds;
     n_rec = h_res->n_records;
     tail_off = h_res->tail_off;
     tail_kind = h_res->tail_kind;
@@ -863,13 +859,11 @@ extern "C" int bamgpu_append_record(bamgpu_reader* R, uint8_t* dst, size_t cap, 
   if (!R || !len) return BAMGPU_ERR_ARG;
   const uint8_t* b;
   size_t n;
-  uint64_t save = R->rec_cursor;
   int rc = bamgpu_next_rec(R, &b, &n);
   if (rc == BAMGPU_EOF) { *len = 0; return BAMGPU_OK; }   // reader.rs:63-73 returns Ok(0) at EOF
   if (rc < 0) return rc;
   if (n > cap || !dst) {
     R->rec_cursor = R->rec_cursor - 1;  // un-consume (same batch by construction)
-    (void)save;
     *len = n;
     return BAMGPU_ERR_BUFFER_TOO_SMALL;
   }

@@ -6,7 +6,7 @@
 // Mapping: a persistent grid of 3-warp CTAs, 3 CTAs per SM (9 warps = 288 lanes per SM, the
 // most that fit in 227 KB of shared memory at 736 B of Huffman tables per lane).  Every LANE
 // owns one BGZF block at a time and pulls the next block index from a global counter, so a
-// warp advances 32 independent DEFLATE streams in lock-step.  The per-lane logic is in
+// warp advances 32 independent DEFLATE streams side by side.  The per-lane logic is in
 // inflate_core.cuh.  Output offsets come from the host's exclusive scan of ISIZE
 // (bamgpu_scan_blocks), so the inflated stream is contiguous and records may straddle blocks.
 #include "inflate_core.cuh"
@@ -18,6 +18,8 @@ constexpr int K1_WARPS_PER_CTA = 3;
 constexpr int K1_CTAS_PER_SM = 3;
 constexpr int K1_SMEM_BYTES = K1_WARPS_PER_CTA * 32 * LANE_WORDS * 4;  // 70656
 
+constexpr uint32_t K1_TOKENS_PER_ROUND = 128;  // tokens a lane decodes between two looks at the warp-wide state
+
 __global__ void __launch_bounds__(K1_WARPS_PER_CTA * 32, K1_CTAS_PER_SM)
 k1_inflate_lane_per_block(InflateJob job, uint32_t* __restrict__ work_counter) {
   extern __shared__ uint32_t smem[];
@@ -27,7 +29,6 @@ k1_inflate_lane_per_block(InflateJob job, uint32_t* __restrict__ work_counter) {
   L.state = ST_NEXT;
   L.blk = 0xffffffffu;
   L.err = 0;
-  uint8_t lens[320];  // code lengths of the block being set up (thread-local scratch)
   for (;;) {
     if (L.state == ST_NEXT) {
       L.finish_block(job);
@@ -36,7 +37,8 @@ k1_inflate_lane_per_block(InflateJob job, uint32_t* __restrict__ work_counter) {
       else { L.state = ST_DONE; L.blk = 0xffffffffu; }
     }
     if (__all_sync(0xffffffffu, L.state == ST_DONE)) break;
-    L.step(lens);
+    L.round(K1_TOKENS_PER_ROUND);
+    __syncwarp();
   }
 }
 

@@ -63,6 +63,8 @@ struct RecordParams {
   uint64_t data_len;
   uint64_t start;       // chain start (absolute offset in data)
   int32_t n_ref;        // number of reference sequences (plausibility filter); <0 = unknown
+  int32_t start_known;  // 1: `start` is a record start (reader.rs:63); 0: shard-edge mode, the chain begins at the
+                        //    first position >= start that looks like a chain of records (caller verifies it)
 };
 
 // Output columns (device pointers, capacity >= n_records). Mirrors bamgpu_columns.
@@ -82,14 +84,13 @@ struct ChainResult {
   uint32_t broken_tile;            // first reachable tile whose successor's speculation mismatched; ~0u if none
   unsigned long long broken_entry; // the true entry for that successor tile
   unsigned long long bad_flags;    // records with flag bits >= 0x1000
-  uint32_t rounds;
+  uint32_t rounds;                 // serial repairs that were needed (0 when every guess was right)
   uint32_t pad;
+  unsigned long long chain_start;  // where the chain began (== start when start_known); ~0ull if nowhere
 };
 
 void launch_tile_walk(const RecordParams& p, const TileArrays& t, cudaStream_t s);
-// Re-walks from `entry` at tile `tile` sequentially until the walk re-synchronises with a tile's speculation.
-void launch_tile_repair(const RecordParams& p, const TileArrays& t, uint32_t tile, uint64_t entry, cudaStream_t s);
-// Link + pointer-doubling reachability + masked scan of counts + result summary.
+// Link + pointer-doubling reachability + (rare) serial repair + masked scan of counts + result summary, one launch.
 void launch_chain_resolve(const RecordParams& p, const TileArrays& t, ChainResult* d_result, cudaStream_t s);
 // Second walk: writes rec_off / rec_len for reachable tiles.
 void launch_tile_emit(const RecordParams& p, const TileArrays& t, uint64_t* rec_off, uint32_t* rec_len, cudaStream_t s);

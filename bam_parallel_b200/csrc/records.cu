@@ -12,16 +12,17 @@
 // (no validation).  We get the identical chain in parallel:
 //   1. k3_tile_walk: the inflated stream is cut into 64 KiB tiles; one thread per tile guesses the
 //      first record start in its tile with a plausibility filter (spec invariants only, so a real
-//      record start of a valid BAM always passes) and walks the chain to the tile end
-//      -> (entry, exit, count).  Tile 0 starts from the KNOWN start (end of the header).
-//   2. k3_link + k3_jump: tile k points at the tile holding its exit iff that tile's guess equals
-//      the exit; pointer DOUBLING from tile 0 marks the tiles on the true chain in log2(n) rounds.
-//   3. a guess that does not match (or a tile jumped over by a long record) is never trusted: the
-//      chain stops there, the host launches k3_tile_repair (serial re-walk from the true entry
-//      until it re-synchronises) and resolves again.  The result is therefore exactly the blind
-//      walk, never the filter's opinion.
-//   4. k3_scan gives every tile its first record index, k3_tile_emit re-walks and writes
-//      rec_off / rec_len, k3_extract (one thread per record) writes the SoA columns + keys.
+//      record start of a valid BAM always passes; a candidate must be followed by three more
+//      look-alike records along its block_size links) and walks the chain to the tile end
+//      -> (entry, exit, count).  The start tile begins at the KNOWN start (end of the header).
+//   2. k3_resolve (one CTA): tile k points at the tile holding its exit iff that tile's guess equals
+//      the exit; pointer DOUBLING from the start tile marks the tiles on the true chain in log2(n)
+//      rounds.  A guess that does not match (or a tile a long record jumped into) is never trusted:
+//      the chain stops there, thread 0 re-walks serially from the true entry until it
+//      re-synchronises, and the resolve repeats.  The result is therefore exactly the blind walk,
+//      never the filter's opinion.  An exclusive scan then gives every tile its first record index.
+//   3. k3_tile_emit re-walks and writes rec_off / rec_len, k3_extract (one thread per record)
+//      writes the SoA columns + keys.
 #include "kernels.h"
 
 namespace bamgpu {
@@ -37,9 +38,9 @@ __device__ __forceinline__ uint32_t ld32(const uint8_t* data, uint64_t off) {
 }
 
 // Spec invariants of a record start (SAM spec §4.2).  Used ONLY to guess; never to decide.
-__device__ bool plausible(const RecordParams& p, uint64_t q) {
+// `bs` is the already loaded block_size at q.
+__device__ __forceinline__ bool plausible_fields(const RecordParams& p, uint64_t q, uint32_t bs) {
   if (p.data_len - q < 36) return false;
-  uint32_t bs = ld32(p.data, q);
   if (bs < 33u || bs > (1u << 28)) return false;
   int32_t ref = (int32_t)ld32(p.data, q + 4);
   if (ref < -1 || (p.n_ref >= 0 && ref >= p.n_ref)) return false;
@@ -58,6 +59,41 @@ __device__ bool plausible(const RecordParams& p, uint64_t q) {
   uint64_t nul = q + 4 + 32 + l_name - 1;
   if (nul < p.data_len && p.data[nul] != 0) return false;
   return true;
+}
+
+// A candidate is accepted when it and the next VERIFY_DEPTH records along its chain all look like
+// records (or the chain runs into the end of the data first).  One look-alike inside sequence or
+// quality bytes is common; four in a row along block_size links is not.
+constexpr int VERIFY_DEPTH = 3;
+__device__ bool plausible_chain(const RecordParams& p, uint64_t q, uint32_t bs) {
+  if (!plausible_fields(p, q, bs)) return false;
+  for (int i = 0; i < VERIFY_DEPTH; ++i) {
+    q += 4ull + bs;
+    if (p.data_len - q < 36 || q > p.data_len) return true;  // ran into the tail: nothing left to check
+    bs = ld32(p.data, q);
+    if (!plausible_fields(p, q, bs)) return false;
+  }
+  return true;
+}
+
+// First accepted candidate in [from, te), or NONE64.  Bytes are scanned through a rolling 64-bit
+// window (one aligned load per 4 candidates); the cheap block_size range test rejects almost all.
+__device__ uint64_t find_entry(const RecordParams& p, uint64_t from, uint64_t te) {
+  if (from >= te) return NONE64;
+  uint64_t a = from & ~3ull;
+  const uint32_t* w = (const uint32_t*)(p.data + a);
+  uint32_t lo = w[0];
+  for (; a < te; a += 4) {
+    uint32_t hi = *(const uint32_t*)(p.data + a + 4);  // data is readable 64 bytes past data_len
+#pragma unroll
+    for (uint32_t b = 0; b < 4; ++b) {
+      uint64_t q = a + b;
+      uint32_t bs = b ? __funnelshift_r(lo, hi, 8 * b) : lo;
+      if (bs - 33u <= (1u << 28) - 33u && q >= from && q < te && plausible_chain(p, q, bs)) return q;
+    }
+    lo = hi;
+  }
+  return NONE64;
 }
 
 struct WalkOut { uint64_t exit_off; uint32_t count; uint32_t kind; };
@@ -83,7 +119,7 @@ __device__ WalkOut walk(const RecordParams& p, uint64_t q, uint64_t tile_end, ui
   return o;
 }
 
-__global__ void k3_tile_walk(RecordParams p, TileArrays t) {
+__global__ void __launch_bounds__(128) k3_tile_walk(RecordParams p, TileArrays t) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= t.n_tiles) return;
   const uint64_t tb = (uint64_t)k * TILE_BYTES;
@@ -91,11 +127,8 @@ __global__ void k3_tile_walk(RecordParams p, TileArrays t) {
   if (te > p.data_len) te = p.data_len;
   const uint32_t k0 = (uint32_t)(p.start / TILE_BYTES);
   uint64_t e = NONE64;
-  if (k == k0) e = p.start;
-  else if (k > k0) {
-    for (uint64_t q = tb; q < te; ++q)
-      if (plausible(p, q)) { e = q; break; }
-  }
+  if (k == k0) e = p.start_known ? p.start : find_entry(p, p.start, te);
+  else if (k > k0) e = find_entry(p, tb, te);
   t.entry[k] = e;
   if (e == NONE64) { t.exit_off[k] = 0; t.count[k] = 0; t.exit_kind[k] = EXIT_NONE; return; }
   WalkOut o = walk<false>(p, e, te, nullptr, nullptr, 0);
@@ -104,74 +137,113 @@ __global__ void k3_tile_walk(RecordParams p, TileArrays t) {
   t.exit_kind[k] = o.kind;
 }
 
-// Serial repair: the true chain enters tile `tile` at `entry` but the tile guessed otherwise.
-__global__ void k3_tile_repair(RecordParams p, TileArrays t, uint32_t tile, uint64_t entry) {
-  if (blockIdx.x || threadIdx.x) return;
-  for (;;) {
-    uint64_t te = (uint64_t)(tile + 1) * TILE_BYTES;
-    if (te > p.data_len) te = p.data_len;
-    WalkOut o = walk<false>(p, entry, te, nullptr, nullptr, 0);
-    t.entry[tile] = entry;
-    t.exit_off[tile] = o.exit_off;
-    t.count[tile] = o.count;
-    t.exit_kind[tile] = o.kind;
-    if (o.kind != EXIT_NORMAL) return;
-    uint32_t j = (uint32_t)(o.exit_off / TILE_BYTES);
-    if (t.entry[j] == o.exit_off) return;  // re-synchronised with the guess
-    tile = j;
-    entry = o.exit_off;
-  }
-}
-
-__global__ void k3_link(RecordParams p, TileArrays t) {
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= t.n_tiles) return;
-  uint32_t nx = k;
-  if (t.entry[k] != NONE64 && t.exit_kind[k] == EXIT_NORMAL) {
-    uint32_t j = (uint32_t)(t.exit_off[k] / TILE_BYTES);
-    if (j < t.n_tiles && t.entry[j] == t.exit_off[k]) nx = j;
-  }
-  t.nxt[k] = nx;
-  t.jump[k] = nx;
-  t.reach[k] = (k == (uint32_t)(p.start / TILE_BYTES)) ? 1 : 0;
-}
-
-__global__ void k3_jump(TileArrays t, const uint32_t* __restrict__ jin, uint32_t* __restrict__ jout) {
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= t.n_tiles) return;
-  uint32_t j = jin[k];
-  if (t.reach[k]) t.reach[j] = 1;
-  jout[k] = jin[j];
-}
-
-// Exclusive scan of (reach ? count : 0) over all tiles + chain summary.  Single CTA.
-__global__ void __launch_bounds__(1024) k3_scan(RecordParams p, TileArrays t, ChainResult* res) {
+// One CTA resolves the whole tile graph:
+//   link:   tile k points at the tile holding its exit iff that tile's guess equals the exit;
+//   reach:  pointer doubling from the start tile marks the tiles on the true chain;
+//   repair: if the chain stops at a tile whose guess was wrong (or that a long record jumped into),
+//           thread 0 re-walks serially from the true entry until it re-synchronises with a guess,
+//           and the resolve repeats.  The result is therefore exactly the blind walk of reader.rs:63-81;
+//   scan:   exclusive scan of the counts of reachable tiles = first record index of every tile.
+__global__ void __launch_bounds__(1024) k3_resolve(RecordParams p, TileArrays t, ChainResult* res) {
   __shared__ unsigned long long warp_sums[32];
   __shared__ unsigned long long carry;
-  if (threadIdx.x == 0) {
-    carry = 0;
-    res->broken_tile = 0xffffffffu;
-    res->tail_off = p.start;
-    res->tail_kind = EXIT_TAIL;
-    res->bad_flags = 0;
-  }
+  __shared__ uint32_t s_broken_tile;
+  __shared__ uint64_t s_broken_entry, s_tail_off;
+  __shared__ uint32_t s_tail_kind, s_repairs;
+  __shared__ uint32_t s_first;
+  const uint32_t n = t.n_tiles;
+  if (threadIdx.x == 0) { s_repairs = 0; s_first = (uint32_t)(p.start / TILE_BYTES); }
   __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < t.n_tiles; base += 1024) {
-    uint32_t k = base + threadIdx.x;
-    bool in = k < t.n_tiles;
-    bool rc = in && t.reach[k];
-    unsigned long long v = rc ? t.count[k] : 0;
+  if (!p.start_known) {
+    // shard-edge mode: the chain begins at the first tile (from the start tile on) that found a guess
+    uint32_t lo = s_first;
+    __syncthreads();
+    if (threadIdx.x == 0) s_first = 0xffffffffu;
+    __syncthreads();
+    uint32_t best = 0xffffffffu;
+    for (uint32_t k = lo + threadIdx.x; k < n; k += blockDim.x)
+      if (t.entry[k] != NONE64) { best = k; break; }
+    if (best != 0xffffffffu) atomicMin(&s_first, best);
+    __syncthreads();
+  }
+  const uint32_t k0 = s_first;
+  if (k0 >= n) {  // nothing that looks like a record anywhere
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) { t.reach[k] = 0; t.base[k] = 0; }
+    if (threadIdx.x == 0) {
+      res->n_records = 0; res->tail_off = p.start; res->tail_kind = EXIT_NONE; res->broken_tile = 0xffffffffu;
+      res->broken_entry = 0; res->bad_flags = 0; res->rounds = 0; res->chain_start = NONE64;
+    }
+    return;
+  }
+  for (;;) {
+    if (threadIdx.x == 0) { s_broken_tile = 0xffffffffu; s_tail_off = p.start; s_tail_kind = EXIT_TAIL; }
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+      uint32_t nx = k;
+      if (t.entry[k] != NONE64 && t.exit_kind[k] == EXIT_NORMAL) {
+        uint32_t j = (uint32_t)(t.exit_off[k] / TILE_BYTES);
+        if (j < n && t.entry[j] == t.exit_off[k]) nx = j;
+      }
+      t.nxt[k] = nx;
+      t.jump[k] = nx;
+      t.reach[k] = (k == k0) ? 1 : 0;
+    }
+    __syncthreads();
+    uint32_t* a = t.jump;
+    uint32_t* b = t.jump2;
+    for (uint64_t span = 1; span < (uint64_t)n * 2; span <<= 1) {
+      for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+        uint32_t j = a[k];
+        if (t.reach[k]) t.reach[j] = 1;
+        b[k] = a[j];
+      }
+      __syncthreads();
+      uint32_t* tmp = a; a = b; b = tmp;
+    }
     // the chain's last tile: reachable and its own successor
-    if (rc && t.nxt[k] == k) {
-      if (t.exit_kind[k] == EXIT_NORMAL) {  // successor's guess mismatched (or successor out of range)
-        res->broken_tile = (uint32_t)(t.exit_off[k] / TILE_BYTES);
-        res->broken_entry = t.exit_off[k];
-      } else {
-        res->tail_off = t.exit_off[k];
-        res->tail_kind = t.exit_kind[k];
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+      if (t.reach[k] && t.nxt[k] == k) {
+        if (t.entry[k] == NONE64) {                 // only the start tile can be reachable without an entry
+          s_tail_off = p.start; s_tail_kind = EXIT_NONE;
+        } else if (t.exit_kind[k] == EXIT_NORMAL) { // successor's guess mismatched (or successor out of range)
+          s_broken_tile = (uint32_t)(t.exit_off[k] / TILE_BYTES);
+          s_broken_entry = t.exit_off[k];
+        } else {
+          s_tail_off = t.exit_off[k];
+          s_tail_kind = t.exit_kind[k];
+        }
       }
     }
+    __syncthreads();
+    if (s_broken_tile == 0xffffffffu || s_broken_tile >= n) break;
+    if (threadIdx.x == 0) {
+      uint32_t tile = s_broken_tile;
+      uint64_t entry = s_broken_entry;
+      for (;;) {
+        uint64_t te = (uint64_t)(tile + 1) * TILE_BYTES;
+        if (te > p.data_len) te = p.data_len;
+        WalkOut o = walk<false>(p, entry, te, nullptr, nullptr, 0);
+        t.entry[tile] = entry;
+        t.exit_off[tile] = o.exit_off;
+        t.count[tile] = o.count;
+        t.exit_kind[tile] = o.kind;
+        ++s_repairs;
+        if (o.kind != EXIT_NORMAL) break;
+        uint32_t j = (uint32_t)(o.exit_off / TILE_BYTES);
+        if (j >= n || t.entry[j] == o.exit_off) break;  // re-synchronised with the guess
+        tile = j;
+        entry = o.exit_off;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- exclusive scan of (reach ? count : 0) ----
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < n; base += 1024) {
+    uint32_t k = base + threadIdx.x;
+    bool in = k < n;
+    unsigned long long v = (in && t.reach[k]) ? t.count[k] : 0;
     unsigned long long x = v;
     for (int o = 1; o < 32; o <<= 1) {
       unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
@@ -194,12 +266,21 @@ __global__ void __launch_bounds__(1024) k3_scan(RecordParams p, TileArrays t, Ch
     if (threadIdx.x == 1023) carry = off + v;
     __syncthreads();
   }
-  if (threadIdx.x == 0) res->n_records = carry;
+  if (threadIdx.x == 0) {
+    res->n_records = carry;
+    res->tail_off = s_tail_off;
+    res->tail_kind = s_tail_kind;
+    res->broken_tile = s_broken_tile;
+    res->broken_entry = 0;
+    res->bad_flags = 0;
+    res->rounds = s_repairs;
+    res->chain_start = t.entry[k0];
+  }
 }
 
-__global__ void k3_tile_emit(RecordParams p, TileArrays t, uint64_t* rec_off, uint32_t* rec_len) {
+__global__ void __launch_bounds__(128) k3_tile_emit(RecordParams p, TileArrays t, uint64_t* rec_off, uint32_t* rec_len) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= t.n_tiles || !t.reach[k]) return;
+  if (k >= t.n_tiles || !t.reach[k] || t.entry[k] == NONE64) return;
   uint64_t te = (uint64_t)(k + 1) * TILE_BYTES;
   if (te > p.data_len) te = p.data_len;
   walk<true>(p, t.entry[k], te, rec_off, rec_len, t.base[k]);
@@ -310,23 +391,9 @@ void launch_tile_walk(const RecordParams& p, const TileArrays& t, cudaStream_t s
   if (t.n_tiles) k3_tile_walk<<<grid_for(t.n_tiles, 128), 128, 0, s>>>(p, t);
 }
 
-void launch_tile_repair(const RecordParams& p, const TileArrays& t, uint32_t tile, uint64_t entry, cudaStream_t s) {
-  k3_tile_repair<<<1, 32, 0, s>>>(p, t, tile, entry);
-}
-
 void launch_chain_resolve(const RecordParams& p, const TileArrays& t, ChainResult* d_result, cudaStream_t s) {
   if (t.n_tiles == 0) return;
-  uint32_t g = grid_for(t.n_tiles, 256);
-  k3_link<<<g, 256, 0, s>>>(p, t);
-  uint32_t* a = t.jump;
-  uint32_t* b = t.jump2;
-  uint32_t rounds = 1;
-  for (uint64_t span = 1; span < t.n_tiles; span <<= 1) ++rounds;
-  for (uint32_t r = 0; r < rounds; ++r) {
-    k3_jump<<<g, 256, 0, s>>>(t, a, b);
-    uint32_t* tmp = a; a = b; b = tmp;
-  }
-  k3_scan<<<1, 1024, 0, s>>>(p, t, d_result);
+  k3_resolve<<<1, 1024, 0, s>>>(p, t, d_result);
 }
 
 void launch_tile_emit(const RecordParams& p, const TileArrays& t, uint64_t* rec_off, uint32_t* rec_len, cudaStream_t s) {

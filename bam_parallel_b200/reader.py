@@ -48,11 +48,15 @@ class RecordBatch:
         self.data_len = int(b.data_len)
         self.first_record_index = int(b.first_record_index)
         self.bad_flag_records = int(b.bad_flag_records)
+        self.chain_start = int(b.chain_start)
+        self.chain_repairs = int(b.chain_repairs)
         self.dev_data = b.data
         self.dev = {n: getattr(b.dev, n) for n, _ in COLUMN_FIELDS}
         self.data = _view(b.h_data, self.data_len, C.c_uint8) if b.h_data else None
         self.columns = None
-        if b.host.rec_off:
+        if self.n_records == 0:
+            self.columns = {n: np.zeros(0, dtype=_NP[ct]) for n, ct in COLUMN_FIELDS}
+        elif b.host.rec_off:
             self.columns = {n: _view(getattr(b.host, n), self.n_records, ct) for n, ct in COLUMN_FIELDS}
 
     def body(self, i: int) -> memoryview:

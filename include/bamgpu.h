@@ -116,6 +116,9 @@ typedef struct bamgpu_batch {
   bamgpu_columns host;          /* pinned host mirrors (BAMGPU_COPY_COLUMNS), else NULLs */
   uint64_t first_record_index;  /* index of record 0 of this batch in the whole stream */
   uint64_t bad_flag_records;    /* records with flag bits >= 0x1000 (reference coord sort would panic) */
+  uint64_t chain_start;         /* offset in `data` of record 0's block_size field (== stream_start unless
+                                   BAMGPU_SPECULATIVE_START); ~0 if the batch holds no record start */
+  uint64_t chain_repairs;       /* tiles whose guessed entry had to be re-walked serially (0 in practice) */
 } bamgpu_batch;
 
 enum {
@@ -123,7 +126,10 @@ enum {
   BAMGPU_COPY_COLUMNS = 2,      /* D2H the SoA columns */
   BAMGPU_WANT_HI = 4,           /* walk aux tags for HI (only the -n -M sort needs it) */
   BAMGPU_NO_CRC = 8,            /* skip the CRC32 check (default: verify) */
-  BAMGPU_NO_RECORDS = 16        /* inflate (+CRC) only: no record kernel (impl Read consumers) */
+  BAMGPU_NO_RECORDS = 16,       /* inflate (+CRC) only: no record kernel (impl Read consumers) */
+  BAMGPU_SPECULATIVE_START = 32 /* shard-edge mode (multi-GPU): stream_start is NOT a known record start; the chain
+                                   begins at the first offset >= stream_start that looks like a run of records.
+                                   The caller must confirm batch.chain_start with the left-hand shard's tail_off. */
 };
 
 typedef struct bamgpu_opts {
@@ -160,7 +166,7 @@ int bamgpu_memcpy_h2d(bamgpu_engine*, void* dst, const void* src, size_t bytes);
 int bamgpu_memcpy_d2h(bamgpu_engine*, void* dst, const void* src, size_t bytes);
 
 /* Decode `n_blocks` BGZF blocks whose payloads live in device buffer d_comp (in_off relative to it;
- * the buffer must be readable for 16 bytes past the last payload).  `stream_start` is the offset in
+ * d_comp must be 16-byte aligned and readable for 64 bytes past the last payload).  `stream_start` is the offset in
  * the inflated stream where the record chain starts (reader.rs:63: right after the BAM header for the
  * first batch, the carry-over position for later ones).  If `cuda_stream` is non-NULL the work is
  * enqueued on that cudaStream_t instead of the engine's own (lets a caller time it with its own

@@ -52,7 +52,7 @@ def py_scan(data: bytes):
 
 def inflate(data: bytes, lanes: int = 32, table=None):
     in_off, in_len, out_off, isize, crc, total = table if table is not None else py_scan(data)
-    comp = np.zeros(len(data) + 16, np.uint8)
+    comp = np.zeros(len(data) + 64, np.uint8)           # K1 prefetches up to 48 bytes past a payload
     comp[: len(data)] = np.frombuffer(data, np.uint8)
     outbuf = np.full(total + 64, 0xEE, np.uint8)       # 32 B lead pad (>=16), tail pad
     lead = 32 + (-outbuf.ctypes.data) % 4              # keep out[0] 4-byte aligned

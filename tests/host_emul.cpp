@@ -13,18 +13,19 @@ using namespace bamgpu;
 extern "C" int host_emul_inflate(const uint8_t* comp, const uint64_t* in_off, const uint32_t* in_len,
                                  const uint64_t* out_off, const uint32_t* isize, uint8_t* out /* 16B lead pad before */,
                                  uint32_t* status, uint32_t n_blocks, int lanes) {
+  const uint32_t budget = 7;  // odd and small: exercises every resume point
   InflateJob job{comp, in_off, in_len, out_off, isize, out, status, n_blocks};
   if (lanes < 1) lanes = 1;
   std::vector<std::vector<uint32_t>> sm(lanes, std::vector<uint32_t>(LANE_WORDS, 0xDEADBEEFu));
   std::vector<Lane<1>> L(lanes);
-  std::vector<std::vector<uint8_t>> lens(lanes, std::vector<uint8_t>(320));
   uint32_t counter = 0;
   for (int i = 0; i < lanes; ++i) {
     L[i].sm = sm[i].data();
     L[i].state = ST_NEXT;
     L[i].blk = 0xffffffffu;
+    L[i].err = 0;
   }
-  // lock-step over lanes, exactly like the kernel's warp loop
+  // round-robin over lanes, exactly like the kernel's warp loop
   for (;;) {
     bool all_done = true;
     for (int i = 0; i < lanes; ++i) {
@@ -37,7 +38,7 @@ extern "C" int host_emul_inflate(const uint8_t* comp, const uint64_t* in_off, co
       if (L[i].state != ST_DONE) all_done = false;
     }
     if (all_done) break;
-    for (int i = 0; i < lanes; ++i) L[i].step(lens[i].data());
+    for (int i = 0; i < lanes; ++i) L[i].round(budget);
   }
   return 0;
 }
