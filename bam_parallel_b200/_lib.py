@@ -68,7 +68,7 @@ REFSEQ_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p)
 EXPORTS = [
     "bamgpu_scan_blocks", "bamgpu_engine_new", "bamgpu_engine_free", "bamgpu_engine_last_error", "bamgpu_device_alloc",
     "bamgpu_device_free", "bamgpu_pinned_alloc", "bamgpu_pinned_free", "bamgpu_memcpy_h2d", "bamgpu_memcpy_d2h",
-    "bamgpu_engine_decode", "bamgpu_engine_stats", "bamgpu_engine_reset_stats", "bamgpu_reader_new",
+    "bamgpu_engine_decode", "bamgpu_engine_set_n_ref", "bamgpu_engine_stats", "bamgpu_engine_reset_stats", "bamgpu_reader_new",
     "bamgpu_reader_from_memory", "bamgpu_reader_free", "bamgpu_last_error", "bamgpu_read_header", "bamgpu_next_rec",
     "bamgpu_append_record", "bamgpu_read", "bamgpu_next_batch", "bamgpu_reader_stats",
     "bamgpu_parse_reference_sequences", "bamgpu_status_str", "bamgpu_build_info",
@@ -106,6 +106,8 @@ def load() -> C.CDLL:
     L.bamgpu_memcpy_d2h.argtypes = [vp, vp, vp, sz]
     L.bamgpu_engine_decode.restype = C.c_int
     L.bamgpu_engine_decode.argtypes = [vp, vp, vp, sz, C.c_uint64, C.c_int, C.c_uint32, vp, C.POINTER(Batch), u64p]
+    L.bamgpu_engine_set_n_ref.restype = None
+    L.bamgpu_engine_set_n_ref.argtypes = [vp, C.c_int32]
     L.bamgpu_engine_stats.restype = C.c_int
     L.bamgpu_engine_stats.argtypes = [vp, C.POINTER(Stats)]
     L.bamgpu_engine_reset_stats.argtypes = [vp]

@@ -201,7 +201,7 @@ extern "C" bamgpu_engine* bamgpu_engine_new(const bamgpu_opts* opts) {
   if (cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking) != cudaSuccess) { delete E; return nullptr; }
   for (auto& e : E->ev) cudaEventCreate(&e);
   E->default_flags = opts ? opts->flags : 0;
-  if (E->d_misc.reserve(4096) != cudaSuccess || E->d_crc_tables.reserve(CRC_TABLE_WORDS * 4) != cudaSuccess ||
+  if (E->d_misc.reserve(8192) != cudaSuccess || E->d_crc_tables.reserve(CRC_TABLE_WORDS * 4) != cudaSuccess ||
       E->h_res.reserve(4096) != cudaSuccess) {
     bamgpu_engine_free(E);
     return nullptr;
@@ -414,7 +414,7 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
                  (uint32_t*)(tb + o_nxt), (uint32_t*)(tb + o_jump), (uint32_t*)(tb + o_jump2), (uint8_t*)(tb + o_reach),
                  (uint64_t*)(tb + o_base), n_tiles};
     launch_tile_walk(p, t, s);
-    launch_chain_resolve(p, t, d_res, s);
+    ECK(launch_chain_resolve(p, t, d_res, (ResolveScratch*)(E->d_misc.as<uint8_t>() + 256), E->num_sms, s));
     E->stats.kernel_launches += 2;
     ECK(cudaMemcpyAsync(h_res, d_res, sizeof(ChainResult), cudaMemcpyDeviceToHost, s));
     ECK(cudaStreamSynchronize(s));
@@ -522,7 +522,7 @@ extern "C" int bamgpu_engine_stats(const bamgpu_engine* E, bamgpu_stats* out) {
 }
 extern "C" void bamgpu_engine_reset_stats(bamgpu_engine* E) { if (E) E->stats = bamgpu_stats{}; }
 
-// Internal hooks used by the Reader (same translation unit keeps them out of the public ABI).
+extern "C" void bamgpu_engine_set_n_ref(bamgpu_engine* E, int32_t n) { if (E) E->n_ref = n; }
 static void engine_set_n_ref(bamgpu_engine* E, int32_t n) { E->n_ref = n; }
 
 // =================================================================================================

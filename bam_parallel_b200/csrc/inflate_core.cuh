@@ -14,10 +14,13 @@
 //   * Input is fetched 16 bytes at a time (LDG.128) into a double-buffered register queue, one
 //     whole chunk ahead of use, so the load latency is off the decode dependency chain.
 //   * Output goes through a 4-byte staging register and is stored as aligned 32-bit words.
-//     An LZ77 copy runs to completion inside the token that produced it: 16 bytes per
-//     iteration (4 aligned loads, funnel shifts, 4 aligned stores) when distance >= 20, 4 bytes
-//     per iteration for 8 <= distance < 20, and from a register-resident periodic window when
-//     distance < 8 (the dist=1 runs of BAM quality strings).
+//   * LZ77 copies are software-pipelined against the Huffman decode: a match with distance >= 35
+//     only REQUESTS its first 36 source bytes (9 aligned loads, no use), the next token is
+//     Huffman-decoded while they are in flight, and only then are they shifted into place and
+//     stored (straight-line code for up to 32 bytes).  The window read is an L2/DRAM access
+//     (thousands of streams x 32 KB of history do not fit in L1), so this takes its latency off
+//     the critical path.  Distances 8..34 copy 4 bytes per step at once, distances < 8 from a
+//     register-resident periodic window (the dist=1 runs of BAM quality strings).
 //   * The DEFLATE block header / code-table build is a cold out-of-line function working on a
 //     copy of the bit reader, so the hot loop's state stays in registers.  (It also has to be
 //     out of line: with ptxas 12.9 -O1..-O3 the fully inlined form miscompiled on sm_100a —
@@ -71,6 +74,13 @@ enum LaneState : uint32_t { ST_NEXT = 0, ST_HEADER, ST_DECODE, ST_STORED, ST_DON
 struct W4 { uint32_t x, y, z, w; };
 
 #if defined(__CUDA_ARCH__)
+// Copies a value through an opaque move so the compiler cannot keep re-reading its memory home (the limits
+// come back from the out-of-line header parser through local memory and must live in registers afterwards).
+BG_HD uint32_t bg_pin(uint32_t x) {
+  uint32_t y;
+  asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
 BG_HD uint32_t bg_brev(uint32_t x) { return __brev(x); }
 BG_HD uint32_t bg_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
 BG_HD uint32_t bg_funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_l(lo, hi, sh); }
@@ -79,6 +89,7 @@ BG_HD W4 bg_ld_in16(const void* p) {
   return W4{v.x, v.y, v.z, v.w};
 }
 #else
+inline uint32_t bg_pin(uint32_t x) { return x; }
 inline uint32_t bg_brev(uint32_t x) {
   x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
   x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
@@ -392,9 +403,13 @@ struct Lane {
   uint32_t head;         // first own byte (0..3)
   uint32_t opos, oend;   // next byte to write / one past the last own byte
   uint32_t sreg;         // bytes of the word at opos & ~3 not yet stored
+  uint32_t full_lo, full_span;  // aligned words a with (a - full_lo) < full_span lie wholly inside the block
   // ---- decode state ----
   uint32_t state, bfinal, err, blk, cp_rem;
   uint32_t llim[16], dlim[16];  // [1..15] used; only ever indexed by constants (registers)
+  // ---- LZ77 copy in flight: its source words were requested one token ago ----
+  uint32_t p_len, p_ssh, p_sa;
+  uint32_t pw0, pw1, pw2, pw3, pw4, pw5, pw6, pw7, pw8;
 
   // ---------------- shared-memory accessors ----------------
   BG_HD uint32_t smr(int w) const { return sm[w * STRIDE]; }
@@ -404,12 +419,22 @@ struct Lane {
   // ---------------- output ----------------
   BG_HD uint32_t ldw(uint32_t a /*aligned*/) const { return *(const uint32_t*)(ob + a); }
   BG_HD void store_word(uint32_t a /*aligned*/, uint32_t w) {
-    if (a >= head && a + 4 <= oend) {
+    if (a - full_lo < full_span) {
       *(uint32_t*)(ob + a) = w;
     } else {  // head / tail word shared with a neighbouring block: touch only our own bytes
       for (uint32_t i = 0; i < 4; ++i)
         if (a + i >= head && a + i < oend) ob[a + i] = (uint8_t)(w >> (8 * i));
     }
+  }
+  // One byte.
+  BG_HD void emit1(uint32_t v) {
+    uint32_t k = opos & 3u;
+    sreg |= v << (8 * k);
+    if (k == 3) {
+      store_word(opos - 3u, sreg);
+      sreg = 0;
+    }
+    opos += 1;
   }
   // v holds n (1..4) valid low bytes, the rest zero.
   BG_HD void emit(uint32_t v, uint32_t n) {
@@ -422,20 +447,29 @@ struct Lane {
     }
     opos += n;
   }
-  // 16 bytes; the caller guarantees opos + 16 <= oend.
-  BG_HD void emit16(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+  // n (1..16) bytes held in v0..v3 (bytes past n may be garbage); the caller guarantees opos + n <= oend.
+  BG_HD void emit_n16(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t n) {
     uint32_t a = opos & ~3u;
-    uint32_t sh = (opos & 3u) * 8;
+    uint32_t k = opos & 3u, sh = k * 8;
     uint32_t o0 = sreg | (v0 << sh);
     uint32_t o1 = bg_funnel_l(v0, v1, sh);
     uint32_t o2 = bg_funnel_l(v1, v2, sh);
     uint32_t o3 = bg_funnel_l(v2, v3, sh);
-    sreg = bg_funnel_l(v3, 0u, sh);
-    store_word(a, o0);                       // may be the head word shared with the previous block
-    *(uint32_t*)(ob + a + 4) = o1;           // a+4 .. a+16 <= opos+16 <= oend: whole own words
-    *(uint32_t*)(ob + a + 8) = o2;
-    *(uint32_t*)(ob + a + 12) = o3;
-    opos += 16;
+    uint32_t o4 = bg_funnel_l(v3, 0u, sh);
+    uint32_t tot = k + n;          // 1..19
+    uint32_t nfull = tot >> 2;     // whole words completed: 0..4
+    if (nfull > 0) store_word(a, o0);   // may be the head word shared with the previous block
+    if (nfull > 1) store_word(a + 4, o1);
+    if (nfull > 2) store_word(a + 8, o2);
+    if (nfull > 3) store_word(a + 12, o3);
+    uint32_t r = o0;
+    if (nfull == 1) r = o1;
+    if (nfull == 2) r = o2;
+    if (nfull == 3) r = o3;
+    if (nfull == 4) r = o4;
+    uint32_t rb = tot & 3u;
+    sreg = r & ((1u << (8 * rb)) - 1u);
+    opos += n;
   }
   // Make every byte below opos visible in memory (bytes of the partially filled word).
   BG_HD void flush_partial() {
@@ -446,33 +480,67 @@ struct Lane {
   }
 
   // ---------------- canonical Huffman ----------------
-  // Number of k in 1..14 with v >= lim[k], plus 1.
+  // 1 + number of k in 1..14 with v >= lim[k].  lim <= 0x8000 and v < 0x8000, so the sign bit of
+  // lim - 1 - v is exactly (v >= lim); two accumulators keep the add chains short.
   BG_HD static uint32_t code_len(const uint32_t* lim, uint32_t v) {
-    uint32_t L = 1;
+    uint32_t nv = ~v, a = 1, b = 0;
 #pragma unroll
-    for (int k = 1; k <= 14; ++k) L += (v >= lim[k]) ? 1u : 0u;
-    return L;
+    for (int k = 1; k <= 13; k += 2) {
+      a += (lim[k] + nv) >> 31;
+      b += (lim[k + 1] + nv) >> 31;
+    }
+    return a + b;
   }
 
-  // ---------------- LZ77 copy, run to completion ----------------
-  BG_HD void copy_match(uint32_t len, uint32_t dist) {
+  // ---------------- LZ77 copies ----------------
+  // dist >= 35: request the first 36 source bytes now, use them one token later (complete_copy), so the
+  // L2/DRAM latency of the window read overlaps the next token's Huffman decode.  All bytes the 9 words
+  // cover lie below opos - 3, i.e. they are already in memory.
+  BG_HD void issue_copy(uint32_t len, uint32_t dist) {
+    uint32_t src = opos - dist;
+    uint32_t sa = src & ~3u;
+    p_ssh = (src & 3u) * 8;
+    pw0 = ldw(sa); pw1 = ldw(sa + 4); pw2 = ldw(sa + 8); pw3 = ldw(sa + 12); pw4 = ldw(sa + 16);
+    pw5 = ldw(sa + 20); pw6 = ldw(sa + 24); pw7 = ldw(sa + 28); pw8 = ldw(sa + 32);
+    p_sa = sa + 36;
+    p_len = len;
+  }
+  BG_HD void complete_copy() {
+    if (p_len) {
+      uint32_t rem = p_len;
+      p_len = 0;
+      uint32_t n = rem < 16 ? rem : 16;
+      emit_n16(bg_funnel_r(pw0, pw1, p_ssh), bg_funnel_r(pw1, pw2, p_ssh), bg_funnel_r(pw2, pw3, p_ssh),
+               bg_funnel_r(pw3, pw4, p_ssh), n);
+      rem -= n;
+      if (rem) {
+        n = rem < 16 ? rem : 16;
+        emit_n16(bg_funnel_r(pw4, pw5, p_ssh), bg_funnel_r(pw5, pw6, p_ssh), bg_funnel_r(pw6, pw7, p_ssh),
+                 bg_funnel_r(pw7, pw8, p_ssh), n);
+        rem -= n;
+        uint32_t sa = p_sa;
+        uint32_t prev = rem ? ldw(sa - 4) : 0u;  // re-read: pw8 was fetched before bytes past src+32 were certain to be stored
+        while (rem) {  // longer than 32 bytes (rare): 16 bytes per trip, loads used at once
+          uint32_t w0 = ldw(sa), w1 = ldw(sa + 4), w2 = ldw(sa + 8), w3 = ldw(sa + 12);
+          sa += 16;
+          n = rem < 16 ? rem : 16;
+          emit_n16(bg_funnel_r(prev, w0, p_ssh), bg_funnel_r(w0, w1, p_ssh), bg_funnel_r(w1, w2, p_ssh),
+                   bg_funnel_r(w2, w3, p_ssh), n);
+          prev = w3;
+          rem -= n;
+        }
+      }
+    }
+  }
+  // dist < 35 (about 6 % of BAM matches): done at once.
+  BG_HD void copy_near(uint32_t len, uint32_t dist) {
     if (dist >= 8) {
-      // Source bytes are always already in memory: with 4-byte steps the read end is <= write pos - 4,
-      // with 16-byte steps (dist >= 20) likewise; the only unstored bytes are the <= 3 in sreg.
+      // 4-byte steps: the read end is <= write pos - 4, the only unstored bytes are the <= 3 in sreg
       uint32_t src = opos - dist;
       uint32_t sa = src & ~3u, ssh = (src & 3u) * 8;
       uint32_t prev = ldw(sa);
       sa += 4;
       uint32_t rem = len;
-      if (dist >= 20) {
-        while (rem >= 16) {
-          uint32_t w0 = ldw(sa), w1 = ldw(sa + 4), w2 = ldw(sa + 8), w3 = ldw(sa + 12);
-          sa += 16;
-          emit16(bg_funnel_r(prev, w0, ssh), bg_funnel_r(w0, w1, ssh), bg_funnel_r(w1, w2, ssh), bg_funnel_r(w2, w3, ssh));
-          prev = w3;
-          rem -= 16;
-        }
-      }
       while (rem) {
         uint32_t n = rem < 4 ? rem : 4;
         uint32_t w = ldw(sa);
@@ -507,48 +575,59 @@ struct Lane {
     }
   }
 
-  // One literal/length (+ distance + copy) token.
+  // One literal/length (+ distance) token.  Order inside a token: (A) Huffman-decode it — bitstream only;
+  // (B) finish the copy the PREVIOUS token started; (C) write this token's literal or start its copy.
   BG_HD void do_token() {
+    // ---- A ----
     br.refill();
     uint32_t c = bg_brev((uint32_t)br.bb) >> 17;
     uint32_t L = code_len(llim, c);
-    if (c >= llim[15]) { err = IST_BAD_SYMBOL; state = ST_NEXT; return; }
+    uint32_t bad = (c >= llim[15]) ? 1u : 0u;
     uint32_t m = smr(SM_LIT_META + L);
-    uint32_t e = lit_sym((m >> 16) + ((c - (m & 0xffffu)) >> (15 - L)));
+    uint32_t e = lit_sym(((m >> 16) + ((c - (m & 0xffffu)) >> (15 - L))) & 0x1ffu);
     br.consume(L);
+    uint32_t len = 0, dist = 0;
+    if (!bad && (e & 0x8000u) && (e & 0x1ffu) != 0u && (e & 0x1ffu) != 0x1ffu) {
+      uint32_t eb = (e >> 12) & 7u;
+      len = (e & 0x1ffu) + ((uint32_t)br.bb & ((1u << eb) - 1u));
+      br.consume(eb);
+      br.refill();
+      c = bg_brev((uint32_t)br.bb) >> 17;
+      L = code_len(dlim, c);
+      if (c >= dlim[15]) bad = 1;
+      m = smr(SM_DIST_META + L);
+      uint32_t ds = dist_sym(((m >> 16) + ((c - (m & 0xffffu)) >> (15 - L))) & 31u);
+      br.consume(L);
+      if (ds >= 30) bad = 1;
+      uint32_t deb = ds < 2 ? 0u : (ds >> 1) - 1u;
+      deb &= 15u;
+      dist = (ds < 2 ? ds + 1u : 1u + ((2u | (ds & 1u)) << deb)) + ((uint32_t)br.bb & ((1u << deb) - 1u));
+      br.consume(deb);
+    }
+    // ---- B ----
+    complete_copy();
+    // ---- C ----
+    if (bad) { err = IST_BAD_SYMBOL; state = ST_NEXT; return; }
     if (!(e & 0x8000u)) {
       if (opos >= oend) { err = IST_OUTPUT_OVERRUN; state = ST_NEXT; return; }
-      emit(e, 1);
+      emit1(e);
       return;
     }
-    uint32_t blen = e & 0x1ffu;
-    if (blen == 0) {  // end of block
-      state = bfinal ? ST_NEXT : ST_HEADER;
+    if (len == 0) {
+      if ((e & 0x1ffu) == 0x1ffu) { err = IST_BAD_SYMBOL; state = ST_NEXT; return; }
+      state = bfinal ? ST_NEXT : ST_HEADER;  // end of block
       return;
     }
-    if (blen == 0x1ffu) { err = IST_BAD_SYMBOL; state = ST_NEXT; return; }
-    uint32_t eb = (e >> 12) & 7u;
-    uint32_t len = blen + ((uint32_t)br.bb & ((1u << eb) - 1u));
-    br.consume(eb);
-    br.refill();
-    c = bg_brev((uint32_t)br.bb) >> 17;
-    L = code_len(dlim, c);
-    if (c >= dlim[15]) { err = IST_BAD_SYMBOL; state = ST_NEXT; return; }
-    m = smr(SM_DIST_META + L);
-    uint32_t ds = dist_sym((m >> 16) + ((c - (m & 0xffffu)) >> (15 - L)));
-    br.consume(L);
-    if (ds >= 30) { err = IST_BAD_SYMBOL; state = ST_NEXT; return; }
-    uint32_t deb = ds < 2 ? 0u : (ds >> 1) - 1u;
-    uint32_t dist = (ds < 2 ? ds + 1u : 1u + ((2u | (ds & 1u)) << deb)) + ((uint32_t)br.bb & ((1u << deb) - 1u));
-    br.consume(deb);
     if (dist > opos - head) { err = IST_BAD_DISTANCE; state = ST_NEXT; return; }
     if (len > oend - opos) { err = IST_OUTPUT_OVERRUN; state = ST_NEXT; return; }
-    copy_match(len, dist);
+    if (dist >= 35) issue_copy(len, dist);
+    else copy_near(len, dist);
   }
 
-  // Up to `budget` tokens of the current Huffman block.
+  // Up to `budget` tokens of the current Huffman block.  No copy is left in flight on return.
   BG_HD void decode_run(uint32_t budget) {
     for (uint32_t t = 0; t < budget && state == ST_DECODE; ++t) do_token();
+    complete_copy();
   }
 
   // Stored block body (rare): 4 bytes per step straight from the bit buffer.
@@ -568,14 +647,16 @@ struct Lane {
 
   BG_HD void header() {
     HeaderResult hr;
-    parse_header<STRIDE>(&br, sm, &hr);
+    BitReader tmp = br;   // only this copy's address escapes: the lane itself stays in registers
+    parse_header<STRIDE>(&tmp, sm, &hr);
+    br = tmp;
     state = hr.state;
     bfinal = hr.bfinal;
     if (hr.err) err = hr.err;
     cp_rem = hr.stored_len;
     if (hr.state == ST_DECODE) {
 #pragma unroll
-      for (int k = 1; k <= 15; ++k) { llim[k] = hr.llim[k]; dlim[k] = hr.dlim[k]; }
+      for (int k = 1; k <= 15; ++k) { llim[k] = bg_pin(hr.llim[k]); dlim[k] = bg_pin(hr.dlim[k]); }
     }
   }
 
@@ -601,6 +682,10 @@ struct Lane {
     opos = head;
     oend = head + job.isize[b];
     sreg = 0;
+    p_len = 0;
+    full_lo = head ? 4u : 0u;
+    uint32_t full_hi = oend & ~3u;
+    full_span = full_hi > full_lo ? full_hi - full_lo : 0u;
     br.begin(job.comp + job.in_off[b], job.in_len[b]);
     state = ST_HEADER;
   }

@@ -91,7 +91,14 @@ struct ChainResult {
 
 void launch_tile_walk(const RecordParams& p, const TileArrays& t, cudaStream_t s);
 // Link + pointer-doubling reachability + (rare) serial repair + masked scan of counts + result summary, one launch.
-void launch_chain_resolve(const RecordParams& p, const TileArrays& t, ChainResult* d_result, cudaStream_t s);
+constexpr int RESOLVE_MAX_CTAS = 256;
+struct ResolveScratch {  // grid-wide state of k3_resolve (device memory, no initialisation needed)
+  uint32_t first, broken_tile, tail_kind, repairs;
+  unsigned long long broken_entry, tail_off;
+  unsigned long long chunk_sum[RESOLVE_MAX_CTAS];
+};
+cudaError_t launch_chain_resolve(const RecordParams& p, const TileArrays& t, ChainResult* d_result, ResolveScratch* d_scratch,
+                                 int num_sms, cudaStream_t s);
 // Second walk: writes rec_off / rec_len for reachable tiles.
 void launch_tile_emit(const RecordParams& p, const TileArrays& t, uint64_t* rec_off, uint32_t* rec_len, cudaStream_t s);
 // Per-record fixed fields, variable offsets, keys (and HI when want_hi).

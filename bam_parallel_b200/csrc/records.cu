@@ -23,7 +23,11 @@
 //      never the filter's opinion.  An exclusive scan then gives every tile its first record index.
 //   3. k3_tile_emit re-walks and writes rec_off / rec_len, k3_extract (one thread per record)
 //      writes the SoA columns + keys.
+#include <cooperative_groups.h>
+
 #include "kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace bamgpu {
 namespace {
@@ -37,7 +41,7 @@ __device__ __forceinline__ uint32_t ld32(const uint8_t* data, uint64_t off) {
   return sh ? __funnelshift_r(lo, a[1], sh) : lo;
 }
 
-// Spec invariants of a record start (SAM spec §4.2).  Used ONLY to guess; never to decide.
+// Spec invariants of a record start (SAM spec §1.4, §4.2).  Used ONLY to guess; never to decide.
 // `bs` is the already loaded block_size at q.
 __device__ __forceinline__ bool plausible_fields(const RecordParams& p, uint64_t q, uint32_t bs) {
   if (p.data_len - q < 36) return false;
@@ -58,18 +62,23 @@ __device__ __forceinline__ bool plausible_fields(const RecordParams& p, uint64_t
   if (need > bs) return false;
   uint64_t nul = q + 4 + 32 + l_name - 1;
   if (nul < p.data_len && p.data[nul] != 0) return false;
+  if (l_name > 1) {  // read names are [!-?A-~]{1,254}
+    uint32_t c0 = p.data[q + 36];
+    if (c0 < 0x21 || c0 > 0x7e) return false;
+  }
   return true;
 }
 
 // A candidate is accepted when it and the next VERIFY_DEPTH records along its chain all look like
-// records (or the chain runs into the end of the data first).  One look-alike inside sequence or
-// quality bytes is common; four in a row along block_size links is not.
+// records, or the chain ends at (or just past) the end of the data first.  One look-alike inside
+// sequence or quality bytes is common; four in a row along block_size links is not.
 constexpr int VERIFY_DEPTH = 3;
 __device__ bool plausible_chain(const RecordParams& p, uint64_t q, uint32_t bs) {
   if (!plausible_fields(p, q, bs)) return false;
   for (int i = 0; i < VERIFY_DEPTH; ++i) {
     q += 4ull + bs;
-    if (p.data_len - q < 36 || q > p.data_len) return true;  // ran into the tail: nothing left to check
+    if (q > p.data_len) return q - p.data_len <= TILE_BYTES;  // last record of a batch may be cut; a wild jump is not
+    if (p.data_len - q < 36) return true;                     // tail: nothing left to check
     bs = ld32(p.data, q);
     if (!plausible_fields(p, q, bs)) return false;
   }
@@ -137,87 +146,93 @@ __global__ void __launch_bounds__(128) k3_tile_walk(RecordParams p, TileArrays t
   t.exit_kind[k] = o.kind;
 }
 
-// One CTA resolves the whole tile graph:
+// One cooperative launch (one CTA per SM, grid-wide barriers) resolves the whole tile graph:
 //   link:   tile k points at the tile holding its exit iff that tile's guess equals the exit;
 //   reach:  pointer doubling from the start tile marks the tiles on the true chain;
 //   repair: if the chain stops at a tile whose guess was wrong (or that a long record jumped into),
-//           thread 0 re-walks serially from the true entry until it re-synchronises with a guess,
+//           one thread re-walks serially from the true entry until it re-synchronises with a guess,
 //           and the resolve repeats.  The result is therefore exactly the blind walk of reader.rs:63-81;
 //   scan:   exclusive scan of the counts of reachable tiles = first record index of every tile.
-__global__ void __launch_bounds__(1024) k3_resolve(RecordParams p, TileArrays t, ChainResult* res) {
-  __shared__ unsigned long long warp_sums[32];
-  __shared__ unsigned long long carry;
-  __shared__ uint32_t s_broken_tile;
-  __shared__ uint64_t s_broken_entry, s_tail_off;
-  __shared__ uint32_t s_tail_kind, s_repairs;
-  __shared__ uint32_t s_first;
+// Arrays written by one CTA and read by another between barriers are read with ld.cg (L2, the
+// coherence point); grid.sync() orders the phases.
+constexpr int RESOLVE_THREADS = 512;
+
+__device__ __forceinline__ uint32_t ldcg32(const uint32_t* p) { return __ldcg(p); }
+__device__ __forceinline__ uint64_t ldcg64(const void* p) { return (uint64_t)__ldcg((const unsigned long long*)p); }
+__device__ __forceinline__ uint8_t ldcg8(const uint8_t* p) { return __ldcg(p); }
+
+__global__ void __launch_bounds__(RESOLVE_THREADS) k3_resolve(RecordParams p, TileArrays t, ChainResult* res,
+                                                              ResolveScratch* g) {
+  cg::grid_group grid = cg::this_grid();
   const uint32_t n = t.n_tiles;
-  if (threadIdx.x == 0) { s_repairs = 0; s_first = (uint32_t)(p.start / TILE_BYTES); }
-  __syncthreads();
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  if (tid == 0) { g->first = p.start_known ? (uint32_t)(p.start / TILE_BYTES) : 0xffffffffu; g->repairs = 0; }
+  grid.sync();
   if (!p.start_known) {
     // shard-edge mode: the chain begins at the first tile (from the start tile on) that found a guess
-    uint32_t lo = s_first;
-    __syncthreads();
-    if (threadIdx.x == 0) s_first = 0xffffffffu;
-    __syncthreads();
     uint32_t best = 0xffffffffu;
-    for (uint32_t k = lo + threadIdx.x; k < n; k += blockDim.x)
+    for (uint32_t k = (uint32_t)(p.start / TILE_BYTES) + tid; k < n; k += nthreads)
       if (t.entry[k] != NONE64) { best = k; break; }
-    if (best != 0xffffffffu) atomicMin(&s_first, best);
-    __syncthreads();
+    if (best != 0xffffffffu) atomicMin(&g->first, best);
+    grid.sync();
   }
-  const uint32_t k0 = s_first;
+  const uint32_t k0 = ldcg32(&g->first);
   if (k0 >= n) {  // nothing that looks like a record anywhere
-    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) { t.reach[k] = 0; t.base[k] = 0; }
-    if (threadIdx.x == 0) {
+    for (uint32_t k = tid; k < n; k += nthreads) { t.reach[k] = 0; t.base[k] = 0; }
+    if (tid == 0) {
       res->n_records = 0; res->tail_off = p.start; res->tail_kind = EXIT_NONE; res->broken_tile = 0xffffffffu;
       res->broken_entry = 0; res->bad_flags = 0; res->rounds = 0; res->chain_start = NONE64;
     }
     return;
   }
   for (;;) {
-    if (threadIdx.x == 0) { s_broken_tile = 0xffffffffu; s_tail_off = p.start; s_tail_kind = EXIT_TAIL; }
-    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+    if (tid == 0) { g->broken_tile = 0xffffffffu; g->tail_off = p.start; g->tail_kind = EXIT_TAIL; }
+    for (uint32_t k = tid; k < n; k += nthreads) {
       uint32_t nx = k;
-      if (t.entry[k] != NONE64 && t.exit_kind[k] == EXIT_NORMAL) {
-        uint32_t j = (uint32_t)(t.exit_off[k] / TILE_BYTES);
-        if (j < n && t.entry[j] == t.exit_off[k]) nx = j;
+      uint64_t ex = ldcg64(&t.exit_off[k]);
+      if (ldcg64(&t.entry[k]) != NONE64 && ldcg32(&t.exit_kind[k]) == EXIT_NORMAL) {
+        uint32_t j = (uint32_t)(ex / TILE_BYTES);
+        if (j < n && ldcg64(&t.entry[j]) == ex) nx = j;
       }
       t.nxt[k] = nx;
       t.jump[k] = nx;
       t.reach[k] = (k == k0) ? 1 : 0;
     }
-    __syncthreads();
+    grid.sync();
     uint32_t* a = t.jump;
     uint32_t* b = t.jump2;
     for (uint64_t span = 1; span < (uint64_t)n * 2; span <<= 1) {
-      for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
-        uint32_t j = a[k];
-        if (t.reach[k]) t.reach[j] = 1;
-        b[k] = a[j];
+      for (uint32_t k = tid; k < n; k += nthreads) {
+        uint32_t j = ldcg32(&a[k]);
+        if (ldcg8(&t.reach[k])) t.reach[j] = 1;
+        b[k] = ldcg32(&a[j]);
       }
-      __syncthreads();
+      grid.sync();
       uint32_t* tmp = a; a = b; b = tmp;
     }
-    // the chain's last tile: reachable and its own successor
-    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
-      if (t.reach[k] && t.nxt[k] == k) {
-        if (t.entry[k] == NONE64) {                 // only the start tile can be reachable without an entry
-          s_tail_off = p.start; s_tail_kind = EXIT_NONE;
-        } else if (t.exit_kind[k] == EXIT_NORMAL) { // successor's guess mismatched (or successor out of range)
-          s_broken_tile = (uint32_t)(t.exit_off[k] / TILE_BYTES);
-          s_broken_entry = t.exit_off[k];
+    // the chain's last tile: reachable and its own successor (exactly one such tile)
+    for (uint32_t k = tid; k < n; k += nthreads) {
+      if (ldcg8(&t.reach[k]) && t.nxt[k] == k) {
+        uint32_t kind = ldcg32(&t.exit_kind[k]);
+        uint64_t ex = ldcg64(&t.exit_off[k]);
+        if (ldcg64(&t.entry[k]) == NONE64) {          // only the start tile can be reachable without an entry
+          g->tail_off = p.start; g->tail_kind = EXIT_NONE;
+        } else if (kind == EXIT_NORMAL) {            // successor's guess mismatched (or successor out of range)
+          g->broken_entry = ex;
+          g->broken_tile = (uint32_t)(ex / TILE_BYTES);
         } else {
-          s_tail_off = t.exit_off[k];
-          s_tail_kind = t.exit_kind[k];
+          g->tail_off = ex;
+          g->tail_kind = kind;
         }
       }
     }
-    __syncthreads();
-    if (s_broken_tile == 0xffffffffu || s_broken_tile >= n) break;
-    if (threadIdx.x == 0) {
-      uint32_t tile = s_broken_tile;
-      uint64_t entry = s_broken_entry;
+    grid.sync();
+    uint32_t broken = ldcg32(&g->broken_tile);
+    if (broken == 0xffffffffu || broken >= n) break;
+    if (tid == 0) {
+      uint32_t tile = broken;
+      uint64_t entry = ldcg64(&g->broken_entry);
+      uint32_t reps = 0;
       for (;;) {
         uint64_t te = (uint64_t)(tile + 1) * TILE_BYTES;
         if (te > p.data_len) te = p.data_len;
@@ -226,55 +241,71 @@ __global__ void __launch_bounds__(1024) k3_resolve(RecordParams p, TileArrays t,
         t.exit_off[tile] = o.exit_off;
         t.count[tile] = o.count;
         t.exit_kind[tile] = o.kind;
-        ++s_repairs;
+        ++reps;
         if (o.kind != EXIT_NORMAL) break;
         uint32_t j = (uint32_t)(o.exit_off / TILE_BYTES);
-        if (j >= n || t.entry[j] == o.exit_off) break;  // re-synchronised with the guess
+        if (j >= n || ldcg64(&t.entry[j]) == o.exit_off) break;  // re-synchronised with the guess
         tile = j;
         entry = o.exit_off;
       }
+      g->repairs += reps;
     }
-    __syncthreads();
+    grid.sync();
   }
-  // ---- exclusive scan of (reach ? count : 0) ----
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
+  // ---- exclusive scan of (reach ? count : 0): every CTA owns a contiguous chunk of tiles ----
+  __shared__ unsigned long long warp_sums[RESOLVE_THREADS / 32];
+  __shared__ unsigned long long s_carry;
+  const uint32_t chunk = (n + gridDim.x - 1) / gridDim.x;
+  const uint32_t c0 = blockIdx.x * chunk, c1 = (c0 + chunk < n) ? c0 + chunk : n;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < n; base += 1024) {
-    uint32_t k = base + threadIdx.x;
-    bool in = k < n;
-    unsigned long long v = (in && t.reach[k]) ? t.count[k] : 0;
-    unsigned long long x = v;
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
+  for (int pass = 0; pass < 2; ++pass) {
+    if (threadIdx.x == 0) {
+      unsigned long long basev = 0;
+      if (pass == 1)
+        for (uint32_t i = 0; i < blockIdx.x; ++i) basev += ldcg64(&g->chunk_sum[i]);
+      s_carry = basev;
     }
-    if (lane == 31) warp_sums[wid] = x;
     __syncthreads();
-    if (wid == 0) {
-      unsigned long long s = warp_sums[lane];
+    for (uint32_t base = c0; base < c1; base += RESOLVE_THREADS) {
+      uint32_t k = base + threadIdx.x;
+      bool in = k < c1;
+      unsigned long long v = (in && ldcg8(&t.reach[k])) ? ldcg32(&t.count[k]) : 0;
+      unsigned long long x = v;
       for (int o = 1; o < 32; o <<= 1) {
-        unsigned long long y = __shfl_up_sync(0xffffffffu, s, o);
-        if (lane >= o) s += y;
+        unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
       }
-      warp_sums[lane] = s;  // inclusive
+      if (lane == 31) warp_sums[wid] = x;
+      __syncthreads();
+      if (wid == 0) {
+        unsigned long long s = lane < RESOLVE_THREADS / 32 ? warp_sums[lane] : 0;
+        for (int o = 1; o < 32; o <<= 1) {
+          unsigned long long y = __shfl_up_sync(0xffffffffu, s, o);
+          if (lane >= o) s += y;
+        }
+        if (lane < RESOLVE_THREADS / 32) warp_sums[lane] = s;  // inclusive
+      }
+      __syncthreads();
+      unsigned long long off = s_carry + (wid ? warp_sums[wid - 1] : 0) + (x - v);
+      if (pass == 1 && in) t.base[k] = off;
+      __syncthreads();
+      if (threadIdx.x == RESOLVE_THREADS - 1) s_carry = off + v;
+      __syncthreads();
     }
-    __syncthreads();
-    unsigned long long off = carry + (wid ? warp_sums[wid - 1] : 0) + (x - v);
-    if (in) t.base[k] = off;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = off + v;
-    __syncthreads();
+    if (pass == 0) {
+      if (threadIdx.x == 0) g->chunk_sum[blockIdx.x] = s_carry;
+      grid.sync();
+    }
   }
-  if (threadIdx.x == 0) {
-    res->n_records = carry;
-    res->tail_off = s_tail_off;
-    res->tail_kind = s_tail_kind;
-    res->broken_tile = s_broken_tile;
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    res->n_records = s_carry;
+    res->tail_off = ldcg64(&g->tail_off);
+    res->tail_kind = ldcg32(&g->tail_kind);
+    res->broken_tile = ldcg32(&g->broken_tile) >= n ? ldcg32(&g->broken_tile) : 0xffffffffu;
     res->broken_entry = 0;
     res->bad_flags = 0;
-    res->rounds = s_repairs;
-    res->chain_start = t.entry[k0];
+    res->rounds = ldcg32(&g->repairs);
+    res->chain_start = ldcg64(&t.entry[k0]);
   }
 }
 
@@ -391,9 +422,16 @@ void launch_tile_walk(const RecordParams& p, const TileArrays& t, cudaStream_t s
   if (t.n_tiles) k3_tile_walk<<<grid_for(t.n_tiles, 128), 128, 0, s>>>(p, t);
 }
 
-void launch_chain_resolve(const RecordParams& p, const TileArrays& t, ChainResult* d_result, cudaStream_t s) {
-  if (t.n_tiles == 0) return;
-  k3_resolve<<<1, 1024, 0, s>>>(p, t, d_result);
+cudaError_t launch_chain_resolve(const RecordParams& p, const TileArrays& t, ChainResult* d_result, ResolveScratch* d_scratch,
+                                 int num_sms, cudaStream_t s) {
+  if (t.n_tiles == 0) return cudaSuccess;
+  int grid = num_sms < RESOLVE_MAX_CTAS ? num_sms : RESOLVE_MAX_CTAS;
+  int need = (int)((t.n_tiles + RESOLVE_THREADS - 1) / RESOLVE_THREADS);
+  if (grid > need) grid = need;
+  RecordParams pp = p;
+  TileArrays tt = t;
+  void* args[] = {&pp, &tt, &d_result, &d_scratch};
+  return cudaLaunchCooperativeKernel((const void*)k3_resolve, dim3(grid), dim3(RESOLVE_THREADS), args, 0, s);
 }
 
 void launch_tile_emit(const RecordParams& p, const TileArrays& t, uint64_t* rec_off, uint32_t* rec_len, cudaStream_t s) {

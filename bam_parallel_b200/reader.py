@@ -267,6 +267,10 @@ class Engine:
             raise BamGpuError(rc, self._L.bamgpu_engine_last_error(self._h).decode())
         return RecordBatch(b), tail.value, rc
 
+    def set_n_ref(self, n_ref: int):
+        """Optional hint (header n_ref) for K3's guess of record starts; results never depend on it."""
+        self._L.bamgpu_engine_set_n_ref(self._h, n_ref)
+
     def stats(self) -> dict:
         s = Stats()
         self._L.bamgpu_engine_stats(self._h, C.byref(s))

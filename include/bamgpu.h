@@ -177,6 +177,10 @@ int bamgpu_engine_decode(bamgpu_engine*, const uint8_t* d_comp, const bamgpu_blo
                          uint64_t stream_start, int final, uint32_t flags, void* cuda_stream,
                          bamgpu_batch* out, uint64_t* tail_off);
 
+/* Number of reference sequences of the BAM header (n_ref), if the caller knows it: tightens the guess of record
+ * starts inside K3 (refID must be in [-1, n_ref)).  Results never depend on it.  < 0 = unknown (default). */
+void bamgpu_engine_set_n_ref(bamgpu_engine*, int32_t n_ref);
+
 int bamgpu_engine_stats(const bamgpu_engine*, bamgpu_stats* out);
 void bamgpu_engine_reset_stats(bamgpu_engine*);
 
