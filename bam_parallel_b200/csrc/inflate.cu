@@ -3,8 +3,8 @@
 // Replaces bam_tools/src/util.rs:10-16 (inflate_data) + reader/readahead.rs:145-150
 // (decompress_block) and the n-2 rayon inflate workers of readahead.rs:88-118.
 //
-// Mapping: a persistent grid of 3-warp CTAs, 3 CTAs per SM (9 warps = 288 lanes per SM, the
-// most that fit in 227 KB of shared memory at 736 B of Huffman tables per lane).  Every LANE
+// Mapping: a persistent grid of 3-warp CTAs, 5 CTAs per SM (15 warps = 480 lanes per SM, the
+// most that fit in 227 KB of shared memory at 420 B of Huffman tables + 32 B of input staging per lane).  Every LANE
 // owns one BGZF block at a time and pulls the next block index from a global counter, so a
 // warp advances 32 independent DEFLATE streams side by side.  The per-lane logic is in
 // inflate_core.cuh.  Output offsets come from the host's exclusive scan of ISIZE
@@ -15,17 +15,19 @@
 namespace bamgpu {
 
 constexpr int K1_WARPS_PER_CTA = 3;
-constexpr int K1_CTAS_PER_SM = 3;
-constexpr int K1_SMEM_BYTES = K1_WARPS_PER_CTA * 32 * LANE_WORDS * 4;  // 70656
+constexpr int K1_CTAS_PER_SM = 5;
+constexpr int K1_TABLE_BYTES = K1_WARPS_PER_CTA * 32 * LANE_WORDS * 4;            // 40320: Huffman tables
+constexpr int K1_SMEM_BYTES = K1_TABLE_BYTES + K1_WARPS_PER_CTA * STAGE_WARP_BYTES;   // + 3072: input staging slots
 
 constexpr uint32_t K1_TOKENS_PER_ROUND = 128;  // tokens a lane decodes between two looks at the warp-wide state
 
 __global__ void __launch_bounds__(K1_WARPS_PER_CTA * 32, K1_CTAS_PER_SM)
 k1_inflate_lane_per_block(InflateJob job, uint32_t* __restrict__ work_counter) {
-  extern __shared__ uint32_t smem[];
+  extern __shared__ __align__(16) uint32_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Lane<32> L;
   L.sm = smem + warp * (32 * LANE_WORDS) + lane;
+  const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(smem) + K1_TABLE_BYTES + warp * STAGE_WARP_BYTES + lane * 16;
   L.state = ST_NEXT;
   L.blk = 0xffffffffu;
   L.err = 0;
@@ -33,7 +35,7 @@ k1_inflate_lane_per_block(InflateJob job, uint32_t* __restrict__ work_counter) {
     if (L.state == ST_NEXT) {
       L.finish_block(job);
       uint32_t b = atomicAdd(work_counter, 1u);
-      if (b < job.n_blocks) L.begin_block(job, b);
+      if (b < job.n_blocks) L.begin_block(job, b, stage0);
       else { L.state = ST_DONE; L.blk = 0xffffffffu; }
     }
     if (__all_sync(0xffffffffu, L.state == ST_DONE)) break;

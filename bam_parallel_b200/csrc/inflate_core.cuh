@@ -6,13 +6,15 @@
 // Design notes (see DESIGN.md "K1"):
 //   * Huffman decode is canonical and LUT-free: the 15 left-aligned code-length limits of the
 //     literal/length and distance codes live in REGISTERS, the code length is found with 14
-//     independent compares (no divergence between lanes, no memory access), and only the
-//     (base,offset) pair and the symbol come from shared memory.  Tables are 736 B per stream
-//     so 288 streams fit in one SM's 227 KB.
+//     independent compares (no divergence between lanes, no memory access), and only one
+//     index offset and the symbol come from shared memory.  Tables are 420 B per stream
+//     (byte-wide sorted symbols + a 288-bit "is a length code / end of block" map), so 480
+//     streams (15 warps) fit in one SM's 227 KB.
 //   * Shared memory is interleaved by lane ([word][lane]) so any per-lane index pattern is
 //     bank-conflict free.
-//   * Input is fetched 16 bytes at a time (LDG.128) into a double-buffered register queue, one
-//     whole chunk ahead of use, so the load latency is off the decode dependency chain.
+//   * Input is fetched 16 bytes at a time with cp.async (LDGSTS) into two shared-memory slots
+//     per lane, two chunks ahead of use, so neither the load latency nor a register scoreboard
+//     sits on the decode dependency chain.
 //   * Output goes through a 4-byte staging register and is stored as aligned 32-bit words.
 //   * LZ77 copies are software-pipelined against the Huffman decode: a match with distance >= 35
 //     only REQUESTS its first 36 source bytes (9 aligned loads, no use), the next token is
@@ -59,15 +61,16 @@ enum : uint32_t {
   IST_SIZE_MISMATCH = 11, // final EOB reached with fewer bytes than ISIZE
 };
 
-// Shared-memory words per lane.
-constexpr int LIT_SYM_WORDS = 144;  // 288 x u16
+// Shared-memory words per lane (each lane's words are interleaved with the other 31 lanes' words).
+constexpr int LIT_SYM_WORDS = 72;   // 288 x u8: low 8 bits of the sorted literal/length symbols
+constexpr int LIT_SPC_WORDS = 9;    // 288 x 1 bit: symbol >= 256 (end of block / length code)
 constexpr int DIST_SYM_WORDS = 8;   // 32 x u8
-constexpr int META_WORDS = 16;      // per code length: base (15 bit, left aligned) | offset << 16
-constexpr int LANE_WORDS = LIT_SYM_WORDS + DIST_SYM_WORDS + 2 * META_WORDS;  // 184 words = 736 B
+constexpr int META_WORDS = 16;      // per code length L: (first index - first code) mod 2^16, lit/len low half, distance high half
+constexpr int LANE_WORDS = LIT_SYM_WORDS + LIT_SPC_WORDS + DIST_SYM_WORDS + META_WORDS;  // 105 words = 420 B
 constexpr int SM_LIT_SYM = 0;
-constexpr int SM_DIST_SYM = LIT_SYM_WORDS;
-constexpr int SM_LIT_META = SM_DIST_SYM + DIST_SYM_WORDS;
-constexpr int SM_DIST_META = SM_LIT_META + META_WORDS;
+constexpr int SM_LIT_SPC = LIT_SYM_WORDS;
+constexpr int SM_DIST_SYM = SM_LIT_SPC + LIT_SPC_WORDS;
+constexpr int SM_META = SM_DIST_SYM + DIST_SYM_WORDS;
 
 enum LaneState : uint32_t { ST_NEXT = 0, ST_HEADER, ST_DECODE, ST_STORED, ST_DONE };
 
@@ -122,26 +125,81 @@ struct InflateJob {
   uint8_t* out;              // inflated stream, 4-byte aligned; readable 16 bytes BEFORE out[0] and 4 past the end
   uint32_t* status;          // per block: IST_*
   uint32_t n_blocks;
+#if defined(BG_BOUNDS)
+  uint64_t out_len, comp_len;  // debug build: every global access is checked against these
+#endif
 };
 
-// ---- input bit reader: 64-bit bit buffer fed from a double-buffered queue of 16-byte chunks -----
+#if defined(BG_BOUNDS) && defined(__CUDA_ARCH__)
+#define BG_CHECK(cond, what, v)                                                                       \
+  do {                                                                                                \
+    if (!(cond)) {                                                                                    \
+      printf("BG_BOUNDS %s: value %lld block %u opos %u oend %u head %u state %u\n", what, (long long)(v), blk, opos, oend, head, state); \
+      __trap();                                                                                       \
+    }                                                                                                 \
+  } while (0)
+#else
+#define BG_CHECK(cond, what, v) do { } while (0)
+#endif
+
+// ---- input bit reader: 64-bit bit buffer fed from 16-byte chunks ------------------------------------
+// On the GPU the chunks after the current one are staged in shared memory by cp.async (LDGSTS): two
+// 16-byte slots per lane hold chunks k+1 and k+2 while chunk k is consumed from registers, so the
+// global-memory latency of the input never sits on the decode dependency chain and no register
+// scoreboard is tied up by a load in flight.  On the host (tests) chunks are read directly.
+constexpr int STAGE_SLOT_BYTES = 32 * 16;              // one slot of one warp: 32 lanes x 16 bytes
+constexpr int STAGE_WARP_BYTES = 2 * STAGE_SLOT_BYTES; // two slots
+
 struct BitReader {
-  const uint8_t* qp;         // next 16-byte chunk to fetch
+  const uint8_t* qp;         // next 16-byte chunk to request
   uint32_t q0, q1, q2, q3;   // current chunk; q0 is the next word to feed
-  uint32_t r0, r1, r2, r3;   // prefetched chunk
   uint32_t qn;               // words left in q
+  uint32_t stage;            // GPU: shared-memory byte address of the slot holding the next chunk
+  uint32_t stage_x;          // slot 0 address XOR slot 1 address: stage ^= stage_x switches slots
   uint64_t bb;
   uint32_t nbits;
   uint32_t fed;              // payload bits moved into bb so far
   uint32_t in_bits;          // payload length in bits
 
-  BG_HD void begin(const uint8_t* p, uint32_t len) {
+#if defined(__CUDA_ARCH__)
+  BG_HD void request(uint32_t slot_addr) {   // chunk at qp -> shared slot, asynchronously
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;" ::"r"(slot_addr), "l"(qp) : "memory");
+    qp += 16;
+  }
+  BG_HD void next_chunk() {
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the newest request has landed
+    uint32_t x, y, z, w;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(stage) : "memory");
+    q0 = x; q1 = y; q2 = z; q3 = w;
+    request(stage);                       // the slot just read takes chunk k+3
+    stage ^= stage_x;                     // the other slot holds the next chunk
+  }
+  BG_HD void begin_chunks(W4& first) {
+    first = bg_ld_in16(qp);
+    qp += 16;
+    request(stage);
+    request(stage ^ stage_x);
+  }
+#else
+  BG_HD void next_chunk() {
+    W4 v = bg_ld_in16(qp);
+    qp += 16;
+    q0 = v.x; q1 = v.y; q2 = v.z; q3 = v.w;
+  }
+  BG_HD void begin_chunks(W4& first) {
+    first = bg_ld_in16(qp);
+    qp += 16;
+  }
+#endif
+
+  // `stage0`: shared-memory address of this lane's slot 0 (16-byte aligned); ignored on the host.
+  BG_HD void begin(const uint8_t* p, uint32_t len, uint32_t stage0) {
     uintptr_t a = (uintptr_t)p;
     qp = (const uint8_t*)(a & ~(uintptr_t)15);
-    W4 q = bg_ld_in16(qp);
-    W4 r = bg_ld_in16(qp + 16);
-    qp += 32;
-    r0 = r.x; r1 = r.y; r2 = r.z; r3 = r.w;
+    stage = stage0;
+    stage_x = stage0 ^ (stage0 + (uint32_t)STAGE_SLOT_BYTES);
+    W4 q;
+    begin_chunks(q);
     uint32_t lead = (uint32_t)(a & 15);
     uint32_t skipw = lead >> 2;
     q0 = q.x; q1 = q.y; q2 = q.z; q3 = q.w;
@@ -160,11 +218,8 @@ struct BitReader {
   BG_HD void refill() {
     if (nbits <= 32) {
       if (qn == 0) {
-        q0 = r0; q1 = r1; q2 = r2; q3 = r3;
+        next_chunk();
         qn = 4;
-        W4 r = bg_ld_in16(qp);   // used a whole chunk (>= 4 refills) from now
-        qp += 16;
-        r0 = r.x; r1 = r.y; r2 = r.z; r3 = r.w;
       }
       bb |= (uint64_t)q0 << nbits;
       nbits += 32;
@@ -175,6 +230,12 @@ struct BitReader {
   }
   BG_HD void consume(uint32_t n) { bb >>= n; nbits -= n; }
   BG_HD uint32_t bits_consumed() const { return fed - nbits; }
+  // Call when done with a stream: no request may stay in flight into a slot the next stream will reuse.
+  BG_HD void drain() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+  }
 };
 
 // ---- cold path: DEFLATE block header + code tables ----------------------------------------------
@@ -187,66 +248,47 @@ template <int STRIDE>
 struct TableBuilder {
   uint32_t* sm;
   BG_HD uint32_t& smw(int w) { return sm[w * STRIDE]; }
-  BG_HD void set_lit_sym(uint32_t i, uint32_t v) {
-    uint32_t& w = smw(SM_LIT_SYM + (i >> 1));
-    uint32_t sh = (i & 1) * 16;
-    w = (w & ~(0xffffu << sh)) | (v << sh);
-  }
-  BG_HD void set_dist_sym(uint32_t i, uint32_t v) {
-    uint32_t& w = smw(SM_DIST_SYM + (i >> 2));
+  BG_HD void set_byte(int base, uint32_t i, uint32_t v) {
+    uint32_t& w = smw(base + (int)(i >> 2));
     uint32_t sh = (i & 3) * 8;
     w = (w & ~(0xffu << sh)) | (v << sh);
   }
-  // Builds sorted-symbol table + per-length meta + limits for `n` symbols whose code lengths are
-  // lens[0..n).  is_lit selects the table and the symbol encoding.  Returns 0 or IST_*.
-  BG_HD uint32_t build(const uint8_t* lens, uint32_t n, bool is_lit, uint32_t* lim) {
-    const int meta = is_lit ? SM_LIT_META : SM_DIST_META;
-    for (int L = 0; L < 16; ++L) smw(meta + L) = 0;
-    for (uint32_t s = 0; s < n; ++s) smw(meta + lens[s]) += 1;
+  // Builds the sorted-symbol table and the limits for `n` symbols whose code lengths are lens[0..n);
+  // a[L] gets (index of the first symbol of length L) - (first code of length L), mod 2^16, so that
+  // symbol index = a[L] + code.  The META words serve as scratch (counts, then scatter cursors).
+  // Returns 0 or IST_*.
+  BG_HD uint32_t build(const uint8_t* lens, uint32_t n, bool is_lit, uint32_t* lim, uint32_t* a) {
+    for (int L = 0; L < 16; ++L) smw(SM_META + L) = 0;
+    for (uint32_t s = 0; s < n; ++s) smw(SM_META + lens[s]) += 1;
     uint32_t cnt[16];
 #pragma unroll
-    for (int L = 1; L <= 15; ++L) cnt[L] = smw(meta + L);
+    for (int L = 1; L <= 15; ++L) cnt[L] = smw(SM_META + L);
     uint32_t code = 0, offs = 0, bad = 0;
 #pragma unroll
     for (int L = 1; L <= 15; ++L) {
       code <<= 1;
       if (code + cnt[L] > (1u << L)) bad = 1;
       lim[L] = (code + cnt[L]) << (15 - L);
-      smw(meta + L) = offs;  // scatter cursor
+      a[L] = (offs - code) & 0xffffu;
+      smw(SM_META + L) = offs;  // scatter cursor
       code += cnt[L];
       offs += cnt[L];
     }
     if (bad) return IST_OVERSUBSCRIBED;
+    if (is_lit)
+      for (int w = 0; w < LIT_SPC_WORDS; ++w) smw(SM_LIT_SPC + w) = 0;
     for (uint32_t s = 0; s < n; ++s) {
       uint32_t l = lens[s];
       if (l) {
-        uint32_t pos = smw(meta + l);
-        smw(meta + l) = pos + 1;
+        uint32_t pos = smw(SM_META + l);
+        smw(SM_META + l) = pos + 1;
         if (is_lit) {
-          uint32_t e;
-          if (s < 256) e = s;
-          else if (s == 256) e = 0x8000u;
-          else if (s > 285) e = 0x8000u | 0x1ffu;  // 286/287: not valid in a stream
-          else {
-            uint32_t c = s - 257, eb, base;
-            if (c < 8) { eb = 0; base = 3 + c; }
-            else if (c == 28) { eb = 0; base = 258; }
-            else { eb = (c - 4) >> 2; base = 3 + ((4 + (c & 3)) << eb); }
-            e = 0x8000u | (eb << 12) | base;
-          }
-          set_lit_sym(pos, e);
+          set_byte(SM_LIT_SYM, pos, s & 0xffu);          // >= 256: 0 = end of block, 1..29 = length codes 257..285
+          if (s >= 256) smw(SM_LIT_SPC + (int)(pos >> 5)) |= 1u << (pos & 31);
         } else {
-          set_dist_sym(pos, s);
+          set_byte(SM_DIST_SYM, pos, s);
         }
       }
-    }
-    code = 0; offs = 0;
-#pragma unroll
-    for (int L = 1; L <= 15; ++L) {
-      code <<= 1;
-      smw(meta + L) = (code << (15 - L)) | (offs << 16);
-      code += cnt[L];
-      offs += cnt[L];
     }
     return IST_OK;
   }
@@ -385,9 +427,11 @@ BG_HD_COLD void parse_header(BitReader* brp, uint32_t* sm, HeaderResult* hr) {
     if (br.bits_consumed() > br.in_bits) BG_FAIL(IST_INPUT_OVERRUN);
   }
   TableBuilder<STRIDE> tb{sm};
-  uint32_t e = tb.build(lens, hlit, true, hr->llim);
-  if (!e) e = tb.build(lens + hlit, hdist, false, hr->dlim);
+  uint32_t al[16], ad[16];
+  uint32_t e = tb.build(lens + hlit, hdist, false, hr->dlim, ad);
+  if (!e) e = tb.build(lens, hlit, true, hr->llim, al);
   if (e) BG_FAIL(e);
+  for (int L = 1; L <= 15; ++L) sm[(SM_META + L) * STRIDE] = al[L] | (ad[L] << 16);
   hr->state = ST_DECODE;
   *brp = br;
 #undef BG_FAIL
@@ -404,24 +448,36 @@ struct Lane {
   uint32_t opos, oend;   // next byte to write / one past the last own byte
   uint32_t sreg;         // bytes of the word at opos & ~3 not yet stored
   uint32_t full_lo, full_span;  // aligned words a with (a - full_lo) < full_span lie wholly inside the block
+  uint32_t fast_span;           // ... and with (a - full_lo) < fast_span so do the three words after a
   // ---- decode state ----
   uint32_t state, bfinal, err, blk, cp_rem;
   uint32_t llim[16], dlim[16];  // [1..15] used; only ever indexed by constants (registers)
   // ---- LZ77 copy in flight: its source words were requested one token ago ----
-  uint32_t p_len, p_ssh, p_sa;
+  uint32_t p_len, p_ssh, p_sa, p_pre;
   uint32_t pw0, pw1, pw2, pw3, pw4, pw5, pw6, pw7, pw8;
 
   // ---------------- shared-memory accessors ----------------
   BG_HD uint32_t smr(int w) const { return sm[w * STRIDE]; }
-  BG_HD uint32_t lit_sym(uint32_t i) const { return (smr(SM_LIT_SYM + (i >> 1)) >> ((i & 1) * 16)) & 0xffffu; }
-  BG_HD uint32_t dist_sym(uint32_t i) const { return (smr(SM_DIST_SYM + (i >> 2)) >> ((i & 3) * 8)) & 0xffu; }
+  BG_HD uint32_t smb(int base, uint32_t i) const {   // byte i of the byte array starting at word `base`
+    return ((const uint8_t*)(sm + (base + (int)(i >> 2)) * STRIDE))[i & 3];
+  }
 
+#if defined(BG_BOUNDS)
+  const uint8_t* dbg_lo; const uint8_t* dbg_hi;   // readable/writable range of the output buffer
+#endif
+  BG_HD const uint32_t* gptr(uint32_t a /*aligned*/, uint32_t nwords) const {
+#if defined(BG_BOUNDS)
+    BG_CHECK(ob + a >= dbg_lo && ob + a + 4 * nwords <= dbg_hi, "out access", (long long)a);
+#endif
+    return (const uint32_t*)(ob + a);
+  }
   // ---------------- output ----------------
-  BG_HD uint32_t ldw(uint32_t a /*aligned*/) const { return *(const uint32_t*)(ob + a); }
+  BG_HD uint32_t ldw(uint32_t a /*aligned*/) const { return *gptr(a, 1); }
+  // Slow, always-correct store of one aligned word: touches only this block's own bytes.
   BG_HD void store_word(uint32_t a /*aligned*/, uint32_t w) {
     if (a - full_lo < full_span) {
-      *(uint32_t*)(ob + a) = w;
-    } else {  // head / tail word shared with a neighbouring block: touch only our own bytes
+      *(uint32_t*)gptr(a, 1) = w;
+    } else {  // head / tail word shared with a neighbouring block
       for (uint32_t i = 0; i < 4; ++i)
         if (a + i >= head && a + i < oend) ob[a + i] = (uint8_t)(w >> (8 * i));
     }
@@ -458,10 +514,19 @@ struct Lane {
     uint32_t o4 = bg_funnel_l(v3, 0u, sh);
     uint32_t tot = k + n;          // 1..19
     uint32_t nfull = tot >> 2;     // whole words completed: 0..4
-    if (nfull > 0) store_word(a, o0);   // may be the head word shared with the previous block
-    if (nfull > 1) store_word(a + 4, o1);
-    if (nfull > 2) store_word(a + 8, o2);
-    if (nfull > 3) store_word(a + 12, o3);
+    if (a - full_lo < fast_span) {
+      // all four words lie wholly inside the block: straight predicated stores
+      uint32_t* w = (uint32_t*)gptr(a, 4);
+      if (nfull > 0) w[0] = o0;
+      if (nfull > 1) w[1] = o1;
+      if (nfull > 2) w[2] = o2;
+      if (nfull > 3) w[3] = o3;
+    } else {
+      if (nfull > 0) store_word(a, o0);
+      if (nfull > 1) store_word(a + 4, o1);
+      if (nfull > 2) store_word(a + 8, o2);
+      if (nfull > 3) store_word(a + 12, o3);
+    }
     uint32_t r = o0;
     if (nfull == 1) r = o1;
     if (nfull == 2) r = o2;
@@ -495,44 +560,51 @@ struct Lane {
   // ---------------- LZ77 copies ----------------
   // dist >= 35: request the first 36 source bytes now, use them one token later (complete_copy), so the
   // L2/DRAM latency of the window read overlaps the next token's Huffman decode.  All bytes the 9 words
-  // cover lie below opos - 3, i.e. they are already in memory.
+  // cover lie below opos - 3, i.e. they are already in memory.  19 <= dist < 35 takes the same route but
+  // loads inside complete_copy, 16 bytes per trip (each trip's source lies below its write position - 3).
   BG_HD void issue_copy(uint32_t len, uint32_t dist) {
     uint32_t src = opos - dist;
     uint32_t sa = src & ~3u;
     p_ssh = (src & 3u) * 8;
-    pw0 = ldw(sa); pw1 = ldw(sa + 4); pw2 = ldw(sa + 8); pw3 = ldw(sa + 12); pw4 = ldw(sa + 16);
-    pw5 = ldw(sa + 20); pw6 = ldw(sa + 24); pw7 = ldw(sa + 28); pw8 = ldw(sa + 32);
-    p_sa = sa + 36;
     p_len = len;
+    p_pre = dist >= 35 ? 1u : 0u;
+    p_sa = sa;
+    if (p_pre) {
+      const uint32_t* w = gptr(sa, 9);
+      pw0 = w[0]; pw1 = w[1]; pw2 = w[2]; pw3 = w[3]; pw4 = w[4];
+      if (len > 16) { pw5 = w[5]; pw6 = w[6]; pw7 = w[7]; pw8 = w[8]; }
+    }
   }
   BG_HD void complete_copy() {
     if (p_len) {
-      uint32_t rem = p_len;
+      uint32_t rem = p_len, sa = p_sa;
       p_len = 0;
-      uint32_t n = rem < 16 ? rem : 16;
-      emit_n16(bg_funnel_r(pw0, pw1, p_ssh), bg_funnel_r(pw1, pw2, p_ssh), bg_funnel_r(pw2, pw3, p_ssh),
-               bg_funnel_r(pw3, pw4, p_ssh), n);
-      rem -= n;
-      if (rem) {
-        n = rem < 16 ? rem : 16;
-        emit_n16(bg_funnel_r(pw4, pw5, p_ssh), bg_funnel_r(pw5, pw6, p_ssh), bg_funnel_r(pw6, pw7, p_ssh),
-                 bg_funnel_r(pw7, pw8, p_ssh), n);
+      if (p_pre) {
+        uint32_t n = rem < 16 ? rem : 16;
+        emit_n16(bg_funnel_r(pw0, pw1, p_ssh), bg_funnel_r(pw1, pw2, p_ssh), bg_funnel_r(pw2, pw3, p_ssh),
+                 bg_funnel_r(pw3, pw4, p_ssh), n);
         rem -= n;
-        uint32_t sa = p_sa;
-        uint32_t prev = rem ? ldw(sa - 4) : 0u;  // re-read: pw8 was fetched before bytes past src+32 were certain to be stored
-        while (rem) {  // longer than 32 bytes (rare): 16 bytes per trip, loads used at once
-          uint32_t w0 = ldw(sa), w1 = ldw(sa + 4), w2 = ldw(sa + 8), w3 = ldw(sa + 12);
-          sa += 16;
+        sa += 16;
+        if (rem) {
           n = rem < 16 ? rem : 16;
-          emit_n16(bg_funnel_r(prev, w0, p_ssh), bg_funnel_r(w0, w1, p_ssh), bg_funnel_r(w1, w2, p_ssh),
-                   bg_funnel_r(w2, w3, p_ssh), n);
-          prev = w3;
+          emit_n16(bg_funnel_r(pw4, pw5, p_ssh), bg_funnel_r(pw5, pw6, p_ssh), bg_funnel_r(pw6, pw7, p_ssh),
+                   bg_funnel_r(pw7, pw8, p_ssh), n);
           rem -= n;
+          sa += 16;
         }
+      }
+      while (rem) {  // not preloaded (mid distance) or longer than 32 bytes: 16 bytes per trip, loads used at once
+        const uint32_t* w = gptr(sa, 5);
+        uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+        sa += 16;
+        uint32_t n = rem < 16 ? rem : 16;
+        emit_n16(bg_funnel_r(w0, w1, p_ssh), bg_funnel_r(w1, w2, p_ssh), bg_funnel_r(w2, w3, p_ssh),
+                 bg_funnel_r(w3, w4, p_ssh), n);
+        rem -= n;
       }
     }
   }
-  // dist < 35 (about 6 % of BAM matches): done at once.
+  // dist < 19 (about 4 % of BAM matches): done at once.
   BG_HD void copy_near(uint32_t len, uint32_t dist) {
     if (dist >= 8) {
       // 4-byte steps: the read end is <= write pos - 4, the only unstored bytes are the <= 3 in sreg
@@ -575,58 +647,78 @@ struct Lane {
     }
   }
 
-  // One literal/length (+ distance) token.  Order inside a token: (A) Huffman-decode it — bitstream only;
-  // (B) finish the copy the PREVIOUS token started; (C) write this token's literal or start its copy.
-  BG_HD void do_token() {
-    // ---- A ----
+  // One literal/length (+ distance) token is handled in three steps that the run loop orders as
+  //   complete_copy (previous token's copy) -> apply_token (this token) -> decode_token (next token)
+  // so that the window words apply_token requests are first used a whole Huffman decode later.
+  struct Tok { uint32_t e, len, dist, kind; };
+
+  // Huffman-decodes the next token: touches only the bitstream and the tables.
+  //   t.kind 0: literal t.e   1: match (t.len, t.dist)   2: end of block   3: invalid code
+  BG_HD void decode_token(Tok& t) {
     br.refill();
     uint32_t c = bg_brev((uint32_t)br.bb) >> 17;
     uint32_t L = code_len(llim, c);
-    uint32_t bad = (c >= llim[15]) ? 1u : 0u;
-    uint32_t m = smr(SM_LIT_META + L);
-    uint32_t e = lit_sym(((m >> 16) + ((c - (m & 0xffffu)) >> (15 - L))) & 0x1ffu);
+    uint32_t m = smr(SM_META + L);
+    uint32_t idx = ((m & 0xffffu) + (c >> (15 - L))) & 0x1ffu;
+    idx = idx < 287u ? idx : 287u;
+    uint32_t e = smb(SM_LIT_SYM, idx);
+    uint32_t spc = (smr(SM_LIT_SPC + (int)(idx >> 5)) >> (idx & 31)) & 1u;
     br.consume(L);
-    uint32_t len = 0, dist = 0;
-    if (!bad && (e & 0x8000u) && (e & 0x1ffu) != 0u && (e & 0x1ffu) != 0x1ffu) {
-      uint32_t eb = (e >> 12) & 7u;
-      len = (e & 0x1ffu) + ((uint32_t)br.bb & ((1u << eb) - 1u));
+    t.e = e;
+    t.len = 0;
+    t.dist = 0;
+    t.kind = spc ? (e == 0 ? 2u : 1u) : 0u;
+    if (c >= llim[15]) t.kind = 3;
+    if (t.kind == 1) {
+      uint32_t lc = e - 1;   // length code 0..28 (29, 30: symbols 286/287, invalid)
+      if (lc > 28) t.kind = 3;
+      uint32_t eb = lc < 8 ? 0u : (lc == 28 ? 0u : (lc - 4) >> 2);
+      uint32_t base = lc < 8 ? 3u + lc : (lc == 28 ? 258u : 3u + ((4u + (lc & 3u)) << eb));
+      eb &= 7u;
+      t.len = base + ((uint32_t)br.bb & ((1u << eb) - 1u));
       br.consume(eb);
       br.refill();
       c = bg_brev((uint32_t)br.bb) >> 17;
       L = code_len(dlim, c);
-      if (c >= dlim[15]) bad = 1;
-      m = smr(SM_DIST_META + L);
-      uint32_t ds = dist_sym(((m >> 16) + ((c - (m & 0xffffu)) >> (15 - L))) & 31u);
+      if (c >= dlim[15]) t.kind = 3;
+      m = smr(SM_META + L);
+      uint32_t di = ((m >> 16) + (c >> (15 - L))) & 31u;
+      uint32_t ds = smb(SM_DIST_SYM, di);
       br.consume(L);
-      if (ds >= 30) bad = 1;
+      if (ds >= 30) t.kind = 3;
       uint32_t deb = ds < 2 ? 0u : (ds >> 1) - 1u;
       deb &= 15u;
-      dist = (ds < 2 ? ds + 1u : 1u + ((2u | (ds & 1u)) << deb)) + ((uint32_t)br.bb & ((1u << deb) - 1u));
+      t.dist = (ds < 2 ? ds + 1u : 1u + ((2u | (ds & 1u)) << deb)) + ((uint32_t)br.bb & ((1u << deb) - 1u));
       br.consume(deb);
     }
-    // ---- B ----
-    complete_copy();
-    // ---- C ----
-    if (bad) { err = IST_BAD_SYMBOL; state = ST_NEXT; return; }
-    if (!(e & 0x8000u)) {
+  }
+
+  // Writes the token's literal, or validates its match and starts (dist >= 19) / performs the copy.
+  BG_HD void apply_token(const Tok& t) {
+    if (t.kind == 0) {
       if (opos >= oend) { err = IST_OUTPUT_OVERRUN; state = ST_NEXT; return; }
-      emit1(e);
+      emit1(t.e);
       return;
     }
-    if (len == 0) {
-      if ((e & 0x1ffu) == 0x1ffu) { err = IST_BAD_SYMBOL; state = ST_NEXT; return; }
-      state = bfinal ? ST_NEXT : ST_HEADER;  // end of block
-      return;
-    }
-    if (dist > opos - head) { err = IST_BAD_DISTANCE; state = ST_NEXT; return; }
-    if (len > oend - opos) { err = IST_OUTPUT_OVERRUN; state = ST_NEXT; return; }
-    if (dist >= 35) issue_copy(len, dist);
-    else copy_near(len, dist);
+    if (t.kind == 3) { err = IST_BAD_SYMBOL; state = ST_NEXT; return; }
+    if (t.kind == 2) { state = bfinal ? ST_NEXT : ST_HEADER; return; }  // end of block
+    if (t.dist > opos - head) { err = IST_BAD_DISTANCE; state = ST_NEXT; return; }
+    if (t.len > oend - opos) { err = IST_OUTPUT_OVERRUN; state = ST_NEXT; return; }
+    if (t.dist >= 19) issue_copy(t.len, t.dist);
+    else copy_near(t.len, t.dist);
   }
 
   // Up to `budget` tokens of the current Huffman block.  No copy is left in flight on return.
   BG_HD void decode_run(uint32_t budget) {
-    for (uint32_t t = 0; t < budget && state == ST_DECODE; ++t) do_token();
+    if (state != ST_DECODE) return;
+    Tok t;
+    decode_token(t);
+    for (uint32_t i = 0;;) {
+      complete_copy();
+      apply_token(t);
+      if (state != ST_DECODE || ++i >= budget) break;
+      decode_token(t);
+    }
     complete_copy();
   }
 
@@ -669,10 +761,12 @@ struct Lane {
         else if (br.bits_consumed() > br.in_bits) err = IST_INPUT_OVERRUN;
       }
       job.status[blk] = err;
+      br.drain();
     }
   }
 
-  BG_HD void begin_block(const InflateJob& job, uint32_t b) {
+  // `stage0`: shared-memory byte address of this lane's input staging slot 0 (GPU only).
+  BG_HD void begin_block(const InflateJob& job, uint32_t b, uint32_t stage0) {
     blk = b;
     err = 0;
     bfinal = 0;
@@ -686,7 +780,13 @@ struct Lane {
     full_lo = head ? 4u : 0u;
     uint32_t full_hi = oend & ~3u;
     full_span = full_hi > full_lo ? full_hi - full_lo : 0u;
-    br.begin(job.comp + job.in_off[b], job.in_len[b]);
+    fast_span = full_span >= 16u ? full_span - 12u : 0u;
+#if defined(BG_BOUNDS)
+    dbg_lo = job.out - 64; dbg_hi = job.out + job.out_len + 64;
+    BG_CHECK(job.in_off[b] >= 16 && job.in_off[b] + job.in_len[b] <= job.comp_len, "in range", (long long)job.in_off[b]);
+    BG_CHECK(o + job.isize[b] <= job.out_len, "out range", (long long)o);
+#endif
+    br.begin(job.comp + job.in_off[b], job.in_len[b], stage0);
     state = ST_HEADER;
   }
 

@@ -32,7 +32,7 @@ extern "C" int host_emul_inflate(const uint8_t* comp, const uint64_t* in_off, co
       if (L[i].state == ST_NEXT) {
         L[i].finish_block(job);
         uint32_t b = counter++;
-        if (b < n_blocks) L[i].begin_block(job, b);
+        if (b < n_blocks) L[i].begin_block(job, b, 0);
         else { L[i].state = ST_DONE; L[i].blk = 0xffffffffu; }
       }
       if (L[i].state != ST_DONE) all_done = false;
