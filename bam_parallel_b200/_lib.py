@@ -15,6 +15,7 @@ ERR_NAMES = {
     -22: "ERR_SHORT_RECORD", -23: "ERR_BUFFER_TOO_SMALL", -24: "ERR_STATE",
 }
 COPY_DATA, COPY_COLUMNS, WANT_HI, NO_CRC, NO_RECORDS, SPECULATIVE_START = 1, 2, 4, 8, 16, 32
+MAX_HALO = 1 << 20
 
 
 class BamGpuError(RuntimeError):
@@ -68,7 +69,8 @@ REFSEQ_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p)
 EXPORTS = [
     "bamgpu_scan_blocks", "bamgpu_engine_new", "bamgpu_engine_free", "bamgpu_engine_last_error", "bamgpu_device_alloc",
     "bamgpu_device_free", "bamgpu_pinned_alloc", "bamgpu_pinned_free", "bamgpu_memcpy_h2d", "bamgpu_memcpy_d2h",
-    "bamgpu_engine_decode", "bamgpu_engine_set_n_ref", "bamgpu_engine_stats", "bamgpu_engine_reset_stats", "bamgpu_reader_new",
+    "bamgpu_engine_decode", "bamgpu_engine_inflate", "bamgpu_engine_data", "bamgpu_engine_append_halo",
+    "bamgpu_engine_records", "bamgpu_engine_set_n_ref", "bamgpu_engine_stats", "bamgpu_engine_reset_stats", "bamgpu_reader_new",
     "bamgpu_reader_from_memory", "bamgpu_reader_free", "bamgpu_last_error", "bamgpu_read_header", "bamgpu_next_rec",
     "bamgpu_append_record", "bamgpu_read", "bamgpu_next_batch", "bamgpu_reader_stats",
     "bamgpu_parse_reference_sequences", "bamgpu_status_str", "bamgpu_build_info",
@@ -106,6 +108,14 @@ def load() -> C.CDLL:
     L.bamgpu_memcpy_d2h.argtypes = [vp, vp, vp, sz]
     L.bamgpu_engine_decode.restype = C.c_int
     L.bamgpu_engine_decode.argtypes = [vp, vp, vp, sz, C.c_uint64, C.c_int, C.c_uint32, vp, C.POINTER(Batch), u64p]
+    L.bamgpu_engine_inflate.restype = C.c_int
+    L.bamgpu_engine_inflate.argtypes = [vp, vp, vp, sz, C.c_uint32, vp]
+    L.bamgpu_engine_data.restype = C.c_int
+    L.bamgpu_engine_data.argtypes = [vp, C.POINTER(vp), u64p]
+    L.bamgpu_engine_append_halo.restype = C.c_int
+    L.bamgpu_engine_append_halo.argtypes = [vp, vp, sz, vp]
+    L.bamgpu_engine_records.restype = C.c_int
+    L.bamgpu_engine_records.argtypes = [vp, C.c_uint64, C.c_int, C.c_uint32, vp, C.POINTER(Batch), u64p]
     L.bamgpu_engine_set_n_ref.restype = None
     L.bamgpu_engine_set_n_ref.argtypes = [vp, C.c_int32]
     L.bamgpu_engine_stats.restype = C.c_int

@@ -91,6 +91,7 @@ struct bamgpu_engine {
   // inflated data
   DevBuf d_out;
   uint64_t data_len = 0;    // bytes valid in d_out (after lead pad), carry included
+  uint64_t halo_len = 0;    // bytes copied behind them from the right-hand shard (multi-GPU)
   uint64_t carry_len = 0;   // bytes at the front of the next batch kept from this one
   uint64_t keep_from = 0;   // where those bytes currently sit
   int32_t n_ref = -1;
@@ -294,9 +295,9 @@ static int engine_inflate(bamgpu_engine* E, const uint8_t* d_comp, const bamgpu_
   uint64_t total = 0;
   for (size_t i = 0; i < n_blocks; ++i) total += blocks[i].isize;
   uint64_t new_len = carry + total;
-  if (E->d_out.cap < OUT_LEAD_PAD + new_len + OUT_TAIL_PAD) {
+  if (E->d_out.cap < OUT_LEAD_PAD + new_len + BAMGPU_MAX_HALO + OUT_TAIL_PAD) {
     DevBuf nb;
-    ECK(nb.reserve(OUT_LEAD_PAD + new_len + OUT_TAIL_PAD));
+    ECK(nb.reserve(OUT_LEAD_PAD + new_len + BAMGPU_MAX_HALO + OUT_TAIL_PAD));
     ECK(cudaMemsetAsync(nb.p, 0, OUT_LEAD_PAD, s));
     if (carry) ECK(cudaMemcpyAsync((uint8_t*)nb.p + OUT_LEAD_PAD, E->out_ptr() + E->keep_from, carry, cudaMemcpyDeviceToDevice, s));
     ECK(cudaStreamSynchronize(s));
@@ -318,6 +319,7 @@ static int engine_inflate(bamgpu_engine* E, const uint8_t* d_comp, const bamgpu_
   E->carry_len = 0;
   E->keep_from = 0;
   E->data_len = new_len;
+  E->halo_len = 0;
   ECK(cudaMemsetAsync(E->out_ptr() + new_len, 0, OUT_TAIL_PAD, s));
   if (n_blocks == 0) return BAMGPU_OK;
   if (n_blocks > 0xfffffff0ull) { E->err = "too many blocks in one batch"; return BAMGPU_ERR_ARG; }
@@ -399,7 +401,7 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
   uint64_t bad_flags = 0;
   ECK(cudaEventRecord(E->ev[3], s));
   if (!(flags & BAMGPU_NO_RECORDS) && start < E->data_len) {
-    RecordParams p{E->out_ptr(), E->data_len, start, E->n_ref, (flags & BAMGPU_SPECULATIVE_START) ? 0 : 1};
+    RecordParams p{E->out_ptr(), E->data_len + E->halo_len, E->data_len, start, E->n_ref, (flags & BAMGPU_SPECULATIVE_START) ? 0 : 1};
     uint32_t n_tiles = (uint32_t)((E->data_len + TILE_BYTES - 1) / TILE_BYTES);
     // tile arrays: entry u64, exit u64, base u64, count u32, kind u32, nxt u32, jump u32, jump2 u32, reach u8
     size_t nt = n_tiles;
@@ -493,7 +495,7 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
   E->first_record_index += n_rec;
   if (tail_off_out) *tail_off_out = tail_off;
   // what the next batch must see in front of its own bytes
-  if (!final && rc == BAMGPU_OK && !(flags & BAMGPU_NO_RECORDS)) {
+  if (!final && rc == BAMGPU_OK && !(flags & BAMGPU_NO_RECORDS) && E->halo_len == 0) {
     E->keep_from = tail_off;
     E->carry_len = E->data_len - tail_off;
   } else {
@@ -512,6 +514,38 @@ extern "C" int bamgpu_engine_decode(bamgpu_engine* E, const uint8_t* d_comp, con
   int rc = engine_inflate(E, d_comp, blocks, n_blocks, flags, s);
   if (rc != BAMGPU_OK) return rc;
   return engine_records(E, stream_start, final, flags, s, out, tail_off);
+}
+
+extern "C" int bamgpu_engine_inflate(bamgpu_engine* E, const uint8_t* d_comp, const bamgpu_block* blocks, size_t n_blocks,
+                                     uint32_t flags, void* cuda_stream) {
+  if (!E || (n_blocks && (!blocks || !d_comp))) return BAMGPU_ERR_ARG;
+  E->carry_len = 0;
+  E->keep_from = 0;
+  return engine_inflate(E, d_comp, blocks, n_blocks, flags | E->default_flags, cuda_stream ? (cudaStream_t)cuda_stream : E->stream);
+}
+
+extern "C" int bamgpu_engine_data(const bamgpu_engine* E, const uint8_t** d_data, uint64_t* len) {
+  if (!E || !d_data || !len) return BAMGPU_ERR_ARG;
+  *d_data = E->out_ptr();
+  *len = E->data_len;
+  return BAMGPU_OK;
+}
+
+extern "C" int bamgpu_engine_append_halo(bamgpu_engine* E, const uint8_t* d_src, size_t len, void* cuda_stream) {
+  if (!E || (len && !d_src) || len > BAMGPU_MAX_HALO) return BAMGPU_ERR_ARG;
+  if (!E->d_out.p) return BAMGPU_ERR_STATE;
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : E->stream;
+  ECK(cudaSetDevice(E->device));
+  if (len) ECK(cudaMemcpyAsync(E->out_ptr() + E->data_len, d_src, len, cudaMemcpyDeviceToDevice, s));
+  ECK(cudaMemsetAsync(E->out_ptr() + E->data_len + len, 0, OUT_TAIL_PAD, s));
+  E->halo_len = len;
+  return BAMGPU_OK;
+}
+
+extern "C" int bamgpu_engine_records(bamgpu_engine* E, uint64_t stream_start, int final, uint32_t flags, void* cuda_stream,
+                                     bamgpu_batch* out, uint64_t* tail_off) {
+  if (!E || !out) return BAMGPU_ERR_ARG;
+  return engine_records(E, stream_start, final, flags | E->default_flags, cuda_stream ? (cudaStream_t)cuda_stream : E->stream, out, tail_off);
 }
 
 extern "C" int bamgpu_engine_stats(const bamgpu_engine* E, bamgpu_stats* out) {

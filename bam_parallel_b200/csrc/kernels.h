@@ -43,6 +43,7 @@ enum : uint32_t {
   EXIT_ZERO = 2,        // block_size == 0 at exit offset (reader.rs:64-72: iteration ends)
   EXIT_INCOMPLETE = 3,  // record at exit offset runs past the data (needs more bytes / SHORT_RECORD)
   EXIT_NONE = 4,        // tile has no candidate entry
+  EXIT_LIMIT = 5,       // exit offset is at/after own_len: the next record starts in the halo, i.e. belongs to the right-hand shard
 };
 
 struct TileArrays {
@@ -60,7 +61,8 @@ struct TileArrays {
 
 struct RecordParams {
   const uint8_t* data;  // inflated bytes (carry + new); readable 16 bytes before and after
-  uint64_t data_len;
+  uint64_t data_len;    // bytes present (own bytes + halo copied from the right-hand shard)
+  uint64_t own_len;     // records are reported iff they START before own_len (== data_len without a halo)
   uint64_t start;       // chain start (absolute offset in data)
   int32_t n_ref;        // number of reference sequences (plausibility filter); <0 = unknown
   int32_t start_known;  // 1: `start` is a record start (reader.rs:63); 0: shard-edge mode, the chain begins at the

@@ -115,7 +115,7 @@ __device__ WalkOut walk(const RecordParams& p, uint64_t q, uint64_t tile_end, ui
   uint32_t cnt = 0;
   for (;;) {
     if (p.data_len - q < 4) { o.kind = EXIT_TAIL; break; }           // :78 UnexpectedEof => 0
-    if (q >= tile_end) { o.kind = EXIT_NORMAL; break; }
+    if (q >= tile_end) { o.kind = q >= p.own_len ? EXIT_LIMIT : EXIT_NORMAL; break; }
     uint32_t bs = ld32(p.data, q);
     if (bs == 0) { o.kind = EXIT_ZERO; break; }                       // :64-72, records.rs:25
     if (p.data_len - (q + 4) < bs) { o.kind = EXIT_INCOMPLETE; break; }  // :69-70 would panic if final
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(128) k3_tile_walk(RecordParams p, TileArrays t
   if (k >= t.n_tiles) return;
   const uint64_t tb = (uint64_t)k * TILE_BYTES;
   uint64_t te = tb + TILE_BYTES;
-  if (te > p.data_len) te = p.data_len;
+  if (te > p.own_len) te = p.own_len;
   const uint32_t k0 = (uint32_t)(p.start / TILE_BYTES);
   uint64_t e = NONE64;
   if (k == k0) e = p.start_known ? p.start : find_entry(p, p.start, te);
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) k3_resolve(RecordParams p, Ti
       uint32_t reps = 0;
       for (;;) {
         uint64_t te = (uint64_t)(tile + 1) * TILE_BYTES;
-        if (te > p.data_len) te = p.data_len;
+        if (te > p.own_len) te = p.own_len;
         WalkOut o = walk<false>(p, entry, te, nullptr, nullptr, 0);
         t.entry[tile] = entry;
         t.exit_off[tile] = o.exit_off;
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(128) k3_tile_emit(RecordParams p, TileArrays t
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= t.n_tiles || !t.reach[k] || t.entry[k] == NONE64) return;
   uint64_t te = (uint64_t)(k + 1) * TILE_BYTES;
-  if (te > p.data_len) te = p.data_len;
+  if (te > p.own_len) te = p.own_len;
   walk<true>(p, t.entry[k], te, rec_off, rec_len, t.base[k]);
 }
 

@@ -267,6 +267,29 @@ class Engine:
             raise BamGpuError(rc, self._L.bamgpu_engine_last_error(self._h).decode())
         return RecordBatch(b), tail.value, rc
 
+    # ---- the two halves of decode(), for block-range sharding over several GPUs (include/bamgpu.h) ----
+    def _eck(self, rc):
+        if rc < 0:
+            raise BamGpuError(rc, self._L.bamgpu_engine_last_error(self._h).decode())
+        return rc
+
+    def inflate(self, d_comp, blocks, n_blocks, flags=0, cuda_stream=None):
+        self._eck(self._L.bamgpu_engine_inflate(self._h, d_comp, blocks, n_blocks, flags, cuda_stream))
+
+    def data(self):
+        """(device pointer, length) of the engine's own inflated bytes."""
+        p, n = C.c_void_p(), C.c_uint64()
+        self._eck(self._L.bamgpu_engine_data(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def append_halo(self, d_src, nbytes, cuda_stream=None):
+        self._eck(self._L.bamgpu_engine_append_halo(self._h, d_src, nbytes, cuda_stream))
+
+    def records(self, stream_start, final=True, flags=0, cuda_stream=None):
+        b, tail = Batch(), C.c_uint64()
+        rc = self._eck(self._L.bamgpu_engine_records(self._h, stream_start, int(final), flags, cuda_stream, C.byref(b), C.byref(tail)))
+        return RecordBatch(b), tail.value, rc
+
     def set_n_ref(self, n_ref: int):
         """Optional hint (header n_ref) for K3's guess of record starts; results never depend on it."""
         self._L.bamgpu_engine_set_n_ref(self._h, n_ref)

@@ -20,7 +20,7 @@ DEFAULT_SEED = 0xBA5EBA11
 
 class _Params(C.Structure):
     _fields_ = [("shape", C.c_int32), ("level", C.c_int32), ("n_records", C.c_uint64), ("seed", C.c_uint64),
-                ("payload", C.c_uint32), ("threads", C.c_int32), ("no_eof", C.c_int32), ("reserved", C.c_int32)]
+                ("payload", C.c_uint32), ("threads", C.c_int32), ("no_eof", C.c_int32), ("header_block", C.c_int32)]
 
 
 _lib = None
@@ -67,9 +67,9 @@ class SynthBam:
 
 
 def generate(shape: str, n_records: int, level: int = 6, payload: int = 0xFF00, seed: int = DEFAULT_SEED,
-             threads: int = 0, no_eof: bool = False) -> SynthBam:
+             threads: int = 0, no_eof: bool = False, header_block: bool = False) -> SynthBam:
     lib = _load()
-    p = _Params(SHAPES[shape], level, n_records, seed, payload, threads, int(no_eof), 0)
+    p = _Params(SHAPES[shape], level, n_records, seed, payload, threads, int(no_eof), int(header_block))
     out, n, u, h = C.c_void_p(), C.c_uint64(), C.c_uint64(), C.c_uint64()
     rc = lib.bamgen_generate(C.byref(p), C.byref(out), C.byref(n), C.byref(u), C.byref(h))
     if rc != 0:

@@ -13,9 +13,10 @@ written by the committed seeded generator (tools/bamgen.cpp) because the boxes h
            bytes and D2H of the record bodies + columns inside the timed region
   roofline / cpu_baseline: see DESIGN.md "Measurement"
 
-With N > 1 (torchrun, one rank per GPU) the file is sharded by BGZF block ranges (same file => strong
-scaling); rank g sends the bytes in front of its first record start to rank g-1 (point-to-point), which
-completes the record straddling the shard edge.  No collective sits on the data path.
+With N > 1 (torchrun, one rank per GPU) the workload is ONE BAM of N x 50M records (the 50M-record body repeated
+N times behind one header: weak scaling, per-GPU work fixed), sharded by contiguous BGZF block ranges; rank g
+receives the first 1 MiB of rank g+1's inflated bytes (point-to-point) so that the record straddling the shard
+edge is whole, and each speculated shard entry is confirmed by its left neighbour.  No collective on the data path.
 """
 from __future__ import annotations
 
@@ -120,14 +121,14 @@ def make_input(a, rank: int, world: int, n_records: int):
 
     if world == 1:
         t0 = time.time()
-        bam = synth.generate(a.shape, n_records, level=a.level)
+        bam = synth.generate(a.shape, n_records, level=a.level, header_block=True)
         return bam.array, bam, time.time() - t0
     import torch.distributed as dist
 
     path = f"/dev/shm/bamgpu_bench_{os.environ.get('MASTER_PORT', '0')}_{n_records}.bam"
     t0 = time.time()
     if rank == 0:
-        bam = synth.generate(a.shape, n_records, level=a.level)
+        bam = synth.generate(a.shape, n_records, level=a.level, header_block=True)
         with open(path + ".tmp", "wb") as f:
             f.write(memoryview(bam.array))
         os.replace(path + ".tmp", path)
@@ -147,18 +148,6 @@ BLOCK_DTYPE = np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("in_len", "<u4")
 def blocks_view(blocks, nb: int) -> np.ndarray:
     """Zero-copy structured numpy view of a ctypes bamgpu_block array."""
     return np.frombuffer(blocks, dtype=BLOCK_DTYPE)[:nb]
-
-
-def shard_blocks(bv: np.ndarray, world: int):
-    """Cuts the block list into `world` contiguous ranges of ~equal compressed bytes. Returns [(b0, b1)]."""
-    nb = bv.size
-    in_off = bv["in_off"]
-    total = int(in_off[-1]) if nb else 0
-    cuts = [0]
-    for g in range(1, world):
-        cuts.append(int(np.searchsorted(in_off, np.uint64(total * g // world))))
-    cuts.append(nb)
-    return [(cuts[g], cuts[g + 1]) for g in range(world)]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -186,7 +175,7 @@ def run_reference(a, rank: int, world: int):
     sample = f"first {n} records of the workload ({ub} inflated bytes) per step"
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic", "config": {"workload": workload_name(a), "sample": sample},
         "records_per_s": recs / t,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -226,35 +215,64 @@ def run_b200(a, rank: int, world: int, local_rank: int):
     stream_start = 4 + len(hdr)
     n_ref = int.from_bytes(hdr[off_refs:off_refs + 4], "little")
 
+    from bam_parallel_b200.sharding import shard_ranges
     bv = blocks_view(blocks, nb)
-    ranges = shard_blocks(bv, world)
-    b0, b1 = ranges[rank]
+    # The workload at N GPUs is ONE BAM of N x a.records records: header block + the record blocks repeated N times
+    # (+ EOF marker), sharded by contiguous block ranges of ~equal compressed bytes.  Per-GPU work is what N=1 does.
+    assert nb >= 3 and int(bv["isize"][0]) == stream_start and int(bv["isize"][nb - 1]) == 0, "unexpected generator layout"
+    nbody = nb - 2
+    src = np.concatenate([[0], np.tile(np.arange(1, nb - 1), world), [nb - 1]])      # virtual block -> block of the file
+    csz = bv["in_len"][src].astype(np.uint64) + np.uint64(26)
+    v_in_off = np.concatenate([[0], np.cumsum(csz)[:-1]]).astype(np.uint64) + np.uint64(18)
+    b0, b1 = shard_ranges(v_in_off, world)[rank]
     my_nb = b1 - b0
-    # compressed byte range of my shard (whole BGZF blocks), rebased block table
-    c0 = int(bv["in_off"][b0]) - 18 if my_nb else 0
-    c1 = int(bv["in_off"][b1 - 1]) + int(bv["in_len"][b1 - 1]) + 8 if my_nb else 0
-    u0 = int(bv["out_off"][b0]) if my_nb else 0
+    my_src = src[b0:b1]
     my_blocks = (_lib.Block * max(my_nb, 1))()
     mv = blocks_view(my_blocks, my_nb)
-    mv[:] = bv[b0:b1]
-    mv["in_off"] -= np.uint64(c0)
-    mv["out_off"] -= np.uint64(u0)
+    mv[:] = bv[my_src]
+    my_csz = csz[b0:b1]
+    mv["in_off"] = np.concatenate([[0], np.cumsum(my_csz)[:-1]]).astype(np.uint64) + np.uint64(18)
+    mv["out_off"] = np.concatenate([[0], np.cumsum(mv["isize"].astype(np.uint64))[:-1]]).astype(np.uint64)
     my_u = int(mv["isize"].sum(dtype=np.uint64))
     my_c_payload = int(mv["in_len"].sum(dtype=np.uint64))
+    # materialise the shard's compressed bytes: runs of consecutive file blocks are copied as one slice
+    f_lo = bv["in_off"].astype(np.int64) - 18
+    f_hi = f_lo + bv["in_len"].astype(np.int64) + 26
+    pieces, i = [], 0
+    brk = np.flatnonzero(np.diff(my_src) != 1) + 1
+    for lo_i, hi_i in zip(np.concatenate([[0], brk]), np.concatenate([brk, [my_nb]])):
+        if hi_i > lo_i:
+            pieces.append(arr[f_lo[my_src[lo_i]]:f_hi[my_src[hi_i - 1]]])
+    shard = np.concatenate(pieces) if len(pieces) != 1 else np.ascontiguousarray(pieces[0])
+    assert shard.size == int(my_csz.sum())
+    c0, c1 = 0, shard.size
+    total_records = a.records * world
     eng = bp.Engine(device=local_rank)
     eng.set_n_ref(n_ref)
-    shard = np.ascontiguousarray(arr[c0:c1])
     d_comp = eng.upload(shard)
     my_start = stream_start if rank == 0 else 0
 
     stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
+    halo = edge = None
+    if world > 1:
+        from bam_parallel_b200.sharding import EdgeExchange
+        edge = EdgeExchange(rank, world, torch, dist)
 
     def step():
-        # Device-resident pass: K1+K2 over the shard's blocks, K3 over its inflated bytes.
-        # TODO(multi-GPU): shard-edge exchange; until then ranks > 0 decode from their first plausible record.
-        batch, tail, rc = eng.decode(d_comp, my_blocks, my_nb, my_start, rank == world - 1, 0, sptr)
-        return batch
+        """One pass of the hot path over this rank's shard, compressed bytes already resident in HBM."""
+        if world == 1:
+            batch, tail, rc = eng.decode(d_comp, my_blocks, my_nb, my_start, True, 0, sptr)
+            return batch, tail
+        # K1 + K2 over the shard's BGZF blocks
+        eng.inflate(d_comp, my_blocks, my_nb, 0, sptr)
+        # shard-edge exchange (point-to-point, neighbour only): the head of my inflated bytes goes to the left-hand
+        # shard, the right-hand shard's head lands behind my bytes, so the record straddling the edge is whole
+        edge.exchange(eng, sptr)
+        # K3 over own bytes (+ halo): records that START in my bytes
+        flags = bp.SPECULATIVE_START if rank > 0 else 0
+        batch, tail, rc = eng.records(my_start, rank == world - 1, flags, sptr)
+        return batch, tail
 
     def sync_all():
         torch.cuda.synchronize()
@@ -263,9 +281,12 @@ def run_b200(a, rank: int, world: int, local_rank: int):
             torch.cuda.synchronize()
 
     for _ in range(max(a.warmup, 3)):
-        batch = step()
+        batch, tail = step()
     n_rec_local = batch.n_records
     chain_repairs = batch.chain_repairs
+    if world > 1:
+        # one u64 per edge: shard g's chain must leave its bytes exactly where shard g+1's chain begins
+        edge.verify(tail - my_u, batch.chain_start, batch.n_records, total_records)
     sync_all()
     eng.reset_stats()
     sampler = ClockSampler(local_rank)
@@ -329,10 +350,13 @@ def run_b200(a, rank: int, world: int, local_rank: int):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic",
-            "config": {"workload": workload_name(a), "records": n_rec_all, "inflated_bytes": u_all, "compressed_bytes": int(consumed),
-                       "bgzf_blocks": nb, "sharding": f"{world} contiguous BGZF block ranges" if world > 1 else "single GPU",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic (seeded generator tools/bamgen.cpp)" + (f"; one BAM of {world} x {a.records} records: the record blocks "
+                    f"of the {a.records}-record file repeated {world} times behind one header" if world > 1 else ""),
+            "config": {"workload": workload_name(a) + (f" per GPU, x{world}" if world > 1 else ""), "records": n_rec_all,
+                       "inflated_bytes": u_all, "compressed_bytes": int(csz.sum()),
+                       "bgzf_blocks": int(src.size), "sharding": f"{world} contiguous BGZF block ranges, neighbour P2P halo "
+                       f"of {bp._lib.MAX_HALO} B per shard edge, no collective" if world > 1 else "single GPU",
                        "l2": "inputs (compressed + inflated) far larger than the 126 MB L2; no flush needed",
                        "generator_seconds": round(gen_s, 1), "k3_chain_repairs": chain_repairs},
             "records_per_s": n_rec_all / (ms_step * 1e-3),

@@ -177,6 +177,21 @@ int bamgpu_engine_decode(bamgpu_engine*, const uint8_t* d_comp, const bamgpu_blo
                          uint64_t stream_start, int final, uint32_t flags, void* cuda_stream,
                          bamgpu_batch* out, uint64_t* tail_off);
 
+/* ---- The two halves of bamgpu_engine_decode, for callers that shard one file over several GPUs (bench.py, N > 1).
+ * Shard g inflates its BGZF block range, copies the first bytes of shard g+1's inflated data behind its own
+ * ("halo", so the record straddling the shard edge is whole), then runs the record kernels: records are reported
+ * iff they START in the shard's own bytes.  Shards g > 0 pass BAMGPU_SPECULATIVE_START; batch.chain_start of shard
+ * g+1 must equal shard g's *tail_off - own length (the caller checks it: one u64 per edge). ---- */
+int bamgpu_engine_inflate(bamgpu_engine*, const uint8_t* d_comp, const bamgpu_block* blocks, size_t n_blocks,
+                          uint32_t flags, void* cuda_stream);
+/* Device pointer / length of the inflated bytes held by the engine (own bytes only). */
+int bamgpu_engine_data(const bamgpu_engine*, const uint8_t** d_data, uint64_t* len);
+/* Appends `len` bytes (device pointer, <= BAMGPU_MAX_HALO) behind the engine's own inflated bytes. */
+#define BAMGPU_MAX_HALO (1u << 20)
+int bamgpu_engine_append_halo(bamgpu_engine*, const uint8_t* d_src, size_t len, void* cuda_stream);
+int bamgpu_engine_records(bamgpu_engine*, uint64_t stream_start, int final, uint32_t flags, void* cuda_stream,
+                          bamgpu_batch* out, uint64_t* tail_off);
+
 /* Number of reference sequences of the BAM header (n_ref), if the caller knows it: tightens the guess of record
  * starts inside K3 (refID must be in [-1, n_ref)).  Results never depend on it.  < 0 = unknown (default). */
 void bamgpu_engine_set_n_ref(bamgpu_engine*, int32_t n_ref);

@@ -361,7 +361,7 @@ struct bamgen_params {
   uint32_t payload;     // uncompressed bytes per BGZF block, 1..0xff00
   int32_t threads;      // 0 = hardware_concurrency
   int32_t no_eof;       // 1 = omit trailing EOF marker block
-  int32_t reserved;
+  int32_t header_block; // 1 = the BAM header gets a BGZF block of its own (records start at a block boundary)
 };
 
 // Generates the whole BAM into a malloc'ed buffer. Returns 0 on success.
@@ -403,7 +403,14 @@ int bamgen_generate(const bamgen_params* p, uint8_t** out, uint64_t* out_len, ui
   goff[0] = H;
   for (uint64_t g = 0; g < n_groups; ++g) goff[g + 1] += goff[g];
   const uint64_t U = goff[n_groups];  // total uncompressed stream bytes
-  const uint64_t n_blocks = (U + P - 1) / P;
+  // Block b covers stream bytes [bstart(b), bstart(b+1)).  With header_block the header is block 0 on its own, so the
+  // record blocks that follow can be repeated verbatim to build a larger valid BAM (bench.py, N > 1 GPUs).
+  const bool hb = p->header_block != 0;
+  const uint64_t n_blocks = hb ? 1 + (U - H + P - 1) / P : (U + P - 1) / P;
+  auto bstart = [&](uint64_t b) -> uint64_t {
+    uint64_t s = hb ? (b == 0 ? 0 : H + (b - 1) * P) : b * P;
+    return std::min(U, s);
+  };
 
   // Pass 2: threads take contiguous runs of blocks.
   const uint64_t RUN = 64;
@@ -420,7 +427,7 @@ int bamgen_generate(const bamgen_params* p, uint8_t** out, uint64_t* out_len, ui
         uint64_t run = next.fetch_add(1);
         if (run >= n_runs) break;
         uint64_t b0 = run * RUN, b1 = std::min(n_blocks, b0 + RUN);
-        uint64_t s0 = b0 * P, s1 = std::min(U, b1 * P);  // stream byte range
+        uint64_t s0 = bstart(b0), s1 = bstart(b1);  // stream byte range
         // Materialise stream bytes [s0, s1) into ubuf.
         ubuf.clear();
         ubuf.reserve((size_t)(s1 - s0) + max_record_bytes(shape));
@@ -451,7 +458,7 @@ int bamgen_generate(const bamgen_params* p, uint8_t** out, uint64_t* out_len, ui
         std::vector<uint8_t>& dst = parts[run];
         dst.reserve((size_t)((s1 - s0) / 2));
         for (uint64_t b = b0; b < b1; ++b) {
-          uint64_t a = b * P - s0, e = std::min(U, (b + 1) * P) - s0;
+          uint64_t a = bstart(b) - s0, e = bstart(b + 1) - s0;
           bgzf_block(zs, ubuf.data() + a, (size_t)(e - a), dst);
         }
       }
@@ -494,6 +501,7 @@ int main(int argc, char** argv) {
     else if (a == "--payload") p.payload = (uint32_t)strtoul(val(), nullptr, 0);
     else if (a == "--threads") p.threads = atoi(val());
     else if (a == "--no-eof") p.no_eof = 1;
+    else if (a == "--header-block") p.header_block = 1;
     else if (a == "--out") path = val();
     else { fprintf(stderr, "usage: bamgen --shape se150|pe150|longname|long10k --records N --level L --payload B --seed S --threads T --out FILE\n"); return 2; }
   }
