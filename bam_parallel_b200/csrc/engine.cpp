@@ -54,19 +54,52 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   template <class T> T* as() const { return (T*)p; }
 };
+// Page-locking host memory is slow (about a second per few GB), and a Reader needs several hundred MB of it, so released
+// pinned buffers are parked in a small process-wide cache and handed to the next Reader instead of being unpinned.
+struct PinnedCache {
+  std::mutex mu;
+  std::vector<std::pair<void*, size_t>> free_list;
+  size_t bytes = 0;
+  static constexpr size_t LIMIT = (size_t)6 << 30;
+  void* take(size_t n, size_t* cap) {
+    std::lock_guard<std::mutex> lk(mu);
+    size_t best = (size_t)-1;
+    for (size_t i = 0; i < free_list.size(); ++i)
+      if (free_list[i].second >= n && (best == (size_t)-1 || free_list[i].second < free_list[best].second)) best = i;
+    if (best == (size_t)-1 || free_list[best].second > 2 * n + (1 << 20)) return nullptr;
+    void* p = free_list[best].first;
+    *cap = free_list[best].second;
+    bytes -= *cap;
+    free_list.erase(free_list.begin() + best);
+    return p;
+  }
+  bool give(void* p, size_t cap) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (bytes + cap > LIMIT) return false;
+    free_list.emplace_back(p, cap);
+    bytes += cap;
+    return true;
+  }
+};
+PinnedCache& pinned_cache() { static PinnedCache* c = new PinnedCache(); return *c; }
+
 struct PinBuf {
   void* p = nullptr;
   size_t cap = 0;
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
-    if (p) cudaFreeHost(p);
-    p = nullptr; cap = 0;
+    release();
     size_t want = n + n / 8 + 256;
+    size_t got = 0;
+    if (void* q = pinned_cache().take(want, &got)) { p = q; cap = got; return cudaSuccess; }
     cudaError_t e = cudaMallocHost(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;
   }
-  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  void release() {
+    if (p && !pinned_cache().give(p, cap)) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+  }
   template <class T> T* as() const { return (T*)p; }
 };
 
@@ -88,8 +121,18 @@ struct bamgpu_engine {
   DevBuf d_status, d_misc;  // d_misc: work counter (u32 @0), first_bad (u64 @8), ChainResult @64
   DevBuf d_crc_tables;
   bool crc_ready = false;
-  // inflated data
-  DevBuf d_out;
+  // inflated data.  The Reader runs with two buffers (pingpong): batch k+1 is inflated into one while batch k is
+  // still being copied to the host out of the other.
+  DevBuf d_outs[2];
+  int cur = 0;
+  bool pingpong = false;
+  cudaStream_t d2h_stream = nullptr;
+  cudaEvent_t ev_k3_done = nullptr, ev_d2h_done = nullptr;
+  bool d2h_pending = false;
+  // launch/finish split of the inflate stage
+  size_t pend_nb = 0;
+  uint64_t pend_total = 0, pend_bytes_in = 0;
+  bool inflate_launched = false;
   uint64_t data_len = 0;    // bytes valid in d_out (after lead pad), carry included
   uint64_t halo_len = 0;    // bytes copied behind them from the right-hand shard (multi-GPU)
   uint64_t carry_len = 0;   // bytes at the front of the next batch kept from this one
@@ -108,7 +151,7 @@ struct bamgpu_engine {
   cudaEvent_t ev[8]{};
   bamgpu_stats stats{};
 
-  uint8_t* out_ptr() const { return d_out.as<uint8_t>() + OUT_LEAD_PAD; }
+  uint8_t* out_ptr() const { return d_outs[cur].as<uint8_t>() + OUT_LEAD_PAD; }
 };
 
 #define ECK(call)                                                                                   \
@@ -200,6 +243,9 @@ extern "C" bamgpu_engine* bamgpu_engine_new(const bamgpu_opts* opts) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) E->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking) != cudaSuccess) { delete E; return nullptr; }
+  if (cudaStreamCreateWithFlags(&E->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) { delete E; return nullptr; }
+  cudaEventCreateWithFlags(&E->ev_k3_done, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&E->ev_d2h_done, cudaEventDisableTiming);
   for (auto& e : E->ev) cudaEventCreate(&e);
   E->default_flags = opts ? opts->flags : 0;
   if (E->d_misc.reserve(8192) != cudaSuccess || E->d_crc_tables.reserve(CRC_TABLE_WORDS * 4) != cudaSuccess ||
@@ -217,9 +263,12 @@ extern "C" void bamgpu_engine_free(bamgpu_engine* E) {
   if (!E) return;
   cudaSetDevice(E->device);
   if (E->stream) { cudaStreamSynchronize(E->stream); cudaStreamDestroy(E->stream); }
+  if (E->d2h_stream) { cudaStreamSynchronize(E->d2h_stream); cudaStreamDestroy(E->d2h_stream); }
+  if (E->ev_k3_done) cudaEventDestroy(E->ev_k3_done);
+  if (E->ev_d2h_done) cudaEventDestroy(E->ev_d2h_done);
   for (auto& e : E->ev) if (e) cudaEventDestroy(e);
   E->h_tab.release(); E->d_tab.release(); E->d_status.release(); E->d_misc.release(); E->d_crc_tables.release();
-  E->d_out.release(); E->d_tiles.release(); E->d_cols.release(); E->h_data.release(); E->h_cols.release(); E->h_res.release();
+  E->d_outs[0].release(); E->d_outs[1].release(); E->d_tiles.release(); E->d_cols.release(); E->h_data.release(); E->h_cols.release(); E->h_res.release();
   delete E;
 }
 
@@ -286,40 +335,56 @@ int map_block_status(uint32_t st) {
 
 }  // namespace
 
-// Stage 1: inflate (+CRC) `n_blocks` blocks into d_out after the carried-over bytes.
-static int engine_inflate(bamgpu_engine* E, const uint8_t* d_comp, const bamgpu_block* blocks, size_t n_blocks,
-                          uint32_t flags, cudaStream_t s) {
+// Stage 1: inflate (+CRC) `n_blocks` blocks behind the carried-over bytes.  Split in two so that the Reader can put
+// batch k+1's kernels on the stream before it waits for batch k's device-to-host copy:
+//   engine_inflate_launch  enqueues carry move, block table upload, K1, K2, status reduce; no host wait
+//   engine_inflate_finish  waits, reads the first failing block (if any), books the stage times
+static int engine_inflate_launch(bamgpu_engine* E, const uint8_t* d_comp, const bamgpu_block* blocks, size_t n_blocks,
+                                 uint32_t flags, cudaStream_t s) {
   ECK(cudaSetDevice(E->device));
-  // 1. move the carry to the front
-  uint64_t carry = E->carry_len;
-  uint64_t total = 0;
-  for (size_t i = 0; i < n_blocks; ++i) total += blocks[i].isize;
-  uint64_t new_len = carry + total;
-  if (E->d_out.cap < OUT_LEAD_PAD + new_len + BAMGPU_MAX_HALO + OUT_TAIL_PAD) {
+  // 1. the destination buffer (the other one when ping-ponging) gets the carry at its front
+  const uint64_t carry = E->carry_len;
+  uint64_t total = 0, bytes_in = 0;
+  for (size_t i = 0; i < n_blocks; ++i) { total += blocks[i].isize; bytes_in += blocks[i].in_len + 26; }
+  const uint64_t new_len = carry + total;
+  const int src = E->cur, dst = E->pingpong ? (E->cur ^ 1) : E->cur;
+  const uint8_t* src_ptr = E->d_outs[src].p ? E->d_outs[src].as<uint8_t>() + OUT_LEAD_PAD : nullptr;
+  const size_t need = OUT_LEAD_PAD + new_len + BAMGPU_MAX_HALO + OUT_TAIL_PAD;
+  if (E->d_outs[dst].cap < need) {
     DevBuf nb;
-    ECK(nb.reserve(OUT_LEAD_PAD + new_len + BAMGPU_MAX_HALO + OUT_TAIL_PAD));
+    ECK(nb.reserve(need));
     ECK(cudaMemsetAsync(nb.p, 0, OUT_LEAD_PAD, s));
-    if (carry) ECK(cudaMemcpyAsync((uint8_t*)nb.p + OUT_LEAD_PAD, E->out_ptr() + E->keep_from, carry, cudaMemcpyDeviceToDevice, s));
+    if (carry) ECK(cudaMemcpyAsync((uint8_t*)nb.p + OUT_LEAD_PAD, src_ptr + E->keep_from, carry, cudaMemcpyDeviceToDevice, s));
     ECK(cudaStreamSynchronize(s));
-    E->d_out.release();
-    E->d_out = nb;
-  } else if (carry && E->keep_from != 0) {
-    // ranges may overlap only if carry > keep_from; stage through the tile buffer in that rare case
-    if (carry <= E->keep_from) {
-      ECK(cudaMemcpyAsync(E->out_ptr(), E->out_ptr() + E->keep_from, carry, cudaMemcpyDeviceToDevice, s));
+    if (dst == src) {
+      E->d_outs[dst].release();
     } else {
+      if (E->d2h_pending) { ECK(cudaStreamSynchronize(E->d2h_stream)); }  // nobody may still read the buffer we free
+      E->d_outs[dst].release();
+    }
+    E->d_outs[dst] = nb;
+  } else if (carry && (dst != src || E->keep_from != 0)) {
+    uint8_t* dst_ptr = E->d_outs[dst].as<uint8_t>() + OUT_LEAD_PAD;
+    if (dst != src || carry <= E->keep_from) {
+      ECK(cudaMemcpyAsync(dst_ptr, src_ptr + E->keep_from, carry, cudaMemcpyDeviceToDevice, s));
+    } else {  // same buffer and the ranges overlap: stage through a temporary (rare)
       DevBuf tmp;
       ECK(tmp.reserve(carry));
-      ECK(cudaMemcpyAsync(tmp.p, E->out_ptr() + E->keep_from, carry, cudaMemcpyDeviceToDevice, s));
-      ECK(cudaMemcpyAsync(E->out_ptr(), tmp.p, carry, cudaMemcpyDeviceToDevice, s));
+      ECK(cudaMemcpyAsync(tmp.p, src_ptr + E->keep_from, carry, cudaMemcpyDeviceToDevice, s));
+      ECK(cudaMemcpyAsync(dst_ptr, tmp.p, carry, cudaMemcpyDeviceToDevice, s));
       ECK(cudaStreamSynchronize(s));
       tmp.release();
     }
   }
+  E->cur = dst;
   E->carry_len = 0;
   E->keep_from = 0;
   E->data_len = new_len;
   E->halo_len = 0;
+  E->pend_nb = n_blocks;
+  E->pend_total = total;
+  E->pend_bytes_in = bytes_in;
+  E->inflate_launched = true;
   ECK(cudaMemsetAsync(E->out_ptr() + new_len, 0, OUT_TAIL_PAD, s));
   if (n_blocks == 0) return BAMGPU_OK;
   if (n_blocks > 0xfffffff0ull) { E->err = "too many blocks in one batch"; return BAMGPU_ERR_ARG; }
@@ -364,18 +429,26 @@ static int engine_inflate(bamgpu_engine* E, const uint8_t* d_comp, const bamgpu_
   ECK(cudaEventRecord(E->ev[2], s));
   launch_status_reduce(E->d_status.as<uint32_t>(), (uint32_t)nb, first_bad, s);
   E->stats.kernel_launches += 1;
-  unsigned long long* h_bad = E->h_res.as<unsigned long long>();
-  ECK(cudaMemcpyAsync(h_bad, first_bad, 8, cudaMemcpyDeviceToHost, s));
+  ECK(cudaMemcpyAsync(E->h_res.as<unsigned long long>(), first_bad, 8, cudaMemcpyDeviceToHost, s));
+  return BAMGPU_OK;
+}
+
+static int engine_inflate_finish(bamgpu_engine* E, cudaStream_t s) {
+  if (!E->inflate_launched) return BAMGPU_OK;
+  E->inflate_launched = false;
+  ECK(cudaSetDevice(E->device));
   ECK(cudaStreamSynchronize(s));
   ECK(cudaGetLastError());
+  if (E->pend_nb == 0) return BAMGPU_OK;
   float ms = 0;
   cudaEventElapsedTime(&ms, E->ev[0], E->ev[1]); E->stats.ms_inflate += ms;
   cudaEventElapsedTime(&ms, E->ev[1], E->ev[2]); E->stats.ms_crc += ms;
-  E->stats.blocks += nb;
-  E->stats.bytes_out += total;
-  for (size_t i = 0; i < nb; ++i) E->stats.bytes_in += blocks[i].in_len + 26;
-  if (*h_bad != ~0ull) {
-    uint32_t idx = (uint32_t)(*h_bad >> 32), st = (uint32_t)*h_bad;
+  E->stats.blocks += E->pend_nb;
+  E->stats.bytes_out += E->pend_total;
+  E->stats.bytes_in += E->pend_bytes_in;
+  unsigned long long bad = *E->h_res.as<unsigned long long>();
+  if (bad != ~0ull) {
+    uint32_t idx = (uint32_t)(bad >> 32), st = (uint32_t)bad;
     char msg[160];
     snprintf(msg, sizeof msg, "BGZF block %u of this batch failed (device status %u): %s", idx, st,
              bamgpu_status_str(map_block_status(st)));
@@ -385,10 +458,30 @@ static int engine_inflate(bamgpu_engine* E, const uint8_t* d_comp, const bamgpu_
   return BAMGPU_OK;
 }
 
+static int engine_inflate(bamgpu_engine* E, const uint8_t* d_comp, const bamgpu_block* blocks, size_t n_blocks,
+                          uint32_t flags, cudaStream_t s) {
+  int rc = engine_inflate_launch(E, d_comp, blocks, n_blocks, flags, s);
+  if (rc != BAMGPU_OK) return rc;
+  return engine_inflate_finish(E, s);
+}
+
+// Waits for the device-to-host copies engine_records left running (defer_d2h).
+static int engine_wait_d2h(bamgpu_engine* E) {
+  if (E->d2h_pending) {
+    E->d2h_pending = false;
+    ECK(cudaStreamSynchronize(E->d2h_stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, E->ev[6], E->ev[7]);
+    E->stats.ms_d2h += ms;
+  }
+  return BAMGPU_OK;
+}
+
 // Stage 2: record chain + columns over d_out[0 .. data_len).
 static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t flags, cudaStream_t s,
-                          bamgpu_batch* out, uint64_t* tail_off_out) {
+                          bamgpu_batch* out, uint64_t* tail_off_out, bool defer_d2h = false) {
   ECK(cudaSetDevice(E->device));
+  { int w = engine_wait_d2h(E); if (w < 0) return w; }
   memset(out, 0, sizeof *out);
   out->data = E->out_ptr();
   out->data_len = E->data_len;
@@ -459,10 +552,17 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
   out->n_records = n_rec;
   out->bad_flag_records = bad_flags;
   fill_public_columns(E->cols, out->dev);
-  // host mirrors
+  // host mirrors: on their own stream, behind the record kernels
+  cudaStream_t cs = E->d2h_stream;
+  const bool any_copy = (flags & BAMGPU_COPY_DATA) || ((flags & BAMGPU_COPY_COLUMNS) && n_rec);
+  if (any_copy) {
+    ECK(cudaEventRecord(E->ev_k3_done, s));
+    ECK(cudaStreamWaitEvent(cs, E->ev_k3_done, 0));
+    ECK(cudaEventRecord(E->ev[6], cs));
+  }
   if (flags & BAMGPU_COPY_DATA) {
     ECK(E->h_data.reserve(E->data_len + 64));
-    if (E->data_len) ECK(cudaMemcpyAsync(E->h_data.p, E->out_ptr(), E->data_len, cudaMemcpyDeviceToHost, s));
+    if (E->data_len) ECK(cudaMemcpyAsync(E->h_data.p, E->out_ptr(), E->data_len, cudaMemcpyDeviceToHost, cs));
     out->h_data = E->h_data.as<uint8_t>();
   }
   if ((flags & BAMGPU_COPY_COLUMNS) && n_rec) {
@@ -472,7 +572,7 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
     ColumnsDev hc;
     carve_columns(E->h_cols.as<uint8_t>(), E->cols_cap, hc);
     auto cp = [&](void* dst, const void* src, size_t elem) {
-      return cudaMemcpyAsync(dst, src, elem * n_rec, cudaMemcpyDeviceToHost, s);
+      return cudaMemcpyAsync(dst, src, elem * n_rec, cudaMemcpyDeviceToHost, cs);
     };
     ECK(cp(hc.rec_off, E->cols.rec_off, 8)); ECK(cp(hc.coord_key, E->cols.coord_key, 8));
     ECK(cp(hc.rec_len, E->cols.rec_len, 4)); ECK(cp(hc.ref_id, E->cols.ref_id, 4)); ECK(cp(hc.pos, E->cols.pos, 4));
@@ -484,12 +584,15 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
     ECK(cp(hc.hi_present, E->cols.hi_present, 1));
     fill_public_columns(hc, out->host);
   }
-  ECK(cudaEventRecord(E->ev[5], s));
   ECK(cudaStreamSynchronize(s));
   ECK(cudaGetLastError());
   float ms = 0;
   cudaEventElapsedTime(&ms, E->ev[3], E->ev[4]); E->stats.ms_records += ms;
-  cudaEventElapsedTime(&ms, E->ev[4], E->ev[5]); E->stats.ms_d2h += ms;
+  if (any_copy) {
+    ECK(cudaEventRecord(E->ev[7], cs));
+    E->d2h_pending = true;
+    if (!defer_d2h) { int w = engine_wait_d2h(E); if (w < 0) return w; }
+  }
   E->stats.records += n_rec;
   E->stats.batches += 1;
   E->first_record_index += n_rec;
@@ -533,7 +636,7 @@ extern "C" int bamgpu_engine_data(const bamgpu_engine* E, const uint8_t** d_data
 
 extern "C" int bamgpu_engine_append_halo(bamgpu_engine* E, const uint8_t* d_src, size_t len, void* cuda_stream) {
   if (!E || (len && !d_src) || len > BAMGPU_MAX_HALO) return BAMGPU_ERR_ARG;
-  if (!E->d_out.p) return BAMGPU_ERR_STATE;
+  if (!E->d_outs[E->cur].p) return BAMGPU_ERR_STATE;
   cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : E->stream;
   ECK(cudaSetDevice(E->device));
   if (len) ECK(cudaMemcpyAsync(E->out_ptr() + E->data_len, d_src, len, cudaMemcpyDeviceToDevice, s));
@@ -647,7 +750,25 @@ static void feeder_main(bamgpu_reader* R) {
       size_t fill = carry.size();
       if (fill) memcpy(h, carry.data(), fill);
       carry.clear();
-      while (!src_eof && fill < R->batch_bytes) {
+      if (R->mem && !src_eof) {
+        // in-memory source: fill the pinned slot with several threads (thread_num, like the reference's inflate pool)
+        size_t want = std::min(R->batch_bytes > fill ? R->batch_bytes - fill : 0, R->mem_len - R->mem_pos);
+        size_t nt = std::min<size_t>(std::max<size_t>(R->thread_num, 1), 16);
+        if (want < (8u << 20)) nt = 1;
+        std::vector<std::thread> th;
+        size_t per = (want + nt - 1) / nt;
+        for (size_t t = 1; t < nt; ++t) {
+          size_t o = t * per, n = o < want ? std::min(per, want - o) : 0;
+          if (n) th.emplace_back([=] { memcpy(h + fill + o, R->mem + R->mem_pos + o, n); });
+        }
+        memcpy(h + fill, R->mem + R->mem_pos, std::min(per, want));
+        for (auto& x : th) x.join();
+        R->mem_pos += want;
+        R->bytes_fed += want;
+        fill += want;
+        if (R->mem_pos >= R->mem_len) src_eof = true;
+      }
+      while (!R->mem && !src_eof && fill < R->batch_bytes) {
         long n = R->read(R->ctx, h + fill, std::min<size_t>(cap - fill, 8u << 20));
         if (n < 0) { S.status = BAMGPU_ERR_IO; src_eof = true; break; }
         if (n == 0) { src_eof = true; break; }
@@ -690,6 +811,7 @@ static bamgpu_reader* reader_create(bamgpu_read_fn read, void* ctx, size_t threa
   if (!E) return nullptr;
   bamgpu_reader* R = new bamgpu_reader();
   R->E = E;
+  E->pingpong = true;
   R->read = read;
   R->ctx = ctx;
   unsigned hc = std::thread::hardware_concurrency();
@@ -746,20 +868,20 @@ extern "C" const char* bamgpu_last_error(const bamgpu_reader* R) {
   return R->err.empty() ? R->E->err.c_str() : R->err.c_str();
 }
 
-// Returns the current slot to the feeder and takes the next one; inflates it. BAMGPU_EOF when input is exhausted.
-static int reader_inflate_next(bamgpu_reader* R, uint32_t flags) {
+// Returns the current slot to the feeder and takes the next one; puts its inflate on the stream (no host wait).
+// BAMGPU_EOF when input is exhausted.  With `nonblocking` it returns BAMGPU_EOF+1 (= 2) instead of waiting when the
+// feeder has no slot ready yet.
+static int reader_inflate_launch_next(bamgpu_reader* R, uint32_t flags, bool nonblocking) {
   if (R->input_done) return BAMGPU_EOF;
-  if (R->cur_slot >= 0) {
-    {
-      std::lock_guard<std::mutex> lk(R->mu);
-      R->freeq.push_back(R->cur_slot);
-    }
-    R->cv.notify_all();
-    R->cur_slot = -1;
-  }
   int si;
   {
     std::unique_lock<std::mutex> lk(R->mu);
+    if (nonblocking && R->ready.empty()) return 2;
+    if (R->cur_slot >= 0) {  // its kernels have finished (every caller synchronises the previous inflate first)
+      R->freeq.push_back(R->cur_slot);
+      R->cur_slot = -1;
+      R->cv.notify_all();
+    }
     R->cv.wait(lk, [&] { return !R->ready.empty(); });
     si = R->ready.front();
     R->ready.pop_front();
@@ -775,10 +897,16 @@ static int reader_inflate_next(bamgpu_reader* R, uint32_t flags) {
   bamgpu_engine* E = R->E;
   cudaSetDevice(E->device);
   if (cudaStreamWaitEvent(E->stream, S.copied, 0) != cudaSuccess) { R->err = "cudaStreamWaitEvent failed"; return BAMGPU_ERR_CUDA; }
-  int rc = engine_inflate(E, S.dev.as<uint8_t>(), S.blocks.data(), S.blocks.size(), flags, E->stream);
+  int rc = engine_inflate_launch(E, S.dev.as<uint8_t>(), S.blocks.data(), S.blocks.size(), flags, E->stream);
   if (rc != BAMGPU_OK) return rc;
   R->inflated_pending = true;
   return BAMGPU_OK;
+}
+
+static int reader_inflate_next(bamgpu_reader* R, uint32_t flags) {
+  int rc = reader_inflate_launch_next(R, flags, false);
+  if (rc != BAMGPU_OK) return rc;
+  return engine_inflate_finish(R->E, R->E->stream);
 }
 
 extern "C" int bamgpu_read_header(bamgpu_reader* R, const uint8_t** bytes, size_t* len, size_t* offset_to_ref_seqs) {
@@ -834,6 +962,9 @@ extern "C" int bamgpu_read_header(bamgpu_reader* R, const uint8_t** bytes, size_
 }
 
 // Produces the next non-empty batch (or EOF). Uses the inflated-but-unparsed batch left by read_header first.
+// Pipeline per call:  finish inflate(k) -> K3(k) -> start D2H(k) on the copy stream -> put inflate(k+1) on the compute
+// stream (other output buffer) -> wait D2H(k).  So the host copy of batch k and the caller's work on it overlap K1 of
+// batch k+1, and the feeder thread's H2D of batch k+2 overlaps both.
 static int reader_next_batch(bamgpu_reader* R, uint32_t extra_flags) {
   if (R->sticky < 0) return R->sticky;
   if (R->eof) return BAMGPU_EOF;
@@ -841,8 +972,9 @@ static int reader_next_batch(bamgpu_reader* R, uint32_t extra_flags) {
   bamgpu_engine* E = R->E;
   uint32_t flags = R->flags | extra_flags;
   for (;;) {
+    int rc;
     if (!R->inflated_pending) {
-      int rc = reader_inflate_next(R, flags);
+      rc = reader_inflate_launch_next(R, flags, false);
       if (rc == BAMGPU_EOF) {
         // input exhausted and nothing pending: whatever carry is left was already judged with final=1
         R->eof = true;
@@ -850,14 +982,23 @@ static int reader_next_batch(bamgpu_reader* R, uint32_t extra_flags) {
       }
       if (rc < 0) { R->sticky = rc; return rc; }
     }
+    rc = engine_inflate_finish(E, E->stream);
+    if (rc < 0) { R->sticky = rc; return rc; }
     R->inflated_pending = false;
+    const bool fin = R->pending_final;
     uint64_t tail = 0;
-    int rc = engine_records(E, R->next_start, R->pending_final ? 1 : 0, flags, E->stream, &R->batch, &tail);
+    rc = engine_records(E, R->next_start, fin ? 1 : 0, flags, E->stream, &R->batch, &tail, /*defer_d2h=*/true);
     R->next_start = 0;
     if (rc < 0) { R->sticky = rc; return rc; }
     R->batch_valid = true;
     R->rec_cursor = 0;
-    if (rc == BAMGPU_EOF || R->pending_final) R->eof = true;
+    if (rc == BAMGPU_EOF || fin) R->eof = true;
+    if (!R->eof) {
+      int pr = reader_inflate_launch_next(R, flags, /*nonblocking=*/true);
+      if (pr < 0) { R->sticky = pr; }  // surfaces on the next call; this batch is still good
+    }
+    int w = engine_wait_d2h(E);
+    if (w < 0) { R->sticky = w; return w; }
     if (R->batch.n_records) return BAMGPU_OK;
     if (R->eof) return BAMGPU_EOF;
   }

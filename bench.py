@@ -379,7 +379,7 @@ def run_e2e(a, bp, arr, c0, c1, rank, world, dist, torch, u_all):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         d2h = 0
-        with bp.Reader.new(arr, 4, flags=flags, batch_bytes=a.batch_mib << 20) as r:
+        with bp.Reader.new(arr, min(os.cpu_count() or 4, 20), flags=flags, batch_bytes=a.batch_mib << 20) as r:   # main.rs:84 thread count
             r.read_header()
             n = 0
             while True:
