@@ -1,0 +1,99 @@
+//! Raw bindings of include/bamgpu.h plus a `bam_tools::Reader`-shaped wrapper.
+//! UNBUILT in this repository's image (no cargo/rustc there): source only, see INTEGRATION.md.
+#![allow(non_camel_case_types)]
+use std::io::{self, Read};
+use std::os::raw::{c_char, c_int, c_long, c_void};
+
+#[repr(C)] pub struct bamgpu_reader { _p: [u8; 0] }
+#[repr(C)] #[derive(Default, Clone, Copy)]
+pub struct bamgpu_opts { pub device: i32, pub flags: u32, pub batch_bytes: u64, pub inflate_impl: i32, pub reserved: i32 }
+pub type bamgpu_read_fn = unsafe extern "C" fn(ctx: *mut c_void, dst: *mut u8, cap: usize) -> c_long;
+pub const BAMGPU_OK: c_int = 0;
+pub const BAMGPU_EOF: c_int = 1;
+
+extern "C" {
+    pub fn bamgpu_reader_new(read: bamgpu_read_fn, ctx: *mut c_void, thread_num: usize, track_progress: *const u64,
+                             opts: *const bamgpu_opts) -> *mut bamgpu_reader;
+    pub fn bamgpu_reader_free(r: *mut bamgpu_reader);
+    pub fn bamgpu_last_error(r: *const bamgpu_reader) -> *const c_char;
+    pub fn bamgpu_read_header(r: *mut bamgpu_reader, bytes: *mut *const u8, len: *mut usize, off_to_refs: *mut usize) -> c_int;
+    pub fn bamgpu_next_rec(r: *mut bamgpu_reader, body: *mut *const u8, len: *mut usize) -> c_int;
+    pub fn bamgpu_append_record(r: *mut bamgpu_reader, dst: *mut u8, cap: usize, len: *mut usize) -> c_int;
+    pub fn bamgpu_read(r: *mut bamgpu_reader, dst: *mut u8, cap: usize) -> c_long;
+}
+
+/// Drop-in for `bam_tools::Reader` (bam_tools/src/reader.rs:17-99).
+pub struct Reader { h: *mut bamgpu_reader, _inner: Box<Box<dyn Read + Send>>, rec: Vec<u8> }
+unsafe impl Send for Reader {}
+
+unsafe extern "C" fn trampoline(ctx: *mut c_void, dst: *mut u8, cap: usize) -> c_long {
+    let inner = &mut *(ctx as *mut Box<dyn Read + Send>);
+    match inner.read(std::slice::from_raw_parts_mut(dst, cap)) { Ok(n) => n as c_long, Err(_) => -1 }
+}
+
+fn err(h: *const bamgpu_reader) -> io::Error {
+    let msg = unsafe { std::ffi::CStr::from_ptr(bamgpu_last_error(h)) }.to_string_lossy().into_owned();
+    io::Error::new(io::ErrorKind::InvalidData, msg)
+}
+
+impl Reader {
+    /// reader.rs:28-32 — `thread_num` is clamped like the reference; `track_progress` is kept as a byte counter.
+    pub fn new<RSS: Read + Send + 'static>(inner: RSS, thread_num: usize, track_progress: Option<u64>) -> Self {
+        let mut boxed: Box<Box<dyn Read + Send>> = Box::new(Box::new(inner));
+        let tp = track_progress.as_ref().map_or(std::ptr::null(), |v| v as *const u64);
+        let h = unsafe { bamgpu_reader_new(trampoline, &mut *boxed as *mut _ as *mut c_void, thread_num, tp, std::ptr::null()) };
+        assert!(!h.is_null(), "bamgpu: no usable CUDA device (there is no CPU fallback)");
+        Reader { h, _inner: boxed, rec: Vec::new() }
+    }
+    /// reader.rs:87-98
+    pub fn read_header(&mut self) -> io::Result<(Vec<u8>, usize)> {
+        let (mut p, mut n, mut off) = (std::ptr::null(), 0usize, 0usize);
+        if unsafe { bamgpu_read_header(self.h, &mut p, &mut n, &mut off) } < 0 { return Err(err(self.h)); }
+        Ok((unsafe { std::slice::from_raw_parts(p, n) }.to_vec(), off))
+    }
+    /// reader.rs:83
+    pub fn records(&mut self) -> Records<'_> { Records { reader: self } }
+    /// reader.rs:63-73 — returns Ok(0) at EOF; a short record body panics like the reference's `expect("Failed to read.")`.
+    pub fn append_record(&mut self, buf: &mut Vec<u8>) -> io::Result<usize> {
+        let (mut p, mut n) = (std::ptr::null(), 0usize);
+        match unsafe { bamgpu_next_rec(self.h, &mut p, &mut n) } {
+            BAMGPU_EOF => Ok(0),
+            BAMGPU_OK => { buf.extend_from_slice(unsafe { std::slice::from_raw_parts(p, n) }); Ok(n) }
+            -22 => panic!("Failed to read."),
+            _ => Err(err(self.h)),
+        }
+    }
+    /// reader.rs:57-61
+    pub fn read_record(&mut self, buf: &mut Vec<u8>) -> io::Result<usize> { buf.clear(); self.append_record(buf) }
+}
+/// reader.rs:114-152
+impl Read for Reader {
+    fn read(&mut self, buf: &mut [u8]) -> io::Result<usize> {
+        let n = unsafe { bamgpu_read(self.h, buf.as_mut_ptr(), buf.len()) };
+        if n < 0 { Err(err(self.h)) } else { Ok(n as usize) }
+    }
+}
+impl Drop for Reader { fn drop(&mut self) { unsafe { bamgpu_reader_free(self.h) } } }
+
+/// reader/records.rs:10-42
+pub struct Records<'a> { reader: &'a mut Reader }
+impl<'a> Records<'a> {
+    /// Lends the next record body (valid until the next call), `None` at EOF — records.rs:23-29.
+    pub fn next_rec(&mut self) -> Option<io::Result<&Vec<u8>>> {
+        let (mut p, mut n) = (std::ptr::null(), 0usize);
+        match unsafe { bamgpu_next_rec(self.reader.h, &mut p, &mut n) } {
+            BAMGPU_EOF => None,
+            BAMGPU_OK => {
+                self.reader.rec.clear();
+                self.reader.rec.extend_from_slice(unsafe { std::slice::from_raw_parts(p, n) });
+                Some(Ok(&self.reader.rec))
+            }
+            -22 => panic!("Failed to read."),
+            _ => Some(Err(err(self.reader.h))),
+        }
+    }
+}
+impl<'a> Iterator for Records<'a> {
+    type Item = io::Result<Vec<u8>>;
+    fn next(&mut self) -> Option<Self::Item> { self.next_rec().map(|r| r.map(|v| v.clone())) }
+}
