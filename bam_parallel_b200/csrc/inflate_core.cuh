@@ -21,8 +21,8 @@
 //     Huffman-decoded while they are in flight, and only then are they shifted into place and
 //     stored (straight-line code for up to 32 bytes).  The window read is an L2/DRAM access
 //     (thousands of streams x 32 KB of history do not fit in L1), so this takes its latency off
-//     the critical path.  Distances 8..34 copy 4 bytes per step at once, distances < 8 from a
-//     register-resident periodic window (the dist=1 runs of BAM quality strings).
+//     the critical path.  Distances 8..34 load inside the copy (up to 16 bytes per trip), distances
+//     < 8 come from a register-resident periodic window (the dist=1 runs of BAM quality strings).
 //   * The DEFLATE block header / code-table build is a cold out-of-line function working on a
 //     copy of the bit reader, so the hot loop's state stays in registers.  (It also has to be
 //     out of line: with ptxas 12.9 -O1..-O3 the fully inlined form miscompiled on sm_100a —
@@ -453,7 +453,7 @@ struct Lane {
   uint32_t state, bfinal, err, blk, cp_rem;
   uint32_t llim[16], dlim[16];  // [1..15] used; only ever indexed by constants (registers)
   // ---- LZ77 copy in flight: its source words were requested one token ago ----
-  uint32_t p_len, p_ssh, p_sa, p_pre;
+  uint32_t p_len, p_src, p_dist;
   uint32_t pw0, pw1, pw2, pw3, pw4, pw5, pw6, pw7, pw8;
 
   // ---------------- shared-memory accessors ----------------
@@ -558,92 +558,77 @@ struct Lane {
   }
 
   // ---------------- LZ77 copies ----------------
-  // dist >= 35: request the first 36 source bytes now, use them one token later (complete_copy), so the
-  // L2/DRAM latency of the window read overlaps the next token's Huffman decode.  All bytes the 9 words
-  // cover lie below opos - 3, i.e. they are already in memory.  19 <= dist < 35 takes the same route but
-  // loads inside complete_copy, 16 bytes per trip (each trip's source lies below its write position - 3).
+  // Every copy with distance >= 8 is only REGISTERED here and performed by complete_copy one token later.
+  // dist >= 35: its first 36 source bytes are requested now (9 aligned loads, no use), so the L2/DRAM latency of the
+  // window read overlaps the next token's Huffman decode.  All bytes the 9 words cover lie below opos - 3, i.e. they
+  // are already in memory (only the <= 3 bytes in sreg are not).
   BG_HD void issue_copy(uint32_t len, uint32_t dist) {
     uint32_t src = opos - dist;
-    uint32_t sa = src & ~3u;
-    p_ssh = (src & 3u) * 8;
     p_len = len;
-    p_pre = dist >= 35 ? 1u : 0u;
-    p_sa = sa;
-    if (p_pre) {
-      const uint32_t* w = gptr(sa, 9);
+    p_src = src;
+    p_dist = dist;
+    if (dist >= 35) {
+      const uint32_t* w = gptr(src & ~3u, 9);
       pw0 = w[0]; pw1 = w[1]; pw2 = w[2]; pw3 = w[3]; pw4 = w[4];
       if (len > 16) { pw5 = w[5]; pw6 = w[6]; pw7 = w[7]; pw8 = w[8]; }
     }
   }
   BG_HD void complete_copy() {
     if (p_len) {
-      uint32_t rem = p_len, sa = p_sa;
+      uint32_t rem = p_len, src = p_src;
+      const uint32_t dist = p_dist;
       p_len = 0;
-      if (p_pre) {
+      if (dist >= 35) {
+        const uint32_t ssh = (src & 3u) * 8;
         uint32_t n = rem < 16 ? rem : 16;
-        emit_n16(bg_funnel_r(pw0, pw1, p_ssh), bg_funnel_r(pw1, pw2, p_ssh), bg_funnel_r(pw2, pw3, p_ssh),
-                 bg_funnel_r(pw3, pw4, p_ssh), n);
+        emit_n16(bg_funnel_r(pw0, pw1, ssh), bg_funnel_r(pw1, pw2, ssh), bg_funnel_r(pw2, pw3, ssh),
+                 bg_funnel_r(pw3, pw4, ssh), n);
         rem -= n;
-        sa += 16;
+        src += n;
         if (rem) {
           n = rem < 16 ? rem : 16;
-          emit_n16(bg_funnel_r(pw4, pw5, p_ssh), bg_funnel_r(pw5, pw6, p_ssh), bg_funnel_r(pw6, pw7, p_ssh),
-                   bg_funnel_r(pw7, pw8, p_ssh), n);
+          emit_n16(bg_funnel_r(pw4, pw5, ssh), bg_funnel_r(pw5, pw6, ssh), bg_funnel_r(pw6, pw7, ssh),
+                   bg_funnel_r(pw7, pw8, ssh), n);
           rem -= n;
-          sa += 16;
+          src += n;
         }
       }
-      while (rem) {  // not preloaded (mid distance) or longer than 32 bytes: 16 bytes per trip, loads used at once
-        const uint32_t* w = gptr(sa, 5);
+      // Everything else — distances 8..34 and the part of a long copy beyond 32 bytes — in one loop: each trip loads
+      // 20 bytes and emits at most min(16, dist - 3) of them, all of which lie below the write position - 3, i.e. are
+      // in memory; the following trips see what this one stored (byte-serial semantics for overlapping copies).
+      const uint32_t step = dist - 3u < 16u ? dist - 3u : 16u;
+      while (rem) {
+        const uint32_t ssh = (src & 3u) * 8;
+        const uint32_t* w = gptr(src & ~3u, 5);
         uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-        sa += 16;
-        uint32_t n = rem < 16 ? rem : 16;
-        emit_n16(bg_funnel_r(w0, w1, p_ssh), bg_funnel_r(w1, w2, p_ssh), bg_funnel_r(w2, w3, p_ssh),
-                 bg_funnel_r(w3, w4, p_ssh), n);
+        uint32_t n = rem < step ? rem : step;
+        emit_n16(bg_funnel_r(w0, w1, ssh), bg_funnel_r(w1, w2, ssh), bg_funnel_r(w2, w3, ssh), bg_funnel_r(w3, w4, ssh), n);
+        src += n;
         rem -= n;
       }
     }
   }
-  // dist < 19 (about 4 % of BAM matches): done at once.
+  // dist < 8 (the dist=1 runs of BAM quality strings, ~2 % of matches): from a register-resident periodic window, at once.
   BG_HD void copy_near(uint32_t len, uint32_t dist) {
-    if (dist >= 8) {
-      // 4-byte steps: the read end is <= write pos - 4, the only unstored bytes are the <= 3 in sreg
-      uint32_t src = opos - dist;
-      uint32_t sa = src & ~3u, ssh = (src & 3u) * 8;
-      uint32_t prev = ldw(sa);
-      sa += 4;
-      uint32_t rem = len;
-      while (rem) {
-        uint32_t n = rem < 4 ? rem : 4;
-        uint32_t w = ldw(sa);
-        sa += 4;
-        uint32_t v = bg_funnel_r(prev, w, ssh);
-        if (n < 4) v &= (1u << (8 * n)) - 1u;
-        prev = w;
-        emit(v, n);
-        rem -= n;
-      }
-    } else {
-      // last 8 bytes before opos (the buffer is readable 16 bytes before out[0]) -> periodic window
-      flush_partial();
-      const uint8_t* qa = ob + opos - 8;
-      const uint32_t* a = (const uint32_t*)((uintptr_t)qa & ~(uintptr_t)3);
-      uint32_t sh = (uint32_t)((uintptr_t)qa & 3) * 8;
-      uint32_t x0 = a[0], x1 = a[1], x2 = a[2];
-      uint64_t X = (uint64_t)bg_funnel_r(x0, x1, sh) | ((uint64_t)bg_funnel_r(x1, x2, sh) << 32);
-      uint64_t W = X >> (8 * (8 - dist));  // low `dist` bytes = the period
-      for (uint32_t k = dist; k < 8; k <<= 1) W |= W << (8 * k);
-      uint32_t deff = dist < 3 ? 4u : (dist == 3 ? 6u : dist);
-      uint32_t wsh = 8 * (8 - deff);
-      uint32_t rem = len;
-      while (rem) {
-        uint32_t n = rem < 4 ? rem : 4;
-        uint32_t v = (uint32_t)W;
-        if (n < 4) v &= (1u << (8 * n)) - 1u;
-        W = (W >> 32) | ((W >> wsh) << 32);
-        emit(v, n);
-        rem -= n;
-      }
+    // last 8 bytes before opos (the buffer is readable 16 bytes before out[0]) -> periodic window
+    flush_partial();
+    const uint8_t* qa = ob + opos - 8;
+    const uint32_t* a = (const uint32_t*)((uintptr_t)qa & ~(uintptr_t)3);
+    uint32_t sh = (uint32_t)((uintptr_t)qa & 3) * 8;
+    uint32_t x0 = a[0], x1 = a[1], x2 = a[2];
+    uint64_t X = (uint64_t)bg_funnel_r(x0, x1, sh) | ((uint64_t)bg_funnel_r(x1, x2, sh) << 32);
+    uint64_t W = X >> (8 * (8 - dist));  // low `dist` bytes = the period
+    for (uint32_t k = dist; k < 8; k <<= 1) W |= W << (8 * k);
+    uint32_t deff = dist < 3 ? 4u : (dist == 3 ? 6u : dist);
+    uint32_t wsh = 8 * (8 - deff);
+    uint32_t rem = len;
+    while (rem) {
+      uint32_t n = rem < 4 ? rem : 4;
+      uint32_t v = (uint32_t)W;
+      if (n < 4) v &= (1u << (8 * n)) - 1u;
+      W = (W >> 32) | ((W >> wsh) << 32);
+      emit(v, n);
+      rem -= n;
     }
   }
 
@@ -693,7 +678,7 @@ struct Lane {
     }
   }
 
-  // Writes the token's literal, or validates its match and starts (dist >= 19) / performs the copy.
+  // Writes the token's literal, or validates its match and registers (dist >= 8) / performs the copy.
   BG_HD void apply_token(const Tok& t) {
     if (t.kind == 0) {
       if (opos >= oend) { err = IST_OUTPUT_OVERRUN; state = ST_NEXT; return; }
@@ -704,7 +689,7 @@ struct Lane {
     if (t.kind == 2) { state = bfinal ? ST_NEXT : ST_HEADER; return; }  // end of block
     if (t.dist > opos - head) { err = IST_BAD_DISTANCE; state = ST_NEXT; return; }
     if (t.len > oend - opos) { err = IST_OUTPUT_OVERRUN; state = ST_NEXT; return; }
-    if (t.dist >= 19) issue_copy(t.len, t.dist);
+    if (t.dist >= 8) issue_copy(t.len, t.dist);
     else copy_near(t.len, t.dist);
   }
 
