@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_ROOT, "bam_parallel_b200", "lib", "libbamgpu.so")
+LIB_PATH = os.environ.get("BAMGPU_LIB") or os.path.join(_ROOT, "bam_parallel_b200", "lib", "libbamgpu.so")  # BAMGPU_LIB: kernel-variant experiments only
 
 OK, EOF = 0, 1
 ERR_NAMES = {

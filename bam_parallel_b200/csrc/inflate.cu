@@ -15,7 +15,10 @@
 namespace bamgpu {
 
 constexpr int K1_WARPS_PER_CTA = 3;
-constexpr int K1_CTAS_PER_SM = 5;
+#ifndef K1_CTAS
+#define K1_CTAS 5
+#endif
+constexpr int K1_CTAS_PER_SM = K1_CTAS;
 constexpr int K1_TABLE_BYTES = K1_WARPS_PER_CTA * 32 * LANE_WORDS * 4;            // 40320: Huffman tables
 constexpr int K1_SMEM_BYTES = K1_TABLE_BYTES + K1_WARPS_PER_CTA * STAGE_WARP_BYTES;   // + 3072: input staging slots
 

@@ -77,7 +77,7 @@ __device__ bool plausible_chain(const RecordParams& p, uint64_t q, uint32_t bs) 
   if (!plausible_fields(p, q, bs)) return false;
   for (int i = 0; i < VERIFY_DEPTH; ++i) {
     q += 4ull + bs;
-    if (q > p.data_len) return q - p.data_len <= TILE_BYTES;  // last record of a batch may be cut; a wild jump is not
+    if (q > p.data_len) return q - p.data_len <= WILD_JUMP_BYTES;  // last record of a batch may be cut; a wild jump is not
     if (p.data_len - q < 36) return true;                     // tail: nothing left to check
     bs = ld32(p.data, q);
     if (!plausible_fields(p, q, bs)) return false;
