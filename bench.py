@@ -195,6 +195,7 @@ def run_b200(a, rank: int, world: int, local_rank: int):
 
     import bam_parallel_b200 as bp
     from bam_parallel_b200 import _lib
+    from bam_parallel_b200.sharding import _DevView
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback")
@@ -274,6 +275,19 @@ def run_b200(a, rank: int, world: int, local_rank: int):
         batch, tail, rc = eng.records(my_start, rank == world - 1, flags, sptr)
         return batch, tail
 
+    def step_host(h_shard, h_stage, stage_bytes):
+        """The sharded pass with HOST buffers: pinned H2D of the shard's compressed bytes, K1-K3 with the edge exchange,
+        then record bodies (through a pinned staging buffer) and SoA columns back to the host."""
+        L.bamgpu_memcpy_h2d(eng._h, d_comp, h_shard, shard.size)
+        eng.inflate(d_comp, my_blocks, my_nb, 0, sptr)
+        edge.exchange(eng, sptr)
+        flags = (bp.SPECULATIVE_START if rank > 0 else 0) | bp.COPY_COLUMNS
+        batch, tail, rc = eng.records(my_start, rank == world - 1, flags, sptr)
+        ptr, n = eng.data()
+        for o in range(0, n, stage_bytes):
+            L.bamgpu_memcpy_d2h(eng._h, h_stage, ptr + o, min(stage_bytes, n - o))
+        return batch
+
     def sync_all():
         torch.cuda.synchronize()
         if dist is not None:
@@ -287,6 +301,12 @@ def run_b200(a, rank: int, world: int, local_rank: int):
     if world > 1:
         # one u64 per edge: shard g's chain must leave its bytes exactly where shard g+1's chain begins
         edge.verify(tail - my_u, batch.chain_start, batch.n_records, total_records)
+    else:
+        # size-independent properties at full size: every block passed its CRC32 + ISIZE check (else decode raises), the
+        # chain covers the stream exactly, and the record count is the generator's
+        assert batch.n_records == a.records and tail == my_u, (batch.n_records, a.records, tail, my_u)
+        rl = torch.as_tensor(_DevView(batch.dev["rec_len"], 4 * batch.n_records), device="cuda").view(torch.int32)
+        assert int(rl.sum(dtype=torch.int64).item()) + 4 * batch.n_records + stream_start == my_u, "record lengths do not tile the stream"
     sync_all()
     eng.reset_stats()
     sampler = ClockSampler(local_rank)
@@ -324,14 +344,24 @@ def run_b200(a, rank: int, world: int, local_rank: int):
     k1_ms = st["ms_inflate"] / a.steps
     k1_bytes = my_c_payload + my_u   # algorithmic: compressed payload read once + inflated bytes written once
     achieved = k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
+    traffic = None
+    try:   # DRAM bytes of one K1 launch from the committed ncu --set full capture of this same workload
+        tj = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        if tj.get("records") == a.records:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "k1_inflate", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
                 "stage_ms_per_step": {"k1_inflate": k1_ms, "k2_crc32": st["ms_crc"] / a.steps, "k3_records": st["ms_records"] / a.steps}}
 
     # ---- e2e: drop-in Reader over the HOST buffer (H2D + D2H inside the timed region) ----
     e2e = None
     if not a.no_e2e:
-        e2e = run_e2e(a, bp, arr, c0, c1, rank, world, dist, torch, u_all)
+        if world == 1:
+            e2e = run_e2e(a, bp, arr, c0, c1, rank, world, dist, torch, u_all)
+        else:
+            e2e = run_e2e_sharded(a, bp, eng, shard, d_comp, step_host, sync_all, rank, world, dist, torch, u_all, my_u, n_rec_local)
 
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
@@ -371,8 +401,6 @@ def run_b200(a, rank: int, world: int, local_rank: int):
 def run_e2e(a, bp, arr, c0, c1, rank, world, dist, torch, u_all):
     """Reader::new(host bytes) -> read_header -> next_batch until EOF, bodies + columns copied back to pinned
     host memory (what records().next_rec() serves from)."""
-    if world > 1:
-        return None  # TODO(multi-GPU e2e)
     flags = bp.COPY_DATA | bp.COPY_COLUMNS
     times, d2h = [], 0
     for it in range(1 + a.e2e_steps):
@@ -396,6 +424,35 @@ def run_e2e(a, bp, arr, c0, c1, rank, world, dist, torch, u_all):
     return {"value": u_all / t / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(c1 - c0), "d2h_bytes_per_step": int(d2h),
             "records_per_s": n / t, "ms_per_step": t * 1e3, "steps": a.e2e_steps,
             "api": "Reader.new(host bytes) / read_header / next_batch, bodies + SoA columns D2H to pinned memory"}
+
+
+def run_e2e_sharded(a, bp, eng, shard, d_comp, step_host, sync_all, rank, world, dist, torch, u_all, my_u, n_rec_local):
+    """N > 1: every rank moves its shard through pinned host memory (H2D compressed bytes, D2H bodies + columns) around
+    the sharded decode; time = max over ranks."""
+    L = bp.load()
+    stage_bytes = 256 << 20
+    h_shard = L.bamgpu_pinned_alloc(max(shard.size, 1))
+    h_stage = L.bamgpu_pinned_alloc(stage_bytes)
+    if not h_shard or not h_stage:
+        return None
+    C.memmove(h_shard, shard.ctypes.data, shard.size)
+    times = []
+    for it in range(1 + a.e2e_steps):
+        sync_all()
+        t0 = time.perf_counter()
+        step_host(h_shard, h_stage, stage_bytes)
+        sync_all()
+        times.append(time.perf_counter() - t0)
+    L.bamgpu_pinned_free(h_shard)
+    L.bamgpu_pinned_free(h_stage)
+    t = torch.tensor([float(np.mean(times[1:]))], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    io = torch.tensor([float(shard.size), float(my_u + 74 * n_rec_local), float(n_rec_local)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(io, op=dist.ReduceOp.SUM)
+    t = float(t.item())
+    return {"value": u_all / t / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
+            "records_per_s": io[2].item() / t, "ms_per_step": t * 1e3, "steps": a.e2e_steps,
+            "api": "per rank: pinned H2D of its block range, bamgpu_engine_inflate / append_halo / records, bodies + SoA columns D2H"}
 
 
 def main():
