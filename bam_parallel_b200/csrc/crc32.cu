@@ -4,7 +4,8 @@
 //
 // One warp per block.  Rows of 128 bytes are loaded fully coalesced (lane i takes word i of the row)
 // and each lane keeps its own partial remainder a_i = sum_r Z_128^(R-1-r)(w[r][i]) using 4 table
-// look-ups per word ("advance by 128 zero bytes" tables).  The 32 remainders are then folded with a
+// look-ups per word ("advance by 128 zero bytes" tables, replicated per lane in shared memory so that the
+// data-dependent look-ups never collide on a bank).  The 32 remainders are then folded with a
 // Horner chain of "advance by 4 zero bytes" steps, and the unaligned head / tail bytes are handled
 // bytewise by lane 0.  CRC is GF(2)-linear, so this equals the serial CRC bit for bit.
 #include "kernels.h"
@@ -40,18 +41,26 @@ __global__ void k_crc_tables(uint32_t* tables) {
 __device__ __forceinline__ uint32_t z_apply(const uint32_t* t, uint32_t s) {
   return t[s & 0xff] ^ t[256 + ((s >> 8) & 0xff)] ^ t[512 + ((s >> 16) & 0xff)] ^ t[768 + (s >> 24)];
 }
+// Same on a table replicated per lane ([entry][lane]): lane l only ever touches bank l, so the four look-ups of a
+// warp are conflict free whatever the data.
+__device__ __forceinline__ uint32_t z_apply_lane(const uint32_t* t /* + lane */, uint32_t s) {
+  return t[(s & 0xff) * 32] ^ t[(256 + ((s >> 8) & 0xff)) * 32] ^ t[(512 + ((s >> 16) & 0xff)) * 32] ^ t[(768 + (s >> 24)) * 32];
+}
 
-constexpr int K2_WARPS = 8;
+constexpr int K2_WARPS = 32;
+constexpr int K2_SMEM_BYTES = 1024 * 32 * 4 + 1024 * 4;   // Z128 per lane (128 KB) + Z4 (4 KB)
 
-__global__ void __launch_bounds__(K2_WARPS * 32)
+__global__ void __launch_bounds__(K2_WARPS * 32, 1)
 k2_crc32(const uint8_t* __restrict__ out, BlockTableDev t, const uint32_t* __restrict__ g_tables,
          uint32_t* __restrict__ status) {
-  __shared__ uint32_t tab[CRC_TABLE_WORDS];
-  for (int i = threadIdx.x; i < CRC_TABLE_WORDS; i += blockDim.x) tab[i] = g_tables[i];
+  extern __shared__ __align__(16) uint32_t k2_smem[];
+  uint32_t* Z128L = k2_smem;                 // [1024][32]
+  uint32_t* Z4 = k2_smem + 1024 * 32;        // [1024]
+  for (int i = threadIdx.x; i < 1024 * 32; i += blockDim.x) Z128L[i] = g_tables[1024 + (i >> 5)];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) Z4[i] = g_tables[i];
   __syncthreads();
-  const uint32_t* Z4 = tab;
-  const uint32_t* Z128 = tab + 1024;
   const int lane = threadIdx.x & 31;
+  const uint32_t* Z128 = Z128L + lane;
   const uint32_t warps_total = gridDim.x * K2_WARPS;
   for (uint32_t b = blockIdx.x * K2_WARPS + (threadIdx.x >> 5); b < t.n_blocks; b += warps_total) {
     if (status[b] != 0) continue;  // warp-uniform
@@ -71,7 +80,15 @@ k2_crc32(const uint8_t* __restrict__ out, BlockTableDev t, const uint32_t* __res
       uint32_t x = w[0];
       if (lane == 0) x ^= s;
       a = x;
-      for (uint32_t r = 1; r < rows; ++r) a = z_apply(Z128, a) ^ w[r * 32];
+      uint32_t r = 1;
+      for (; r + 4 <= rows; r += 4) {   // four rows in flight: the loads do not wait for the table walk
+        uint32_t x0 = w[r * 32], x1 = w[(r + 1) * 32], x2 = w[(r + 2) * 32], x3 = w[(r + 3) * 32];
+        a = z_apply_lane(Z128, a) ^ x0;
+        a = z_apply_lane(Z128, a) ^ x1;
+        a = z_apply_lane(Z128, a) ^ x2;
+        a = z_apply_lane(Z128, a) ^ x3;
+      }
+      for (; r < rows; ++r) a = z_apply_lane(Z128, a) ^ w[r * 32];
       // fold the 32 lanes: total = Z4(...Z4(Z4(a0) ^ a1) ...) ^ a31, then one more Z4
       uint32_t acc = 0;
       for (int i = 0; i < 32; ++i) {
@@ -94,11 +111,12 @@ k2_crc32(const uint8_t* __restrict__ out, BlockTableDev t, const uint32_t* __res
 void crc32_init_tables(uint32_t* d_tables, cudaStream_t s) { k_crc_tables<<<1, 256, 0, s>>>(d_tables); }
 
 void launch_crc32(const uint8_t* out, const BlockTableDev& t, const uint32_t* d_tables, uint32_t* status,
-                  cudaStream_t s) {
+                  int num_sms, cudaStream_t s) {
   if (t.n_blocks == 0) return;
   uint32_t grid = (t.n_blocks + K2_WARPS - 1) / K2_WARPS;
-  if (grid > 148 * 8) grid = 148 * 8;
-  k2_crc32<<<grid, K2_WARPS * 32, 0, s>>>(out, t, d_tables, status);
+  if (grid > (uint32_t)num_sms) grid = (uint32_t)num_sms;   // one CTA per SM: the per-lane table takes 132 KB of shared memory
+  cudaFuncSetAttribute(k2_crc32, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_BYTES);
+  k2_crc32<<<grid, K2_WARPS * 32, K2_SMEM_BYTES, s>>>(out, t, d_tables, status);
 }
 
 }  // namespace bamgpu

@@ -423,7 +423,7 @@ static int engine_inflate_launch(bamgpu_engine* E, const uint8_t* d_comp, const 
   ECK(cudaEventRecord(E->ev[1], s));
   E->stats.kernel_launches += 1;
   if (!(flags & BAMGPU_NO_CRC)) {
-    launch_crc32(E->out_ptr(), t, E->d_crc_tables.as<uint32_t>(), E->d_status.as<uint32_t>(), s);
+    launch_crc32(E->out_ptr(), t, E->d_crc_tables.as<uint32_t>(), E->d_status.as<uint32_t>(), E->num_sms, s);
     E->stats.kernel_launches += 1;
   }
   ECK(cudaEventRecord(E->ev[2], s));

@@ -635,38 +635,71 @@ struct Lane {
   // One literal/length (+ distance) token is handled in three steps that the run loop orders as
   //   complete_copy (previous token's copy) -> apply_token (this token) -> decode_token (next token)
   // so that the window words apply_token requests are first used a whole Huffman decode later.
-  struct Tok { uint32_t e, len, dist, kind; };
+  // A "token" is up to LITS_PER_TOKEN leading literals plus one closing symbol (literal, match, end of block or an
+  // invalid code).  Decoding several literals per trip amortises the sparse, divergent match code of the run loop over
+  // more output: most lanes start with a literal, and a lane that sees a length stops there.
+#ifndef BG_LITS_PER_TOKEN
+#define BG_LITS_PER_TOKEN 3
+#endif
+  static constexpr int LITS_PER_TOKEN = BG_LITS_PER_TOKEN;   // symbols per trip: this many - 1 leading literals + the closing symbol
+  struct Tok { uint32_t lits, nlit, e, len, dist, kind; };
 
-  // Huffman-decodes the next token: touches only the bitstream and the tables.
-  //   t.kind 0: literal t.e   1: match (t.len, t.dist)   2: end of block   3: invalid code
-  BG_HD void decode_token(Tok& t) {
-    br.refill();
+  // One literal/length symbol.  Needs 15 valid bits in br.bb; consumes the code.  Returns 0 literal (value in e),
+  // 1 length code (e = code + 1), 2 end of block, 3 invalid.
+  BG_HD uint32_t decode_litlen(uint32_t& e) {
     uint32_t c = bg_brev((uint32_t)br.bb) >> 17;
     uint32_t L = code_len(llim, c);
     uint32_t m = smr(SM_META + L);
     uint32_t idx = ((m & 0xffffu) + (c >> (15 - L))) & 0x1ffu;
     idx = idx < 287u ? idx : 287u;
-    uint32_t e = smb(SM_LIT_SYM, idx);
+    e = smb(SM_LIT_SYM, idx);
     uint32_t spc = (smr(SM_LIT_SPC + (int)(idx >> 5)) >> (idx & 31)) & 1u;
     br.consume(L);
-    t.e = e;
+    uint32_t kind = spc ? (e == 0 ? 2u : 1u) : 0u;
+    if (c >= llim[15]) kind = 3;
+    return kind;
+  }
+
+  // Huffman-decodes the next token: touches only the bitstream and the tables.
+  //   t.nlit literals packed in t.lits, then t.kind 1: match (t.len, t.dist)   2: end of block   3: invalid code
+  //   4: nothing (the trip ended on a literal, already packed)
+  BG_HD void decode_token(Tok& t) {
+    br.refill();   // >= 33 bits: enough for two codes (<= 15 bits each) without another refill
+    t.lits = 0;
+    t.nlit = 0;
     t.len = 0;
     t.dist = 0;
-    t.kind = spc ? (e == 0 ? 2u : 1u) : 0u;
-    if (c >= llim[15]) t.kind = 3;
-    if (t.kind == 1) {
+    uint32_t e;
+    uint32_t kind = decode_litlen(e);
+#pragma unroll
+    for (int i = 1; i < LITS_PER_TOKEN; ++i) {
+      if (kind == 0) {
+        if (i >= 2) br.refill();
+        t.lits |= e << (8 * t.nlit);
+        t.nlit += 1;
+        kind = decode_litlen(e);
+      }
+    }
+    if (kind == 0) {   // a closing literal simply joins the leading ones: one emit for up to LITS_PER_TOKEN bytes
+      t.lits |= e << (8 * t.nlit);
+      t.nlit += 1;
+      kind = 4;
+    }
+    t.e = e;
+    t.kind = kind;
+    if (kind == 1) {
       uint32_t lc = e - 1;   // length code 0..28 (29, 30: symbols 286/287, invalid)
       if (lc > 28) t.kind = 3;
       uint32_t eb = lc < 8 ? 0u : (lc == 28 ? 0u : (lc - 4) >> 2);
       uint32_t base = lc < 8 ? 3u + lc : (lc == 28 ? 258u : 3u + ((4u + (lc & 3u)) << eb));
       eb &= 7u;
+      br.refill();
       t.len = base + ((uint32_t)br.bb & ((1u << eb) - 1u));
       br.consume(eb);
-      br.refill();
-      c = bg_brev((uint32_t)br.bb) >> 17;
-      L = code_len(dlim, c);
+      uint32_t c = bg_brev((uint32_t)br.bb) >> 17;   // >= 28 bits left: the distance code and its <= 13 extra bits fit
+      uint32_t L = code_len(dlim, c);
       if (c >= dlim[15]) t.kind = 3;
-      m = smr(SM_META + L);
+      uint32_t m = smr(SM_META + L);
       uint32_t di = ((m >> 16) + (c >> (15 - L))) & 31u;
       uint32_t ds = smb(SM_DIST_SYM, di);
       br.consume(L);
@@ -678,13 +711,14 @@ struct Lane {
     }
   }
 
-  // Writes the token's literal, or validates its match and registers (dist >= 8) / performs the copy.
+  // Writes the token's literals, then its closing symbol: a literal, or a match that is validated and registered
+  // (dist >= 8) / performed at once.
   BG_HD void apply_token(const Tok& t) {
-    if (t.kind == 0) {
-      if (opos >= oend) { err = IST_OUTPUT_OVERRUN; state = ST_NEXT; return; }
-      emit1(t.e);
-      return;
+    if (t.nlit) {
+      if (t.nlit > oend - opos) { err = IST_OUTPUT_OVERRUN; state = ST_NEXT; return; }
+      emit(t.lits, t.nlit);
     }
+    if (t.kind == 4) return;   // literals only
     if (t.kind == 3) { err = IST_BAD_SYMBOL; state = ST_NEXT; return; }
     if (t.kind == 2) { state = bfinal ? ST_NEXT : ST_HEADER; return; }  // end of block
     if (t.dist > opos - head) { err = IST_BAD_DISTANCE; state = ST_NEXT; return; }

@@ -28,7 +28,7 @@ constexpr uint32_t IST_CRC_MISMATCH = 100;
 void crc32_init_tables(uint32_t* d_tables /* CRC_TABLE_WORDS words */, cudaStream_t s);
 constexpr int CRC_TABLE_WORDS = 2 * 4 * 256;
 void launch_crc32(const uint8_t* out, const BlockTableDev& t, const uint32_t* d_tables, uint32_t* status,
-                  cudaStream_t s);
+                  int num_sms, cudaStream_t s);
 
 // first_bad[0] = min over blocks with status != 0 of (block index << 32 | status); ~0ull if none.
 void launch_status_reduce(const uint32_t* status, uint32_t n_blocks, unsigned long long* first_bad, cudaStream_t s);
