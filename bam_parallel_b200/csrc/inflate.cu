@@ -3,8 +3,8 @@
 // Replaces bam_tools/src/util.rs:10-16 (inflate_data) + reader/readahead.rs:145-150
 // (decompress_block) and the n-2 rayon inflate workers of readahead.rs:88-118.
 //
-// Mapping: a persistent grid of 3-warp CTAs, 5 CTAs per SM (15 warps = 480 lanes per SM, the
-// most that fit in 227 KB of shared memory at 420 B of Huffman tables + 32 B of input staging per lane).  Every LANE
+// Mapping: a persistent grid of 4-warp CTAs, 4 CTAs per SM (16 warps = 512 lanes per SM, the
+// most that fit in 227 KB of shared memory at 384 B of Huffman tables + 32 B of input staging per lane).  Every LANE
 // owns one BGZF block at a time and pulls the next block index from a global counter, so a
 // warp advances 32 independent DEFLATE streams side by side.  The per-lane logic is in
 // inflate_core.cuh.  Output offsets come from the host's exclusive scan of ISIZE
@@ -14,9 +14,9 @@
 
 namespace bamgpu {
 
-constexpr int K1_WARPS_PER_CTA = 3;
+constexpr int K1_WARPS_PER_CTA = 4;
 #ifndef K1_CTAS
-#define K1_CTAS 5
+#define K1_CTAS 4
 #endif
 constexpr int K1_CTAS_PER_SM = K1_CTAS;
 constexpr int K1_TABLE_BYTES = K1_WARPS_PER_CTA * 32 * LANE_WORDS * 4;            // 40320: Huffman tables

@@ -7,9 +7,10 @@
 //   * Huffman decode is canonical and LUT-free: the 15 left-aligned code-length limits of the
 //     literal/length and distance codes live in REGISTERS, the code length is found with 14
 //     independent compares (no divergence between lanes, no memory access), and only one
-//     index offset and the symbol come from shared memory.  Tables are 420 B per stream
-//     (byte-wide sorted symbols + a 288-bit "is a length code / end of block" map), so 480
-//     streams (15 warps) fit in one SM's 227 KB.
+//     index offset and the symbol come from shared memory.  Tables are 384 B per stream
+//     (byte-wide sorted symbols; canonical order puts the symbols >= 256 of each code length
+//     behind its literals, so one threshold per length replaces a per-symbol flag), so 512
+//     streams (16 warps) fit in one SM's 227 KB.
 //   * Shared memory is interleaved by lane ([word][lane]) so any per-lane index pattern is
 //     bank-conflict free.
 //   * Input is fetched 16 bytes at a time with cp.async (LDGSTS) into two shared-memory slots
@@ -63,13 +64,12 @@ enum : uint32_t {
 
 // Shared-memory words per lane (each lane's words are interleaved with the other 31 lanes' words).
 constexpr int LIT_SYM_WORDS = 72;   // 288 x u8: low 8 bits of the sorted literal/length symbols
-constexpr int LIT_SPC_WORDS = 9;    // 288 x 1 bit: symbol >= 256 (end of block / length code)
 constexpr int DIST_SYM_WORDS = 8;   // 32 x u8
-constexpr int META_WORDS = 16;      // per code length L: (first index - first code) mod 2^16, lit/len low half, distance high half
-constexpr int LANE_WORDS = LIT_SYM_WORDS + LIT_SPC_WORDS + DIST_SYM_WORDS + META_WORDS;  // 105 words = 420 B
+constexpr int META_WORDS = 16;      // per code length L: bits 0-8 (first lit/len index - first code) mod 512, bits 9-13 the same
+                                    // for the distance code mod 32, bits 14-22 the index of the first lit/len symbol >= 256 of that length
+constexpr int LANE_WORDS = LIT_SYM_WORDS + DIST_SYM_WORDS + META_WORDS;  // 96 words = 384 B
 constexpr int SM_LIT_SYM = 0;
-constexpr int SM_LIT_SPC = LIT_SYM_WORDS;
-constexpr int SM_DIST_SYM = SM_LIT_SPC + LIT_SPC_WORDS;
+constexpr int SM_DIST_SYM = LIT_SYM_WORDS;
 constexpr int SM_META = SM_DIST_SYM + DIST_SYM_WORDS;
 
 enum LaneState : uint32_t { ST_NEXT = 0, ST_HEADER, ST_DECODE, ST_STORED, ST_DONE };
@@ -257,7 +257,7 @@ struct TableBuilder {
   // a[L] gets (index of the first symbol of length L) - (first code of length L), mod 2^16, so that
   // symbol index = a[L] + code.  The META words serve as scratch (counts, then scatter cursors).
   // Returns 0 or IST_*.
-  BG_HD uint32_t build(const uint8_t* lens, uint32_t n, bool is_lit, uint32_t* lim, uint32_t* a) {
+  BG_HD uint32_t build(const uint8_t* lens, uint32_t n, bool is_lit, uint32_t* lim, uint32_t* a, uint32_t* thr) {
     for (int L = 0; L < 16; ++L) smw(SM_META + L) = 0;
     for (uint32_t s = 0; s < n; ++s) smw(SM_META + lens[s]) += 1;
     uint32_t cnt[16];
@@ -275,8 +275,20 @@ struct TableBuilder {
       offs += cnt[L];
     }
     if (bad) return IST_OVERSUBSCRIBED;
-    if (is_lit)
-      for (int w = 0; w < LIT_SPC_WORDS; ++w) smw(SM_LIT_SPC + w) = 0;
+    // Canonical order sorts by (length, symbol), so within one length every symbol >= 256 (end of block, length
+    // codes) comes after every literal: one threshold index per length tells them apart.
+    if (is_lit) {
+      uint32_t nlit[16];
+#pragma unroll
+      for (int L = 0; L < 16; ++L) nlit[L] = 0;
+      for (uint32_t s = 0; s < n && s < 256; ++s) {
+        uint32_t l = lens[s];
+#pragma unroll
+        for (int L = 1; L <= 15; ++L) nlit[L] += (l == (uint32_t)L) ? 1u : 0u;
+      }
+#pragma unroll
+      for (int L = 1; L <= 15; ++L) thr[L] = smw(SM_META + L) + nlit[L];   // cursor == first index of length L here
+    }
     for (uint32_t s = 0; s < n; ++s) {
       uint32_t l = lens[s];
       if (l) {
@@ -284,7 +296,6 @@ struct TableBuilder {
         smw(SM_META + l) = pos + 1;
         if (is_lit) {
           set_byte(SM_LIT_SYM, pos, s & 0xffu);          // >= 256: 0 = end of block, 1..29 = length codes 257..285
-          if (s >= 256) smw(SM_LIT_SPC + (int)(pos >> 5)) |= 1u << (pos & 31);
         } else {
           set_byte(SM_DIST_SYM, pos, s);
         }
@@ -427,11 +438,11 @@ BG_HD_COLD void parse_header(BitReader* brp, uint32_t* sm, HeaderResult* hr) {
     if (br.bits_consumed() > br.in_bits) BG_FAIL(IST_INPUT_OVERRUN);
   }
   TableBuilder<STRIDE> tb{sm};
-  uint32_t al[16], ad[16];
-  uint32_t e = tb.build(lens + hlit, hdist, false, hr->dlim, ad);
-  if (!e) e = tb.build(lens, hlit, true, hr->llim, al);
+  uint32_t al[16], ad[16], thr[16];
+  uint32_t e = tb.build(lens + hlit, hdist, false, hr->dlim, ad, thr);
+  if (!e) e = tb.build(lens, hlit, true, hr->llim, al, thr);
   if (e) BG_FAIL(e);
-  for (int L = 1; L <= 15; ++L) sm[(SM_META + L) * STRIDE] = al[L] | (ad[L] << 16);
+  for (int L = 1; L <= 15; ++L) sm[(SM_META + L) * STRIDE] = (al[L] & 0x1ffu) | ((ad[L] & 31u) << 9) | ((thr[L] & 0x1ffu) << 14);
   hr->state = ST_DECODE;
   *brp = br;
 #undef BG_FAIL
@@ -650,10 +661,10 @@ struct Lane {
     uint32_t c = bg_brev((uint32_t)br.bb) >> 17;
     uint32_t L = code_len(llim, c);
     uint32_t m = smr(SM_META + L);
-    uint32_t idx = ((m & 0xffffu) + (c >> (15 - L))) & 0x1ffu;
+    uint32_t idx = (m + (c >> (15 - L))) & 0x1ffu;
+    uint32_t spc = idx >= ((m >> 14) & 0x1ffu) ? 1u : 0u;
     idx = idx < 287u ? idx : 287u;
     e = smb(SM_LIT_SYM, idx);
-    uint32_t spc = (smr(SM_LIT_SPC + (int)(idx >> 5)) >> (idx & 31)) & 1u;
     br.consume(L);
     uint32_t kind = spc ? (e == 0 ? 2u : 1u) : 0u;
     if (c >= llim[15]) kind = 3;
@@ -700,7 +711,7 @@ struct Lane {
       uint32_t L = code_len(dlim, c);
       if (c >= dlim[15]) t.kind = 3;
       uint32_t m = smr(SM_META + L);
-      uint32_t di = ((m >> 16) + (c >> (15 - L))) & 31u;
+      uint32_t di = ((m >> 9) + (c >> (15 - L))) & 31u;
       uint32_t ds = smb(SM_DIST_SYM, di);
       br.consume(L);
       if (ds >= 30) t.kind = 3;
