@@ -464,7 +464,7 @@ struct Lane {
   uint32_t state, bfinal, err, blk, cp_rem;
   uint32_t llim[16], dlim[16];  // [1..15] used; only ever indexed by constants (registers)
   // ---- LZ77 copy in flight: its source words were requested one token ago ----
-  uint32_t p_len, p_src, p_dist;
+  uint32_t p_len, p_dist, p_n, p_ssh;   // bytes left, distance, bytes of the next step, bit shift of its source words
   uint32_t pw0, pw1, pw2, pw3, pw4, pw5, pw6, pw7, pw8;
 
   // ---------------- shared-memory accessors ----------------
@@ -556,90 +556,82 @@ struct Lane {
   }
 
   // ---------------- canonical Huffman ----------------
-  // 1 + number of k in 1..14 with v >= lim[k].  lim <= 0x8000 and v < 0x8000, so the sign bit of
-  // lim - 1 - v is exactly (v >= lim); two accumulators keep the add chains short.
+  // 1 + number of k in 1..15 with v >= lim[k] (16 = v is beyond the last code: invalid).  The limits are exclusive
+  // upper bounds of the codes of length <= k, left-aligned, hence non-decreasing in k: the count is found by a
+  // 4-level binary search whose candidates are picked with selects as soon as each comparison is known
+  // (4 compares + 11 selects, against 14 compare-and-add pairs for the linear form).
   BG_HD static uint32_t code_len(const uint32_t* lim, uint32_t v) {
-    uint32_t nv = ~v, a = 1, b = 0;
-#pragma unroll
-    for (int k = 1; k <= 13; k += 2) {
-      a += (lim[k] + nv) >> 31;
-      b += (lim[k + 1] + nv) >> 31;
-    }
-    return a + b;
+    const bool p3 = v >= lim[8];
+    const uint32_t a = p3 ? lim[12] : lim[4];
+    const uint32_t b2 = p3 ? lim[10] : lim[2], b6 = p3 ? lim[14] : lim[6];
+    const uint32_t c1 = p3 ? lim[9] : lim[1], c3 = p3 ? lim[11] : lim[3], c5 = p3 ? lim[13] : lim[5], c7 = p3 ? lim[15] : lim[7];
+    const bool p2 = v >= a;
+    const uint32_t b = p2 ? b6 : b2;
+    const uint32_t d1 = p2 ? c5 : c1, d3 = p2 ? c7 : c3;
+    const bool p1 = v >= b;
+    const uint32_t d = p1 ? d3 : d1;
+    const bool p0 = v >= d;
+    return 1u + (p3 ? 8u : 0u) + (p2 ? 4u : 0u) + (p1 ? 2u : 0u) + (p0 ? 1u : 0u);
   }
 
   // ---------------- LZ77 copies ----------------
-  // Every copy with distance >= 8 is only REGISTERED here and performed by complete_copy one token later.
-  // dist >= 35: its first 36 source bytes are requested now (9 aligned loads, no use), so the L2/DRAM latency of the
-  // window read overlaps the next token's Huffman decode.  All bytes the 9 words cover lie below opos - 3, i.e. they
-  // are already in memory (only the <= 3 bytes in sreg are not).
+  // Every copy is only REGISTERED by issue_copy and performed by complete_copy one trip of the run loop later, in
+  // straight-line code, at most 16 (dist < 35) or 32 bytes per trip; what is left is registered again and the lane
+  // holds its next token until the copy is done.  So no lane ever loops over a window load inside a trip while the
+  // other 31 wait for its latency.
+  //   dist >= 8: the first 20 (36 for dist >= 35 and more than 16 bytes) source bytes are requested now as aligned
+  //     words, no use; the L2/DRAM latency of the window read overlaps the next token's Huffman decode.  A step uses
+  //     at most dist - 3 of them: those lie below opos - 3, i.e. are in memory (only the <= 3 bytes of sreg are not),
+  //     and the following steps see what this one stored (byte-serial semantics for overlapping copies).
+  //   dist < 8 (the dist=1 runs of BAM quality strings, ~2 % of matches): the first 16 bytes are synthesised in
+  //     registers from the last 8 output bytes; the rest continues as an ordinary copy at a multiple of the period
+  //     (17..21, so 14..16 bytes per step), which by then lies wholly inside the periodic region.
   BG_HD void issue_copy(uint32_t len, uint32_t dist) {
-    uint32_t src = opos - dist;
     p_len = len;
-    p_src = src;
-    p_dist = dist;
-    if (dist >= 35) {
+    if (dist >= 8) {
+      const uint32_t src = opos - dist;
+      p_dist = dist;
+      p_ssh = (src & 3u) * 8;
+      const uint32_t lim = dist - 3u < 16u ? dist - 3u : 16u;
+      p_n = len < lim ? len : lim;
       const uint32_t* w = gptr(src & ~3u, 9);
       pw0 = w[0]; pw1 = w[1]; pw2 = w[2]; pw3 = w[3]; pw4 = w[4];
-      if (len > 16) { pw5 = w[5]; pw6 = w[6]; pw7 = w[7]; pw8 = w[8]; }
+      if (dist >= 35 && len > 16) { pw5 = w[5]; pw6 = w[6]; pw7 = w[7]; pw8 = w[8]; }
+    } else {
+      // last 8 bytes before opos: two stored words + the staging register
+      const uint32_t a = opos & ~3u, ksh = (opos & 3u) * 8;
+      const uint32_t* w = gptr(a, 0) - 2;   // the buffer is readable 16 bytes before out[0]
+      const uint32_t m0 = w[0], m1 = w[1];
+      const uint64_t X = (uint64_t)bg_funnel_r(m0, m1, ksh) | ((uint64_t)bg_funnel_r(m1, sreg, ksh) << 32);
+      uint64_t W = X >> (8 * (8 - dist));  // low `dist` bytes = the period
+      for (uint32_t k = dist; k < 8; k <<= 1) W |= W << (8 * k);
+      const uint32_t deff = dist < 3 ? 4u : (dist == 3 ? 6u : dist);   // a multiple of the period in 4..7
+      const uint32_t wsh = 8 * (8 - deff);
+      pw0 = (uint32_t)W; W = (W >> 32) | ((W >> wsh) << 32);
+      pw1 = (uint32_t)W; W = (W >> 32) | ((W >> wsh) << 32);
+      pw2 = (uint32_t)W; W = (W >> 32) | ((W >> wsh) << 32);
+      pw3 = (uint32_t)W;
+      pw4 = 0;
+      p_ssh = 0;
+      p_n = len < 16u ? len : 16u;
+      p_dist = (uint32_t)(0x5654A4A51ull >> (5 * (dist - 1))) & 31u;   // dist * floor((16 + dist) / dist): 17,18,18,20,20,18,21
     }
   }
   BG_HD void complete_copy() {
     if (p_len) {
-      uint32_t rem = p_len, src = p_src;
-      const uint32_t dist = p_dist;
-      p_len = 0;
-      if (dist >= 35) {
-        const uint32_t ssh = (src & 3u) * 8;
-        uint32_t n = rem < 16 ? rem : 16;
-        emit_n16(bg_funnel_r(pw0, pw1, ssh), bg_funnel_r(pw1, pw2, ssh), bg_funnel_r(pw2, pw3, ssh),
-                 bg_funnel_r(pw3, pw4, ssh), n);
-        rem -= n;
-        src += n;
-        if (rem) {
-          n = rem < 16 ? rem : 16;
-          emit_n16(bg_funnel_r(pw4, pw5, ssh), bg_funnel_r(pw5, pw6, ssh), bg_funnel_r(pw6, pw7, ssh),
-                   bg_funnel_r(pw7, pw8, ssh), n);
-          rem -= n;
-          src += n;
-        }
-      }
-      // Everything else — distances 8..34 and the part of a long copy beyond 32 bytes — in one loop: each trip loads
-      // 20 bytes and emits at most min(16, dist - 3) of them, all of which lie below the write position - 3, i.e. are
-      // in memory; the following trips see what this one stored (byte-serial semantics for overlapping copies).
-      const uint32_t step = dist - 3u < 16u ? dist - 3u : 16u;
-      while (rem) {
-        const uint32_t ssh = (src & 3u) * 8;
-        const uint32_t* w = gptr(src & ~3u, 5);
-        uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-        uint32_t n = rem < step ? rem : step;
-        emit_n16(bg_funnel_r(w0, w1, ssh), bg_funnel_r(w1, w2, ssh), bg_funnel_r(w2, w3, ssh), bg_funnel_r(w3, w4, ssh), n);
-        src += n;
-        rem -= n;
-      }
-    }
-  }
-  // dist < 8 (the dist=1 runs of BAM quality strings, ~2 % of matches): from a register-resident periodic window, at once.
-  BG_HD void copy_near(uint32_t len, uint32_t dist) {
-    // last 8 bytes before opos (the buffer is readable 16 bytes before out[0]) -> periodic window
-    flush_partial();
-    const uint8_t* qa = ob + opos - 8;
-    const uint32_t* a = (const uint32_t*)((uintptr_t)qa & ~(uintptr_t)3);
-    uint32_t sh = (uint32_t)((uintptr_t)qa & 3) * 8;
-    uint32_t x0 = a[0], x1 = a[1], x2 = a[2];
-    uint64_t X = (uint64_t)bg_funnel_r(x0, x1, sh) | ((uint64_t)bg_funnel_r(x1, x2, sh) << 32);
-    uint64_t W = X >> (8 * (8 - dist));  // low `dist` bytes = the period
-    for (uint32_t k = dist; k < 8; k <<= 1) W |= W << (8 * k);
-    uint32_t deff = dist < 3 ? 4u : (dist == 3 ? 6u : dist);
-    uint32_t wsh = 8 * (8 - deff);
-    uint32_t rem = len;
-    while (rem) {
-      uint32_t n = rem < 4 ? rem : 4;
-      uint32_t v = (uint32_t)W;
-      if (n < 4) v &= (1u << (8 * n)) - 1u;
-      W = (W >> 32) | ((W >> wsh) << 32);
-      emit(v, n);
+      const uint32_t dist = p_dist, ssh = p_ssh;
+      uint32_t rem = p_len, n = p_n;
+      emit_n16(bg_funnel_r(pw0, pw1, ssh), bg_funnel_r(pw1, pw2, ssh), bg_funnel_r(pw2, pw3, ssh),
+               bg_funnel_r(pw3, pw4, ssh), n);
       rem -= n;
+      if (rem && dist >= 35) {
+        n = rem < 16 ? rem : 16;
+        emit_n16(bg_funnel_r(pw4, pw5, ssh), bg_funnel_r(pw5, pw6, ssh), bg_funnel_r(pw6, pw7, ssh),
+                 bg_funnel_r(pw7, pw8, ssh), n);
+        rem -= n;
+      }
+      p_len = rem;
+      if (rem) issue_copy(rem, dist);   // dist >= 8 here
     }
   }
 
@@ -660,6 +652,8 @@ struct Lane {
   BG_HD uint32_t decode_litlen(uint32_t& e) {
     uint32_t c = bg_brev((uint32_t)br.bb) >> 17;
     uint32_t L = code_len(llim, c);
+    const bool bad = L > 15u;          // c >= llim[15]: no such code
+    L &= 15u;                          // (0 then: nothing consumed, the table reads stay in range)
     uint32_t m = smr(SM_META + L);
     uint32_t idx = (m + (c >> (15 - L))) & 0x1ffu;
     uint32_t spc = idx >= ((m >> 14) & 0x1ffu) ? 1u : 0u;
@@ -667,7 +661,7 @@ struct Lane {
     e = smb(SM_LIT_SYM, idx);
     br.consume(L);
     uint32_t kind = spc ? (e == 0 ? 2u : 1u) : 0u;
-    if (c >= llim[15]) kind = 3;
+    if (bad) kind = 3;
     return kind;
   }
 
@@ -709,7 +703,8 @@ struct Lane {
       br.consume(eb);
       uint32_t c = bg_brev((uint32_t)br.bb) >> 17;   // >= 28 bits left: the distance code and its <= 13 extra bits fit
       uint32_t L = code_len(dlim, c);
-      if (c >= dlim[15]) t.kind = 3;
+      if (L > 15u) t.kind = 3;
+      L &= 15u;
       uint32_t m = smr(SM_META + L);
       uint32_t di = ((m >> 9) + (c >> (15 - L))) & 31u;
       uint32_t ds = smb(SM_DIST_SYM, di);
@@ -734,22 +729,22 @@ struct Lane {
     if (t.kind == 2) { state = bfinal ? ST_NEXT : ST_HEADER; return; }  // end of block
     if (t.dist > opos - head) { err = IST_BAD_DISTANCE; state = ST_NEXT; return; }
     if (t.len > oend - opos) { err = IST_OUTPUT_OVERRUN; state = ST_NEXT; return; }
-    if (t.dist >= 8) issue_copy(t.len, t.dist);
-    else copy_near(t.len, t.dist);
+    issue_copy(t.len, t.dist);
   }
 
-  // Up to `budget` tokens of the current Huffman block.  No copy is left in flight on return.
+  // Up to `budget` trips over the current Huffman block.  No copy is left in flight on return.
   BG_HD void decode_run(uint32_t budget) {
     if (state != ST_DECODE) return;
     Tok t;
     decode_token(t);
-    for (uint32_t i = 0;;) {
+    for (uint32_t i = 0;; ++i) {
       complete_copy();
+      if (p_len) continue;   // a long copy goes on: the token decoded ahead waits
       apply_token(t);
-      if (state != ST_DECODE || ++i >= budget) break;
+      if (state != ST_DECODE || i + 1 >= budget) break;
       decode_token(t);
     }
-    complete_copy();
+    while (p_len) complete_copy();
   }
 
   // Stored block body (rare): 4 bytes per step straight from the bit buffer.
