@@ -575,7 +575,8 @@ struct Lane {
   }
 
   // ---------------- LZ77 copies ----------------
-  // Every copy is only REGISTERED by issue_copy and performed by complete_copy one trip of the run loop later, in
+  // Every copy is only REGISTERED (p_len, p_dist; request_copy asks for its source words) and performed by
+  // complete_copy one trip of the run loop later, in
   // straight-line code, at most 16 (dist < 35) or 32 bytes per trip; what is left is registered again and the lane
   // holds its next token until the copy is done.  So no lane ever loops over a window load inside a trip while the
   // other 31 wait for its latency.
@@ -586,40 +587,41 @@ struct Lane {
   //   dist < 8 (the dist=1 runs of BAM quality strings, ~2 % of matches): the first 16 bytes are synthesised in
   //     registers from the last 8 output bytes; the rest continues as an ordinary copy at a multiple of the period
   //     (17..21, so 14..16 bytes per step), which by then lies wholly inside the periodic region.
-  BG_HD void issue_copy(uint32_t len, uint32_t dist) {
-    p_len = len;
-    if (dist >= 8) {
-      const uint32_t src = opos - dist;
-      p_dist = dist;
-      p_ssh = (src & 3u) * 8;
-      const uint32_t lim = dist - 3u < 16u ? dist - 3u : 16u;
-      p_n = len < lim ? len : lim;
-      const uint32_t* w = gptr(src & ~3u, 9);
-      pw0 = w[0]; pw1 = w[1]; pw2 = w[2]; pw3 = w[3]; pw4 = w[4];
-      if (dist >= 35 && len > 16) { pw5 = w[5]; pw6 = w[6]; pw7 = w[7]; pw8 = w[8]; }
-    } else {
-      // last 8 bytes before opos: two stored words + the staging register
-      const uint32_t a = opos & ~3u, ksh = (opos & 3u) * 8;
-      const uint32_t* w = gptr(a, 0) - 2;   // the buffer is readable 16 bytes before out[0]
-      const uint32_t m0 = w[0], m1 = w[1];
-      const uint64_t X = (uint64_t)bg_funnel_r(m0, m1, ksh) | ((uint64_t)bg_funnel_r(m1, sreg, ksh) << 32);
-      uint64_t W = X >> (8 * (8 - dist));  // low `dist` bytes = the period
-      for (uint32_t k = dist; k < 8; k <<= 1) W |= W << (8 * k);
-      const uint32_t deff = dist < 3 ? 4u : (dist == 3 ? 6u : dist);   // a multiple of the period in 4..7
-      const uint32_t wsh = 8 * (8 - deff);
-      pw0 = (uint32_t)W; W = (W >> 32) | ((W >> wsh) << 32);
-      pw1 = (uint32_t)W; W = (W >> 32) | ((W >> wsh) << 32);
-      pw2 = (uint32_t)W; W = (W >> 32) | ((W >> wsh) << 32);
-      pw3 = (uint32_t)W;
-      pw4 = 0;
-      p_ssh = 0;
-      p_n = len < 16u ? len : 16u;
-      p_dist = (uint32_t)(0x5654A4A51ull >> (5 * (dist - 1))) & 31u;   // dist * floor((16 + dist) / dist): 17,18,18,20,20,18,21
-    }
+  // Requests the source words of the pending copy (p_len bytes at distance p_dist).  One site, one instruction
+  // sequence for every kind of copy: a second set of loads into the same registers elsewhere in the loop would
+  // have to wait for these to land (register scoreboard), exposing the window latency to the whole warp.
+  BG_HD void request_copy() {
+    const uint32_t len = p_len, dist = p_dist;
+    const bool near = dist < 8;
+    const uint32_t src = opos - dist;
+    const uint32_t lim = near ? 16u : (dist - 3u < 16u ? dist - 3u : 16u);
+    p_n = len < lim ? len : lim;
+    p_ssh = ((near ? opos : src) & 3u) * 8;
+    // far: the aligned words holding src..; near: the two words before the partially filled one (the buffer is
+    // readable 16 bytes before out[0])
+    const uint32_t* w = gptr((near ? opos : src) & ~3u, 0) - (near ? 2 : 0);
+    pw0 = w[0]; pw1 = w[1]; pw2 = w[2]; pw3 = w[3]; pw4 = w[4];
+    if (dist >= 35 && len > 16) { pw5 = w[5]; pw6 = w[6]; pw7 = w[7]; pw8 = w[8]; }
   }
   BG_HD void complete_copy() {
     if (p_len) {
-      const uint32_t dist = p_dist, ssh = p_ssh;
+      uint32_t dist = p_dist, ssh = p_ssh;
+      if (dist < 8) {
+        // last 8 bytes before opos = two stored words + the staging register -> 16 bytes of the periodic pattern
+        const uint64_t X = (uint64_t)bg_funnel_r(pw0, pw1, ssh) | ((uint64_t)bg_funnel_r(pw1, sreg, ssh) << 32);
+        uint64_t W = X >> (8 * (8 - dist));  // low `dist` bytes = the period
+        for (uint32_t k = dist; k < 8; k <<= 1) W |= W << (8 * k);
+        const uint32_t deff = dist < 3 ? 4u : (dist == 3 ? 6u : dist);   // a multiple of the period in 4..7
+        const uint32_t wsh = 8 * (8 - deff);
+        pw0 = (uint32_t)W; W = (W >> 32) | ((W >> wsh) << 32);
+        pw1 = (uint32_t)W; W = (W >> 32) | ((W >> wsh) << 32);
+        pw2 = (uint32_t)W; W = (W >> 32) | ((W >> wsh) << 32);
+        pw3 = (uint32_t)W;
+        pw4 = 0;
+        ssh = 0;
+        dist = (uint32_t)(0x5654A4A51ull >> (5 * (dist - 1))) & 31u;   // dist * floor((16 + dist) / dist): 17,18,18,20,20,18,21
+        p_dist = dist;
+      }
       uint32_t rem = p_len, n = p_n;
       emit_n16(bg_funnel_r(pw0, pw1, ssh), bg_funnel_r(pw1, pw2, ssh), bg_funnel_r(pw2, pw3, ssh),
                bg_funnel_r(pw3, pw4, ssh), n);
@@ -630,8 +632,7 @@ struct Lane {
                  bg_funnel_r(pw7, pw8, ssh), n);
         rem -= n;
       }
-      p_len = rem;
-      if (rem) issue_copy(rem, dist);   // dist >= 8 here
+      p_len = rem;   // != 0: the copy goes on next trip at the same distance
     }
   }
 
@@ -729,7 +730,8 @@ struct Lane {
     if (t.kind == 2) { state = bfinal ? ST_NEXT : ST_HEADER; return; }  // end of block
     if (t.dist > opos - head) { err = IST_BAD_DISTANCE; state = ST_NEXT; return; }
     if (t.len > oend - opos) { err = IST_OUTPUT_OVERRUN; state = ST_NEXT; return; }
-    issue_copy(t.len, t.dist);
+    p_len = t.len;
+    p_dist = t.dist;
   }
 
   // Up to `budget` trips over the current Huffman block.  No copy is left in flight on return.
@@ -739,12 +741,14 @@ struct Lane {
     decode_token(t);
     for (uint32_t i = 0;; ++i) {
       complete_copy();
-      if (p_len) continue;   // a long copy goes on: the token decoded ahead waits
-      apply_token(t);
+      const bool hold = p_len != 0;   // a long copy goes on: the token decoded ahead waits
+      if (!hold) apply_token(t);
+      if (p_len) request_copy();
+      if (hold) continue;
       if (state != ST_DECODE || i + 1 >= budget) break;
       decode_token(t);
     }
-    while (p_len) complete_copy();
+    while (p_len) { complete_copy(); if (p_len) request_copy(); }
   }
 
   // Stored block body (rare): 4 bytes per step straight from the bit buffer.
