@@ -3,47 +3,85 @@
 // Replaces bam_tools/src/util.rs:10-16 (inflate_data) + reader/readahead.rs:145-150
 // (decompress_block) and the n-2 rayon inflate workers of readahead.rs:88-118.
 //
-// Mapping: a persistent grid of 4-warp CTAs, 4 CTAs per SM (16 warps = 512 lanes per SM, the
-// most that fit in 227 KB of shared memory at 384 B of Huffman tables + 32 B of input staging per lane).  Every LANE
-// owns one BGZF block at a time and pulls the next block index from a global counter, so a
-// warp advances 32 independent DEFLATE streams side by side.  The per-lane logic is in
-// inflate_core.cuh.  Output offsets come from the host's exclusive scan of ISIZE
-// (bamgpu_scan_blocks), so the inflated stream is contiguous and records may straddle blocks.
+// Mapping: a persistent grid of 8-warp CTAs, 3 CTAs per SM.  Every BGZF block is one stream, worked on by a pair of
+// lanes: lane l of decoder warp w (warps 0-3: bit reader + Huffman tables -> tokens) and lane l of copier warp w + 4
+// (tokens -> literals and LZ77 copies in the output), talking through a 16-token ring in shared memory.  So a CTA
+// advances 128 streams, an SM 384, with 24 warps resident: twice the warps per scheduler of the one-lane-per-stream
+// form (which was pinned to 16 warps per SM by its 128 registers and 416 B of shared memory per lane) to hide the
+// Huffman dependency chains, the shared-memory look-ups and the window-load latency behind one another.  A decoder
+// lane pulls its next block index from a global counter, so block sizes need not balance.  The per-lane logic is in
+// inflate_core.cuh.  Output offsets come from the host's exclusive scan of ISIZE (bamgpu_scan_blocks), so the
+// inflated stream is contiguous and records may straddle blocks.
 #include "inflate_core.cuh"
 #include "kernels.h"
 
 namespace bamgpu {
 
-constexpr int K1_WARPS_PER_CTA = 4;
+constexpr int K1_PAIR_WARPS = 4;                              // decoder warps per CTA (= copier warps per CTA)
+constexpr int K1_THREADS = 2 * K1_PAIR_WARPS * 32;
 #ifndef K1_CTAS
-#define K1_CTAS 4
+#define K1_CTAS 3
 #endif
 constexpr int K1_CTAS_PER_SM = K1_CTAS;
-constexpr int K1_TABLE_BYTES = K1_WARPS_PER_CTA * 32 * LANE_WORDS * 4;            // 40320: Huffman tables
-constexpr int K1_SMEM_BYTES = K1_TABLE_BYTES + K1_WARPS_PER_CTA * STAGE_WARP_BYTES;   // + 3072: input staging slots
+constexpr int K1_TABLE_BYTES = K1_PAIR_WARPS * 32 * LANE_WORDS * 4;                // 49152: Huffman tables
+constexpr int K1_STAGE_BYTES = K1_PAIR_WARPS * STAGE_WARP_BYTES;                   //  4096: input staging slots
+constexpr int K1_RING_BYTES = K1_PAIR_WARPS * RING_WARP_BYTES;                     // 17408: token rings
+constexpr int K1_SMEM_BYTES = K1_TABLE_BYTES + K1_STAGE_BYTES + K1_RING_BYTES;
 
-constexpr uint32_t K1_TOKENS_PER_ROUND = 128;  // tokens a lane decodes between two looks at the warp-wide state
+constexpr uint32_t K1_TRIPS_PER_ROUND = 128;  // trips a decoder lane makes between two looks at the warp-wide state
 
-__global__ void __launch_bounds__(K1_WARPS_PER_CTA * 32, K1_CTAS_PER_SM)
-k1_inflate_lane_per_block(InflateJob job, uint32_t* __restrict__ work_counter) {
+__global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM)
+k1_inflate_pairs(InflateJob job, uint32_t* __restrict__ work_counter) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  Lane<32> L;
-  L.sm = smem + warp * (32 * LANE_WORDS) + lane;
-  const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(smem) + K1_TABLE_BYTES + warp * STAGE_WARP_BYTES + lane * 16;
-  L.state = ST_NEXT;
-  L.blk = 0xffffffffu;
-  L.err = 0;
-  for (;;) {
-    if (L.state == ST_NEXT) {
-      L.finish_block(job);
-      uint32_t b = atomicAdd(work_counter, 1u);
-      if (b < job.n_blocks) L.begin_block(job, b, stage0);
-      else { L.state = ST_DONE; L.blk = 0xffffffffu; }
+  const int pw = warp & (K1_PAIR_WARPS - 1);
+  const bool is_decoder = warp < K1_PAIR_WARPS;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  TokRing ring;
+  ring.init(smem_base + K1_TABLE_BYTES + K1_STAGE_BYTES + pw * RING_WARP_BYTES, lane);
+  if (is_decoder) ring.reset();
+  __syncthreads();
+  if (is_decoder) {
+    Decoder<32> D;
+    D.sm = smem + pw * (32 * LANE_WORDS) + lane;
+    D.ring = ring;
+    D.head = 0;
+    D.state = ST_NEXT;
+    D.blk = 0xffffffffu;
+    D.err = 0;
+    const uint32_t stage0 = smem_base + K1_TABLE_BYTES + pw * STAGE_WARP_BYTES + lane * 16;
+    for (;;) {
+      if (D.state == ST_NEXT) {
+        uint32_t b = atomicAdd(work_counter, 1u);
+        if (b < job.n_blocks) D.begin_block(job, b, stage0);
+        else D.state = ST_FINISH;
+      }
+      if (__all_sync(0xffffffffu, D.state == ST_DONE)) break;
+      if (D.state == ST_HEADER) D.header();
+      __syncwarp();
+      for (uint32_t i = 0; i < K1_TRIPS_PER_ROUND; ++i) {
+        const bool worked = D.trip(job, stage0);
+        if (!__any_sync(0xffffffffu, worked)) {
+          // every lane is waiting (ring full, or for the round to end): leave the issue slots to the copiers
+          if (__all_sync(0xffffffffu, D.state == ST_HEADER || D.state == ST_NEXT || D.state == ST_DONE)) break;
+          __nanosleep(100);
+        }
+      }
     }
-    if (__all_sync(0xffffffffu, L.state == ST_DONE)) break;
-    L.round(K1_TOKENS_PER_ROUND);
-    __syncwarp();
+  } else {
+    Copier C;
+    C.ring = ring;
+    C.tail = 0;
+    C.done = 0;
+    C.p_len = 0;
+    C.blk = 0xffffffffu;
+    for (;;) {
+      const bool worked = C.trip(job);
+      if (!__any_sync(0xffffffffu, worked)) {
+        if (__all_sync(0xffffffffu, C.done != 0)) break;
+        __nanosleep(100);
+      }
+    }
   }
 }
 
@@ -53,13 +91,13 @@ void launch_inflate(const uint8_t* comp, const BlockTableDev& t, uint8_t* out, u
                     uint32_t* work_counter, int num_sms, cudaStream_t s) {
   if (t.n_blocks == 0) return;
   // per-device attribute; cheap enough to set on every launch (keeps multi-device processes correct)
-  cudaFuncSetAttribute(k1_inflate_lane_per_block, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES);
+  cudaFuncSetAttribute(k1_inflate_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES);
   InflateJob job{comp, t.in_off, t.in_len, t.out_off, t.isize, out, status, t.n_blocks};
-  uint32_t lanes_per_cta = K1_WARPS_PER_CTA * 32;
+  uint32_t lanes_per_cta = K1_PAIR_WARPS * 32;   // streams per CTA
   uint32_t max_ctas = (uint32_t)num_sms * K1_CTAS_PER_SM;
   uint32_t need = (t.n_blocks + lanes_per_cta - 1) / lanes_per_cta;
   uint32_t grid = need < max_ctas ? need : max_ctas;
-  k1_inflate_lane_per_block<<<grid, lanes_per_cta, K1_SMEM_BYTES, s>>>(job, work_counter);
+  k1_inflate_pairs<<<grid, K1_THREADS, K1_SMEM_BYTES, s>>>(job, work_counter);
 }
 
 // ---- first failing block ----------------------------------------------------------------------

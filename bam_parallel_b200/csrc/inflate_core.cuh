@@ -1,33 +1,40 @@
-// inflate_core.cuh — per-lane raw-DEFLATE (RFC 1951) decoder used by kernel K1.
+// inflate_core.cuh — per-stream raw-DEFLATE (RFC 1951) decoder used by kernel K1.
 //
 // Replaces the reference's `inflate_data` (bam_tools/src/util.rs:10-16, i.e. flate2's
-// DeflateDecoder::read_to_end) for one BGZF block per LANE: 32 independent streams advance
-// side by side inside a warp, so every issued instruction does useful work for up to 32 blocks.
+// DeflateDecoder::read_to_end).  Every BGZF block is one independent stream, and a stream is worked on by a PAIR of
+// lanes in two different warps of one CTA:
+//   * the DECODER lane (Decoder<>) owns the bit reader and the Huffman tables, turns the bitstream into tokens
+//     (up to 3 literals + one match) and validates them (distances, output size);
+//   * the COPIER lane (Copier) owns the output position, writes the literals and performs the LZ77 copies.
+// They talk through a small token ring in shared memory (single producer / single consumer, no blocking waits: a lane
+// whose ring is full or empty just skips the trip).  32 streams advance side by side inside a warp either way, so
+// every issued instruction does useful work for up to 32 blocks, but the two halves are separate instruction streams:
+// the scheduler overlaps the copiers' window-load latency with the decoders' ALU/shared-memory chains, each half
+// needs roughly half the registers (twice the warps per SM), and each loop body is half as divergent.
 // Design notes (see DESIGN.md "K1"):
 //   * Huffman decode is canonical and LUT-free: the 15 left-aligned code-length limits of the
-//     literal/length and distance codes live in REGISTERS, the code length is found with 14
-//     independent compares (no divergence between lanes, no memory access), and only one
+//     literal/length and distance codes live in REGISTERS, the code length is found by a 4-level
+//     select search over them (no divergence between lanes, no memory access), and only one
 //     index offset and the symbol come from shared memory.  Tables are 384 B per stream
 //     (byte-wide sorted symbols; canonical order puts the symbols >= 256 of each code length
-//     behind its literals, so one threshold per length replaces a per-symbol flag), so 512
-//     streams (16 warps) fit in one SM's 227 KB.
+//     behind its literals, so one threshold per length replaces a per-symbol flag).
 //   * Shared memory is interleaved by lane ([word][lane]) so any per-lane index pattern is
 //     bank-conflict free.
 //   * Input is fetched 16 bytes at a time with cp.async (LDGSTS) into two shared-memory slots
 //     per lane, two chunks ahead of use, so neither the load latency nor a register scoreboard
 //     sits on the decode dependency chain.
 //   * Output goes through a 4-byte staging register and is stored as aligned 32-bit words.
-//   * LZ77 copies are software-pipelined against the Huffman decode: a match with distance >= 35
-//     only REQUESTS its first 36 source bytes (9 aligned loads, no use), the next token is
-//     Huffman-decoded while they are in flight, and only then are they shifted into place and
-//     stored (straight-line code for up to 32 bytes).  The window read is an L2/DRAM access
-//     (thousands of streams x 32 KB of history do not fit in L1), so this takes its latency off
-//     the critical path.  Distances 8..34 load inside the copy (up to 16 bytes per trip), distances
-//     < 8 come from a register-resident periodic window (the dist=1 runs of BAM quality strings).
+//   * LZ77 copies are software-pipelined: a copy is only REGISTERED when its token is taken; its source words are
+//     requested (aligned loads, no use) at the end of that trip and shifted into place and stored at the start of
+//     the next one, at most 16 (distance < 35) or 32 bytes per trip in straight-line code; what is left is
+//     requested again.  The window read is an L2/DRAM access (tens of thousands of streams x 32 KB of history do
+//     not fit in L1), so this takes its latency off the critical path, and no lane ever loops over a load inside a
+//     trip while the other 31 wait.  Distances < 8 (the dist=1 runs of BAM quality strings) are synthesised in
+//     registers from the last 8 output bytes and continue as an ordinary copy at a multiple of the period.
 //   * The DEFLATE block header / code-table build is a cold out-of-line function working on a
 //     copy of the bit reader, so the hot loop's state stays in registers.  (It also has to be
 //     out of line: with ptxas 12.9 -O1..-O3 the fully inlined form miscompiled on sm_100a —
-//     tools/debug/k1_debug3.cu reproduces it.)
+//     tools/debug/k1_debug2.cu reproduces it.)
 //
 // Everything here is __host__ __device__ so tests/host_emul.cpp can run the identical logic on
 // the CPU build box (no GPU there).  That emulation is a TEST of this code, not a fallback:
@@ -72,7 +79,8 @@ constexpr int SM_LIT_SYM = 0;
 constexpr int SM_DIST_SYM = LIT_SYM_WORDS;
 constexpr int SM_META = SM_DIST_SYM + DIST_SYM_WORDS;
 
-enum LaneState : uint32_t { ST_NEXT = 0, ST_HEADER, ST_DECODE, ST_STORED, ST_DONE };
+// Decoder lane states.  ST_BEGIN/ST_END/ST_FINISH/ST_STORED wait for room in the token ring to push their token.
+enum LaneState : uint32_t { ST_NEXT = 0, ST_BEGIN, ST_HEADER, ST_DECODE, ST_STORED, ST_END, ST_FINISH, ST_DONE };
 
 struct W4 { uint32_t x, y, z, w; };
 
@@ -125,22 +133,7 @@ struct InflateJob {
   uint8_t* out;              // inflated stream, 4-byte aligned; readable 16 bytes BEFORE out[0] and 4 past the end
   uint32_t* status;          // per block: IST_*
   uint32_t n_blocks;
-#if defined(BG_BOUNDS)
-  uint64_t out_len, comp_len;  // debug build: every global access is checked against these
-#endif
 };
-
-#if defined(BG_BOUNDS) && defined(__CUDA_ARCH__)
-#define BG_CHECK(cond, what, v)                                                                       \
-  do {                                                                                                \
-    if (!(cond)) {                                                                                    \
-      printf("BG_BOUNDS %s: value %lld block %u opos %u oend %u head %u state %u\n", what, (long long)(v), blk, opos, oend, head, state); \
-      __trap();                                                                                       \
-    }                                                                                                 \
-  } while (0)
-#else
-#define BG_CHECK(cond, what, v) do { } while (0)
-#endif
 
 // ---- input bit reader: 64-bit bit buffer fed from 16-byte chunks ------------------------------------
 // On the GPU the chunks after the current one are staged in shared memory by cp.async (LDGSTS): two
@@ -448,111 +441,75 @@ BG_HD_COLD void parse_header(BitReader* brp, uint32_t* sm, HeaderResult* hr) {
 #undef BG_FAIL
 }
 
-// ---- the lane --------------------------------------------------------------------------------------
-template <int STRIDE>  // shared-memory word stride between consecutive entries of one lane (32 on GPU)
-struct Lane {
-  uint32_t* sm;          // this lane's shared-memory column
+// ---- token ring between a decoder lane and its copier lane ------------------------------------------
+// A token is two 32-bit words:
+//   w0: bits 0-23 up to three literal bytes, bits 24-25 their count, bits 26-28 the kind
+//   w1: TK_MATCH len | dist << 16     TK_BEGIN block index     TK_END final IST_* status of the block
+//       TK_RAW   len | offset in the payload << 16 (stored block: bytes copied straight from the input)
+// Single producer, single consumer, free-running 32-bit counters; nobody ever blocks on it.
+enum : uint32_t { TK_LITS = 0, TK_MATCH = 1, TK_BEGIN = 2, TK_END = 3, TK_RAW = 4, TK_DONE = 5 };
+constexpr uint32_t RING_TOKENS = 16;                      // per stream (power of two)
+constexpr int RING_ROW_BYTES = 32 * 8;                    // one slot of every lane of a warp
+constexpr int RING_WARP_BYTES = RING_TOKENS * RING_ROW_BYTES + 2 * 32 * 4;   // slots + head row + tail row
+
+struct TokRing {
+#if defined(__CUDACC__)
+  uint32_t slots;   // shared-memory byte address of this lane's slot 0 (slot stride RING_ROW_BYTES)
+  uint32_t ctr;     // ... of this lane's head counter; the tail counter is one row (128 B) behind it
+  __device__ __forceinline__ void init(uint32_t warp_base, uint32_t lane) {
+    slots = warp_base + lane * 8;
+    ctr = warp_base + RING_TOKENS * RING_ROW_BYTES + lane * 4;
+  }
+#if defined(__CUDA_ARCH__)
+  BG_HD void reset() { asm volatile("st.shared.u32 [%0], %1;\n\tst.shared.u32 [%0+128], %1;" ::"r"(ctr), "r"(0u) : "memory"); }
+  BG_HD uint32_t head() const { uint32_t v; asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(ctr) : "memory"); return v; }
+  BG_HD uint32_t tail() const { uint32_t v; asm volatile("ld.acquire.cta.shared.u32 %0, [%1+128];" : "=r"(v) : "r"(ctr) : "memory"); return v; }
+  BG_HD void push(uint32_t idx, uint32_t w0, uint32_t w1) {   // idx = current head
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(slots + (idx & (RING_TOKENS - 1)) * RING_ROW_BYTES), "r"(w0), "r"(w1) : "memory");
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(ctr), "r"(idx + 1) : "memory");
+  }
+  BG_HD void pop(uint32_t idx, uint32_t& w0, uint32_t& w1) {  // idx = current tail; publishes idx + 1
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(slots + (idx & (RING_TOKENS - 1)) * RING_ROW_BYTES) : "memory");
+    asm volatile("st.release.cta.shared.u32 [%0+128], %1;" ::"r"(ctr), "r"(idx + 1) : "memory");
+  }
+#else   // host pass of nvcc: never called
+  BG_HD void reset() {}
+  BG_HD uint32_t head() const { return 0; }
+  BG_HD uint32_t tail() const { return 0; }
+  BG_HD void push(uint32_t, uint32_t, uint32_t) {}
+  BG_HD void pop(uint32_t, uint32_t&, uint32_t&) {}
+#endif
+#else
+  uint32_t* mem;    // RING_TOKENS * 2 words of slots, then head, then tail
+  BG_HD void reset() { mem[2 * RING_TOKENS] = 0; mem[2 * RING_TOKENS + 1] = 0; }
+  BG_HD uint32_t head() const { return mem[2 * RING_TOKENS]; }
+  BG_HD uint32_t tail() const { return mem[2 * RING_TOKENS + 1]; }
+  BG_HD void push(uint32_t idx, uint32_t w0, uint32_t w1) {
+    mem[2 * (idx & (RING_TOKENS - 1))] = w0; mem[2 * (idx & (RING_TOKENS - 1)) + 1] = w1;
+    mem[2 * RING_TOKENS] = idx + 1;
+  }
+  BG_HD void pop(uint32_t idx, uint32_t& w0, uint32_t& w1) {
+    w0 = mem[2 * (idx & (RING_TOKENS - 1))]; w1 = mem[2 * (idx & (RING_TOKENS - 1)) + 1];
+    mem[2 * RING_TOKENS + 1] = idx + 1;
+  }
+#endif
+};
+
+// ---- the decoder lane --------------------------------------------------------------------------------
+template <int STRIDE>  // shared-memory word stride between consecutive table entries of one lane (32 on GPU)
+struct Decoder {
+  uint32_t* sm;          // this lane's shared-memory table column
   BitReader br;
-  // ---- output: byte offsets relative to ob (the 4-byte aligned address at or below the block start) ----
-  uint8_t* ob;
-  uint32_t head;         // first own byte (0..3)
-  uint32_t opos, oend;   // next byte to write / one past the last own byte
-  uint32_t sreg;         // bytes of the word at opos & ~3 not yet stored
-  uint32_t full_lo, full_span;  // aligned words a with (a - full_lo) < full_span lie wholly inside the block
-  uint32_t fast_span;           // ... and with (a - full_lo) < fast_span so do the three words after a
-  // ---- decode state ----
+  TokRing ring;
+  uint32_t head;         // tokens pushed so far
   uint32_t state, bfinal, err, blk, cp_rem;
+  uint32_t produced, isize;     // bytes the tokens pushed so far stand for / ISIZE of the block
   uint32_t llim[16], dlim[16];  // [1..15] used; only ever indexed by constants (registers)
-  // ---- LZ77 copy in flight: its source words were requested one token ago ----
-  uint32_t p_len, p_dist, p_n, p_ssh;   // bytes left, distance, bytes of the next step, bit shift of its source words
-  uint32_t pw0, pw1, pw2, pw3, pw4, pw5, pw6, pw7, pw8;
 
   // ---------------- shared-memory accessors ----------------
   BG_HD uint32_t smr(int w) const { return sm[w * STRIDE]; }
   BG_HD uint32_t smb(int base, uint32_t i) const {   // byte i of the byte array starting at word `base`
     return ((const uint8_t*)(sm + (base + (int)(i >> 2)) * STRIDE))[i & 3];
-  }
-
-#if defined(BG_BOUNDS)
-  const uint8_t* dbg_lo; const uint8_t* dbg_hi;   // readable/writable range of the output buffer
-#endif
-  BG_HD const uint32_t* gptr(uint32_t a /*aligned*/, uint32_t nwords) const {
-#if defined(BG_BOUNDS)
-    BG_CHECK(ob + a >= dbg_lo && ob + a + 4 * nwords <= dbg_hi, "out access", (long long)a);
-#endif
-    return (const uint32_t*)(ob + a);
-  }
-  // ---------------- output ----------------
-  BG_HD uint32_t ldw(uint32_t a /*aligned*/) const { return *gptr(a, 1); }
-  // Slow, always-correct store of one aligned word: touches only this block's own bytes.
-  BG_HD void store_word(uint32_t a /*aligned*/, uint32_t w) {
-    if (a - full_lo < full_span) {
-      *(uint32_t*)gptr(a, 1) = w;
-    } else {  // head / tail word shared with a neighbouring block
-      for (uint32_t i = 0; i < 4; ++i)
-        if (a + i >= head && a + i < oend) ob[a + i] = (uint8_t)(w >> (8 * i));
-    }
-  }
-  // One byte.
-  BG_HD void emit1(uint32_t v) {
-    uint32_t k = opos & 3u;
-    sreg |= v << (8 * k);
-    if (k == 3) {
-      store_word(opos - 3u, sreg);
-      sreg = 0;
-    }
-    opos += 1;
-  }
-  // v holds n (1..4) valid low bytes, the rest zero.
-  BG_HD void emit(uint32_t v, uint32_t n) {
-    uint32_t k = opos & 3u;
-    uint32_t sh = k * 8;
-    sreg |= v << sh;
-    if (k + n >= 4) {
-      store_word(opos & ~3u, sreg);
-      sreg = sh ? (v >> (32 - sh)) : 0u;
-    }
-    opos += n;
-  }
-  // n (1..16) bytes held in v0..v3 (bytes past n may be garbage); the caller guarantees opos + n <= oend.
-  BG_HD void emit_n16(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t n) {
-    uint32_t a = opos & ~3u;
-    uint32_t k = opos & 3u, sh = k * 8;
-    uint32_t o0 = sreg | (v0 << sh);
-    uint32_t o1 = bg_funnel_l(v0, v1, sh);
-    uint32_t o2 = bg_funnel_l(v1, v2, sh);
-    uint32_t o3 = bg_funnel_l(v2, v3, sh);
-    uint32_t o4 = bg_funnel_l(v3, 0u, sh);
-    uint32_t tot = k + n;          // 1..19
-    uint32_t nfull = tot >> 2;     // whole words completed: 0..4
-    if (a - full_lo < fast_span) {
-      // all four words lie wholly inside the block: straight predicated stores
-      uint32_t* w = (uint32_t*)gptr(a, 4);
-      if (nfull > 0) w[0] = o0;
-      if (nfull > 1) w[1] = o1;
-      if (nfull > 2) w[2] = o2;
-      if (nfull > 3) w[3] = o3;
-    } else {
-      if (nfull > 0) store_word(a, o0);
-      if (nfull > 1) store_word(a + 4, o1);
-      if (nfull > 2) store_word(a + 8, o2);
-      if (nfull > 3) store_word(a + 12, o3);
-    }
-    uint32_t r = o0;
-    if (nfull == 1) r = o1;
-    if (nfull == 2) r = o2;
-    if (nfull == 3) r = o3;
-    if (nfull == 4) r = o4;
-    uint32_t rb = tot & 3u;
-    sreg = r & ((1u << (8 * rb)) - 1u);
-    opos += n;
-  }
-  // Make every byte below opos visible in memory (bytes of the partially filled word).
-  BG_HD void flush_partial() {
-    uint32_t k = opos & 3u;
-    uint32_t a = opos - k;
-    for (uint32_t i = 0; i < k; ++i)
-      if (a + i >= head) ob[a + i] = (uint8_t)(sreg >> (8 * i));
   }
 
   // ---------------- canonical Huffman ----------------
@@ -574,79 +531,14 @@ struct Lane {
     return 1u + (p3 ? 8u : 0u) + (p2 ? 4u : 0u) + (p1 ? 2u : 0u) + (p0 ? 1u : 0u);
   }
 
-  // ---------------- LZ77 copies ----------------
-  // Every copy is only REGISTERED (p_len, p_dist; request_copy asks for its source words) and performed by
-  // complete_copy one trip of the run loop later, in
-  // straight-line code, at most 16 (dist < 35) or 32 bytes per trip; what is left is registered again and the lane
-  // holds its next token until the copy is done.  So no lane ever loops over a window load inside a trip while the
-  // other 31 wait for its latency.
-  //   dist >= 8: the first 20 (36 for dist >= 35 and more than 16 bytes) source bytes are requested now as aligned
-  //     words, no use; the L2/DRAM latency of the window read overlaps the next token's Huffman decode.  A step uses
-  //     at most dist - 3 of them: those lie below opos - 3, i.e. are in memory (only the <= 3 bytes of sreg are not),
-  //     and the following steps see what this one stored (byte-serial semantics for overlapping copies).
-  //   dist < 8 (the dist=1 runs of BAM quality strings, ~2 % of matches): the first 16 bytes are synthesised in
-  //     registers from the last 8 output bytes; the rest continues as an ordinary copy at a multiple of the period
-  //     (17..21, so 14..16 bytes per step), which by then lies wholly inside the periodic region.
-  // Requests the source words of the pending copy (p_len bytes at distance p_dist).  One site, one instruction
-  // sequence for every kind of copy: a second set of loads into the same registers elsewhere in the loop would
-  // have to wait for these to land (register scoreboard), exposing the window latency to the whole warp.
-  BG_HD void request_copy() {
-    const uint32_t len = p_len, dist = p_dist;
-    const bool near = dist < 8;
-    const uint32_t src = opos - dist;
-    const uint32_t lim = near ? 16u : (dist - 3u < 16u ? dist - 3u : 16u);
-    p_n = len < lim ? len : lim;
-    p_ssh = ((near ? opos : src) & 3u) * 8;
-    // far: the aligned words holding src..; near: the two words before the partially filled one (the buffer is
-    // readable 16 bytes before out[0])
-    const uint32_t* w = gptr((near ? opos : src) & ~3u, 0) - (near ? 2 : 0);
-    pw0 = w[0]; pw1 = w[1]; pw2 = w[2]; pw3 = w[3]; pw4 = w[4];
-    if (dist >= 35 && len > 16) { pw5 = w[5]; pw6 = w[6]; pw7 = w[7]; pw8 = w[8]; }
-  }
-  BG_HD void complete_copy() {
-    if (p_len) {
-      uint32_t dist = p_dist, ssh = p_ssh;
-      if (dist < 8) {
-        // last 8 bytes before opos = two stored words + the staging register -> 16 bytes of the periodic pattern
-        const uint64_t X = (uint64_t)bg_funnel_r(pw0, pw1, ssh) | ((uint64_t)bg_funnel_r(pw1, sreg, ssh) << 32);
-        uint64_t W = X >> (8 * (8 - dist));  // low `dist` bytes = the period
-        for (uint32_t k = dist; k < 8; k <<= 1) W |= W << (8 * k);
-        const uint32_t deff = dist < 3 ? 4u : (dist == 3 ? 6u : dist);   // a multiple of the period in 4..7
-        const uint32_t wsh = 8 * (8 - deff);
-        pw0 = (uint32_t)W; W = (W >> 32) | ((W >> wsh) << 32);
-        pw1 = (uint32_t)W; W = (W >> 32) | ((W >> wsh) << 32);
-        pw2 = (uint32_t)W; W = (W >> 32) | ((W >> wsh) << 32);
-        pw3 = (uint32_t)W;
-        pw4 = 0;
-        ssh = 0;
-        dist = (uint32_t)(0x5654A4A51ull >> (5 * (dist - 1))) & 31u;   // dist * floor((16 + dist) / dist): 17,18,18,20,20,18,21
-        p_dist = dist;
-      }
-      uint32_t rem = p_len, n = p_n;
-      emit_n16(bg_funnel_r(pw0, pw1, ssh), bg_funnel_r(pw1, pw2, ssh), bg_funnel_r(pw2, pw3, ssh),
-               bg_funnel_r(pw3, pw4, ssh), n);
-      rem -= n;
-      if (rem && dist >= 35) {
-        n = rem < 16 ? rem : 16;
-        emit_n16(bg_funnel_r(pw4, pw5, ssh), bg_funnel_r(pw5, pw6, ssh), bg_funnel_r(pw6, pw7, ssh),
-                 bg_funnel_r(pw7, pw8, ssh), n);
-        rem -= n;
-      }
-      p_len = rem;   // != 0: the copy goes on next trip at the same distance
-    }
-  }
-
-  // One literal/length (+ distance) token is handled in three steps that the run loop orders as
-  //   complete_copy (previous token's copy) -> apply_token (this token) -> decode_token (next token)
-  // so that the window words apply_token requests are first used a whole Huffman decode later.
-  // A "token" is up to LITS_PER_TOKEN leading literals plus one closing symbol (literal, match, end of block or an
-  // invalid code).  Decoding several literals per trip amortises the sparse, divergent match code of the run loop over
-  // more output: most lanes start with a literal, and a lane that sees a length stops there.
+  // A "token" is up to LITS_PER_TOKEN - 1 leading literals plus one closing symbol (literal, match, end of block or
+  // an invalid code).  Decoding several literals per trip amortises the sparse match code over more output: most
+  // lanes start with a literal, and a lane that sees a length stops there.
 #ifndef BG_LITS_PER_TOKEN
 #define BG_LITS_PER_TOKEN 3
 #endif
-  static constexpr int LITS_PER_TOKEN = BG_LITS_PER_TOKEN;   // symbols per trip: this many - 1 leading literals + the closing symbol
-  struct Tok { uint32_t lits, nlit, e, len, dist, kind; };
+  static constexpr int LITS_PER_TOKEN = BG_LITS_PER_TOKEN;
+  struct Tok { uint32_t lits, nlit, len, dist, kind; };
 
   // One literal/length symbol.  Needs 15 valid bits in br.bb; consumes the code.  Returns 0 literal (value in e),
   // 1 length code (e = code + 1), 2 end of block, 3 invalid.
@@ -686,12 +578,11 @@ struct Lane {
         kind = decode_litlen(e);
       }
     }
-    if (kind == 0) {   // a closing literal simply joins the leading ones: one emit for up to LITS_PER_TOKEN bytes
+    if (kind == 0) {   // a closing literal simply joins the leading ones: one token for up to LITS_PER_TOKEN bytes
       t.lits |= e << (8 * t.nlit);
       t.nlit += 1;
       kind = 4;
     }
-    t.e = e;
     t.kind = kind;
     if (kind == 1) {
       uint32_t lc = e - 1;   // length code 0..28 (29, 30: symbols 286/287, invalid)
@@ -718,52 +609,71 @@ struct Lane {
     }
   }
 
-  // Writes the token's literals, then its closing symbol: a literal, or a match that is validated and registered
-  // (dist >= 8) / performed at once.
-  BG_HD void apply_token(const Tok& t) {
-    if (t.nlit) {
-      if (t.nlit > oend - opos) { err = IST_OUTPUT_OVERRUN; state = ST_NEXT; return; }
-      emit(t.lits, t.nlit);
-    }
-    if (t.kind == 4) return;   // literals only
-    if (t.kind == 3) { err = IST_BAD_SYMBOL; state = ST_NEXT; return; }
-    if (t.kind == 2) { state = bfinal ? ST_NEXT : ST_HEADER; return; }  // end of block
-    if (t.dist > opos - head) { err = IST_BAD_DISTANCE; state = ST_NEXT; return; }
-    if (t.len > oend - opos) { err = IST_OUTPUT_OVERRUN; state = ST_NEXT; return; }
-    p_len = t.len;
-    p_dist = t.dist;
-  }
+  BG_HD void push(uint32_t w0, uint32_t w1) { ring.push(head, w0, w1); head += 1; }
 
-  // Up to `budget` trips over the current Huffman block.  No copy is left in flight on return.
-  BG_HD void decode_run(uint32_t budget) {
-    if (state != ST_DECODE) return;
-    Tok t;
-    decode_token(t);
-    for (uint32_t i = 0;; ++i) {
-      complete_copy();
-      const bool hold = p_len != 0;   // a long copy goes on: the token decoded ahead waits
-      if (!hold) apply_token(t);
-      if (p_len) request_copy();
-      if (hold) continue;
-      if (state != ST_DECODE || i + 1 >= budget) break;
+  // Everything a trip does outside the Huffman decode: the tokens that open and close a block, stored blocks.
+  BG_HD void cold_trip(const InflateJob& job, uint32_t stage0) {
+    if (state == ST_BEGIN) {
+      push(TK_BEGIN << 26, blk);
+      state = ST_HEADER;
+    } else if (state == ST_STORED) {
+      // stored block: the copier takes the bytes straight from the input; skip them here
+      const uint32_t off = pay_skipped + (br.bits_consumed() >> 3), len = cp_rem, in_len = job.in_len[blk];
+      if (off + len > in_len) { err = IST_INPUT_OVERRUN; state = ST_END; return; }
+      if (len > isize - produced) { err = IST_OUTPUT_OVERRUN; state = ST_END; return; }
+      push(TK_RAW << 26, len | (off << 16));
+      produced += len;
+      br.drain();
+      br.begin(job.comp + job.in_off[blk] + off + len, in_len - (off + len), stage0);
+      pay_skipped = off + len;
+      state = bfinal ? ST_END : ST_HEADER;
+    } else if (state == ST_END) {
+      if (!err) {
+        if (produced != isize) err = IST_SIZE_MISMATCH;
+        else if (br.bits_consumed() > br.in_bits) err = IST_INPUT_OVERRUN;
+      }
+      br.drain();
+      push(TK_END << 26, err);
+      state = ST_NEXT;
+    } else if (state == ST_FINISH) {
+      push(TK_DONE << 26, 0);
+      state = ST_DONE;
+    }
+  }
+  uint32_t pay_skipped;   // payload bytes before the position the bit reader was last (re)started at
+
+  // One trip: at most one token.  A lane whose ring is full just skips it.  Returns false if the lane had nothing
+  // to do (ring full, or waiting for the warp-level part of the loop: next block, header).
+  BG_HD bool trip(const InflateJob& job, uint32_t stage0) {
+    if (state == ST_HEADER || state == ST_NEXT || state == ST_DONE) return false;
+    if (head - ring.tail() >= RING_TOKENS) return false;
+    if (state == ST_DECODE) {
+      Tok t;
       decode_token(t);
+      uint32_t w0 = t.lits | (t.nlit << 24), w1 = 0;
+      uint32_t np = produced + t.nlit, bad = 0;
+      bool any = t.nlit != 0;
+      if (t.kind == 1) {
+        if (t.dist > np) bad = IST_BAD_DISTANCE;
+        np += t.len;
+        w0 |= TK_MATCH << 26;
+        w1 = t.len | (t.dist << 16);
+        any = true;
+      }
+      if (t.kind == 3) bad = IST_BAD_SYMBOL;
+      if (!bad && np > isize) bad = IST_OUTPUT_OVERRUN;
+      if (bad) {
+        err = bad;
+        state = ST_END;
+      } else {
+        produced = np;
+        if (t.kind == 2) state = bfinal ? ST_END : ST_HEADER;
+        if (any) push(w0, w1);
+      }
+    } else {
+      cold_trip(job, stage0);
     }
-    while (p_len) { complete_copy(); if (p_len) request_copy(); }
-  }
-
-  // Stored block body (rare): 4 bytes per step straight from the bit buffer.
-  BG_HD void stored_run(uint32_t budget) {
-    for (uint32_t t = 0; t < budget && state == ST_STORED; ++t) {
-      br.refill();
-      uint32_t n = cp_rem < 4 ? cp_rem : 4;
-      if (n > oend - opos) { err = IST_OUTPUT_OVERRUN; state = ST_NEXT; return; }
-      uint32_t v = (uint32_t)br.bb;
-      if (n < 4) v &= (1u << (8 * n)) - 1u;
-      br.consume(8 * n);
-      emit(v, n);
-      cp_rem -= n;
-      if (cp_rem == 0) state = bfinal ? ST_NEXT : ST_HEADER;
-    }
+    return true;
   }
 
   BG_HD void header() {
@@ -771,26 +681,13 @@ struct Lane {
     BitReader tmp = br;   // only this copy's address escapes: the lane itself stays in registers
     parse_header<STRIDE>(&tmp, sm, &hr);
     br = tmp;
-    state = hr.state;
     bfinal = hr.bfinal;
-    if (hr.err) err = hr.err;
     cp_rem = hr.stored_len;
+    state = hr.state == ST_NEXT ? (uint32_t)ST_END : hr.state;   // parse_header: ST_NEXT = this was the last block (or an error)
+    if (hr.err) { err = hr.err; state = ST_END; }
     if (hr.state == ST_DECODE) {
 #pragma unroll
       for (int k = 1; k <= 15; ++k) { llim[k] = bg_pin(hr.llim[k]); dlim[k] = bg_pin(hr.dlim[k]); }
-    }
-  }
-
-  // Finishes the current block (if any): flush, verify sizes, write status.
-  BG_HD void finish_block(const InflateJob& job) {
-    if (blk != 0xffffffffu) {
-      flush_partial();
-      if (!err) {
-        if (opos != oend) err = IST_SIZE_MISMATCH;
-        else if (br.bits_consumed() > br.in_bits) err = IST_INPUT_OVERRUN;
-      }
-      job.status[blk] = err;
-      br.drain();
     }
   }
 
@@ -799,31 +696,211 @@ struct Lane {
     blk = b;
     err = 0;
     bfinal = 0;
+    produced = 0;
+    isize = job.isize[b];
+    pay_skipped = 0;
+    br.begin(job.comp + job.in_off[b], job.in_len[b], stage0);
+    state = ST_BEGIN;
+  }
+};
+
+// ---- the copier lane ---------------------------------------------------------------------------------
+struct Copier {
+  TokRing ring;
+  uint32_t tail;         // tokens taken so far
+  uint32_t done;         // TK_DONE seen
+  uint32_t blk;
+  // ---- output: byte offsets relative to ob (the 4-byte aligned address at or below the block start) ----
+  uint8_t* ob;
+  uint32_t head;         // first own byte (0..3)
+  uint32_t opos, oend;   // next byte to write / one past the last own byte
+  uint32_t sreg;         // bytes of the word at opos & ~3 not yet stored
+  uint32_t full_lo, full_span;  // aligned words a with (a - full_lo) < full_span lie wholly inside the block
+  uint32_t fast_span;           // ... and with (a - full_lo) < fast_span so do the three words after a
+  // ---- copy in flight: its source words were requested one trip ago ----
+  uint32_t p_len, p_dist, p_n, p_ssh;   // bytes left, distance (0: from the input, stored block), bytes of the next step, bit shift of its source words
+  const uint8_t* p_raw;                  // p_dist == 0: where the next input byte is
+  uint32_t pw0, pw1, pw2, pw3, pw4, pw5, pw6, pw7, pw8;
+
+  BG_HD const uint32_t* gptr(uint32_t a /*aligned*/) const { return (const uint32_t*)(ob + a); }
+  // ---------------- output ----------------
+  // Slow, always-correct store of one aligned word: touches only this block's own bytes.
+  BG_HD void store_word(uint32_t a /*aligned*/, uint32_t w) {
+    if (a - full_lo < full_span) {
+      *(uint32_t*)(ob + a) = w;
+    } else {  // head / tail word shared with a neighbouring block
+      for (uint32_t i = 0; i < 4; ++i)
+        if (a + i >= head && a + i < oend) ob[a + i] = (uint8_t)(w >> (8 * i));
+    }
+  }
+  // v holds n (1..4) valid low bytes, the rest zero.
+  BG_HD void emit(uint32_t v, uint32_t n) {
+    uint32_t k = opos & 3u;
+    uint32_t sh = k * 8;
+    sreg |= v << sh;
+    if (k + n >= 4) {
+      store_word(opos & ~3u, sreg);
+      sreg = sh ? (v >> (32 - sh)) : 0u;
+    }
+    opos += n;
+  }
+  // n (1..16) bytes held in v0..v3 (bytes past n may be garbage); opos + n <= oend (the decoder checked it).
+  BG_HD void emit_n16(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t n) {
+    uint32_t a = opos & ~3u;
+    uint32_t k = opos & 3u, sh = k * 8;
+    uint32_t o0 = sreg | (v0 << sh);
+    uint32_t o1 = bg_funnel_l(v0, v1, sh);
+    uint32_t o2 = bg_funnel_l(v1, v2, sh);
+    uint32_t o3 = bg_funnel_l(v2, v3, sh);
+    uint32_t o4 = bg_funnel_l(v3, 0u, sh);
+    uint32_t tot = k + n;          // 1..19
+    uint32_t nfull = tot >> 2;     // whole words completed: 0..4
+    if (a - full_lo < fast_span) {
+      // all four words lie wholly inside the block: straight predicated stores
+      uint32_t* w = (uint32_t*)(ob + a);
+      if (nfull > 0) w[0] = o0;
+      if (nfull > 1) w[1] = o1;
+      if (nfull > 2) w[2] = o2;
+      if (nfull > 3) w[3] = o3;
+    } else {
+      if (nfull > 0) store_word(a, o0);
+      if (nfull > 1) store_word(a + 4, o1);
+      if (nfull > 2) store_word(a + 8, o2);
+      if (nfull > 3) store_word(a + 12, o3);
+    }
+    uint32_t r = o0;
+    if (nfull == 1) r = o1;
+    if (nfull == 2) r = o2;
+    if (nfull == 3) r = o3;
+    if (nfull == 4) r = o4;
+    uint32_t rb = tot & 3u;
+    sreg = r & ((1u << (8 * rb)) - 1u);
+    opos += n;
+  }
+  // Make every byte below opos visible in memory (bytes of the partially filled word).
+  BG_HD void flush_partial() {
+    uint32_t k = opos & 3u;
+    uint32_t a = opos - k;
+    for (uint32_t i = 0; i < k; ++i)
+      if (a + i >= head) ob[a + i] = (uint8_t)(sreg >> (8 * i));
+  }
+
+  // ---------------- copies ----------------
+  // Every copy is only REGISTERED (p_len, p_dist; request_copy asks for its source words) and performed by
+  // complete_copy one trip later, in straight-line code, at most 16 (dist < 35) or 32 bytes per trip; what is left
+  // is requested again and the lane takes no new token until the copy is done.  So no lane ever loops over a window
+  // load inside a trip while the other 31 wait for its latency.
+  //   dist >= 8: the first 20 (36 for dist >= 35 and more than 16 bytes) source bytes are requested as aligned
+  //     words, no use; the L2/DRAM latency of the window read overlaps the rest of the trip and the ring hand-over.
+  //     A step uses at most dist - 3 of them: those lie below opos - 3, i.e. are in memory (only the <= 3 bytes of
+  //     sreg are not), and the following steps see what this one stored (byte-serial semantics for overlapping copies).
+  //   dist < 8 (the dist=1 runs of BAM quality strings, ~2 % of matches): the two words before the partially filled
+  //     one are requested; complete_copy builds 16 bytes of the periodic pattern from them and the staging register,
+  //     and the rest continues as an ordinary copy at a multiple of the period (17..21, so 14..16 bytes per step),
+  //     which by then lies wholly inside the periodic region.
+  //   dist == 0: a stored block; the source is the compressed input at p_raw.
+  // One request site, one instruction sequence for every kind of copy: a second set of loads into the same
+  // registers elsewhere in the loop would have to wait for these to land (register scoreboard).
+  BG_HD void request_copy() {
+    const uint32_t len = p_len, dist = p_dist;
+    const bool raw = dist == 0, near = dist < 8 && !raw;
+    const uint32_t src = opos - dist;
+    const uint32_t lim = (raw || near) ? 16u : (dist - 3u < 16u ? dist - 3u : 16u);
+    p_n = len < lim ? len : lim;
+    const uint32_t sa = raw ? (uint32_t)(uintptr_t)p_raw : (near ? opos : src);
+    p_ssh = (sa & 3u) * 8;
+    // far: the aligned words holding src..; near: the two words before the partially filled one (the buffer is
+    // readable 16 bytes before out[0]); raw: the aligned words holding p_raw..
+    const uint32_t* w = raw ? (const uint32_t*)((uintptr_t)p_raw & ~(uintptr_t)3) : gptr(sa & ~3u) - (near ? 2 : 0);
+    pw0 = w[0]; pw1 = w[1]; pw2 = w[2]; pw3 = w[3]; pw4 = w[4];
+    if ((dist >= 35 || raw) && len > 16) { pw5 = w[5]; pw6 = w[6]; pw7 = w[7]; pw8 = w[8]; }
+  }
+  BG_HD void complete_copy() {
+    if (p_len) {
+      uint32_t dist = p_dist, ssh = p_ssh;
+      if (dist - 1u < 7u) {
+        // last 8 bytes before opos = two stored words + the staging register -> 16 bytes of the periodic pattern
+        const uint64_t X = (uint64_t)bg_funnel_r(pw0, pw1, ssh) | ((uint64_t)bg_funnel_r(pw1, sreg, ssh) << 32);
+        uint64_t W = X >> (8 * (8 - dist));  // low `dist` bytes = the period
+        for (uint32_t k = dist; k < 8; k <<= 1) W |= W << (8 * k);
+        const uint32_t deff = dist < 3 ? 4u : (dist == 3 ? 6u : dist);   // a multiple of the period in 4..7
+        const uint32_t wsh = 8 * (8 - deff);
+        pw0 = (uint32_t)W; W = (W >> 32) | ((W >> wsh) << 32);
+        pw1 = (uint32_t)W; W = (W >> 32) | ((W >> wsh) << 32);
+        pw2 = (uint32_t)W; W = (W >> 32) | ((W >> wsh) << 32);
+        pw3 = (uint32_t)W;
+        pw4 = 0;
+        ssh = 0;
+        dist = (uint32_t)(0x5654A4A51ull >> (5 * (dist - 1))) & 31u;   // dist * floor((16 + dist) / dist): 17,18,18,20,20,18,21
+        p_dist = dist;
+      }
+      const bool two = dist >= 35 || dist == 0;
+      uint32_t rem = p_len, n = p_n;
+      emit_n16(bg_funnel_r(pw0, pw1, ssh), bg_funnel_r(pw1, pw2, ssh), bg_funnel_r(pw2, pw3, ssh),
+               bg_funnel_r(pw3, pw4, ssh), n);
+      rem -= n;
+      if (rem && two) {
+        n = rem < 16 ? rem : 16;
+        emit_n16(bg_funnel_r(pw4, pw5, ssh), bg_funnel_r(pw5, pw6, ssh), bg_funnel_r(pw6, pw7, ssh),
+                 bg_funnel_r(pw7, pw8, ssh), n);
+        rem -= n;
+      }
+      if (dist == 0) p_raw += p_len - rem;
+      p_len = rem;   // != 0: the copy goes on next trip at the same distance
+    }
+  }
+
+  BG_HD void begin_block(const InflateJob& job, uint32_t b) {
+    blk = b;
     uint64_t o = job.out_off[b];
     ob = job.out + (o & ~(uint64_t)3);
     head = (uint32_t)(o & 3);
     opos = head;
     oend = head + job.isize[b];
     sreg = 0;
-    p_len = 0;
     full_lo = head ? 4u : 0u;
     uint32_t full_hi = oend & ~3u;
     full_span = full_hi > full_lo ? full_hi - full_lo : 0u;
     fast_span = full_span >= 16u ? full_span - 12u : 0u;
-#if defined(BG_BOUNDS)
-    dbg_lo = job.out - 64; dbg_hi = job.out + job.out_len + 64;
-    BG_CHECK(job.in_off[b] >= 16 && job.in_off[b] + job.in_len[b] <= job.comp_len, "in range", (long long)job.in_off[b]);
-    BG_CHECK(o + job.isize[b] <= job.out_len, "out range", (long long)o);
-#endif
-    br.begin(job.comp + job.in_off[b], job.in_len[b], stage0);
-    state = ST_HEADER;
   }
 
-  // One scheduling round of the lane (everything except ST_NEXT, which needs the work counter).
-  BG_HD void round(uint32_t budget) {
-    if (state == ST_HEADER) header();
-    if (state == ST_STORED) stored_run(budget);
-    decode_run(budget);
+  // Tokens that open / close a block or carry a stored block.
+  BG_HD void cold_token(const InflateJob& job, uint32_t kind, uint32_t w1) {
+    if (kind == TK_BEGIN) {
+      begin_block(job, w1);
+    } else if (kind == TK_END) {
+      flush_partial();
+      job.status[blk] = w1;
+    } else if (kind == TK_RAW) {
+      p_len = w1 & 0xffffu;
+      p_dist = 0;
+      p_raw = job.comp + job.in_off[blk] + (w1 >> 16);
+    } else if (kind == TK_DONE) {
+      done = 1;
+    }
+  }
+
+  // One trip: finish the pending copy step, take at most one token, request the source words of what is pending.
+  // Returns false if there was nothing to do.
+  BG_HD bool trip(const InflateJob& job) {
+    bool worked = p_len != 0;
+    complete_copy();
+    if (p_len == 0 && !done && ring.head() != tail) {
+      uint32_t w0, w1;
+      ring.pop(tail, w0, w1);
+      tail += 1;
+      worked = true;
+      const uint32_t nlit = (w0 >> 24) & 3u, kind = (w0 >> 26) & 7u;
+      if (nlit) emit(w0 & 0xffffffu, nlit);
+      if (kind == TK_MATCH) {
+        p_len = w1 & 0x1ffu;
+        p_dist = w1 >> 16;
+      } else if (kind != TK_LITS) {
+        cold_token(job, kind, w1);
+      }
+    }
+    if (p_len) request_copy();
+    return worked;
   }
 };
 
