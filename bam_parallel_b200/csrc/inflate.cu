@@ -28,6 +28,11 @@ constexpr int K1_STAGE_BYTES = K1_PAIR_WARPS * STAGE_WARP_BYTES;                
 constexpr int K1_RING_BYTES = K1_PAIR_WARPS * RING_WARP_BYTES;                     // 17408: token rings
 constexpr int K1_SMEM_BYTES = K1_TABLE_BYTES + K1_STAGE_BYTES + K1_RING_BYTES;
 
+// The kernel is compiled for 80 registers per thread (3 CTAs x 256 threads per SM); the copier warpgroup gives 32 of
+// them back and the decoder warpgroup, which keeps the 30 code-length limits of both Huffman codes in registers, takes them.
+constexpr int K1_DECODER_REGS = 112, K1_COPIER_REGS = 48;
+
+constexpr int K1_COPIER_MIN_READY = 20;        // lanes with work a copier warp wants before it spends a trip
 constexpr uint32_t K1_TRIPS_PER_ROUND = 128;  // trips a decoder lane makes between two looks at the warp-wide state
 
 __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM)
@@ -42,6 +47,7 @@ k1_inflate_pairs(InflateJob job, uint32_t* __restrict__ work_counter) {
   if (is_decoder) ring.reset();
   __syncthreads();
   if (is_decoder) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(K1_DECODER_REGS));
     Decoder<32> D;
     D.sm = smem + pw * (32 * LANE_WORDS) + lane;
     D.ring = ring;
@@ -69,18 +75,36 @@ k1_inflate_pairs(InflateJob job, uint32_t* __restrict__ work_counter) {
       }
     }
   } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(K1_COPIER_REGS));
     Copier C;
     C.ring = ring;
     C.tail = 0;
     C.done = 0;
     C.p_len = 0;
     C.blk = 0xffffffffu;
+    // A copier trip costs the same issue slots whether 3 or 30 of its lanes have something to do, and copiers are
+    // faster than decoders, so the warp waits until most lanes have a token (or a copy in flight), a ring is half
+    // full (never hold a decoder up), or it has waited a few times (the tail of the job, where few lanes are live).
+    uint32_t waited = 0;
     for (;;) {
-      const bool worked = C.trip(job);
-      if (!__any_sync(0xffffffffu, worked)) {
+      uint32_t w0, w1, u0, u1;
+      const bool have = !C.done && C.ring.peek(C.tail, w0, w1);
+      const uint32_t ready = __ballot_sync(0xffffffffu, C.p_len != 0 || have);
+      if (ready == 0) {
         if (__all_sync(0xffffffffu, C.done != 0)) break;
         __nanosleep(100);
+        continue;
       }
+      if (__popc(ready) < K1_COPIER_MIN_READY && ++waited < 4) {
+        // is any ring at least half full?
+        const bool urgent = have && C.ring.peek(C.tail + RING_TOKENS / 2 - 1, u0, u1);
+        if (!__any_sync(0xffffffffu, urgent)) {
+          __nanosleep(40);
+          continue;
+        }
+      }
+      waited = 0;
+      C.trip(job, have, w0, w1);
     }
   }
 }

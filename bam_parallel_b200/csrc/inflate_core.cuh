@@ -306,6 +306,7 @@ BG_HD_COLD void parse_header(BitReader* brp, uint32_t* sm, HeaderResult* hr) {
   hr->err = 0;
   hr->stored_len = 0;
   hr->bfinal = 0;
+  for (int k = 0; k < 16; ++k) hr->llim[k] = hr->dlim[k] = 0;
 #define BG_FAIL(code) do { hr->err = (code); hr->state = ST_NEXT; *brp = br; return; } while (0)
   br.refill();
   if (br.bits_consumed() + 3 > br.in_bits) BG_FAIL(IST_INPUT_OVERRUN);
@@ -442,56 +443,68 @@ BG_HD_COLD void parse_header(BitReader* brp, uint32_t* sm, HeaderResult* hr) {
 }
 
 // ---- token ring between a decoder lane and its copier lane ------------------------------------------
-// A token is two 32-bit words:
-//   w0: bits 0-23 up to three literal bytes, bits 24-25 their count, bits 26-28 the kind
+// A token is two 32-bit words, written and read with ONE 64-bit shared-memory access:
+//   w0: bits 0-23 up to three literal bytes, bits 24-25 their count, bits 26-28 the kind, bit 31 the phase
 //   w1: TK_MATCH len | dist << 16     TK_BEGIN block index     TK_END final IST_* status of the block
 //       TK_RAW   len | offset in the payload << 16 (stored block: bytes copied straight from the input)
-// Single producer, single consumer, free-running 32-bit counters; nobody ever blocks on it.
+// Single producer, single consumer, nobody ever blocks on it.  Token i lives in slot i mod RING_TOKENS and carries
+// phase (i / RING_TOKENS) & 1, so the consumer sees a token appear by polling the slot itself: there is no head
+// counter whose store would have to be ordered behind the slot's (st.release = MEMBAR.ALL.CTA, which was measured
+// to wait for the copier's global stores every trip).  The consumer publishes its count with a plain store after
+// the read; shared-memory accesses of one warp are performed in issue order.
 enum : uint32_t { TK_LITS = 0, TK_MATCH = 1, TK_BEGIN = 2, TK_END = 3, TK_RAW = 4, TK_DONE = 5 };
 constexpr uint32_t RING_TOKENS = 16;                      // per stream (power of two)
+constexpr uint32_t RING_SHIFT = 4;
 constexpr int RING_ROW_BYTES = 32 * 8;                    // one slot of every lane of a warp
-constexpr int RING_WARP_BYTES = RING_TOKENS * RING_ROW_BYTES + 2 * 32 * 4;   // slots + head row + tail row
+constexpr int RING_WARP_BYTES = RING_TOKENS * RING_ROW_BYTES + 32 * 4;   // slots + the row of tail counters
 
 struct TokRing {
+  BG_HD static uint32_t phase(uint32_t idx) { return ((idx >> RING_SHIFT) & 1u) << 31; }
 #if defined(__CUDACC__)
   uint32_t slots;   // shared-memory byte address of this lane's slot 0 (slot stride RING_ROW_BYTES)
-  uint32_t ctr;     // ... of this lane's head counter; the tail counter is one row (128 B) behind it
+  uint32_t ctr;     // ... of this lane's tail counter
   __device__ __forceinline__ void init(uint32_t warp_base, uint32_t lane) {
     slots = warp_base + lane * 8;
     ctr = warp_base + RING_TOKENS * RING_ROW_BYTES + lane * 4;
   }
 #if defined(__CUDA_ARCH__)
-  BG_HD void reset() { asm volatile("st.shared.u32 [%0], %1;\n\tst.shared.u32 [%0+128], %1;" ::"r"(ctr), "r"(0u) : "memory"); }
-  BG_HD uint32_t head() const { uint32_t v; asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(ctr) : "memory"); return v; }
-  BG_HD uint32_t tail() const { uint32_t v; asm volatile("ld.acquire.cta.shared.u32 %0, [%1+128];" : "=r"(v) : "r"(ctr) : "memory"); return v; }
-  BG_HD void push(uint32_t idx, uint32_t w0, uint32_t w1) {   // idx = current head
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(slots + (idx & (RING_TOKENS - 1)) * RING_ROW_BYTES), "r"(w0), "r"(w1) : "memory");
-    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(ctr), "r"(idx + 1) : "memory");
+  BG_HD void reset() {   // every slot holds the phase the first lap does NOT use
+    for (uint32_t i = 0; i < RING_TOKENS; ++i)
+      asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(slots + i * RING_ROW_BYTES), "r"(0x80000000u), "r"(0u));
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ctr), "r"(0u));
   }
-  BG_HD void pop(uint32_t idx, uint32_t& w0, uint32_t& w1) {  // idx = current tail; publishes idx + 1
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(slots + (idx & (RING_TOKENS - 1)) * RING_ROW_BYTES) : "memory");
-    asm volatile("st.release.cta.shared.u32 [%0+128], %1;" ::"r"(ctr), "r"(idx + 1) : "memory");
+  BG_HD uint32_t tail() const { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(ctr)); return v; }
+  BG_HD void push(uint32_t idx, uint32_t w0, uint32_t w1) {   // idx = tokens pushed so far
+    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(slots + (idx & (RING_TOKENS - 1)) * RING_ROW_BYTES), "r"(w0 | phase(idx)), "r"(w1));
   }
+  // token number idx if it has been pushed
+  BG_HD bool peek(uint32_t idx, uint32_t& w0, uint32_t& w1) const {
+    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(slots + (idx & (RING_TOKENS - 1)) * RING_ROW_BYTES));
+    return ((w0 ^ phase(idx)) >> 31) == 0;
+  }
+  BG_HD void set_tail(uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ctr), "r"(v)); }
 #else   // host pass of nvcc: never called
   BG_HD void reset() {}
-  BG_HD uint32_t head() const { return 0; }
   BG_HD uint32_t tail() const { return 0; }
   BG_HD void push(uint32_t, uint32_t, uint32_t) {}
-  BG_HD void pop(uint32_t, uint32_t&, uint32_t&) {}
+  BG_HD bool peek(uint32_t, uint32_t&, uint32_t&) const { return false; }
+  BG_HD void set_tail(uint32_t) {}
 #endif
 #else
-  uint32_t* mem;    // RING_TOKENS * 2 words of slots, then head, then tail
-  BG_HD void reset() { mem[2 * RING_TOKENS] = 0; mem[2 * RING_TOKENS + 1] = 0; }
-  BG_HD uint32_t head() const { return mem[2 * RING_TOKENS]; }
-  BG_HD uint32_t tail() const { return mem[2 * RING_TOKENS + 1]; }
+  uint32_t* mem;    // RING_TOKENS * 2 words of slots, then the tail counter
+  BG_HD void reset() {
+    for (uint32_t i = 0; i < RING_TOKENS; ++i) { mem[2 * i] = 0x80000000u; mem[2 * i + 1] = 0; }
+    mem[2 * RING_TOKENS] = 0;
+  }
+  BG_HD uint32_t tail() const { return mem[2 * RING_TOKENS]; }
   BG_HD void push(uint32_t idx, uint32_t w0, uint32_t w1) {
-    mem[2 * (idx & (RING_TOKENS - 1))] = w0; mem[2 * (idx & (RING_TOKENS - 1)) + 1] = w1;
-    mem[2 * RING_TOKENS] = idx + 1;
+    mem[2 * (idx & (RING_TOKENS - 1))] = w0 | phase(idx); mem[2 * (idx & (RING_TOKENS - 1)) + 1] = w1;
   }
-  BG_HD void pop(uint32_t idx, uint32_t& w0, uint32_t& w1) {
+  BG_HD bool peek(uint32_t idx, uint32_t& w0, uint32_t& w1) const {
     w0 = mem[2 * (idx & (RING_TOKENS - 1))]; w1 = mem[2 * (idx & (RING_TOKENS - 1)) + 1];
-    mem[2 * RING_TOKENS + 1] = idx + 1;
+    return ((w0 ^ phase(idx)) >> 31) == 0;
   }
+  BG_HD void set_tail(uint32_t v) { mem[2 * RING_TOKENS] = v; }
 #endif
 };
 
@@ -504,7 +517,7 @@ struct Decoder {
   uint32_t head;         // tokens pushed so far
   uint32_t state, bfinal, err, blk, cp_rem;
   uint32_t produced, isize;     // bytes the tokens pushed so far stand for / ISIZE of the block
-  uint32_t llim[16], dlim[16];  // [1..15] used; only ever indexed by constants (registers)
+  uint32_t lpk[8], dpk[8];   // code-length limits of the literal/length and distance codes, packed in pairs (code_len_packed); registers
 
   // ---------------- shared-memory accessors ----------------
   BG_HD uint32_t smr(int w) const { return sm[w * STRIDE]; }
@@ -531,6 +544,30 @@ struct Decoder {
     return 1u + (p3 ? 8u : 0u) + (p2 ? 4u : 0u) + (p1 ? 2u : 0u) + (p0 ? 1u : 0u);
   }
 
+  // The same search over limits packed two to a register (lim[k] | lim[k + 8] << 16 in pk[k], k = 1..7; pk[0] =
+  // lim[8]): the first comparison picks the halves with one byte permute each.  Used for the distance code, which is
+  // decoded once per match: 8 registers instead of 15 for one more instruction.
+  BG_HD static uint32_t code_len_packed(const uint32_t* pk, uint32_t v) {
+    const bool p3 = v >= pk[0];
+#if defined(__CUDA_ARCH__)
+    const uint32_t sel = p3 ? 0x4432u : 0x4410u;
+#define BG_HALF(x) __byte_perm((x), 0u, sel)
+#else
+#define BG_HALF(x) (p3 ? (x) >> 16 : (x) & 0xffffu)
+#endif
+    const uint32_t a = BG_HALF(pk[4]);
+    const uint32_t b2 = BG_HALF(pk[2]), b6 = BG_HALF(pk[6]);
+    const uint32_t c1 = BG_HALF(pk[1]), c3 = BG_HALF(pk[3]), c5 = BG_HALF(pk[5]), c7 = BG_HALF(pk[7]);
+#undef BG_HALF
+    const bool p2 = v >= a;
+    const uint32_t b = p2 ? b6 : b2;
+    const uint32_t d1 = p2 ? c5 : c1, d3 = p2 ? c7 : c3;
+    const bool p1 = v >= b;
+    const uint32_t d = p1 ? d3 : d1;
+    const bool p0 = v >= d;
+    return 1u + (p3 ? 8u : 0u) + (p2 ? 4u : 0u) + (p1 ? 2u : 0u) + (p0 ? 1u : 0u);
+  }
+
   // A "token" is up to LITS_PER_TOKEN - 1 leading literals plus one closing symbol (literal, match, end of block or
   // an invalid code).  Decoding several literals per trip amortises the sparse match code over more output: most
   // lanes start with a literal, and a lane that sees a length stops there.
@@ -544,7 +581,7 @@ struct Decoder {
   // 1 length code (e = code + 1), 2 end of block, 3 invalid.
   BG_HD uint32_t decode_litlen(uint32_t& e) {
     uint32_t c = bg_brev((uint32_t)br.bb) >> 17;
-    uint32_t L = code_len(llim, c);
+    uint32_t L = code_len_packed(lpk, c);
     const bool bad = L > 15u;          // c >= llim[15]: no such code
     L &= 15u;                          // (0 then: nothing consumed, the table reads stay in range)
     uint32_t m = smr(SM_META + L);
@@ -594,7 +631,7 @@ struct Decoder {
       t.len = base + ((uint32_t)br.bb & ((1u << eb) - 1u));
       br.consume(eb);
       uint32_t c = bg_brev((uint32_t)br.bb) >> 17;   // >= 28 bits left: the distance code and its <= 13 extra bits fit
-      uint32_t L = code_len(dlim, c);
+      uint32_t L = code_len_packed(dpk, c);
       if (L > 15u) t.kind = 3;
       L &= 15u;
       uint32_t m = smr(SM_META + L);
@@ -685,9 +722,14 @@ struct Decoder {
     cp_rem = hr.stored_len;
     state = hr.state == ST_NEXT ? (uint32_t)ST_END : hr.state;   // parse_header: ST_NEXT = this was the last block (or an error)
     if (hr.err) { err = hr.err; state = ST_END; }
-    if (hr.state == ST_DECODE) {
+    {   // unconditional: the limits must not be live across the call above (ptxas then keeps them in local memory)
+      lpk[0] = bg_pin(hr.llim[8]);
+      dpk[0] = bg_pin(hr.dlim[8]);
 #pragma unroll
-      for (int k = 1; k <= 15; ++k) { llim[k] = bg_pin(hr.llim[k]); dlim[k] = bg_pin(hr.dlim[k]); }
+      for (int k = 1; k <= 7; ++k) {
+        lpk[k] = bg_pin(hr.llim[k] | (hr.llim[k + 8] << 16));
+        dpk[k] = bg_pin(hr.dlim[k] | (hr.dlim[k + 8] << 16));
+      }
     }
   }
 
@@ -880,16 +922,13 @@ struct Copier {
     }
   }
 
-  // One trip: finish the pending copy step, take at most one token, request the source words of what is pending.
-  // Returns false if there was nothing to do.
-  BG_HD bool trip(const InflateJob& job) {
-    bool worked = p_len != 0;
+  // One trip: finish the pending copy step; take the token (w0, w1) the caller peeked (`have`; never after TK_DONE)
+  // unless the copy is still not done; request the source words of what is pending.
+  BG_HD void trip(const InflateJob& job, bool have, uint32_t w0, uint32_t w1) {
     complete_copy();
-    if (p_len == 0 && !done && ring.head() != tail) {
-      uint32_t w0, w1;
-      ring.pop(tail, w0, w1);
+    if (have && p_len == 0) {
       tail += 1;
-      worked = true;
+      ring.set_tail(tail);
       const uint32_t nlit = (w0 >> 24) & 3u, kind = (w0 >> 26) & 7u;
       if (nlit) emit(w0 & 0xffffffu, nlit);
       if (kind == TK_MATCH) {
@@ -900,7 +939,6 @@ struct Copier {
       }
     }
     if (p_len) request_copy();
-    return worked;
   }
 };
 

@@ -16,7 +16,7 @@ extern "C" int host_emul_inflate(const uint8_t* comp, const uint64_t* in_off, co
   InflateJob job{comp, in_off, in_len, out_off, isize, out, status, n_blocks};
   if (lanes < 1) lanes = 1;
   std::vector<std::vector<uint32_t>> sm(lanes, std::vector<uint32_t>(LANE_WORDS, 0xDEADBEEFu));
-  std::vector<std::vector<uint32_t>> rings(lanes, std::vector<uint32_t>(2 * RING_TOKENS + 2, 0));
+  std::vector<std::vector<uint32_t>> rings(lanes, std::vector<uint32_t>(2 * RING_TOKENS + 1, 0));
   std::vector<Decoder<1>> D(lanes);
   std::vector<Copier> C(lanes);
   uint32_t counter = 0;
@@ -48,7 +48,11 @@ extern "C" int host_emul_inflate(const uint8_t* comp, const uint64_t* in_off, co
       const int dt = 1 + (int)((round * 7 + i) % 23);
       for (int k = 0; k < dt; ++k) D[i].trip(job, 0);
       const int ct = 1 + (int)((round * 5 + i * 3) % 19);
-      for (int k = 0; k < ct; ++k) C[i].trip(job);
+      for (int k = 0; k < ct; ++k) {
+        uint32_t w0 = 0, w1 = 0;
+        const bool have = !C[i].done && C[i].ring.peek(C[i].tail, w0, w1);   // taken only if no copy is left pending
+        C[i].trip(job, have, w0, w1);
+      }
       if (!C[i].done) all_done = false;
     }
     if (all_done) break;
