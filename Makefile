@@ -12,7 +12,7 @@ CC        ?= gcc
 LIBDIR    := bam_parallel_b200/lib
 CSRC      := bam_parallel_b200/csrc
 NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
-             -Xcompiler -fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas -Wno-deprecated-gpu-targets -Iinclude -I$(CSRC)
+             -Xcompiler -fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas -Wno-deprecated-gpu-targets -Iinclude -I$(CSRC) $(EXTRA)
 CXXFLAGS  := -O2 -std=c++17 -fPIC -Wall -pthread
 
 CU_SRCS   := $(wildcard $(CSRC)/*.cu)

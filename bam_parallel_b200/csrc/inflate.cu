@@ -14,10 +14,15 @@
 // inflated stream is contiguous and records may straddle blocks.
 #include "inflate_core.cuh"
 #include "kernels.h"
+#include <cstdio>
+#include <cstdlib>
 
 namespace bamgpu {
 
-constexpr int K1_PAIR_WARPS = 4;                              // decoder warps per CTA (= copier warps per CTA)
+#ifndef K1_PAIR_WARPS_N
+#define K1_PAIR_WARPS_N 4
+#endif
+constexpr int K1_PAIR_WARPS = K1_PAIR_WARPS_N;                // decoder warps per CTA (= copier warps per CTA); a multiple of 4 (setmaxnreg works on warpgroups)
 constexpr int K1_THREADS = 2 * K1_PAIR_WARPS * 32;
 #ifndef K1_CTAS
 #define K1_CTAS 3
@@ -29,17 +34,39 @@ constexpr int K1_RING_BYTES = K1_PAIR_WARPS * RING_WARP_BYTES;                  
 constexpr int K1_SMEM_BYTES = K1_TABLE_BYTES + K1_STAGE_BYTES + K1_RING_BYTES;
 
 // The kernel is compiled for 80 registers per thread (3 CTAs x 256 threads per SM); the copier warpgroup gives 32 of
-// them back and the decoder warpgroup, which keeps the 30 code-length limits of both Huffman codes in registers, takes them.
-constexpr int K1_DECODER_REGS = 112, K1_COPIER_REGS = 48;
+// them back (setmaxnreg.dec) and the decoder warpgroup, whose Huffman state lives in registers, may take them.
+constexpr int K1_DECODER_REGS = K1_CTAS * K1_THREADS > 768 ? 80 : 112, K1_COPIER_REGS = 48;
 
-constexpr int K1_COPIER_MIN_READY = 20;        // lanes with work a copier warp wants before it spends a trip
+// Copier scheduling.  A copier trip costs the same issue slots whether 3 or 30 of its lanes have something to do, so
+// the warp sleeps until K1_MIN_READY lanes have a token or a copy in flight, some ring holds K1_URGENT tokens (never
+// hold a decoder up), or it has slept K1_WAIT_LIMIT times (the tail of the job, where few lanes are live).  Measured
+// on the 50 M-record file every setting between "no batching" and (28, 14, 256) lands within 2 % (71.8-73.4 ms): the
+// decoders' dependency chains, not the copiers' issue slots, bound K1.  tools/debug/k1_sweep.sh reruns it.
+#ifndef K1_URGENT
+#define K1_URGENT (RING_TOKENS >= 8 ? RING_TOKENS / 2 : RING_TOKENS)
+#endif
+#ifndef K1_MIN_READY
+#define K1_MIN_READY 20
+#endif
+#ifndef K1_IDLE_NS
+#define K1_IDLE_NS 100     // sleep when no lane has anything to do
+#endif
+#ifndef K1_SLEEP_NS
+#define K1_SLEEP_NS 100    // sleep while waiting for more lanes
+#endif
+#ifndef K1_WAIT_LIMIT
+#define K1_WAIT_LIMIT 16
+#endif
+constexpr uint32_t K1_URGENT_FILL = K1_URGENT;
+constexpr int K1_COPIER_MIN_READY = K1_MIN_READY;
+constexpr uint32_t K1_COPIER_WAIT_LIMIT = K1_WAIT_LIMIT;
 constexpr uint32_t K1_TRIPS_PER_ROUND = 128;  // trips a decoder lane makes between two looks at the warp-wide state
 
 __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM)
 k1_inflate_pairs(InflateJob job, uint32_t* __restrict__ work_counter) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pw = warp & (K1_PAIR_WARPS - 1);
+  const int pw = warp % K1_PAIR_WARPS;
   const bool is_decoder = warp < K1_PAIR_WARPS;
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
   TokRing ring;
@@ -50,6 +77,7 @@ k1_inflate_pairs(InflateJob job, uint32_t* __restrict__ work_counter) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(K1_DECODER_REGS));
     Decoder<32> D;
     D.sm = smem + pw * (32 * LANE_WORDS) + lane;
+    D.sma = smem_base + (pw * (32 * LANE_WORDS) + lane) * 4;
     D.ring = ring;
     D.head = 0;
     D.state = ST_NEXT;
@@ -82,9 +110,6 @@ k1_inflate_pairs(InflateJob job, uint32_t* __restrict__ work_counter) {
     C.done = 0;
     C.p_len = 0;
     C.blk = 0xffffffffu;
-    // A copier trip costs the same issue slots whether 3 or 30 of its lanes have something to do, and copiers are
-    // faster than decoders, so the warp waits until most lanes have a token (or a copy in flight), a ring is half
-    // full (never hold a decoder up), or it has waited a few times (the tail of the job, where few lanes are live).
     uint32_t waited = 0;
     for (;;) {
       uint32_t w0, w1, u0, u1;
@@ -92,14 +117,14 @@ k1_inflate_pairs(InflateJob job, uint32_t* __restrict__ work_counter) {
       const uint32_t ready = __ballot_sync(0xffffffffu, C.p_len != 0 || have);
       if (ready == 0) {
         if (__all_sync(0xffffffffu, C.done != 0)) break;
-        __nanosleep(100);
+        __nanosleep(K1_IDLE_NS);
         continue;
       }
-      if (__popc(ready) < K1_COPIER_MIN_READY && ++waited < 4) {
+      if (__popc(ready) < K1_COPIER_MIN_READY && ++waited < K1_COPIER_WAIT_LIMIT) {
         // is any ring at least half full?
-        const bool urgent = have && C.ring.peek(C.tail + RING_TOKENS / 2 - 1, u0, u1);
+        const bool urgent = have && C.ring.peek(C.tail + K1_URGENT_FILL - 1, u0, u1);
         if (!__any_sync(0xffffffffu, urgent)) {
-          __nanosleep(40);
+          __nanosleep(K1_SLEEP_NS);
           continue;
         }
       }
@@ -121,6 +146,14 @@ void launch_inflate(const uint8_t* comp, const BlockTableDev& t, uint8_t* out, u
   uint32_t max_ctas = (uint32_t)num_sms * K1_CTAS_PER_SM;
   uint32_t need = (t.n_blocks + lanes_per_cta - 1) / lanes_per_cta;
   uint32_t grid = need < max_ctas ? need : max_ctas;
+  static bool once = false;
+  if (!once && getenv("BAMGPU_DEBUG")) {
+    once = true;
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k1_inflate_pairs, K1_THREADS, K1_SMEM_BYTES);
+    fprintf(stderr, "[bamgpu] K1: %d threads/CTA, %d B smem/CTA, %d CTAs/SM resident (wanted %d), ring %u tokens\n", K1_THREADS,
+            K1_SMEM_BYTES, nb, K1_CTAS_PER_SM, RING_TOKENS);
+  }
   k1_inflate_pairs<<<grid, K1_THREADS, K1_SMEM_BYTES, s>>>(job, work_counter);
 }
 

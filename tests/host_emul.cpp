@@ -22,6 +22,7 @@ extern "C" int host_emul_inflate(const uint8_t* comp, const uint64_t* in_off, co
   uint32_t counter = 0;
   for (int i = 0; i < lanes; ++i) {
     D[i].sm = sm[i].data();
+    D[i].sma = 0;
     D[i].ring.mem = rings[i].data();
     D[i].ring.reset();
     D[i].head = 0;
