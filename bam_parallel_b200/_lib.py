@@ -12,8 +12,10 @@ OK, EOF = 0, 1
 ERR_NAMES = {
     -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_NOMEM", -4: "ERR_IO", -10: "ERR_BLOCK_TOO_SMALL", -11: "ERR_TRUNCATED_BLOCK",
     -12: "ERR_INFLATE", -13: "ERR_ISIZE", -14: "ERR_CRC", -20: "ERR_BAD_MAGIC", -21: "ERR_SHORT_HEADER",
-    -22: "ERR_SHORT_RECORD", -23: "ERR_BUFFER_TOO_SMALL", -24: "ERR_STATE",
+    -22: "ERR_SHORT_RECORD", -23: "ERR_BUFFER_TOO_SMALL", -24: "ERR_STATE", -30: "ERR_SORT_HI_MIXED",
+    -31: "ERR_SORT_BAD_FLAGS", -32: "ERR_SORT_BAD_TAGS", -33: "ERR_TOO_LARGE",
 }
+SORT_NAME, SORT_NAME_AND_MATCH_MATES, SORT_COORDINATES_AND_STRAND = 0, 1, 2   # sorting/sort.rs:92-96 SortBy
 COPY_DATA, COPY_COLUMNS, WANT_HI, NO_CRC, NO_RECORDS, SPECULATIVE_START = 1, 2, 4, 8, 16, 32
 MAX_HALO = 1 << 20
 
@@ -56,13 +58,20 @@ class Opts(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("blocks", "bytes_in", "bytes_out", "records", "batches", "kernel_launches")] + \
-               [(n, C.c_double) for n in ("ms_h2d", "ms_inflate", "ms_crc", "ms_records", "ms_d2h", "ms_total")]
+               [(n, C.c_double) for n in ("ms_h2d", "ms_inflate", "ms_crc", "ms_records", "ms_d2h", "ms_total", "ms_sort",
+                                          "ms_gather")]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class Sorted(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("bodies_len", C.c_uint64), ("perm", C.c_void_p), ("body_off", C.c_void_p),
+                ("bodies", C.c_void_p), ("h_perm", C.c_void_p), ("h_bodies", C.c_void_p)]
+
+
 READ_FN = C.CFUNCTYPE(C.c_long, C.c_void_p, C.POINTER(C.c_uint8), C.c_size_t)
+WRITE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint8), C.c_size_t)
 REFSEQ_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p)
 
 # every symbol include/bamgpu.h declares
@@ -73,7 +82,7 @@ EXPORTS = [
     "bamgpu_engine_records", "bamgpu_engine_set_n_ref", "bamgpu_engine_stats", "bamgpu_engine_reset_stats", "bamgpu_reader_new",
     "bamgpu_reader_from_memory", "bamgpu_reader_free", "bamgpu_last_error", "bamgpu_read_header", "bamgpu_next_rec",
     "bamgpu_append_record", "bamgpu_read", "bamgpu_next_batch", "bamgpu_reader_stats",
-    "bamgpu_parse_reference_sequences", "bamgpu_status_str", "bamgpu_build_info",
+    "bamgpu_parse_reference_sequences", "bamgpu_status_str", "bamgpu_build_info", "bamgpu_engine_sort", "bamgpu_sort_bam",
 ]
 
 _lib = None
@@ -145,5 +154,9 @@ def load() -> C.CDLL:
     L.bamgpu_status_str.restype = C.c_char_p
     L.bamgpu_status_str.argtypes = [C.c_int]
     L.bamgpu_build_info.restype = C.c_char_p
+    L.bamgpu_engine_sort.restype = C.c_int
+    L.bamgpu_engine_sort.argtypes = [vp, C.c_int, C.c_uint32, vp, C.POINTER(Sorted)]
+    L.bamgpu_sort_bam.restype = C.c_int
+    L.bamgpu_sort_bam.argtypes = [READ_FN, vp, WRITE_FN, vp, sz, C.c_int, C.POINTER(Opts), C.POINTER(Stats), C.c_char_p, sz]
     _lib = L
     return L

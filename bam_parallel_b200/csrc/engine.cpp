@@ -144,6 +144,12 @@ struct bamgpu_engine {
   DevBuf d_cols;
   uint64_t cols_cap = 0;
   ColumnsDev cols{};
+  // sort (bamgpu_engine_sort)
+  DevBuf d_sort, d_perm, d_soff, d_sorted;
+  PinBuf h_sorted, h_perm;
+  uint64_t last_n = 0, last_bad_flags = 0;
+  uint32_t last_flags = 0;
+  bool last_valid = false;
   // host mirrors
   PinBuf h_data, h_cols, h_res;
   uint64_t first_record_index = 0;
@@ -181,6 +187,10 @@ extern "C" const char* bamgpu_status_str(int s) {
     case BAMGPU_ERR_SHORT_RECORD: return "record runs past end of stream";
     case BAMGPU_ERR_BUFFER_TOO_SMALL: return "destination buffer too small";
     case BAMGPU_ERR_STATE: return "call out of order";
+    case BAMGPU_ERR_SORT_HI_MIXED: return "equal read names with HI on one record only (the reference panics, comparators.rs:90)";
+    case BAMGPU_ERR_SORT_BAD_FLAGS: return "flag bits >= 0x1000 (the reference panics, comparators.rs:178)";
+    case BAMGPU_ERR_SORT_BAD_TAGS: return "aux tags the reference's HI walk panics on (tags.rs:64-129)";
+    case BAMGPU_ERR_TOO_LARGE: return "input does not fit in device memory as one batch";
     default: return "unknown";
   }
 }
@@ -551,6 +561,10 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
   }
   out->n_records = n_rec;
   out->bad_flag_records = bad_flags;
+  E->last_n = n_rec;
+  E->last_bad_flags = bad_flags;
+  E->last_flags = flags;
+  E->last_valid = !(flags & BAMGPU_NO_RECORDS);
   fill_public_columns(E->cols, out->dev);
   // host mirrors: on their own stream, behind the record kernels
   cudaStream_t cs = E->d2h_stream;
@@ -654,13 +668,82 @@ extern "C" int bamgpu_engine_records(bamgpu_engine* E, uint64_t stream_start, in
 extern "C" int bamgpu_engine_stats(const bamgpu_engine* E, bamgpu_stats* out) {
   if (!E || !out) return BAMGPU_ERR_ARG;
   *out = E->stats;
-  out->ms_total = out->ms_h2d + out->ms_inflate + out->ms_crc + out->ms_records + out->ms_d2h;
+  out->ms_total = out->ms_h2d + out->ms_inflate + out->ms_crc + out->ms_records + out->ms_d2h + out->ms_sort + out->ms_gather;
   return BAMGPU_OK;
 }
 extern "C" void bamgpu_engine_reset_stats(bamgpu_engine* E) { if (E) E->stats = bamgpu_stats{}; }
 
 extern "C" void bamgpu_engine_set_n_ref(bamgpu_engine* E, int32_t n) { if (E) E->n_ref = n; }
 static void engine_set_n_ref(bamgpu_engine* E, int32_t n) { E->n_ref = n; }
+
+// -------------------------------------------------------------------------------------------------
+// Sort (sorting/sort.rs:138-178 sort_bam, the part behind the reader): stable sort of the last batch's records by the
+// chosen comparator, bodies gathered in that order.
+// -------------------------------------------------------------------------------------------------
+extern "C" int bamgpu_engine_sort(bamgpu_engine* E, int sort_by, uint32_t flags, void* cuda_stream, bamgpu_sorted* out) {
+  if (!E || !out || sort_by < BAMGPU_SORT_NAME || sort_by > BAMGPU_SORT_COORDINATES_AND_STRAND) return BAMGPU_ERR_ARG;
+  memset(out, 0, sizeof *out);
+  if (!E->last_valid) { E->err = "sort: no decoded batch on this engine"; return BAMGPU_ERR_STATE; }
+  if (sort_by == BAMGPU_SORT_NAME_AND_MATCH_MATES && !(E->last_flags & BAMGPU_WANT_HI)) {
+    E->err = "sort: NameAndMatchMates needs the batch decoded with BAMGPU_WANT_HI";
+    return BAMGPU_ERR_STATE;
+  }
+  if (sort_by == BAMGPU_SORT_COORDINATES_AND_STRAND && E->last_bad_flags) {
+    E->err = "sort: " + std::to_string(E->last_bad_flags) + " record(s) with flag bits >= 0x1000 (Flags::from_bits().unwrap() panics, comparators.rs:178)";
+    return BAMGPU_ERR_SORT_BAD_FLAGS;
+  }
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : E->stream;
+  ECK(cudaSetDevice(E->device));
+  { int w = engine_wait_d2h(E); if (w < 0) return w; }
+  const uint64_t n = E->last_n;
+  if (n >= (1ull << 31)) { E->err = "sort: more than 2^31 records in one batch"; return BAMGPU_ERR_TOO_LARGE; }
+  out->n_records = n;
+  ECK(E->d_sort.reserve(sort_scratch_bytes(n)));
+  ECK(E->d_perm.reserve(4 * (n + 1)));
+  ECK(E->d_soff.reserve(8 * (n + 2)));
+  SortResult* d_sr = (SortResult*)(E->d_misc.as<uint8_t>() + 192);
+  SortResult* h_sr = (SortResult*)(E->h_res.as<uint8_t>() + 192);
+  int launches = 0;
+  ECK(cudaEventRecord(E->ev[3], s));
+  ECK(sort_permutation(E->out_ptr(), E->cols, n, sort_by, E->d_sort.p, E->d_perm.as<uint32_t>(), d_sr, &launches, s));
+  ECK(cudaMemcpyAsync(h_sr, d_sr, sizeof(SortResult), cudaMemcpyDeviceToHost, s));
+  ECK(cudaEventRecord(E->ev[4], s));
+  uint64_t total = 0;
+  ECK(sorted_offsets(E->cols, E->d_perm.as<uint32_t>(), n, E->d_sort.p, E->d_soff.as<uint64_t>(), &total, s));   // synchronises
+  if (sort_by == BAMGPU_SORT_NAME_AND_MATCH_MATES) {
+    if (h_sr->hi_bad_tags) { E->err = "sort: aux tags the reference's HI walk panics on"; return BAMGPU_ERR_SORT_BAD_TAGS; }
+    if (h_sr->hi_mixed) {
+      E->err = "sort: " + std::to_string(h_sr->hi_mixed) + " pair(s) of equal read names with HI on one record only (Option::unwrap() panics, comparators.rs:90)";
+      return BAMGPU_ERR_SORT_HI_MIXED;
+    }
+  }
+  ECK(E->d_sorted.reserve(total + 64));
+  ECK(gather_sorted_bodies(E->out_ptr(), E->cols, E->d_perm.as<uint32_t>(), n, E->d_sort.p, E->d_soff.as<uint64_t>(),
+                           E->d_sorted.as<uint8_t>(), s));
+  ECK(cudaEventRecord(E->ev[5], s));
+  launches += 3;
+  out->bodies_len = total;
+  out->perm = E->d_perm.as<uint32_t>();
+  out->body_off = E->d_soff.as<uint64_t>();
+  out->bodies = E->d_sorted.as<uint8_t>();
+  if ((flags & BAMGPU_COPY_COLUMNS) && n) {
+    ECK(E->h_perm.reserve(4 * n));
+    ECK(cudaMemcpyAsync(E->h_perm.p, E->d_perm.p, 4 * n, cudaMemcpyDeviceToHost, s));
+    out->h_perm = E->h_perm.as<uint32_t>();
+  }
+  if ((flags & BAMGPU_COPY_DATA) && total) {
+    ECK(E->h_sorted.reserve(total));
+    ECK(cudaMemcpyAsync(E->h_sorted.p, E->d_sorted.p, total, cudaMemcpyDeviceToHost, s));
+    out->h_bodies = E->h_sorted.as<uint8_t>();
+  }
+  ECK(cudaStreamSynchronize(s));
+  ECK(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, E->ev[3], E->ev[4]); E->stats.ms_sort += ms;
+  cudaEventElapsedTime(&ms, E->ev[4], E->ev[5]); E->stats.ms_gather += ms;
+  E->stats.kernel_launches += launches;
+  return BAMGPU_OK;
+}
 
 // =================================================================================================
 // Reader
@@ -1097,5 +1180,100 @@ extern "C" int bamgpu_parse_reference_sequences(const uint8_t* b, size_t len, ba
     uint32_t l_ref = rd32(b + p); p += 4;
     if (cb) cb(name, l - 1, l_ref, user);
   }
+  return BAMGPU_OK;
+}
+
+// =================================================================================================
+// sort_bam (sorting/sort.rs:138-178): reader -> records -> stable sort -> bodies to the sink
+// =================================================================================================
+extern "C" int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write_fn write, void* write_ctx, size_t reader_thread_num,
+                               int sort_by, const bamgpu_opts* opts, bamgpu_stats* stats, char* err_buf, size_t err_cap) {
+  auto fail = [&](int rc, const std::string& msg) {
+    if (err_buf && err_cap) snprintf(err_buf, err_cap, "%s", msg.c_str());
+    return rc;
+  };
+  if (!read || !write || sort_by < BAMGPU_SORT_NAME || sort_by > BAMGPU_SORT_COORDINATES_AND_STRAND) return fail(BAMGPU_ERR_ARG, "bad argument");
+  // 1. the whole input (its size decides the batch size; the reference's reading thread streams it instead, readahead.rs:88-118)
+  size_t cap = (size_t)64 << 20, len = 0;
+  uint8_t* buf = (uint8_t*)malloc(cap);
+  if (!buf) return fail(BAMGPU_ERR_NOMEM, "out of host memory");
+  for (;;) {
+    if (len == cap) {
+      cap *= 2;
+      uint8_t* nb = (uint8_t*)realloc(buf, cap);
+      if (!nb) { free(buf); return fail(BAMGPU_ERR_NOMEM, "out of host memory"); }
+      buf = nb;
+    }
+    long got = read(read_ctx, buf + len, std::min(cap - len, (size_t)256 << 20));
+    if (got < 0) { free(buf); return fail(BAMGPU_ERR_IO, "read callback failed"); }
+    if (got == 0) break;
+    len += (size_t)got;
+  }
+  // 2. one batch = the whole file
+  bamgpu_opts o{};
+  if (opts) o = *opts; else o.device = -1;
+  o.batch_bytes = len + 65536;
+  o.flags &= ~(uint32_t)(BAMGPU_COPY_DATA | BAMGPU_COPY_COLUMNS | BAMGPU_NO_RECORDS | BAMGPU_SPECULATIVE_START);
+  if (sort_by == BAMGPU_SORT_NAME_AND_MATCH_MATES) o.flags |= BAMGPU_WANT_HI;
+  reader_thread_num = std::max<size_t>(reader_thread_num, 1);   // sort.rs:150
+  bamgpu_reader* R = bamgpu_reader_from_memory(buf, len, reader_thread_num, &o);
+  if (!R) { free(buf); return fail(BAMGPU_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)"); }
+  int rc = BAMGPU_OK;
+  std::string msg;
+  do {
+    const uint8_t* hb; size_t hl, ho;
+    rc = bamgpu_read_header(R, &hb, &hl, &ho);   // read and discarded: sort.rs:152-153
+    if (rc != BAMGPU_OK) { msg = bamgpu_last_error(R); break; }
+    bamgpu_batch b;
+    rc = bamgpu_next_batch(R, &b);
+    if (rc == BAMGPU_EOF) { rc = BAMGPU_OK; break; }   // no records: empty output
+    if (rc != BAMGPU_OK) { msg = bamgpu_last_error(R); break; }
+    if (!R->eof) { rc = BAMGPU_ERR_TOO_LARGE; msg = "input was split into several batches"; break; }
+    bamgpu_engine* E = R->E;
+    bamgpu_sorted srt;
+    rc = bamgpu_engine_sort(E, sort_by, 0, nullptr, &srt);
+    if (rc != BAMGPU_OK) { msg = E->err; break; }
+    // 3. bodies to the sink through two pinned staging buffers (the copy of chunk k+1 overlaps write(k))
+    const size_t CH = (size_t)64 << 20;
+    PinBuf st[2];
+    cudaEvent_t ev[2];
+    if (st[0].reserve(CH) != cudaSuccess || st[1].reserve(CH) != cudaSuccess) { rc = BAMGPU_ERR_NOMEM; msg = "pinned staging"; break; }
+    cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    cudaEventRecord(t0, E->stream);
+    const uint64_t total = srt.bodies_len;
+    uint64_t issued = 0, written = 0;
+    int k = 0;
+    size_t pending[2] = {0, 0};
+    auto issue = [&](int slot) {
+      size_t m = (size_t)std::min<uint64_t>(CH, total - issued);
+      cudaMemcpyAsync(st[slot].p, srt.bodies + issued, m, cudaMemcpyDeviceToHost, E->stream);
+      cudaEventRecord(ev[slot], E->stream);
+      pending[slot] = m;
+      issued += m;
+    };
+    if (total) issue(0);
+    while (written < total) {
+      int slot = k & 1;
+      if (issued < total) issue(slot ^ 1);
+      if (cudaEventSynchronize(ev[slot]) != cudaSuccess) { rc = BAMGPU_ERR_CUDA; msg = "D2H of sorted bodies failed"; break; }
+      if (write(write_ctx, st[slot].as<uint8_t>(), pending[slot]) < 0) { rc = BAMGPU_ERR_IO; msg = "write callback failed"; break; }
+      written += pending[slot];
+      ++k;
+    }
+    cudaEventRecord(t1, E->stream);
+    cudaStreamSynchronize(E->stream);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t0, t1);
+    E->stats.ms_d2h += ms;
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]); cudaEventDestroy(t0); cudaEventDestroy(t1);
+    st[0].release(); st[1].release();
+  } while (0);
+  if (stats) bamgpu_reader_stats(R, stats);
+  bamgpu_reader_free(R);
+  free(buf);
+  if (rc != BAMGPU_OK) return fail(rc, msg.empty() ? bamgpu_status_str(rc) : msg);
   return BAMGPU_OK;
 }

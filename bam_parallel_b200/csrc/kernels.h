@@ -108,4 +108,20 @@ void launch_tile_emit(const RecordParams& p, const TileArrays& t, uint64_t* rec_
 void launch_extract(const RecordParams& p, const ColumnsDev& c, uint64_t n_records, bool want_hi,
                     ChainResult* d_result, cudaStream_t s);
 
+// ---- sort + gather (sort.cu): the output bytes of the reference's sort_bam (sorting/sort.rs:138-178) -------------
+enum : int { SORT_NAME = 0, SORT_NAME_AND_MATCH_MATES = 1, SORT_COORDINATES_AND_STRAND = 2 };   // sort.rs:92-96 SortBy
+struct SortResult {
+  unsigned long long hi_mixed;     // neighbours with equal names where only one has HI (comparators.rs:90 would panic)
+  unsigned long long hi_bad_tags;  // records whose aux walk the reference would panic on (hi_present == 2)
+  uint32_t max_name_len;
+  uint32_t pad;
+};
+size_t sort_scratch_bytes(uint64_t n_records);
+cudaError_t sort_permutation(const uint8_t* data, const ColumnsDev& c, uint64_t n_records, int sort_by, void* scratch, uint32_t* perm,
+                             SortResult* d_res, int* launches, cudaStream_t s);
+cudaError_t sorted_offsets(const ColumnsDev& c, const uint32_t* perm, uint64_t n_records, void* scratch, uint64_t* out_off,
+                           uint64_t* total_bytes, cudaStream_t s);
+cudaError_t gather_sorted_bodies(const uint8_t* data, const ColumnsDev& c, const uint32_t* perm, uint64_t n_records, void* scratch,
+                                 uint64_t* out_off, uint8_t* out, cudaStream_t s);
+
 }  // namespace bamgpu

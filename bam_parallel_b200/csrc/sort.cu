@@ -1,0 +1,303 @@
+// sort.cu — GPU sort of decoded records + gather of their bodies: reproduces the OUTPUT BYTES of the reference's
+// external merge sort (BASELINE.json configs[3], configs[4]).
+//
+// Replaces bam_tools/src/sorting/sort.rs:138-178 (sort_bam): read_split_sort_dump_chunks (:185-308; per chunk
+// extract_key + rayon par_sort_by, stable, :351-371) and merge_sorted_chunks_and_write (:590-652; N-way heap merge, ties
+// to the lower chunk index :487-510) — i.e. ONE globally stable sort of all records by the comparator of the chosen
+// SortBy (sorting/comparators.rs:61-147), whose output is the concatenation of the record BODIES (no block_size, no
+// header, no BGZF; sort.rs:643).  Everything is resident in HBM, so there are no chunks, no temp files and no merge.
+//
+//   CoordinatesAndStrand (comparators.rs:117-147): key = (refID == -1 ? i32::MAX : refID, pos, reverse strand).
+//     K3 already wrote coord_key (both i32 biased to unsigned, refID in the high word) and strand; the order is a
+//     stable LSD radix sort: 1 bit of strand, then the 64 bits of coord_key.
+//   Name (comparators.rs:61-65): str::cmp of the read names INCLUDING their NUL (bamrawrecord.rs:118-123) = bytewise
+//     lexicographic, a proper prefix first.  Variable-length keys: MSD refinement, 8 name bytes per round (big-endian
+//     u64, zero-padded past l_read_name), each round a stable sort of (group, chunk); groups = runs of records equal
+//     so far.  Zero padding alone would tie "A\0" with "A\0\0"; sorting by l_read_name BEFORE the rounds (stable sorts
+//     keep it as the order inside fully tied groups) makes the result exact for arbitrary name bytes.
+//   NameAndMatchMates (comparators.rs:78-93): name, then HI (Option<i32>; None == None; None vs Some panics in the
+//     reference -> reported in SortResult.hi_mixed), then the full u16 flag: the same, with flag and HI sorted first.
+// The radix sort primitive is CUB's DeviceRadixSort (stable, onesweep); key construction, group refinement and the
+// body gather — the HBM-heavy part — are the kernels below.
+#include <cub/cub.cuh>
+
+#include "kernels.h"
+
+namespace bamgpu {
+namespace {
+
+__global__ void k_iota(uint32_t* v, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = i;
+}
+
+template <typename T, typename K>
+__global__ void k_gather_key(const T* __restrict__ col, const uint32_t* __restrict__ idx, K* __restrict__ key, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) key[i] = (K)col[idx[i]];
+}
+
+// HI as an unsigned key: Some(v) -> v biased; None -> 0 (a name group mixing None and Some is an error anyway).
+__global__ void k_hi_key(const uint8_t* __restrict__ present, const int32_t* __restrict__ value, const uint32_t* __restrict__ idx,
+                         uint32_t* __restrict__ key, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint32_t r = idx[i];
+    key[i] = present[r] == 1 ? ((uint32_t)value[r] ^ 0x80000000u) : 0u;
+  }
+}
+
+// Bytes [8r, 8r+8) of the name of record idx[i], big-endian, zero past l_read_name.
+__device__ __forceinline__ uint64_t name_chunk(const uint8_t* __restrict__ data, uint64_t off, uint32_t len, uint32_t r) {
+  const uint32_t b = 8 * r;
+  uint64_t k = 0;
+  if (b < len) {
+    const uint8_t* p = data + off + 32 + b;
+    const uint32_t m = len - b < 8 ? len - b : 8;
+    for (uint32_t j = 0; j < m; ++j) k |= (uint64_t)p[j] << (56 - 8 * j);
+  }
+  return k;
+}
+__global__ void k_name_chunk(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, const uint8_t* __restrict__ l_name,
+                             const uint32_t* __restrict__ idx, uint32_t r, uint64_t* __restrict__ key, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint32_t rec = idx[i];
+    key[i] = name_chunk(data, rec_off[rec], l_name[rec], r);
+  }
+}
+
+// After a round: position i starts a new group iff its (group, chunk) differs from position i-1's.
+__global__ void k_boundaries(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, const uint8_t* __restrict__ l_name,
+                             const uint32_t* __restrict__ idx, const uint32_t* __restrict__ seg_elem, uint32_t r,
+                             uint32_t* __restrict__ flag, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint32_t f = 1;
+    if (i) {
+      uint32_t a = idx[i - 1], b = idx[i];
+      f = seg_elem[a] != seg_elem[b] || name_chunk(data, rec_off[a], l_name[a], r) != name_chunk(data, rec_off[b], l_name[b], r);
+    }
+    flag[i] = f;
+  }
+}
+// flag has been inclusive-scanned: group id of position i = scan[i] - 1; hand it to the element.
+__global__ void k_assign_groups(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ scan, uint32_t* __restrict__ seg_elem, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) seg_elem[idx[i]] = scan[i] - 1;
+}
+
+__global__ void k_max_u8(const uint8_t* __restrict__ v, uint32_t n, uint32_t* out) {
+  uint32_t m = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, (uint32_t)v[i]);
+  for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// NameAndMatchMates: neighbours with the same full name must agree on HI being present (comparators.rs:90 unwrap).
+__global__ void k_check_hi(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ seg_elem, const uint8_t* __restrict__ l_name,
+                           const uint8_t* __restrict__ present, uint32_t n, SortResult* res) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint32_t b = idx[i];
+    if (present[b] == 2) atomicAdd(&res->hi_bad_tags, 1ull);
+    if (i) {
+      uint32_t a = idx[i - 1];
+      if (seg_elem[a] == seg_elem[b] && l_name[a] == l_name[b] && (present[a] == 1) != (present[b] == 1)) atomicAdd(&res->hi_mixed, 1ull);
+    }
+  }
+}
+
+__global__ void k_perm_len(const uint32_t* __restrict__ rec_len, const uint32_t* __restrict__ perm, uint64_t* __restrict__ len64, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) len64[i] = rec_len[perm[i]];
+}
+
+// One warp per record: body bytes data[rec_off .. +rec_len) -> out[out_off ..).  Destination-aligned 16-byte stores;
+// each is assembled from the two aligned source vectors that cover it (the second is the next iteration's first, so
+// every source byte is loaded once per warp).  HBM-bound: reads and writes every body byte once.
+__global__ void __launch_bounds__(256) k_gather_bodies(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off,
+                                                       const uint32_t* __restrict__ rec_len, const uint32_t* __restrict__ perm,
+                                                       const uint64_t* __restrict__ out_off, uint8_t* __restrict__ out, uint32_t n) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    const uint32_t rec = perm[i];
+    const uint8_t* src = data + rec_off[rec];
+    uint8_t* dst = out + out_off[i];
+    const uint32_t len = rec_len[rec];
+    // head: up to 15 bytes until dst is 16-byte aligned
+    uint32_t headn = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
+    if (headn > len) headn = len;
+    if (lane < headn) dst[lane] = src[lane];
+    const uint32_t body = (len - headn) & ~15u;
+    const uint8_t* s = src + headn;
+    uint8_t* d = dst + headn;
+    const uint32_t sh = (uint32_t)((uintptr_t)s & 3) * 8;
+    const uint32_t* sw = (const uint32_t*)((uintptr_t)s & ~(uintptr_t)3);   // readable: the stream has pads on both sides
+    for (uint32_t o = lane * 16; o < body; o += 32 * 16) {
+      const uint32_t* w = sw + (o >> 2);
+      uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0u;
+      uint4 v;
+      v.x = __funnelshift_r(w0, w1, sh);
+      v.y = __funnelshift_r(w1, w2, sh);
+      v.z = __funnelshift_r(w2, w3, sh);
+      v.w = __funnelshift_r(w3, w4, sh);
+      *(uint4*)(d + o) = v;
+    }
+    const uint32_t tail = len - headn - body;   // < 16
+    if (lane < tail) d[body + lane] = s[body + lane];
+  }
+}
+
+inline uint32_t blocks_for(uint32_t n, uint32_t threads = 256) { return (n + threads - 1) / threads; }
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Carve {
+  uint8_t* p;
+  size_t used = 0;
+  template <class T> T* take(size_t count) {
+    T* r = (T*)(p + used);
+    used = align256(used + count * sizeof(T));
+    return r;
+  }
+};
+
+size_t cub_temp_bytes(uint32_t n) {
+  size_t a = 0, b = 0, c = 0, d = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 64);
+  cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 32);
+  cub::DeviceScan::InclusiveSum(nullptr, c, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+  cub::DeviceScan::ExclusiveSum(nullptr, d, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int)n + 1);
+  size_t m = a > b ? a : b;
+  m = m > c ? m : c;
+  m = m > d ? m : d;
+  return align256(m + 256);
+}
+
+}  // namespace
+
+size_t sort_scratch_bytes(uint64_t n) {
+  const uint32_t m = (uint32_t)n + 1;
+  // key64 A/B, val A/B, key32 A/B, seg_elem, flags/scan, cub temp
+  return align256(8ull * m) * 2 + align256(4ull * m) * 6 + cub_temp_bytes((uint32_t)n) + 4096;
+}
+
+// Writes perm[0..n): perm[i] = index of the i-th record of the sorted order.  `scratch` >= sort_scratch_bytes(n).
+cudaError_t sort_permutation(const uint8_t* data, const ColumnsDev& c, uint64_t n64, int sort_by, void* scratch, uint32_t* perm,
+                             SortResult* d_res, int* launches, cudaStream_t s) {
+  const uint32_t n = (uint32_t)n64;
+  cudaMemsetAsync(d_res, 0, sizeof(SortResult), s);
+  if (n == 0) return cudaGetLastError();
+  Carve cv{(uint8_t*)scratch};
+  uint64_t* k64a = cv.take<uint64_t>(n + 1);
+  uint64_t* k64b = cv.take<uint64_t>(n + 1);
+  uint32_t* va = cv.take<uint32_t>(n + 1);
+  uint32_t* vb = cv.take<uint32_t>(n + 1);
+  uint32_t* k32a = cv.take<uint32_t>(n + 1);
+  uint32_t* k32b = cv.take<uint32_t>(n + 1);
+  uint32_t* seg_elem = cv.take<uint32_t>(n + 1);
+  uint32_t* flags = cv.take<uint32_t>(n + 1);
+  void* tmp = cv.p + cv.used;
+  size_t tmp_bytes = cub_temp_bytes(n);
+  const uint32_t g = blocks_for(n);
+  int nl = 0;
+  auto sort32 = [&](int bits) {   // (k32a, va) -> (k32b, vb), then swap names
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const uint32_t*)k32a, k32b, (const uint32_t*)va, vb, (int)n, 0, bits, s);
+    std::swap(va, vb);
+    std::swap(k32a, k32b);
+    nl += 3;
+  };
+  auto sort64 = [&]() {
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const uint64_t*)k64a, k64b, (const uint32_t*)va, vb, (int)n, 0, 64, s);
+    std::swap(va, vb);
+    std::swap(k64a, k64b);
+    nl += 5;
+  };
+  k_iota<<<g, 256, 0, s>>>(va, n);
+  ++nl;
+  if (sort_by == SORT_COORDINATES_AND_STRAND) {
+    k_gather_key<uint8_t, uint32_t><<<g, 256, 0, s>>>(c.strand, va, k32a, n);
+    sort32(1);
+    k_gather_key<uint64_t, uint64_t><<<g, 256, 0, s>>>(c.coord_key, va, k64a, n);
+    sort64();
+    nl += 2;
+  } else {
+    if (sort_by == SORT_NAME_AND_MATCH_MATES) {
+      k_gather_key<uint16_t, uint32_t><<<g, 256, 0, s>>>(c.flag, va, k32a, n);
+      sort32(16);
+      k_hi_key<<<g, 256, 0, s>>>(c.hi_present, c.hi_value, va, k32a, n);
+      sort32(32);
+      nl += 2;
+    }
+    k_gather_key<uint8_t, uint32_t><<<g, 256, 0, s>>>(c.l_read_name, va, k32a, n);
+    sort32(8);
+    ++nl;
+    // number of 8-byte rounds
+    uint32_t* d_max = (uint32_t*)&d_res->max_name_len;
+    k_max_u8<<<592, 256, 0, s>>>(c.l_read_name, n, d_max);
+    uint32_t max_len = 0;
+    cudaMemcpyAsync(&max_len, d_max, 4, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return e;
+    cudaMemsetAsync(seg_elem, 0, 4ull * n, s);
+    const uint32_t rounds = (max_len + 7) / 8;
+    uint32_t groups = 1;
+    for (uint32_t r = 0; r < rounds && groups < n; ++r) {
+      k_name_chunk<<<g, 256, 0, s>>>(data, c.rec_off, c.l_read_name, va, r, k64a, n);
+      sort64();
+      if (r) {   // back into the groups of the previous rounds (stable, so the chunk order survives inside each)
+        k_gather_key<uint32_t, uint32_t><<<g, 256, 0, s>>>(seg_elem, va, k32a, n);
+        int bits = 1;
+        while (bits < 32 && (1u << bits) < groups) ++bits;
+        sort32(bits);
+        ++nl;
+      }
+      k_boundaries<<<g, 256, 0, s>>>(data, c.rec_off, c.l_read_name, va, seg_elem, r, flags, n);
+      cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, (const uint32_t*)flags, k32a, (int)n, s);
+      k_assign_groups<<<g, 256, 0, s>>>(va, k32a, seg_elem, n);
+      cudaMemcpyAsync(&groups, k32a + (n - 1), 4, cudaMemcpyDeviceToHost, s);
+      nl += 5;
+      e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) return e;
+    }
+    if (sort_by == SORT_NAME_AND_MATCH_MATES) {
+      k_check_hi<<<g, 256, 0, s>>>(va, seg_elem, c.l_read_name, c.hi_present, n, d_res);
+      ++nl;
+    }
+  }
+  cudaMemcpyAsync(perm, va, 4ull * n, cudaMemcpyDeviceToDevice, s);
+  if (launches) *launches += nl;
+  return cudaGetLastError();
+}
+
+// out_off[0..n] = exclusive scan of the body lengths in sorted order; bodies copied to out back to back.
+// `scratch` as above (only the front is used).  *total_bytes is read back (synchronises).
+cudaError_t gather_sorted_bodies(const uint8_t* data, const ColumnsDev& c, const uint32_t* perm, uint64_t n64, void* scratch,
+                                 uint64_t* out_off, uint8_t* out, cudaStream_t s) {
+  const uint32_t n = (uint32_t)n64;
+  if (n == 0) return cudaSuccess;
+  k_gather_bodies<<<148 * 8, 256, 0, s>>>(data, c.rec_off, c.rec_len, perm, out_off, out, n);
+  return cudaGetLastError();
+}
+
+cudaError_t sorted_offsets(const ColumnsDev& c, const uint32_t* perm, uint64_t n64, void* scratch, uint64_t* out_off, uint64_t* total,
+                           cudaStream_t s) {
+  const uint32_t n = (uint32_t)n64;
+  *total = 0;
+  if (n == 0) return cudaMemsetAsync(out_off, 0, 8, s);
+  Carve cv{(uint8_t*)scratch};
+  uint64_t* len64 = cv.take<uint64_t>(n + 1);
+  cv.take<uint64_t>(n + 1);
+  for (int k = 0; k < 6; ++k) cv.take<uint32_t>(n + 1);
+  void* tmp = cv.p + cv.used;
+  size_t tmp_bytes = cub_temp_bytes(n);
+  k_perm_len<<<blocks_for(n), 256, 0, s>>>(c.rec_len, perm, len64, n);
+  cudaMemsetAsync(len64 + n, 0, 8, s);
+  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (const uint64_t*)len64, out_off, (int)n + 1, s);
+  cudaMemcpyAsync(total, out_off + n, 8, cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+}  // namespace bamgpu

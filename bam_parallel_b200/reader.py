@@ -28,7 +28,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (COLUMN_FIELDS, COPY_COLUMNS, COPY_DATA, NO_CRC, NO_RECORDS, WANT_HI, BamGpuError, Batch, Block, Opts,
-                   Stats)
+                   Sorted, Stats)
 
 _NP = {C.c_uint64: np.uint64, C.c_uint32: np.uint32, C.c_int32: np.int32, C.c_uint16: np.uint16, C.c_uint8: np.uint8}
 
@@ -289,6 +289,17 @@ class Engine:
         b, tail = Batch(), C.c_uint64()
         rc = self._eck(self._L.bamgpu_engine_records(self._h, stream_start, int(final), flags, cuda_stream, C.byref(b), C.byref(tail)))
         return RecordBatch(b), tail.value, rc
+
+    def sort(self, sort_by: int, flags=COPY_DATA | COPY_COLUMNS, cuda_stream=None):
+        """bamgpu_engine_sort: stable sort of the last decoded batch by the reference's comparator (sort.rs:92-96 SortBy,
+        comparators.rs:61-147).  Returns (perm as uint32 numpy or None, sorted bodies as uint8 numpy or None, Sorted struct):
+        the bodies are the bytes bam_binary writes (sort.rs:643)."""
+        srt = Sorted()
+        self._eck(self._L.bamgpu_engine_sort(self._h, sort_by, flags, cuda_stream, C.byref(srt)))
+        n, nb = int(srt.n_records), int(srt.bodies_len)
+        perm = (_view(srt.h_perm, n, C.c_uint32) if srt.h_perm else np.zeros(0, np.uint32)) if flags & COPY_COLUMNS else None
+        bodies = (_view(srt.h_bodies, nb, C.c_uint8) if srt.h_bodies else np.zeros(0, np.uint8)) if flags & COPY_DATA else None
+        return perm, bodies, srt
 
     def set_n_ref(self, n_ref: int):
         """Optional hint (header n_ref) for K3's guess of record starts; results never depend on it."""

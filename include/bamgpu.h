@@ -49,7 +49,11 @@ typedef enum bamgpu_status {
   BAMGPU_ERR_SHORT_HEADER = -21,    /* reader.rs:172-190 unwrap()/? on a short header */
   BAMGPU_ERR_SHORT_RECORD = -22,    /* reader.rs:69-70 expect("Failed to read.") */
   BAMGPU_ERR_BUFFER_TOO_SMALL = -23,
-  BAMGPU_ERR_STATE = -24            /* call out of order (e.g. records before read_header) */
+  BAMGPU_ERR_STATE = -24,           /* call out of order (e.g. records before read_header) */
+  BAMGPU_ERR_SORT_HI_MIXED = -30,   /* sorting/comparators.rs:90 unwrap(): equal names, HI on one record only -> the reference panics */
+  BAMGPU_ERR_SORT_BAD_FLAGS = -31,  /* comparators.rs:178 Flags::from_bits().unwrap(): flag bits >= 0x1000 -> the reference panics */
+  BAMGPU_ERR_SORT_BAD_TAGS = -32,   /* record/tags.rs:64-129: the aux walk for HI hits a type it panics on */
+  BAMGPU_ERR_TOO_LARGE = -33        /* sort: the whole BAM must fit in device memory as one batch */
 } bamgpu_status;
 
 /* ------------------------------------------------------------------------------------------
@@ -144,6 +148,7 @@ typedef struct bamgpu_opts {
 typedef struct bamgpu_stats {
   uint64_t blocks, bytes_in, bytes_out, records, batches, kernel_launches;
   double ms_h2d, ms_inflate, ms_crc, ms_records, ms_d2h, ms_total;
+  double ms_sort, ms_gather;      /* bamgpu_engine_sort: key sort / body gather */
 } bamgpu_stats;
 
 /* ------------------------------------------------------------------------------------------
@@ -240,6 +245,47 @@ int bamgpu_reader_stats(const bamgpu_reader*, bamgpu_stats* out);
  * BAMGPU_ERR_SHORT_HEADER (short input / name not NUL-terminated or with an interior NUL). */
 typedef void (*bamgpu_refseq_cb)(const char* name, size_t name_len, uint32_t l_ref, void* user);
 int bamgpu_parse_reference_sequences(const uint8_t* bytes, size_t len, bamgpu_refseq_cb cb, void* user);
+
+/* ------------------------------------------------------------------------------------------
+ * Sort: what the reference's sort modes do with the records the reader hands them
+ *     sort_bam(mem_limit, reader, sorted_sink, tmp_dir, .., reader_thread_num, temp_files_mode, None, sort_by, ..)
+ *                                                             bam_tools/src/sorting/sort.rs:138-178
+ *     SortBy { Name, NameAndMatchMates, CoordinatesAndStrand }               sort.rs:92-96
+ *     comparators                                                            sorting/comparators.rs:61-147
+ * The output is the concatenation of the record BODIES in globally stable sorted order (sort.rs:643: no block_size,
+ * no header, no BGZF).  On the GPU everything stays resident in HBM: no chunks, temp files or merge
+ * (mem_limit / tmp_dir / temp_files_mode have no counterpart).
+ * ---------------------------------------------------------------------------------------- */
+typedef enum bamgpu_sort_by {
+  BAMGPU_SORT_NAME = 0,                    /* bam_binary -n       : read_name bytes incl. NUL, bytewise */
+  BAMGPU_SORT_NAME_AND_MATCH_MATES = 1,    /* bam_binary -n -M    : name, then HI, then the full u16 flag; needs BAMGPU_WANT_HI at decode */
+  BAMGPU_SORT_COORDINATES_AND_STRAND = 2   /* bam_binary (default): (refID == -1 ? i32::MAX : refID, pos, reverse strand) */
+} bamgpu_sort_by;
+
+typedef struct bamgpu_sorted {
+  uint64_t n_records;
+  uint64_t bodies_len;          /* sum of block_size over all records */
+  const uint32_t* perm;         /* device: perm[i] = index in the decoded batch of the i-th record of the sorted order */
+  const uint64_t* body_off;     /* device: n_records + 1 offsets of the sorted bodies in `bodies` */
+  const uint8_t* bodies;        /* device: the reference's output bytes */
+  const uint32_t* h_perm;       /* pinned host mirror (BAMGPU_COPY_COLUMNS), else NULL */
+  const uint8_t* h_bodies;      /* pinned host mirror (BAMGPU_COPY_DATA), else NULL */
+} bamgpu_sorted;
+
+/* Sorts the records of the batch the engine decoded last (bamgpu_engine_decode / _records / bamgpu_next_batch on the
+ * owning reader) and gathers their bodies.  Valid until the next decode or sort on the engine.
+ * Errors where the reference would panic: BAMGPU_ERR_SORT_HI_MIXED, _BAD_TAGS (NameAndMatchMates), _BAD_FLAGS
+ * (CoordinatesAndStrand). */
+int bamgpu_engine_sort(bamgpu_engine*, int sort_by, uint32_t flags /* BAMGPU_COPY_* */, void* cuda_stream, bamgpu_sorted* out);
+
+/* std::io::Write::write_all: return 0, or < 0 on error. */
+typedef int (*bamgpu_write_fn)(void* ctx, const uint8_t* src, size_t len);
+/* sort_bam (sort.rs:138-178): reads the whole BGZF stream from `read`, decodes and sorts it on the device and writes
+ * the sorted bodies to `write`.  The header is read and discarded like the reference does (sort.rs:152-153).
+ * The whole file must fit in device memory (BAMGPU_ERR_TOO_LARGE otherwise). *stats (nullable) gets the stage times. */
+int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write_fn write, void* write_ctx, size_t reader_thread_num,
+                    int sort_by, const bamgpu_opts* opts /*nullable*/, bamgpu_stats* stats /*nullable*/,
+                    char* err_buf /*nullable*/, size_t err_cap);
 
 const char* bamgpu_status_str(int status);
 /* "sm_100a;<build id>" — lets callers assert the CUDA library (not a fallback) is loaded. */
