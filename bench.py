@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-records", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sort", action="store_true", help="skip the sort-path timing (BASELINE.json configs[3], reported beside the headline)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--batch-mib", type=int, default=256, help="compressed MiB per Reader pipeline batch (e2e)")
     return ap.parse_args()
@@ -355,6 +356,24 @@ def run_b200(a, rank: int, world: int, local_rank: int):
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
                 "stage_ms_per_step": {"k1_inflate": k1_ms, "k2_crc32": st["ms_crc"] / a.steps, "k3_records": st["ms_records"] / a.steps}}
 
+    # ---- sort path (BASELINE.json configs[3]): stable sort of the decoded records + body gather, device-resident ----
+    sort_info = None
+    if world == 1 and not a.no_sort:
+        from bam_parallel_b200.sorting import SortBy
+        sort_info = {}
+        for sb in (SortBy.CoordinatesAndStrand, SortBy.Name):
+            for rep in range(2):
+                eng.reset_stats()
+                _, _, srt = eng.sort(int(sb), flags=0, cuda_stream=sptr)
+                stt = eng.stats()
+            nb_out = int(srt.bodies_len)
+            sort_info[sb.name] = {"ms_key_sort": round(stt["ms_sort"], 2), "ms_body_gather": round(stt["ms_gather"], 2),
+                                  "records_per_s": a.records / ((stt["ms_sort"] + stt["ms_gather"]) * 1e-3),
+                                  "gather_GB_per_s": 2 * nb_out / (stt["ms_gather"] * 1e-3) / 1e9 if stt["ms_gather"] > 0 else None,
+                                  "output_bytes": nb_out}
+        sort_info["note"] = ("bamgpu_engine_sort on the batch just decoded: output bytes = bam_binary's (record bodies in stable sorted "
+                             "order, sort.rs:643); parity vs the oracle in tests/test_gpu_sort.py; gather GB/s counts bodies read + written")
+
     # ---- e2e: drop-in Reader over the HOST buffer (H2D + D2H inside the timed region) ----
     e2e = e2e_cols = None
     if not a.no_e2e:
@@ -392,7 +411,7 @@ def run_b200(a, rank: int, world: int, local_rank: int):
                        "l2": "inputs (compressed + inflated) far larger than the 126 MB L2; no flush needed",
                        "generator_seconds": round(gen_s, 1), "k3_chain_repairs": chain_repairs},
             "records_per_s": n_rec_all / (ms_step * 1e-3),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_columns_only": e2e_cols, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_columns_only": e2e_cols, "sort": sort_info, "gpu_launches": launches,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
