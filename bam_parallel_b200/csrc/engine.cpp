@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
@@ -159,6 +161,9 @@ struct bamgpu_engine {
 
   uint8_t* out_ptr() const { return d_outs[cur].as<uint8_t>() + OUT_LEAD_PAD; }
 };
+
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static int dbg_level() { static int v = -1; if (v < 0) { const char* e = getenv("BAMGPU_DEBUG"); v = e ? atoi(e) : 0; } return v; }
 
 #define ECK(call)                                                                                   \
   do {                                                                                              \
@@ -351,6 +356,7 @@ int map_block_status(uint32_t st) {
 //   engine_inflate_finish  waits, reads the first failing block (if any), books the stage times
 static int engine_inflate_launch(bamgpu_engine* E, const uint8_t* d_comp, const bamgpu_block* blocks, size_t n_blocks,
                                  uint32_t flags, cudaStream_t s) {
+  const double t_in = now_ms();
   ECK(cudaSetDevice(E->device));
   // 1. the destination buffer (the other one when ping-ponging) gets the carry at its front
   const uint64_t carry = E->carry_len;
@@ -440,15 +446,18 @@ static int engine_inflate_launch(bamgpu_engine* E, const uint8_t* d_comp, const 
   launch_status_reduce(E->d_status.as<uint32_t>(), (uint32_t)nb, first_bad, s);
   E->stats.kernel_launches += 1;
   ECK(cudaMemcpyAsync(E->h_res.as<unsigned long long>(), first_bad, 8, cudaMemcpyDeviceToHost, s));
+  if (dbg_level() >= 2) fprintf(stderr, "[bamgpu] inflate_launch host %.2f ms (%zu blocks)\n", now_ms() - t_in, n_blocks);
   return BAMGPU_OK;
 }
 
 static int engine_inflate_finish(bamgpu_engine* E, cudaStream_t s) {
   if (!E->inflate_launched) return BAMGPU_OK;
   E->inflate_launched = false;
+  const double t_in = now_ms();
   ECK(cudaSetDevice(E->device));
   ECK(cudaStreamSynchronize(s));
   ECK(cudaGetLastError());
+  if (dbg_level() >= 2) fprintf(stderr, "[bamgpu] inflate_finish wait %.2f ms\n", now_ms() - t_in);
   if (E->pend_nb == 0) return BAMGPU_OK;
   float ms = 0;
   cudaEventElapsedTime(&ms, E->ev[0], E->ev[1]); E->stats.ms_inflate += ms;
@@ -490,6 +499,7 @@ static int engine_wait_d2h(bamgpu_engine* E) {
 // Stage 2: record chain + columns over d_out[0 .. data_len).
 static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t flags, cudaStream_t s,
                           bamgpu_batch* out, uint64_t* tail_off_out, bool defer_d2h = false) {
+  const double t_in = now_ms();
   ECK(cudaSetDevice(E->device));
   { int w = engine_wait_d2h(E); if (w < 0) return w; }
   memset(out, 0, sizeof *out);
@@ -607,6 +617,7 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
     E->d2h_pending = true;
     if (!defer_d2h) { int w = engine_wait_d2h(E); if (w < 0) return w; }
   }
+  if (dbg_level() >= 2) fprintf(stderr, "[bamgpu] records host wall %.2f ms\n", now_ms() - t_in);
   E->stats.records += n_rec;
   E->stats.batches += 1;
   E->first_record_index += n_rec;

@@ -60,7 +60,10 @@ constexpr int K1_DECODER_REGS = K1_CTAS * K1_THREADS > 768 ? 80 : 112, K1_COPIER
 constexpr uint32_t K1_URGENT_FILL = K1_URGENT;
 constexpr int K1_COPIER_MIN_READY = K1_MIN_READY;
 constexpr uint32_t K1_COPIER_WAIT_LIMIT = K1_WAIT_LIMIT;
-constexpr uint32_t K1_TRIPS_PER_ROUND = 128;  // trips a decoder lane makes between two looks at the warp-wide state
+#ifndef K1_ROUND_TRIPS
+#define K1_ROUND_TRIPS 128
+#endif
+constexpr uint32_t K1_TRIPS_PER_ROUND = K1_ROUND_TRIPS;  // trips a decoder lane makes between two looks at the warp-wide state
 
 __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM)
 k1_inflate_pairs(InflateJob job, uint32_t* __restrict__ work_counter) {

@@ -444,8 +444,9 @@ BG_HD_COLD void parse_header(BitReader* brp, uint32_t* sm, HeaderResult* hr) {
 
 // ---- token ring between a decoder lane and its copier lane ------------------------------------------
 // A token is two 32-bit words, written and read with ONE 64-bit shared-memory access:
-//   w0: bits 0-23 up to three literal bytes, bits 24-25 their count, bits 26-28 the kind, bit 31 the phase
-//   w1: TK_MATCH len | dist << 16     TK_BEGIN block index     TK_END final IST_* status of the block
+//   w0: bits 0-23 the first three literal bytes, bits 24-26 the literal count (0..4), bits 27-29 the kind, bit 31 the phase
+//   w1: TK_LITS / TK_MATCH  (len - 3) | (dist - 1) << 8 | fourth literal << 23
+//       TK_BEGIN block index     TK_END final IST_* status of the block
 //       TK_RAW   len | offset in the payload << 16 (stored block: bytes copied straight from the input)
 // Single producer, single consumer, nobody ever blocks on it.  Token i lives in slot i mod RING_TOKENS and carries
 // phase (i / RING_TOKENS) & 1, so the consumer sees a token appear by polling the slot itself: there is no head
@@ -590,7 +591,7 @@ struct Decoder {
   // an invalid code).  Decoding several literals per trip amortises the sparse match code over more output: most
   // lanes start with a literal, and a lane that sees a length stops there.
 #ifndef BG_LITS_PER_TOKEN
-#define BG_LITS_PER_TOKEN 3
+#define BG_LITS_PER_TOKEN 4
 #endif
   static constexpr int LITS_PER_TOKEN = BG_LITS_PER_TOKEN;
   struct Tok { uint32_t lits, nlit, len, dist, kind; };
@@ -627,7 +628,7 @@ struct Decoder {
 #pragma unroll
     for (int i = 1; i < LITS_PER_TOKEN; ++i) {
       if (kind == 0) {
-        if (i >= 2) br.refill();
+        if (i == 2) br.refill();   // two codes per refill; the fourth symbol still has >= 18 bits
         t.lits |= e << (8 * t.nlit);
         t.nlit += 1;
         kind = decode_litlen(e);
@@ -669,14 +670,14 @@ struct Decoder {
   // Everything a trip does outside the Huffman decode: the tokens that open and close a block, stored blocks.
   BG_HD void cold_trip(const InflateJob& job, uint32_t stage0) {
     if (state == ST_BEGIN) {
-      push(TK_BEGIN << 26, blk);
+      push(TK_BEGIN << 27, blk);
       state = ST_HEADER;
     } else if (state == ST_STORED) {
       // stored block: the copier takes the bytes straight from the input; skip them here
       const uint32_t off = pay_skipped + (br.bits_consumed() >> 3), len = cp_rem, in_len = job.in_len[blk];
       if (off + len > in_len) { err = IST_INPUT_OVERRUN; state = ST_END; return; }
       if (len > isize - produced) { err = IST_OUTPUT_OVERRUN; state = ST_END; return; }
-      push(TK_RAW << 26, len | (off << 16));
+      push(TK_RAW << 27, len | (off << 16));
       produced += len;
       br.drain();
       br.begin(job.comp + job.in_off[blk] + off + len, in_len - (off + len), stage0);
@@ -688,10 +689,10 @@ struct Decoder {
         else if (br.bits_consumed() > br.in_bits) err = IST_INPUT_OVERRUN;
       }
       br.drain();
-      push(TK_END << 26, err);
+      push(TK_END << 27, err);
       state = ST_NEXT;
     } else if (state == ST_FINISH) {
-      push(TK_DONE << 26, 0);
+      push(TK_DONE << 27, 0);
       state = ST_DONE;
     }
   }
@@ -707,14 +708,14 @@ struct Decoder {
     if (state == ST_DECODE) {
       Tok t;
       decode_token(t);
-      uint32_t w0 = t.lits | (t.nlit << 24), w1 = 0;
+      uint32_t w0 = (t.lits & 0xffffffu) | (t.nlit << 24), w1 = (t.lits >> 24) << 23;
       uint32_t np = produced + t.nlit, bad = 0;
       bool any = t.nlit != 0;
       if (t.kind == 1) {
         if (t.dist > np) bad = IST_BAD_DISTANCE;
         np += t.len;
-        w0 |= TK_MATCH << 26;
-        w1 = t.len | (t.dist << 16);
+        w0 |= TK_MATCH << 27;
+        w1 |= (t.len - 3u) | ((t.dist - 1u) << 8);
         any = true;
       }
       if (t.kind == 3) bad = IST_BAD_SYMBOL;
@@ -949,11 +950,11 @@ struct Copier {
     if (have && p_len == 0) {
       tail += 1;
       ring.set_tail(tail);
-      const uint32_t nlit = (w0 >> 24) & 3u, kind = (w0 >> 26) & 7u;
-      if (nlit) emit(w0 & 0xffffffu, nlit);
+      const uint32_t nlit = (w0 >> 24) & 7u, kind = (w0 >> 27) & 7u;
+      if (nlit) emit((w0 & 0xffffffu) | (((w1 >> 23) & 0xffu) << 24), nlit);
       if (kind == TK_MATCH) {
-        p_len = w1 & 0x1ffu;
-        p_dist = w1 >> 16;
+        p_len = (w1 & 0xffu) + 3u;
+        p_dist = ((w1 >> 8) & 0x7fffu) + 1u;
       } else if (kind != TK_LITS) {
         cold_token(job, kind, w1);
       }
