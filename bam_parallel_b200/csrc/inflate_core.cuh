@@ -526,16 +526,14 @@ struct Decoder {
 
   // ---------------- shared-memory accessors ----------------
 #if defined(__CUDA_ARCH__)
-  // 32-bit shared-window addresses: one multiply-add per access instead of 64-bit generic pointer arithmetic
+  // 32-bit shared-window addresses: one multiply-add per access instead of 64-bit generic pointer arithmetic.
+  // Ordinary loads (the compiler folds the cvta into LDS), so they are ordered against the table builder's stores
+  // and free to be scheduled early; volatile asm loads were measured to triple the decoders' shared-memory stalls.
   BG_HD uint32_t smr(uint32_t w) const {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sma + w * (4u * STRIDE)));
-    return v;
+    return *(const uint32_t*)__cvta_shared_to_generic(sma + w * (4u * STRIDE));
   }
   BG_HD uint32_t smb(uint32_t base, uint32_t i) const {   // byte i of the byte array starting at word `base`
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sma + (base + (i >> 2)) * (4u * STRIDE) + (i & 3u)));
-    return v;
+    return *(const uint8_t*)__cvta_shared_to_generic(sma + (base + (i >> 2)) * (4u * STRIDE) + (i & 3u));
   }
 #else
   BG_HD uint32_t smr(uint32_t w) const { return sm[w * STRIDE]; }
