@@ -16,7 +16,7 @@ ERR_NAMES = {
     -31: "ERR_SORT_BAD_FLAGS", -32: "ERR_SORT_BAD_TAGS", -33: "ERR_TOO_LARGE",
 }
 SORT_NAME, SORT_NAME_AND_MATCH_MATES, SORT_COORDINATES_AND_STRAND = 0, 1, 2   # sorting/sort.rs:92-96 SortBy
-COPY_DATA, COPY_COLUMNS, WANT_HI, NO_CRC, NO_RECORDS, SPECULATIVE_START = 1, 2, 4, 8, 16, 32
+COPY_DATA, COPY_COLUMNS, WANT_HI, NO_CRC, NO_RECORDS, SPECULATIVE_START, COPY_OFFSETS = 1, 2, 4, 8, 16, 32, 64
 MAX_HALO = 1 << 20
 
 

@@ -578,7 +578,7 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
   fill_public_columns(E->cols, out->dev);
   // host mirrors: on their own stream, behind the record kernels
   cudaStream_t cs = E->d2h_stream;
-  const bool any_copy = (flags & BAMGPU_COPY_DATA) || ((flags & BAMGPU_COPY_COLUMNS) && n_rec);
+  const bool any_copy = (flags & BAMGPU_COPY_DATA) || ((flags & (BAMGPU_COPY_COLUMNS | BAMGPU_COPY_OFFSETS)) && n_rec);
   if (any_copy) {
     ECK(cudaEventRecord(E->ev_k3_done, s));
     ECK(cudaStreamWaitEvent(cs, E->ev_k3_done, 0));
@@ -588,6 +588,16 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
     ECK(E->h_data.reserve(E->data_len + 64));
     if (E->data_len) ECK(cudaMemcpyAsync(E->h_data.p, E->out_ptr(), E->data_len, cudaMemcpyDeviceToHost, cs));
     out->h_data = E->h_data.as<uint8_t>();
+  }
+  if ((flags & BAMGPU_COPY_OFFSETS) && !(flags & BAMGPU_COPY_COLUMNS) && n_rec) {
+    // what next_rec() needs besides the bodies: where each one starts and how long it is
+    ECK(E->h_cols.reserve(columns_bytes(E->cols_cap)));
+    ColumnsDev hc;
+    carve_columns(E->h_cols.as<uint8_t>(), E->cols_cap, hc);
+    ECK(cudaMemcpyAsync(hc.rec_off, E->cols.rec_off, 8 * n_rec, cudaMemcpyDeviceToHost, cs));
+    ECK(cudaMemcpyAsync(hc.rec_len, E->cols.rec_len, 4 * n_rec, cudaMemcpyDeviceToHost, cs));
+    out->host.rec_off = hc.rec_off;
+    out->host.rec_len = hc.rec_len;
   }
   if ((flags & BAMGPU_COPY_COLUMNS) && n_rec) {
     size_t bytes = columns_bytes(E->cols_cap);
@@ -836,6 +846,9 @@ static void feeder_main(bamgpu_reader* R) {
     S.blocks.clear();
     S.status = BAMGPU_OK;
     S.final = false;
+    // (Smaller first batches were tried to fill the pipeline sooner: every growth of the output buffers then costs a
+    // cudaFree, which waits for the D2H in flight - slower overall.)
+    const size_t bb = R->batch_bytes;
     size_t cap = R->batch_bytes + 65536 + 64;
     if (S.host.reserve(cap + IN_TAIL_PAD) != cudaSuccess || S.dev.reserve(cap + IN_TAIL_PAD) != cudaSuccess) {
       S.status = BAMGPU_ERR_NOMEM; S.final = true;
@@ -846,7 +859,7 @@ static void feeder_main(bamgpu_reader* R) {
       carry.clear();
       if (R->mem && !src_eof) {
         // in-memory source: fill the pinned slot with several threads (thread_num, like the reference's inflate pool)
-        size_t want = std::min(R->batch_bytes > fill ? R->batch_bytes - fill : 0, R->mem_len - R->mem_pos);
+        size_t want = std::min(bb > fill ? bb - fill : 0, R->mem_len - R->mem_pos);
         size_t nt = std::min<size_t>(std::max<size_t>(R->thread_num, 1), 16);
         if (want < (8u << 20)) nt = 1;
         std::vector<std::thread> th;
@@ -862,8 +875,8 @@ static void feeder_main(bamgpu_reader* R) {
         fill += want;
         if (R->mem_pos >= R->mem_len) src_eof = true;
       }
-      while (!R->mem && !src_eof && fill < R->batch_bytes) {
-        long n = R->read(R->ctx, h + fill, std::min<size_t>(cap - fill, 8u << 20));
+      while (!R->mem && !src_eof && fill < bb) {
+        long n = R->read(R->ctx, h + fill, std::min<size_t>(bb + 65536 - fill, 8u << 20));
         if (n < 0) { S.status = BAMGPU_ERR_IO; src_eof = true; break; }
         if (n == 0) { src_eof = true; break; }
         fill += (size_t)n;
@@ -1076,12 +1089,15 @@ static int reader_next_batch(bamgpu_reader* R, uint32_t extra_flags) {
       }
       if (rc < 0) { R->sticky = rc; return rc; }
     }
+    const double t0 = now_ms();
     rc = engine_inflate_finish(E, E->stream);
     if (rc < 0) { R->sticky = rc; return rc; }
     R->inflated_pending = false;
     const bool fin = R->pending_final;
     uint64_t tail = 0;
+    const double t1 = now_ms();
     rc = engine_records(E, R->next_start, fin ? 1 : 0, flags, E->stream, &R->batch, &tail, /*defer_d2h=*/true);
+    const double t2 = now_ms();
     R->next_start = 0;
     if (rc < 0) { R->sticky = rc; return rc; }
     R->batch_valid = true;
@@ -1091,8 +1107,12 @@ static int reader_next_batch(bamgpu_reader* R, uint32_t extra_flags) {
       int pr = reader_inflate_launch_next(R, flags, /*nonblocking=*/true);
       if (pr < 0) { R->sticky = pr; }  // surfaces on the next call; this batch is still good
     }
+    const double t3 = now_ms();
     int w = engine_wait_d2h(E);
     if (w < 0) { R->sticky = w; return w; }
+    if (dbg_level() >= 2)
+      fprintf(stderr, "[bamgpu] next_batch @%.1f: wait inflate %.2f, records %.2f, launch next %.2f, wait d2h %.2f ms (%llu records)\n",
+              t0, t1 - t0, t2 - t1, t3 - t2, now_ms() - t3, (unsigned long long)R->batch.n_records);
     if (R->batch.n_records) return BAMGPU_OK;
     if (R->eof) return BAMGPU_EOF;
   }
@@ -1114,7 +1134,7 @@ extern "C" int bamgpu_next_rec(bamgpu_reader* R, const uint8_t** body, size_t* l
   if (R->raw_mode) { R->err = "next_rec after read()"; return BAMGPU_ERR_STATE; }
   while (!R->batch_valid || R->rec_cursor >= R->batch.n_records) {
     if (R->eof) { *body = nullptr; *len = 0; return R->sticky < 0 ? R->sticky : BAMGPU_EOF; }
-    int rc = reader_next_batch(R, BAMGPU_COPY_DATA | BAMGPU_COPY_COLUMNS);
+    int rc = reader_next_batch(R, BAMGPU_COPY_DATA | BAMGPU_COPY_OFFSETS);
     if (rc != BAMGPU_OK) { *body = nullptr; *len = 0; return rc; }
   }
   if (!R->batch.h_data || !R->batch.host.rec_off) { R->err = "internal: batch has no host mirror"; return BAMGPU_ERR_STATE; }

@@ -56,8 +56,8 @@ class RecordBatch:
         self.columns = None
         if self.n_records == 0:
             self.columns = {n: np.zeros(0, dtype=_NP[ct]) for n, ct in COLUMN_FIELDS}
-        elif b.host.rec_off:
-            self.columns = {n: _view(getattr(b.host, n), self.n_records, ct) for n, ct in COLUMN_FIELDS}
+        elif b.host.rec_off:   # BAMGPU_COPY_OFFSETS alone fills only rec_off / rec_len
+            self.columns = {n: _view(getattr(b.host, n), self.n_records, ct) for n, ct in COLUMN_FIELDS if getattr(b.host, n)}
 
     def body(self, i: int) -> memoryview:
         o = int(self.columns["rec_off"][i])

@@ -249,6 +249,35 @@ def run_b200(a, rank: int, world: int, local_rank: int):
     assert shard.size == int(my_csz.sum())
     c0, c1 = 0, shard.size
     total_records = a.records * world
+    # ---- e2e (N=1): drop-in Reader over the HOST buffer, H2D + D2H inside the timed region.  Measured FIRST, in a process
+    # that holds nothing else on the device or in pinned memory (the same loop run after the device-resident phase, with its
+    # 45 GB of buffers alive, was measured 15-20 % slower on the D2H side; tools/debug/e2e_timeline.py is the standalone form) ----
+    e2e = e2e_cols = e2e_all = pcie = None
+    if not a.no_e2e and world == 1:
+        # what the link gives a plain pinned copy: the bound of every e2e number below
+        hbuf = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+        dbuf = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+        pcie = {}
+        for name, dst, srcb in (("d2h_GB_per_s", hbuf, dbuf), ("h2d_GB_per_s", dbuf, hbuf)):
+            dst.copy_(srcb, non_blocking=True)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                dst.copy_(srcb, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            pcie[name] = round(3 * (1 << 30) / (e0.elapsed_time(e1) * 1e-3) / 1e9, 1)
+        del hbuf, dbuf
+    if not a.no_e2e:
+        if world == 1:
+            e2e = run_e2e(a, bp, arr, c0, c1, rank, world, dist, torch, int(total_isize) * 1)
+            e2e_all = run_e2e(a, bp, arr, c0, c1, rank, world, dist, torch, int(total_isize), flags=bp.COPY_DATA | bp.COPY_COLUMNS,
+                              api="same, plus all 21 SoA columns (fixed fields, offsets, sort keys) D2H")
+            e2e_cols = run_e2e(a, bp, arr, c0, c1, rank, world, dist, torch, int(total_isize), flags=bp.COPY_COLUMNS,
+                               api="only the SoA columns + sort keys come back (what a host-side sort of keys needs); bodies stay in HBM")
+
+
     eng = bp.Engine(device=local_rank)
     eng.set_n_ref(n_ref)
     d_comp = eng.upload(shard)
@@ -375,14 +404,9 @@ def run_b200(a, rank: int, world: int, local_rank: int):
                              "order, sort.rs:643); parity vs the oracle in tests/test_gpu_sort.py; gather GB/s counts bodies read + written")
 
     # ---- e2e: drop-in Reader over the HOST buffer (H2D + D2H inside the timed region) ----
-    e2e = e2e_cols = None
-    if not a.no_e2e:
-        if world == 1:
-            e2e = run_e2e(a, bp, arr, c0, c1, rank, world, dist, torch, u_all)
-            e2e_cols = run_e2e(a, bp, arr, c0, c1, rank, world, dist, torch, u_all, flags=bp.COPY_COLUMNS,
-                               api="same, but only the SoA columns + sort keys come back (what a GPU-fed sort needs); bodies stay in HBM")
-        else:
-            e2e = run_e2e_sharded(a, bp, eng, shard, d_comp, step_host, sync_all, rank, world, dist, torch, u_all, my_u, n_rec_local)
+    # ---- e2e (N>1): per-rank pinned H2D / D2H around the sharded decode ----
+    if not a.no_e2e and world > 1:
+        e2e = run_e2e_sharded(a, bp, eng, shard, d_comp, step_host, sync_all, rank, world, dist, torch, u_all, my_u, n_rec_local)
 
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
@@ -411,7 +435,7 @@ def run_b200(a, rank: int, world: int, local_rank: int):
                        "l2": "inputs (compressed + inflated) far larger than the 126 MB L2; no flush needed",
                        "generator_seconds": round(gen_s, 1), "k3_chain_repairs": chain_repairs},
             "records_per_s": n_rec_all / (ms_step * 1e-3),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_columns_only": e2e_cols, "sort": sort_info, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_with_columns": e2e_all, "e2e_columns_only": e2e_cols, "pcie_pinned_copy": pcie, "sort": sort_info, "gpu_launches": launches,
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -421,11 +445,12 @@ def run_b200(a, rank: int, world: int, local_rank: int):
 
 
 def run_e2e(a, bp, arr, c0, c1, rank, world, dist, torch, u_all, flags=None, api=None):
-    """Reader::new(host bytes) -> read_header -> next_batch until EOF, bodies + columns copied back to pinned
-    host memory (what records().next_rec() serves from)."""
-    full = flags is None
-    if full:
-        flags = bp.COPY_DATA | bp.COPY_COLUMNS
+    """Reader::new(host bytes) -> read_header -> next_batch until EOF, with the batch's host mirrors filled as `flags` say;
+    default: bodies + (rec_off, rec_len), i.e. exactly what records().next_rec() serves from."""
+    if flags is None:
+        flags = bp.COPY_DATA | bp.COPY_OFFSETS
+    per_rec = 74 if flags & bp.COPY_COLUMNS else (12 if flags & bp.COPY_OFFSETS else 0)   # bytes of columns D2H per record
+    full = bool(flags & bp.COPY_DATA)
     times, d2h = [], 0
     warm = 2   # the first Readers of a process page-lock their buffers (parked in the library's cache afterwards)
     for it in range(warm + a.e2e_steps):
@@ -440,7 +465,7 @@ def run_e2e(a, bp, arr, c0, c1, rank, world, dist, torch, u_all, flags=None, api
                 if b is None:
                     break
                 n += b.n_records
-                d2h += (b.data_len if full else 0) + 74 * b.n_records
+                d2h += (b.data_len if full else 0) + per_rec * b.n_records
             st = r.stats()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -451,7 +476,8 @@ def run_e2e(a, bp, arr, c0, c1, rank, world, dist, torch, u_all, flags=None, api
             "records_per_s": n / t, "ms_per_step": t * 1e3, "steps": a.e2e_steps, "warmup": warm,
             "device_ms": {k: round(st[k], 1) for k in ("ms_inflate", "ms_crc", "ms_records", "ms_d2h")}, "batches": st["batches"],
             "step_ms": [round(x * 1e3, 1) for x in times],
-            "api": api or "Reader.new(host bytes) / read_header / next_batch, bodies + SoA columns D2H to pinned memory"}
+            "api": api or "Reader.new(host bytes, min(cpus, 20)) / read_header / next_batch: every record body + (offset, length) in pinned "
+                          "host memory = what records().next_rec() lends (the reference hands out bodies, nothing else)"}
 
 
 def run_e2e_sharded(a, bp, eng, shard, d_comp, step_host, sync_all, rank, world, dist, torch, u_all, my_u, n_rec_local):

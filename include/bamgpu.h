@@ -131,6 +131,8 @@ enum {
   BAMGPU_WANT_HI = 4,           /* walk aux tags for HI (only the -n -M sort needs it) */
   BAMGPU_NO_CRC = 8,            /* skip the CRC32 check (default: verify) */
   BAMGPU_NO_RECORDS = 16,       /* inflate (+CRC) only: no record kernel (impl Read consumers) */
+  BAMGPU_COPY_OFFSETS = 64,     /* D2H only rec_off + rec_len of the columns (with BAMGPU_COPY_DATA this is all that
+                                   next_rec / append_record need: the reference lends bodies, nothing else) */
   BAMGPU_SPECULATIVE_START = 32 /* shard-edge mode (multi-GPU): stream_start is NOT a known record start; the chain
                                    begins at the first offset >= stream_start that looks like a run of records.
                                    The caller must confirm batch.chain_start with the left-hand shard's tail_off. */
