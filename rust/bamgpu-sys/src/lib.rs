@@ -1,7 +1,7 @@
 //! Raw bindings of include/bamgpu.h plus a `bam_tools::Reader`-shaped wrapper.
 //! UNBUILT in this repository's image (no cargo/rustc there): source only, see INTEGRATION.md.
 #![allow(non_camel_case_types)]
-use std::io::{self, Read};
+use std::io::{self, Read, Write};
 use std::os::raw::{c_char, c_int, c_long, c_void};
 
 #[repr(C)] pub struct bamgpu_reader { _p: [u8; 0] }
@@ -20,7 +20,10 @@ extern "C" {
     pub fn bamgpu_next_rec(r: *mut bamgpu_reader, body: *mut *const u8, len: *mut usize) -> c_int;
     pub fn bamgpu_append_record(r: *mut bamgpu_reader, dst: *mut u8, cap: usize, len: *mut usize) -> c_int;
     pub fn bamgpu_read(r: *mut bamgpu_reader, dst: *mut u8, cap: usize) -> c_long;
+    pub fn bamgpu_sort_bam(read: bamgpu_read_fn, rctx: *mut c_void, write: bamgpu_write_fn, wctx: *mut c_void, reader_thread_num: usize,
+                           sort_by: c_int, opts: *const bamgpu_opts, stats: *mut c_void, err: *mut c_char, err_cap: usize) -> c_int;
 }
+pub type bamgpu_write_fn = unsafe extern "C" fn(ctx: *mut c_void, src: *const u8, len: usize) -> c_int;
 
 /// Drop-in for `bam_tools::Reader` (bam_tools/src/reader.rs:17-99).
 pub struct Reader { h: *mut bamgpu_reader, _inner: Box<Box<dyn Read + Send>>, rec: Vec<u8> }
@@ -96,4 +99,33 @@ impl<'a> Records<'a> {
 impl<'a> Iterator for Records<'a> {
     type Item = io::Result<Vec<u8>>;
     fn next(&mut self) -> Option<Self::Item> { self.next_rec().map(|r| r.map(|v| v.clone())) }
+}
+
+/// sorting/sort.rs:92-96
+#[derive(Clone, Copy, Debug, PartialEq)]
+pub enum SortBy { Name = 0, NameAndMatchMates = 1, CoordinatesAndStrand = 2 }
+
+unsafe extern "C" fn write_trampoline(ctx: *mut c_void, src: *const u8, len: usize) -> c_int {
+    let sink = &mut *(ctx as *mut &mut dyn Write);
+    match sink.write_all(std::slice::from_raw_parts(src, len)) { Ok(()) => 0, Err(_) => -1 }
+}
+
+/// Drop-in for `bam_tools::sorting::sort::sort_bam` (sort.rs:138-178) without the GBAM index mode (unreachable from
+/// bam_binary, main.rs:74).  mem_limit / tmp_dir / temp_files_mode steer the reference's external merge and have no
+/// counterpart: the records stay in HBM from decode to output.  Panics where the reference's comparators panic.
+pub fn sort_bam<R: Read + Send + 'static, W: Write>(_mem_limit: usize, reader: R, sorted_sink: &mut W, reader_thread_num: usize,
+                                                   sort_by: SortBy) -> io::Result<()> {
+    let mut boxed: Box<Box<dyn Read + Send>> = Box::new(Box::new(reader));
+    let mut sink: &mut dyn Write = sorted_sink;
+    let mut msg = [0 as c_char; 512];
+    let rc = unsafe {
+        bamgpu_sort_bam(trampoline, &mut *boxed as *mut _ as *mut c_void, write_trampoline, &mut sink as *mut _ as *mut c_void,
+                        reader_thread_num, sort_by as c_int, std::ptr::null(), std::ptr::null_mut(), msg.as_mut_ptr(), msg.len())
+    };
+    let text = unsafe { std::ffi::CStr::from_ptr(msg.as_ptr()) }.to_string_lossy().into_owned();
+    match rc {
+        0 => Ok(()),
+        -30 | -31 | -32 => panic!("{}", text),   // comparators.rs:90, :178, tags.rs: the reference panics here
+        _ => Err(io::Error::new(io::ErrorKind::InvalidData, text)),
+    }
 }
