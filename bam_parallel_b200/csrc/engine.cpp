@@ -62,13 +62,13 @@ struct PinnedCache {
   std::mutex mu;
   std::vector<std::pair<void*, size_t>> free_list;
   size_t bytes = 0;
-  static constexpr size_t LIMIT = (size_t)6 << 30;
+  static constexpr size_t LIMIT = (size_t)12 << 30;
   void* take(size_t n, size_t* cap) {
     std::lock_guard<std::mutex> lk(mu);
     size_t best = (size_t)-1;
     for (size_t i = 0; i < free_list.size(); ++i)
       if (free_list[i].second >= n && (best == (size_t)-1 || free_list[i].second < free_list[best].second)) best = i;
-    if (best == (size_t)-1 || free_list[best].second > 2 * n + (1 << 20)) return nullptr;
+    if (best == (size_t)-1 || free_list[best].second > n + n / 4 + (1 << 20)) return nullptr;   // a snug fit only: a big buffer taken for a small need is missed later
     void* p = free_list[best].first;
     *cap = free_list[best].second;
     bytes -= *cap;
@@ -129,8 +129,7 @@ struct bamgpu_engine {
   int cur = 0;
   bool pingpong = false;
   cudaStream_t d2h_stream = nullptr;
-  cudaEvent_t ev_k3_done = nullptr, ev_d2h_done = nullptr;
-  bool d2h_pending = false;
+  cudaEvent_t ev_k3_done = nullptr;
   // launch/finish split of the inflate stage
   size_t pend_nb = 0;
   uint64_t pend_total = 0, pend_bytes_in = 0;
@@ -142,18 +141,26 @@ struct bamgpu_engine {
   int32_t n_ref = -1;
   // tiles
   DevBuf d_tiles;
-  // columns
-  DevBuf d_cols;
-  uint64_t cols_cap = 0;
-  ColumnsDev cols{};
+  // One batch's columns on the device, its host mirrors and the bookkeeping of the D2H that fills them.  The Reader
+  // (pingpong) alternates between two sets, so that batch k+1's record kernels and D2H can be queued while batch k's
+  // D2H is still running and while the caller still holds batch k's pointers.
+  struct Mirror {
+    DevBuf d_cols;
+    uint64_t cols_cap = 0;
+    ColumnsDev cols{};
+    PinBuf h_data, h_cols;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    bool pending = false;
+  };
+  Mirror mir[2];
+  int msel = 0;
   // sort (bamgpu_engine_sort)
   DevBuf d_sort, d_perm, d_soff, d_sorted;
   PinBuf h_sorted, h_perm;
   uint64_t last_n = 0, last_bad_flags = 0;
   uint32_t last_flags = 0;
   bool last_valid = false;
-  // host mirrors
-  PinBuf h_data, h_cols, h_res;
+  PinBuf h_res;
   uint64_t first_record_index = 0;
   // timing
   cudaEvent_t ev[8]{};
@@ -260,7 +267,7 @@ extern "C" bamgpu_engine* bamgpu_engine_new(const bamgpu_opts* opts) {
   if (cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking) != cudaSuccess) { delete E; return nullptr; }
   if (cudaStreamCreateWithFlags(&E->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) { delete E; return nullptr; }
   cudaEventCreateWithFlags(&E->ev_k3_done, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&E->ev_d2h_done, cudaEventDisableTiming);
+  for (auto& M : E->mir) { cudaEventCreate(&M.ev_begin); cudaEventCreate(&M.ev_end); }
   for (auto& e : E->ev) cudaEventCreate(&e);
   E->default_flags = opts ? opts->flags : 0;
   if (E->d_misc.reserve(8192) != cudaSuccess || E->d_crc_tables.reserve(CRC_TABLE_WORDS * 4) != cudaSuccess ||
@@ -280,10 +287,10 @@ extern "C" void bamgpu_engine_free(bamgpu_engine* E) {
   if (E->stream) { cudaStreamSynchronize(E->stream); cudaStreamDestroy(E->stream); }
   if (E->d2h_stream) { cudaStreamSynchronize(E->d2h_stream); cudaStreamDestroy(E->d2h_stream); }
   if (E->ev_k3_done) cudaEventDestroy(E->ev_k3_done);
-  if (E->ev_d2h_done) cudaEventDestroy(E->ev_d2h_done);
+  for (auto& M : E->mir) { if (M.ev_begin) cudaEventDestroy(M.ev_begin); if (M.ev_end) cudaEventDestroy(M.ev_end); M.d_cols.release(); M.h_data.release(); M.h_cols.release(); }
   for (auto& e : E->ev) if (e) cudaEventDestroy(e);
   E->h_tab.release(); E->d_tab.release(); E->d_status.release(); E->d_misc.release(); E->d_crc_tables.release();
-  E->d_outs[0].release(); E->d_outs[1].release(); E->d_tiles.release(); E->d_cols.release(); E->h_data.release(); E->h_cols.release(); E->h_res.release();
+  E->d_outs[0].release(); E->d_outs[1].release(); E->d_tiles.release(); E->h_res.release();
   delete E;
 }
 
@@ -354,6 +361,7 @@ int map_block_status(uint32_t st) {
 // batch k+1's kernels on the stream before it waits for batch k's device-to-host copy:
 //   engine_inflate_launch  enqueues carry move, block table upload, K1, K2, status reduce; no host wait
 //   engine_inflate_finish  waits, reads the first failing block (if any), books the stage times
+static int engine_wait_d2h(bamgpu_engine* E);
 static int engine_inflate_launch(bamgpu_engine* E, const uint8_t* d_comp, const bamgpu_block* blocks, size_t n_blocks,
                                  uint32_t flags, cudaStream_t s) {
   const double t_in = now_ms();
@@ -375,7 +383,7 @@ static int engine_inflate_launch(bamgpu_engine* E, const uint8_t* d_comp, const 
     if (dst == src) {
       E->d_outs[dst].release();
     } else {
-      if (E->d2h_pending) { ECK(cudaStreamSynchronize(E->d2h_stream)); }  // nobody may still read the buffer we free
+      { int w = engine_wait_d2h(E); if (w < 0) return w; }  // nobody may still read the buffer we free
       E->d_outs[dst].release();
     }
     E->d_outs[dst] = nb;
@@ -445,7 +453,7 @@ static int engine_inflate_launch(bamgpu_engine* E, const uint8_t* d_comp, const 
   ECK(cudaEventRecord(E->ev[2], s));
   launch_status_reduce(E->d_status.as<uint32_t>(), (uint32_t)nb, first_bad, s);
   E->stats.kernel_launches += 1;
-  ECK(cudaMemcpyAsync(E->h_res.as<unsigned long long>(), first_bad, 8, cudaMemcpyDeviceToHost, s));
+  launch_copy_small_to_host(E->h_res.p, first_bad, 8, s);
   if (dbg_level() >= 2) fprintf(stderr, "[bamgpu] inflate_launch host %.2f ms (%zu blocks)\n", now_ms() - t_in, n_blocks);
   return BAMGPU_OK;
 }
@@ -485,14 +493,19 @@ static int engine_inflate(bamgpu_engine* E, const uint8_t* d_comp, const bamgpu_
 }
 
 // Waits for the device-to-host copies engine_records left running (defer_d2h).
-static int engine_wait_d2h(bamgpu_engine* E) {
-  if (E->d2h_pending) {
-    E->d2h_pending = false;
-    ECK(cudaStreamSynchronize(E->d2h_stream));
+static int engine_wait_mirror(bamgpu_engine* E, int i) {
+  bamgpu_engine::Mirror& M = E->mir[i];
+  if (M.pending) {
+    M.pending = false;
+    ECK(cudaEventSynchronize(M.ev_end));
     float ms = 0;
-    cudaEventElapsedTime(&ms, E->ev[6], E->ev[7]);
+    cudaEventElapsedTime(&ms, M.ev_begin, M.ev_end);
     E->stats.ms_d2h += ms;
   }
+  return BAMGPU_OK;
+}
+static int engine_wait_d2h(bamgpu_engine* E) {
+  for (int i = 0; i < 2; ++i) { int w = engine_wait_mirror(E, i); if (w < 0) return w; }
   return BAMGPU_OK;
 }
 
@@ -501,7 +514,11 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
                           bamgpu_batch* out, uint64_t* tail_off_out, bool defer_d2h = false) {
   const double t_in = now_ms();
   ECK(cudaSetDevice(E->device));
-  { int w = engine_wait_d2h(E); if (w < 0) return w; }
+  // the mirror set this batch goes to: its previous D2H (two batches ago when ping-ponging) must be over
+  if (E->pingpong) E->msel ^= 1;
+  bamgpu_engine::Mirror& M = E->mir[E->msel];
+  if (E->pingpong) { int w = engine_wait_mirror(E, E->msel); if (w < 0) return w; }
+  else { int w = engine_wait_d2h(E); if (w < 0) return w; }
   memset(out, 0, sizeof *out);
   out->data = E->out_ptr();
   out->data_len = E->data_len;
@@ -531,7 +548,7 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
     launch_tile_walk(p, t, s);
     ECK(launch_chain_resolve(p, t, d_res, (ResolveScratch*)(E->d_misc.as<uint8_t>() + 256), E->num_sms, s));
     E->stats.kernel_launches += 2;
-    ECK(cudaMemcpyAsync(h_res, d_res, sizeof(ChainResult), cudaMemcpyDeviceToHost, s));
+    launch_copy_small_to_host(h_res, d_res, sizeof(ChainResult), s);
     ECK(cudaStreamSynchronize(s));
     ECK(cudaGetLastError());
     if (h_res->broken_tile != 0xffffffffu) { E->err = "internal: record chain left the buffer"; return BAMGPU_ERR_STATE; }
@@ -541,16 +558,16 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
     tail_off = h_res->tail_off;
     tail_kind = h_res->tail_kind;
     if (n_rec) {
-      if (n_rec > E->cols_cap) {
+      if (n_rec > M.cols_cap) {
         uint64_t cap = n_rec + n_rec / 8 + 1024;
-        ECK(E->d_cols.reserve(columns_bytes(cap)));
-        E->cols_cap = cap;
-        carve_columns(E->d_cols.as<uint8_t>(), cap, E->cols);
+        ECK(M.d_cols.reserve(columns_bytes(cap)));
+        M.cols_cap = cap;
+        carve_columns(M.d_cols.as<uint8_t>(), cap, M.cols);
       }
-      launch_tile_emit(p, t, E->cols.rec_off, E->cols.rec_len, s);
-      launch_extract(p, E->cols, n_rec, (flags & BAMGPU_WANT_HI) != 0, d_res, s);
+      launch_tile_emit(p, t, M.cols.rec_off, M.cols.rec_len, s);
+      launch_extract(p, M.cols, n_rec, (flags & BAMGPU_WANT_HI) != 0, d_res, s);
       E->stats.kernel_launches += 2;
-      ECK(cudaMemcpyAsync(h_res, d_res, sizeof(ChainResult), cudaMemcpyDeviceToHost, s));
+      launch_copy_small_to_host(h_res, d_res, sizeof(ChainResult), s);
       ECK(cudaStreamSynchronize(s));
       ECK(cudaGetLastError());
       bad_flags = h_res->bad_flags;
@@ -575,47 +592,47 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
   E->last_bad_flags = bad_flags;
   E->last_flags = flags;
   E->last_valid = !(flags & BAMGPU_NO_RECORDS);
-  fill_public_columns(E->cols, out->dev);
+  fill_public_columns(M.cols, out->dev);
   // host mirrors: on their own stream, behind the record kernels
   cudaStream_t cs = E->d2h_stream;
   const bool any_copy = (flags & BAMGPU_COPY_DATA) || ((flags & (BAMGPU_COPY_COLUMNS | BAMGPU_COPY_OFFSETS)) && n_rec);
   if (any_copy) {
     ECK(cudaEventRecord(E->ev_k3_done, s));
     ECK(cudaStreamWaitEvent(cs, E->ev_k3_done, 0));
-    ECK(cudaEventRecord(E->ev[6], cs));
+    ECK(cudaEventRecord(M.ev_begin, cs));
   }
   if (flags & BAMGPU_COPY_DATA) {
-    ECK(E->h_data.reserve(E->data_len + 64));
-    if (E->data_len) ECK(cudaMemcpyAsync(E->h_data.p, E->out_ptr(), E->data_len, cudaMemcpyDeviceToHost, cs));
-    out->h_data = E->h_data.as<uint8_t>();
+    ECK(M.h_data.reserve(E->data_len + 64));
+    if (E->data_len) ECK(cudaMemcpyAsync(M.h_data.p, E->out_ptr(), E->data_len, cudaMemcpyDeviceToHost, cs));
+    out->h_data = M.h_data.as<uint8_t>();
   }
   if ((flags & BAMGPU_COPY_OFFSETS) && !(flags & BAMGPU_COPY_COLUMNS) && n_rec) {
     // what next_rec() needs besides the bodies: where each one starts and how long it is
-    ECK(E->h_cols.reserve(columns_bytes(E->cols_cap)));
+    ECK(M.h_cols.reserve(columns_bytes(M.cols_cap)));
     ColumnsDev hc;
-    carve_columns(E->h_cols.as<uint8_t>(), E->cols_cap, hc);
-    ECK(cudaMemcpyAsync(hc.rec_off, E->cols.rec_off, 8 * n_rec, cudaMemcpyDeviceToHost, cs));
-    ECK(cudaMemcpyAsync(hc.rec_len, E->cols.rec_len, 4 * n_rec, cudaMemcpyDeviceToHost, cs));
+    carve_columns(M.h_cols.as<uint8_t>(), M.cols_cap, hc);
+    ECK(cudaMemcpyAsync(hc.rec_off, M.cols.rec_off, 8 * n_rec, cudaMemcpyDeviceToHost, cs));
+    ECK(cudaMemcpyAsync(hc.rec_len, M.cols.rec_len, 4 * n_rec, cudaMemcpyDeviceToHost, cs));
     out->host.rec_off = hc.rec_off;
     out->host.rec_len = hc.rec_len;
   }
   if ((flags & BAMGPU_COPY_COLUMNS) && n_rec) {
-    size_t bytes = columns_bytes(E->cols_cap);
-    ECK(E->h_cols.reserve(bytes));
+    size_t bytes = columns_bytes(M.cols_cap);
+    ECK(M.h_cols.reserve(bytes));
     // copy only the used prefix of every column
     ColumnsDev hc;
-    carve_columns(E->h_cols.as<uint8_t>(), E->cols_cap, hc);
+    carve_columns(M.h_cols.as<uint8_t>(), M.cols_cap, hc);
     auto cp = [&](void* dst, const void* src, size_t elem) {
       return cudaMemcpyAsync(dst, src, elem * n_rec, cudaMemcpyDeviceToHost, cs);
     };
-    ECK(cp(hc.rec_off, E->cols.rec_off, 8)); ECK(cp(hc.coord_key, E->cols.coord_key, 8));
-    ECK(cp(hc.rec_len, E->cols.rec_len, 4)); ECK(cp(hc.ref_id, E->cols.ref_id, 4)); ECK(cp(hc.pos, E->cols.pos, 4));
-    ECK(cp(hc.l_seq, E->cols.l_seq, 4)); ECK(cp(hc.next_ref_id, E->cols.next_ref_id, 4)); ECK(cp(hc.next_pos, E->cols.next_pos, 4));
-    ECK(cp(hc.tlen, E->cols.tlen, 4)); ECK(cp(hc.cigar_off, E->cols.cigar_off, 4)); ECK(cp(hc.seq_off, E->cols.seq_off, 4));
-    ECK(cp(hc.qual_off, E->cols.qual_off, 4)); ECK(cp(hc.tags_off, E->cols.tags_off, 4)); ECK(cp(hc.hi_value, E->cols.hi_value, 4));
-    ECK(cp(hc.bin, E->cols.bin, 2)); ECK(cp(hc.n_cigar_op, E->cols.n_cigar_op, 2)); ECK(cp(hc.flag, E->cols.flag, 2));
-    ECK(cp(hc.l_read_name, E->cols.l_read_name, 1)); ECK(cp(hc.mapq, E->cols.mapq, 1)); ECK(cp(hc.strand, E->cols.strand, 1));
-    ECK(cp(hc.hi_present, E->cols.hi_present, 1));
+    ECK(cp(hc.rec_off, M.cols.rec_off, 8)); ECK(cp(hc.coord_key, M.cols.coord_key, 8));
+    ECK(cp(hc.rec_len, M.cols.rec_len, 4)); ECK(cp(hc.ref_id, M.cols.ref_id, 4)); ECK(cp(hc.pos, M.cols.pos, 4));
+    ECK(cp(hc.l_seq, M.cols.l_seq, 4)); ECK(cp(hc.next_ref_id, M.cols.next_ref_id, 4)); ECK(cp(hc.next_pos, M.cols.next_pos, 4));
+    ECK(cp(hc.tlen, M.cols.tlen, 4)); ECK(cp(hc.cigar_off, M.cols.cigar_off, 4)); ECK(cp(hc.seq_off, M.cols.seq_off, 4));
+    ECK(cp(hc.qual_off, M.cols.qual_off, 4)); ECK(cp(hc.tags_off, M.cols.tags_off, 4)); ECK(cp(hc.hi_value, M.cols.hi_value, 4));
+    ECK(cp(hc.bin, M.cols.bin, 2)); ECK(cp(hc.n_cigar_op, M.cols.n_cigar_op, 2)); ECK(cp(hc.flag, M.cols.flag, 2));
+    ECK(cp(hc.l_read_name, M.cols.l_read_name, 1)); ECK(cp(hc.mapq, M.cols.mapq, 1)); ECK(cp(hc.strand, M.cols.strand, 1));
+    ECK(cp(hc.hi_present, M.cols.hi_present, 1));
     fill_public_columns(hc, out->host);
   }
   ECK(cudaStreamSynchronize(s));
@@ -623,9 +640,9 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
   float ms = 0;
   cudaEventElapsedTime(&ms, E->ev[3], E->ev[4]); E->stats.ms_records += ms;
   if (any_copy) {
-    ECK(cudaEventRecord(E->ev[7], cs));
-    E->d2h_pending = true;
-    if (!defer_d2h) { int w = engine_wait_d2h(E); if (w < 0) return w; }
+    ECK(cudaEventRecord(M.ev_end, cs));
+    M.pending = true;
+    if (!defer_d2h) { int w = engine_wait_mirror(E, E->msel); if (w < 0) return w; }
   }
   if (dbg_level() >= 2) fprintf(stderr, "[bamgpu] records host wall %.2f ms\n", now_ms() - t_in);
   E->stats.records += n_rec;
@@ -726,11 +743,11 @@ extern "C" int bamgpu_engine_sort(bamgpu_engine* E, int sort_by, uint32_t flags,
   SortResult* h_sr = (SortResult*)(E->h_res.as<uint8_t>() + 192);
   int launches = 0;
   ECK(cudaEventRecord(E->ev[3], s));
-  ECK(sort_permutation(E->out_ptr(), E->cols, n, sort_by, E->d_sort.p, E->d_perm.as<uint32_t>(), d_sr, &launches, s));
+  ECK(sort_permutation(E->out_ptr(), E->mir[E->msel].cols, n, sort_by, E->d_sort.p, E->d_perm.as<uint32_t>(), d_sr, &launches, s));
   ECK(cudaMemcpyAsync(h_sr, d_sr, sizeof(SortResult), cudaMemcpyDeviceToHost, s));
   ECK(cudaEventRecord(E->ev[4], s));
   uint64_t total = 0;
-  ECK(sorted_offsets(E->cols, E->d_perm.as<uint32_t>(), n, E->d_sort.p, E->d_soff.as<uint64_t>(), &total, s));   // synchronises
+  ECK(sorted_offsets(E->mir[E->msel].cols, E->d_perm.as<uint32_t>(), n, E->d_sort.p, E->d_soff.as<uint64_t>(), &total, s));   // synchronises
   if (sort_by == BAMGPU_SORT_NAME_AND_MATCH_MATES) {
     if (h_sr->hi_bad_tags) { E->err = "sort: aux tags the reference's HI walk panics on"; return BAMGPU_ERR_SORT_BAD_TAGS; }
     if (h_sr->hi_mixed) {
@@ -739,7 +756,7 @@ extern "C" int bamgpu_engine_sort(bamgpu_engine* E, int sort_by, uint32_t flags,
     }
   }
   ECK(E->d_sorted.reserve(total + 64));
-  ECK(gather_sorted_bodies(E->out_ptr(), E->cols, E->d_perm.as<uint32_t>(), n, E->d_sort.p, E->d_soff.as<uint64_t>(),
+  ECK(gather_sorted_bodies(E->out_ptr(), E->mir[E->msel].cols, E->d_perm.as<uint32_t>(), n, E->d_sort.p, E->d_soff.as<uint64_t>(),
                            E->d_sorted.as<uint8_t>(), s));
   ECK(cudaEventRecord(E->ev[5], s));
   launches += 3;
@@ -814,6 +831,10 @@ struct bamgpu_reader {
   uint64_t next_start = 0;          // chain start inside the next engine_records call
   bamgpu_batch batch{};
   bool batch_valid = false;
+  bamgpu_batch prep{};              // the batch staged behind `batch`: record kernels done, D2H queued
+  bool prep_valid = false, no_more = false;
+  int prep_sel = 0;
+  int sticky_next = BAMGPU_OK;
   uint64_t rec_cursor = 0;          // next record of `batch` to hand out
   uint64_t byte_cursor = 0;         // raw mode: next byte of batch.h_data
   bool pending_final = false;
@@ -1068,54 +1089,72 @@ extern "C" int bamgpu_read_header(bamgpu_reader* R, const uint8_t** bytes, size_
   return BAMGPU_OK;
 }
 
+// Stages the next non-empty batch: waits for its inflate (launching it first if need be), runs the record kernels and
+// queues its D2H (not waited for) -> R->prep / R->prep_sel.  BAMGPU_OK, BAMGPU_EOF (no more input) or an error.
+static int reader_stage_next(bamgpu_reader* R, uint32_t flags) {
+  bamgpu_engine* E = R->E;
+  for (;;) {
+    if (R->no_more) return BAMGPU_EOF;
+    int rc;
+    if (!R->inflated_pending) {
+      rc = reader_inflate_launch_next(R, flags, false);
+      if (rc == BAMGPU_EOF) { R->no_more = true; return BAMGPU_EOF; }   // whatever carry was left has been judged with final=1
+      if (rc < 0) return rc;
+    }
+    const double t0 = now_ms();
+    rc = engine_inflate_finish(E, E->stream);
+    if (rc < 0) return rc;
+    R->inflated_pending = false;
+    const bool fin = R->pending_final;
+    uint64_t tail = 0;
+    const double t1 = now_ms();
+    rc = engine_records(E, R->next_start, fin ? 1 : 0, flags, E->stream, &R->prep, &tail, /*defer_d2h=*/true);
+    R->next_start = 0;
+    if (rc < 0) return rc;
+    if (rc == BAMGPU_EOF || fin) R->no_more = true;
+    R->prep_sel = E->msel;
+    if (dbg_level() >= 2)
+      fprintf(stderr, "[bamgpu] stage @%.1f: wait inflate %.2f, records %.2f ms (%llu records)\n", t0, t1 - t0, now_ms() - t1,
+              (unsigned long long)R->prep.n_records);
+    if (R->prep.n_records) return BAMGPU_OK;
+    { int w = engine_wait_mirror(E, E->msel); if (w < 0) return w; }   // an empty batch: drop it
+  }
+}
+
 // Produces the next non-empty batch (or EOF). Uses the inflated-but-unparsed batch left by read_header first.
-// Pipeline per call:  finish inflate(k) -> K3(k) -> start D2H(k) on the copy stream -> put inflate(k+1) on the compute
-// stream (other output buffer) -> wait D2H(k).  So the host copy of batch k and the caller's work on it overlap K1 of
-// batch k+1, and the feeder thread's H2D of batch k+2 overlaps both.
+// Pipeline per call k:  [batch k was staged by the previous call: its D2H is running]  ->  launch inflate(k+1) into the
+// device buffer the caller has just released, wait for it, K3(k+1), queue D2H(k+1) behind D2H(k) (other mirror set)  ->
+// wait D2H(k)  ->  hand out batch k.  So the copy engine goes from one batch's D2H straight into the next one's, K1/K3 of
+// batch k+1 run under D2H(k), the feeder thread's H2D of batch k+2 under both, and batch k's device and host pointers
+// stay valid until the next call.
 static int reader_next_batch(bamgpu_reader* R, uint32_t extra_flags) {
   if (R->sticky < 0) return R->sticky;
   if (R->eof) return BAMGPU_EOF;
   if (!R->header_done) { R->err = "records requested before read_header()"; return BAMGPU_ERR_STATE; }
   bamgpu_engine* E = R->E;
-  uint32_t flags = R->flags | extra_flags;
-  for (;;) {
-    int rc;
-    if (!R->inflated_pending) {
-      rc = reader_inflate_launch_next(R, flags, false);
-      if (rc == BAMGPU_EOF) {
-        // input exhausted and nothing pending: whatever carry is left was already judged with final=1
-        R->eof = true;
-        return BAMGPU_EOF;
-      }
-      if (rc < 0) { R->sticky = rc; return rc; }
-    }
-    const double t0 = now_ms();
-    rc = engine_inflate_finish(E, E->stream);
+  const uint32_t flags = R->flags | extra_flags;
+  if (!R->prep_valid) {
+    if (R->sticky_next < 0) { R->sticky = R->sticky_next; return R->sticky; }
+    int rc = reader_stage_next(R, flags);
+    if (rc == BAMGPU_EOF) { R->eof = true; return BAMGPU_EOF; }
     if (rc < 0) { R->sticky = rc; return rc; }
-    R->inflated_pending = false;
-    const bool fin = R->pending_final;
-    uint64_t tail = 0;
-    const double t1 = now_ms();
-    rc = engine_records(E, R->next_start, fin ? 1 : 0, flags, E->stream, &R->batch, &tail, /*defer_d2h=*/true);
-    const double t2 = now_ms();
-    R->next_start = 0;
-    if (rc < 0) { R->sticky = rc; return rc; }
-    R->batch_valid = true;
-    R->rec_cursor = 0;
-    if (rc == BAMGPU_EOF || fin) R->eof = true;
-    if (!R->eof) {
-      int pr = reader_inflate_launch_next(R, flags, /*nonblocking=*/true);
-      if (pr < 0) { R->sticky = pr; }  // surfaces on the next call; this batch is still good
-    }
-    const double t3 = now_ms();
-    int w = engine_wait_d2h(E);
-    if (w < 0) { R->sticky = w; return w; }
-    if (dbg_level() >= 2)
-      fprintf(stderr, "[bamgpu] next_batch @%.1f: wait inflate %.2f, records %.2f, launch next %.2f, wait d2h %.2f ms (%llu records)\n",
-              t0, t1 - t0, t2 - t1, t3 - t2, now_ms() - t3, (unsigned long long)R->batch.n_records);
-    if (R->batch.n_records) return BAMGPU_OK;
-    if (R->eof) return BAMGPU_EOF;
+    R->prep_valid = true;
   }
+  const bamgpu_batch cur = R->prep;
+  const int cur_sel = R->prep_sel;
+  R->prep_valid = false;
+  const double t0 = now_ms();
+  const int rn = reader_stage_next(R, flags);
+  if (rn == BAMGPU_OK) R->prep_valid = true;
+  else if (rn < 0) R->sticky_next = rn;      // surfaces on the next call; this batch is still good
+  const double t1 = now_ms();
+  int w = engine_wait_mirror(E, cur_sel);
+  if (w < 0) { R->sticky = w; return w; }
+  if (dbg_level() >= 2) fprintf(stderr, "[bamgpu] next_batch @%.1f: stage next %.2f, wait d2h %.2f ms\n", t0, t1 - t0, now_ms() - t1);
+  R->batch = cur;
+  R->batch_valid = true;
+  R->rec_cursor = 0;
+  return BAMGPU_OK;
 }
 
 extern "C" int bamgpu_next_batch(bamgpu_reader* R, bamgpu_batch* out) {
@@ -1259,7 +1298,7 @@ extern "C" int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write
     rc = bamgpu_next_batch(R, &b);
     if (rc == BAMGPU_EOF) { rc = BAMGPU_OK; break; }   // no records: empty output
     if (rc != BAMGPU_OK) { msg = bamgpu_last_error(R); break; }
-    if (!R->eof) { rc = BAMGPU_ERR_TOO_LARGE; msg = "input was split into several batches"; break; }
+    if (R->prep_valid || !R->no_more) { rc = BAMGPU_ERR_TOO_LARGE; msg = "input was split into several batches"; break; }
     bamgpu_engine* E = R->E;
     bamgpu_sorted srt;
     rc = bamgpu_engine_sort(E, sort_by, 0, nullptr, &srt);

@@ -174,6 +174,14 @@ __global__ void k_status_reduce(const uint32_t* __restrict__ status, uint32_t n,
   if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(first_bad, best);
 }
 
+__global__ void k_copy_small(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint32_t words) {
+  for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
+void launch_copy_small_to_host(void* h_pinned, const void* d_src, uint32_t bytes, cudaStream_t s) {
+  k_copy_small<<<1, 64, 0, s>>>((uint32_t*)h_pinned, (const uint32_t*)d_src, bytes / 4);
+}
+
 void launch_status_reduce(const uint32_t* status, uint32_t n_blocks, unsigned long long* first_bad, cudaStream_t s) {
   cudaMemsetAsync(first_bad, 0xff, sizeof(unsigned long long), s);
   if (n_blocks == 0) return;

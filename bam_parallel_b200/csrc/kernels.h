@@ -30,6 +30,11 @@ constexpr int CRC_TABLE_WORDS = 2 * 4 * 256;
 void launch_crc32(const uint8_t* out, const BlockTableDev& t, const uint32_t* d_tables, uint32_t* status,
                   int num_sms, cudaStream_t s);
 
+// Copies `bytes` (multiple of 4, <= 4096) from device memory to PINNED HOST memory with SM stores.  Result words of a few
+// bytes must not go through cudaMemcpyAsync: the D2H copy engine serves transfers in order, so an 8-byte status read queues
+// behind a gigabyte of record bodies of the previous batch.
+void launch_copy_small_to_host(void* h_pinned, const void* d_src, uint32_t bytes, cudaStream_t s);
+
 // first_bad[0] = min over blocks with status != 0 of (block index << 32 | status); ~0ull if none.
 void launch_status_reduce(const uint32_t* status, uint32_t n_blocks, unsigned long long* first_bad, cudaStream_t s);
 
