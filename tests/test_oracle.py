@@ -298,3 +298,29 @@ def test_md5_of_bodies_is_stable(oracle):
     g = json.load(open(gpath))
     assert h.hexdigest() == g["pe150_5000_L6_md5_bodies"]
     assert orc.zlib.crc32(ub) == oracle.crc32(u)
+
+
+@pytest.mark.parametrize("shape,n,payload,level", [("pe150", 4000, 0xFF00, 6), ("longname", 2000, 0xFF00, 1), ("long10k", 40, 4096, 9)])
+def test_inflate_against_pythons_gzip_reader(oracle, shape, n, payload, level):
+    """An implementation that shares nothing with the oracle's framing code: CPython's gzip module reads a BGZF file as
+    a multi-member gzip stream (and, unlike the reference, checks every CRC32 and ISIZE).  Same bytes."""
+    import gzip
+    data = synth.generate(shape, n, level=level, payload=payload, threads=2).tobytes()
+    u, sizes = oracle.inflate_all(data)
+    assert gzip.decompress(data) == u.tobytes()
+    assert int(sizes.sum()) == u.size
+
+
+def test_sorted_output_format_matches_sort_rs(oracle):
+    """sort.rs:643 writes rec bodies only (no block_size); a stable sort by the coordinate comparator of a file that is
+    already sorted must reproduce the hash-mode byte stream (main.rs:83-99) exactly."""
+    recs = [bc.bam_record(ref_id=r, pos=p, flag=f, name=b"n%d" % i) for i, (r, p, f) in
+            enumerate([(0, 1, 0), (0, 1, 16), (0, 5, 0), (1, 0, 0), (1, 0, 0), (-1, -1, 4)])]
+    data = bc.bgzf(bc.bam_header() + b"".join(recs), payload=100)
+    u, _ = oracle.inflate_all(data)
+    _, _, start = oracle.read_header(u)
+    off, ln = oracle.walk_records(u, start)
+    cols, _, _ = oracle.extract(u, off, ln, True)
+    assert oracle.sort_perm(u, off, cols, 0).tolist() == list(range(len(recs)))
+    ub = u.tobytes()
+    assert b"".join(ub[int(o):int(o) + int(l)] for o, l in zip(off, ln)) == b"".join(r[4:] for r in recs)
