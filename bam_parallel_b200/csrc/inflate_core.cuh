@@ -455,7 +455,7 @@ BG_HD_COLD void parse_header(BitReader* brp, uint32_t* sm, HeaderResult* hr) {
 // the read; shared-memory accesses of one warp are performed in issue order.
 enum : uint32_t { TK_LITS = 0, TK_MATCH = 1, TK_BEGIN = 2, TK_END = 3, TK_RAW = 4, TK_DONE = 5 };
 #ifndef BG_RING_SHIFT
-#define BG_RING_SHIFT 4
+#define BG_RING_SHIFT 3
 #endif
 constexpr uint32_t RING_SHIFT = BG_RING_SHIFT;
 constexpr uint32_t RING_TOKENS = 1u << RING_SHIFT;        // per stream
