@@ -144,6 +144,9 @@ void launch_inflate(const uint8_t* comp, const BlockTableDev& t, uint8_t* out, u
   if (t.n_blocks == 0) return;
   // per-device attribute; cheap enough to set on every launch (keeps multi-device processes correct)
   cudaFuncSetAttribute(k1_inflate_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES);
+#ifdef K1_CARVEOUT
+  cudaFuncSetAttribute(k1_inflate_pairs, cudaFuncAttributePreferredSharedMemoryCarveout, K1_CARVEOUT);   // experiments: percent of the 228 KB
+#endif
   InflateJob job{comp, t.in_off, t.in_len, t.out_off, t.isize, out, status, t.n_blocks};
   uint32_t lanes_per_cta = K1_PAIR_WARPS * 32;   // streams per CTA
   uint32_t max_ctas = (uint32_t)num_sms * K1_CTAS_PER_SM;

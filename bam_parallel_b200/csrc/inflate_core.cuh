@@ -72,9 +72,16 @@ enum : uint32_t {
 // Shared-memory words per lane (each lane's words are interleaved with the other 31 lanes' words).
 constexpr int LIT_SYM_WORDS = 72;   // 288 x u8: low 8 bits of the sorted literal/length symbols
 constexpr int DIST_SYM_WORDS = 8;   // 32 x u8
-constexpr int META_WORDS = 16;      // per code length L: bits 0-8 (first lit/len index - first code) mod 512, bits 9-13 the same
-                                    // for the distance code mod 32, bits 14-22 the index of the first lit/len symbol >= 256 of that length
-constexpr int LANE_WORDS = LIT_SYM_WORDS + DIST_SYM_WORDS + META_WORDS;  // 96 words = 384 B
+// META, per code length L: bits 0-8 (first lit/len index - first code) mod 512, bits 9-13 the same for the distance
+// code mod 32, bits 14-22 the index of the first lit/len symbol >= 256 of that length.  With -DBG_META_REGS=1 the 15
+// words live in the decoder's registers and are picked by the same select network as the code-length limits: 64 B less
+// shared memory per stream and one shared-memory round trip less per symbol, for 15 more selects per look-up.  Measured
+// (8-token rings): 65.6 ms at 3 CTAs per SM against 63.8 with META in shared memory, 74.1 ms at 4 CTAs -> off by default.
+#ifndef BG_META_REGS
+#define BG_META_REGS 0
+#endif
+constexpr int META_WORDS = BG_META_REGS ? 0 : 16;
+constexpr int LANE_WORDS = LIT_SYM_WORDS + DIST_SYM_WORDS + META_WORDS;  // 80 words = 320 B (96 = 384 B with META in shared memory)
 constexpr int SM_LIT_SYM = 0;
 constexpr int SM_DIST_SYM = LIT_SYM_WORDS;
 constexpr int SM_META = SM_DIST_SYM + DIST_SYM_WORDS;
@@ -234,6 +241,7 @@ struct BitReader {
 // ---- cold path: DEFLATE block header + code tables ----------------------------------------------
 struct HeaderResult {
   uint32_t llim[16], dlim[16];  // [1..15]: exclusive limits, left-aligned to 15 bits
+  uint32_t meta[16];            // [1..15]: the META words
   uint32_t state, err, bfinal, stored_len;
 };
 
@@ -248,14 +256,12 @@ struct TableBuilder {
   }
   // Builds the sorted-symbol table and the limits for `n` symbols whose code lengths are lens[0..n);
   // a[L] gets (index of the first symbol of length L) - (first code of length L), mod 2^16, so that
-  // symbol index = a[L] + code.  The META words serve as scratch (counts, then scatter cursors).
+  // symbol index = a[L] + code.
   // Returns 0 or IST_*.
   BG_HD uint32_t build(const uint8_t* lens, uint32_t n, bool is_lit, uint32_t* lim, uint32_t* a, uint32_t* thr) {
-    for (int L = 0; L < 16; ++L) smw(SM_META + L) = 0;
-    for (uint32_t s = 0; s < n; ++s) smw(SM_META + lens[s]) += 1;
-    uint32_t cnt[16];
-#pragma unroll
-    for (int L = 1; L <= 15; ++L) cnt[L] = smw(SM_META + L);
+    uint32_t cnt[16], cur[16];   // counts, then scatter cursors (cold path: local memory is fine)
+    for (int L = 0; L < 16; ++L) cnt[L] = 0;
+    for (uint32_t s = 0; s < n; ++s) cnt[lens[s]] += 1;
     uint32_t code = 0, offs = 0, bad = 0;
 #pragma unroll
     for (int L = 1; L <= 15; ++L) {
@@ -263,7 +269,7 @@ struct TableBuilder {
       if (code + cnt[L] > (1u << L)) bad = 1;
       lim[L] = (code + cnt[L]) << (15 - L);
       a[L] = (offs - code) & 0xffffu;
-      smw(SM_META + L) = offs;  // scatter cursor
+      cur[L] = offs;  // scatter cursor
       code += cnt[L];
       offs += cnt[L];
     }
@@ -280,13 +286,13 @@ struct TableBuilder {
         for (int L = 1; L <= 15; ++L) nlit[L] += (l == (uint32_t)L) ? 1u : 0u;
       }
 #pragma unroll
-      for (int L = 1; L <= 15; ++L) thr[L] = smw(SM_META + L) + nlit[L];   // cursor == first index of length L here
+      for (int L = 1; L <= 15; ++L) thr[L] = cur[L] + nlit[L];   // cursor == first index of length L here
     }
     for (uint32_t s = 0; s < n; ++s) {
       uint32_t l = lens[s];
       if (l) {
-        uint32_t pos = smw(SM_META + l);
-        smw(SM_META + l) = pos + 1;
+        uint32_t pos = cur[l];
+        cur[l] = pos + 1;
         if (is_lit) {
           set_byte(SM_LIT_SYM, pos, s & 0xffu);          // >= 256: 0 = end of block, 1..29 = length codes 257..285
         } else {
@@ -306,7 +312,7 @@ BG_HD_COLD void parse_header(BitReader* brp, uint32_t* sm, HeaderResult* hr) {
   hr->err = 0;
   hr->stored_len = 0;
   hr->bfinal = 0;
-  for (int k = 0; k < 16; ++k) hr->llim[k] = hr->dlim[k] = 0;
+  for (int k = 0; k < 16; ++k) hr->llim[k] = hr->dlim[k] = hr->meta[k] = 0;
 #define BG_FAIL(code) do { hr->err = (code); hr->state = ST_NEXT; *brp = br; return; } while (0)
   br.refill();
   if (br.bits_consumed() + 3 > br.in_bits) BG_FAIL(IST_INPUT_OVERRUN);
@@ -436,7 +442,11 @@ BG_HD_COLD void parse_header(BitReader* brp, uint32_t* sm, HeaderResult* hr) {
   uint32_t e = tb.build(lens + hlit, hdist, false, hr->dlim, ad, thr);
   if (!e) e = tb.build(lens, hlit, true, hr->llim, al, thr);
   if (e) BG_FAIL(e);
-  for (int L = 1; L <= 15; ++L) sm[(SM_META + L) * STRIDE] = (al[L] & 0x1ffu) | ((ad[L] & 31u) << 9) | ((thr[L] & 0x1ffu) << 14);
+  hr->meta[0] = 0;
+  for (int L = 1; L <= 15; ++L) {
+    hr->meta[L] = (al[L] & 0x1ffu) | ((ad[L] & 31u) << 9) | ((thr[L] & 0x1ffu) << 14);
+    if (!BG_META_REGS) sm[(SM_META + L) * STRIDE] = hr->meta[L];
+  }
   hr->state = ST_DECODE;
   *brp = br;
 #undef BG_FAIL
@@ -523,6 +533,7 @@ struct Decoder {
   uint32_t state, bfinal, err, blk, cp_rem;
   uint32_t produced, isize;     // bytes the tokens pushed so far stand for / ISIZE of the block
   uint32_t lpk[8], dpk[8];   // code-length limits of the literal/length and distance codes, packed in pairs (code_len_packed); registers
+  uint32_t mreg[16];         // BG_META_REGS: the META words, [1..15] (+ [0] for an invalid code); registers
 
   // ---------------- shared-memory accessors ----------------
 #if defined(__CUDA_ARCH__)
@@ -564,7 +575,9 @@ struct Decoder {
   // The same search over limits packed two to a register (lim[k] | lim[k + 8] << 16 in pk[k], k = 1..7; pk[0] =
   // lim[8]): the first comparison picks the halves with one byte permute each.  Used for the distance code, which is
   // decoded once per match: 8 registers instead of 15 for one more instruction.
-  BG_HD static uint32_t code_len_packed(const uint32_t* pk, uint32_t v) {
+  // `mr` ([1..15], BG_META_REGS): the META word of the found length is picked by the same four comparisons — 8 selects on
+  // the first one (known long before the last), then 4, 2, 1 — and returned in m; [0] serves the invalid "length 16".
+  BG_HD static uint32_t code_len_packed(const uint32_t* pk, const uint32_t* mr, uint32_t v, uint32_t& m) {
     const bool p3 = v >= pk[0];
 #if defined(__CUDA_ARCH__)
     const uint32_t sel = p3 ? 0x4432u : 0x4410u;
@@ -582,6 +595,17 @@ struct Decoder {
     const bool p1 = v >= b;
     const uint32_t d = p1 ? d3 : d1;
     const bool p0 = v >= d;
+#if BG_META_REGS
+    // length = 1 + 8 p3 + 4 p2 + 2 p1 + p0: candidates by p3 first
+    const uint32_t e1 = p3 ? mr[9] : mr[1], e2 = p3 ? mr[10] : mr[2], e3 = p3 ? mr[11] : mr[3], e4 = p3 ? mr[12] : mr[4];
+    const uint32_t e5 = p3 ? mr[13] : mr[5], e6 = p3 ? mr[14] : mr[6], e7 = p3 ? mr[15] : mr[7], e8 = p3 ? mr[0] : mr[8];
+    const uint32_t f1 = p2 ? e5 : e1, f2 = p2 ? e6 : e2, f3 = p2 ? e7 : e3, f4 = p2 ? e8 : e4;
+    const uint32_t g1 = p1 ? f3 : f1, g2 = p1 ? f4 : f2;
+    m = p0 ? g2 : g1;
+#else
+    (void)mr;
+    m = 0;
+#endif
     return 1u + (p3 ? 8u : 0u) + (p2 ? 4u : 0u) + (p1 ? 2u : 0u) + (p0 ? 1u : 0u);
   }
 
@@ -598,10 +622,13 @@ struct Decoder {
   // 1 length code (e = code + 1), 2 end of block, 3 invalid.
   BG_HD uint32_t decode_litlen(uint32_t& e) {
     uint32_t c = bg_brev((uint32_t)br.bb) >> 17;
-    uint32_t L = code_len_packed(lpk, c);
+    uint32_t m;
+    uint32_t L = code_len_packed(lpk, mreg, c, m);
     const bool bad = L > 15u;          // c >= llim[15]: no such code
     L &= 15u;                          // (0 then: nothing consumed, the table reads stay in range)
-    uint32_t m = smr(SM_META + L);
+#if !BG_META_REGS
+    m = smr(SM_META + L);
+#endif
     uint32_t idx = (m + (c >> (15 - L))) & 0x1ffu;
     uint32_t spc = idx >= ((m >> 14) & 0x1ffu) ? 1u : 0u;
     idx = idx < 287u ? idx : 287u;
@@ -648,10 +675,13 @@ struct Decoder {
       t.len = base + ((uint32_t)br.bb & ((1u << eb) - 1u));
       br.consume(eb);
       uint32_t c = bg_brev((uint32_t)br.bb) >> 17;   // >= 28 bits left: the distance code and its <= 13 extra bits fit
-      uint32_t L = code_len_packed(dpk, c);
+      uint32_t m;
+      uint32_t L = code_len_packed(dpk, mreg, c, m);
       if (L > 15u) t.kind = 3;
       L &= 15u;
-      uint32_t m = smr(SM_META + L);
+#if !BG_META_REGS
+      m = smr(SM_META + L);
+#endif
       uint32_t di = ((m >> 9) + (c >> (15 - L))) & 31u;
       uint32_t ds = smb(SM_DIST_SYM, di);
       br.consume(L);
@@ -749,6 +779,10 @@ struct Decoder {
         lpk[k] = bg_pin(hr.llim[k] | (hr.llim[k + 8] << 16));
         dpk[k] = bg_pin(hr.dlim[k] | (hr.dlim[k + 8] << 16));
       }
+#if BG_META_REGS
+#pragma unroll
+      for (int k = 0; k <= 15; ++k) mreg[k] = bg_pin(hr.meta[k]);
+#endif
     }
   }
 
