@@ -121,7 +121,7 @@ struct bamgpu_engine {
   PinBuf h_tab;
   DevBuf d_tab;
   DevBuf d_status, d_misc;  // d_misc: work counter (u32 @0), first_bad (u64 @8), ChainResult @64
-  DevBuf d_crc_tables;
+  DevBuf d_crc_tables, d_k1ring;
   bool crc_ready = false;
   // inflated data.  The Reader runs with two buffers (pingpong): batch k+1 is inflated into one while batch k is
   // still being copied to the host out of the other.
@@ -290,7 +290,7 @@ extern "C" void bamgpu_engine_free(bamgpu_engine* E) {
   for (auto& M : E->mir) { if (M.ev_begin) cudaEventDestroy(M.ev_begin); if (M.ev_end) cudaEventDestroy(M.ev_end); M.d_cols.release(); M.h_data.release(); M.h_cols.release(); }
   for (auto& e : E->ev) if (e) cudaEventDestroy(e);
   E->h_tab.release(); E->d_tab.release(); E->d_status.release(); E->d_misc.release(); E->d_crc_tables.release();
-  E->d_outs[0].release(); E->d_outs[1].release(); E->d_tiles.release(); E->h_res.release();
+  E->d_outs[0].release(); E->d_outs[1].release(); E->d_tiles.release(); E->d_k1ring.release(); E->h_res.release();
   delete E;
 }
 
@@ -443,7 +443,8 @@ static int engine_inflate_launch(bamgpu_engine* E, const uint8_t* d_comp, const 
   ECK(cudaMemsetAsync(counter, 0, 4, s));
   ECK(cudaMemsetAsync(E->d_status.p, 0xff, 4 * nb, s));
   ECK(cudaEventRecord(E->ev[0], s));
-  launch_inflate(d_comp, t, E->out_ptr(), E->d_status.as<uint32_t>(), counter, E->num_sms, s);
+  if (inflate_ring_bytes(E->num_sms)) ECK(E->d_k1ring.reserve(inflate_ring_bytes(E->num_sms)));
+  launch_inflate(d_comp, t, E->out_ptr(), E->d_status.as<uint32_t>(), counter, E->d_k1ring.p, E->num_sms, s);
   ECK(cudaEventRecord(E->ev[1], s));
   E->stats.kernel_launches += 1;
   if (!(flags & BAMGPU_NO_CRC)) {

@@ -66,14 +66,18 @@ constexpr uint32_t K1_COPIER_WAIT_LIMIT = K1_WAIT_LIMIT;
 constexpr uint32_t K1_TRIPS_PER_ROUND = K1_ROUND_TRIPS;  // trips a decoder lane makes between two looks at the warp-wide state
 
 __global__ void __launch_bounds__(K1_THREADS, K1_CTAS_PER_SM)
-k1_inflate_pairs(InflateJob job, uint32_t* __restrict__ work_counter) {
+k1_inflate_pairs(InflateJob job, uint32_t* __restrict__ work_counter, uint8_t* __restrict__ ring_mem) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pw = warp % K1_PAIR_WARPS;
   const bool is_decoder = warp < K1_PAIR_WARPS;
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
   TokRing ring;
+#if BG_RING_GLOBAL
+  ring.init_global(ring_mem + ((size_t)(blockIdx.x * K1_PAIR_WARPS + pw) * 32 + lane) * RING_GLOBAL_STREAM_BYTES);
+#else
   ring.init(smem_base + K1_TABLE_BYTES + K1_STAGE_BYTES + pw * RING_WARP_BYTES, lane);
+#endif
   if (is_decoder) ring.reset();
   __syncthreads();
   if (is_decoder) {
@@ -83,6 +87,7 @@ k1_inflate_pairs(InflateJob job, uint32_t* __restrict__ work_counter) {
     D.sma = smem_base + (pw * (32 * LANE_WORDS) + lane) * 4;
     D.ring = ring;
     D.head = 0;
+    D.tail_seen = 0;
     D.state = ST_NEXT;
     D.blk = 0xffffffffu;
     D.err = 0;
@@ -138,9 +143,10 @@ k1_inflate_pairs(InflateJob job, uint32_t* __restrict__ work_counter) {
 }
 
 size_t inflate_smem_bytes() { return K1_SMEM_BYTES; }
+size_t inflate_ring_bytes(int num_sms) { return BG_RING_GLOBAL ? (size_t)num_sms * K1_CTAS_PER_SM * K1_PAIR_WARPS * 32 * RING_GLOBAL_STREAM_BYTES : 0; }
 
 void launch_inflate(const uint8_t* comp, const BlockTableDev& t, uint8_t* out, uint32_t* status,
-                    uint32_t* work_counter, int num_sms, cudaStream_t s) {
+                    uint32_t* work_counter, void* ring_mem, int num_sms, cudaStream_t s) {
   if (t.n_blocks == 0) return;
   // per-device attribute; cheap enough to set on every launch (keeps multi-device processes correct)
   cudaFuncSetAttribute(k1_inflate_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES);
@@ -160,7 +166,7 @@ void launch_inflate(const uint8_t* comp, const BlockTableDev& t, uint8_t* out, u
     fprintf(stderr, "[bamgpu] K1: %d threads/CTA, %d B smem/CTA, %d CTAs/SM resident (wanted %d), ring %u tokens\n", K1_THREADS,
             K1_SMEM_BYTES, nb, K1_CTAS_PER_SM, RING_TOKENS);
   }
-  k1_inflate_pairs<<<grid, K1_THREADS, K1_SMEM_BYTES, s>>>(job, work_counter);
+  k1_inflate_pairs<<<grid, K1_THREADS, K1_SMEM_BYTES, s>>>(job, work_counter, (uint8_t*)ring_mem);
 }
 
 // ---- first failing block ----------------------------------------------------------------------

@@ -469,19 +469,49 @@ enum : uint32_t { TK_LITS = 0, TK_MATCH = 1, TK_BEGIN = 2, TK_END = 3, TK_RAW = 
 #endif
 constexpr uint32_t RING_SHIFT = BG_RING_SHIFT;
 constexpr uint32_t RING_TOKENS = 1u << RING_SHIFT;        // per stream
-constexpr int RING_ROW_BYTES = 32 * 8;                    // one slot of every lane of a warp
-constexpr int RING_WARP_BYTES = RING_TOKENS * RING_ROW_BYTES + 32 * 4;   // slots + the row of tail counters
+// The ring lives in shared memory ([slot][lane], 8 B per lane) or, with -DBG_RING_GLOBAL=1, in global memory (128 B per
+// stream: 8-byte slots, then the tail counter; volatile accesses, i.e. served by L2).  The global form frees 68 B of
+// shared memory per stream - the next smaller carve-out, 32 KB more L1 per SM for the copiers' window loads - for
+// ~300 cycles of latency per poll, which only the copiers (not the bottleneck) wait for: the decoder reads the tail
+// one trip ahead of using it.
+#ifndef BG_RING_GLOBAL
+#define BG_RING_GLOBAL 0
+#endif
+constexpr int RING_ROW_BYTES = 32 * 8;                    // shared form: one slot of every lane of a warp
+constexpr int RING_WARP_BYTES = BG_RING_GLOBAL ? 0 : (int)(RING_TOKENS * RING_ROW_BYTES + 32 * 4);   // slots + the row of tail counters
+constexpr int RING_GLOBAL_STREAM_BYTES = RING_TOKENS * 8 + 8 <= 128 ? 128 : (RING_TOKENS * 8 + 8 <= 256 ? 256 : (RING_TOKENS * 8 + 8 <= 512 ? 512 : 1024));   // global form: whole lines per stream
 
 struct TokRing {
   BG_HD static uint32_t phase(uint32_t idx) { return ((idx >> RING_SHIFT) & 1u) << 31; }
 #if defined(__CUDACC__)
+#if BG_RING_GLOBAL
+  uint8_t* g;       // this stream's 128-byte line: RING_TOKENS 8-byte slots, then the tail counter
+  __device__ __forceinline__ void init_global(uint8_t* stream_line) { g = stream_line; }
+#else
   uint32_t slots;   // shared-memory byte address of this lane's slot 0 (slot stride RING_ROW_BYTES)
   uint32_t ctr;     // ... of this lane's tail counter
   __device__ __forceinline__ void init(uint32_t warp_base, uint32_t lane) {
     slots = warp_base + lane * 8;
     ctr = warp_base + RING_TOKENS * RING_ROW_BYTES + lane * 4;
   }
+#endif
 #if defined(__CUDA_ARCH__)
+#if BG_RING_GLOBAL
+  BG_HD void reset() {
+    for (uint32_t i = 0; i < RING_TOKENS; ++i)
+      asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(g + 8 * i), "r"(0x80000000u), "r"(0u));
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(g + 8 * RING_TOKENS), "r"(0u));
+  }
+  BG_HD uint32_t tail() const { uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(g + 8 * RING_TOKENS)); return v; }
+  BG_HD void push(uint32_t idx, uint32_t w0, uint32_t w1) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(g + 8 * (idx & (RING_TOKENS - 1))), "r"(w0 | phase(idx)), "r"(w1));
+  }
+  BG_HD bool peek(uint32_t idx, uint32_t& w0, uint32_t& w1) const {
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "l"(g + 8 * (idx & (RING_TOKENS - 1))));
+    return ((w0 ^ phase(idx)) >> 31) == 0;
+  }
+  BG_HD void set_tail(uint32_t v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(g + 8 * RING_TOKENS), "r"(v)); }
+#else
   BG_HD void reset() {   // every slot holds the phase the first lap does NOT use
     for (uint32_t i = 0; i < RING_TOKENS; ++i)
       asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(slots + i * RING_ROW_BYTES), "r"(0x80000000u), "r"(0u));
@@ -497,6 +527,7 @@ struct TokRing {
     return ((w0 ^ phase(idx)) >> 31) == 0;
   }
   BG_HD void set_tail(uint32_t v) { asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ctr), "r"(v)); }
+#endif
 #else   // host pass of nvcc: never called
   BG_HD void reset() {}
   BG_HD uint32_t tail() const { return 0; }
@@ -530,6 +561,7 @@ struct Decoder {
   BitReader br;
   TokRing ring;
   uint32_t head;         // tokens pushed so far
+  uint32_t tail_seen;    // BG_RING_GLOBAL: the copier's count as of the previous trip
   uint32_t state, bfinal, err, blk, cp_rem;
   uint32_t produced, isize;     // bytes the tokens pushed so far stand for / ISIZE of the block
   uint32_t lpk[8], dpk[8];   // code-length limits of the literal/length and distance codes, packed in pairs (code_len_packed); registers
@@ -732,7 +764,15 @@ struct Decoder {
     if (state == ST_HEADER || state == ST_NEXT || state == ST_DONE) return false;
     // (Re-reading the copier's count only when the ring looks full was measured 18 % SLOWER: the extra branch splits
     // the warp and the decode below then runs once per half.)
+#if BG_RING_GLOBAL
+    {   // the copier's count as read one trip ago (its L2 latency is off the chain); stale = conservative
+      const uint32_t seen = tail_seen;
+      tail_seen = ring.tail();
+      if (head - seen >= RING_TOKENS) return false;
+    }
+#else
     if (head - ring.tail() >= RING_TOKENS) return false;
+#endif
     if (state == ST_DECODE) {
       Tok t;
       decode_token(t);

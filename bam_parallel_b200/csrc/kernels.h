@@ -19,8 +19,9 @@ struct BlockTableDev {
 // ---- K1: DEFLATE inflate, one BGZF block per lane (inflate.cu) -------------------------------
 // status[b] = IST_* (inflate_core.cuh).  work_counter: one zeroed u32 in device memory.
 void launch_inflate(const uint8_t* comp, const BlockTableDev& t, uint8_t* out, uint32_t* status,
-                    uint32_t* work_counter, int num_sms, cudaStream_t s);
+                    uint32_t* work_counter, void* ring_mem, int num_sms, cudaStream_t s);
 size_t inflate_smem_bytes();
+size_t inflate_ring_bytes(int num_sms);   // device scratch for the token rings when they live in global memory (else 0)
 
 // ---- K2: CRC32 of every inflated block vs its footer (crc32.cu) ------------------------------
 // Sets status[b] = IST_CRC_MISMATCH where status[b]==0 and the CRC differs.

@@ -26,6 +26,7 @@ extern "C" int host_emul_inflate(const uint8_t* comp, const uint64_t* in_off, co
     D[i].ring.mem = rings[i].data();
     D[i].ring.reset();
     D[i].head = 0;
+    D[i].tail_seen = 0;
     D[i].state = ST_NEXT;
     D[i].blk = 0xffffffffu;
     D[i].err = 0;
