@@ -41,19 +41,57 @@ inline uint32_t rd32(const uint8_t* p) {
 }
 
 // Growable device / pinned buffers ---------------------------------------------------------------
+// cudaFree synchronises the whole device and now and then takes hundreds of milliseconds for a gigabyte; a Reader holds
+// ~4 GB of device buffers, and a process that opens Readers one after the other (bam_binary runs, bench.py's e2e loop)
+// paid that inside every open/close.  Released device buffers are parked per device and handed to the next taker.
+struct DevCache {
+  struct Item { void* p; size_t cap; int dev; };
+  std::mutex mu;
+  std::vector<Item> free_list;
+  size_t bytes = 0;
+  static constexpr size_t LIMIT = (size_t)8 << 30, ITEM_LIMIT = (size_t)2 << 30;
+  void* take(size_t n, int dev, size_t* cap) {
+    std::lock_guard<std::mutex> lk(mu);
+    size_t best = (size_t)-1;
+    for (size_t i = 0; i < free_list.size(); ++i)
+      if (free_list[i].dev == dev && free_list[i].cap >= n && (best == (size_t)-1 || free_list[i].cap < free_list[best].cap)) best = i;
+    if (best == (size_t)-1 || free_list[best].cap > n + n / 4 + (1 << 20)) return nullptr;
+    void* p = free_list[best].p;
+    *cap = free_list[best].cap;
+    bytes -= *cap;
+    free_list.erase(free_list.begin() + best);
+    return p;
+  }
+  bool give(void* p, size_t cap, int dev) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cap > ITEM_LIMIT || bytes + cap > LIMIT) return false;
+    free_list.push_back({p, cap, dev});
+    bytes += cap;
+    return true;
+  }
+};
+DevCache& dev_cache() { static DevCache* c = new DevCache(); return *c; }
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  int dev = -1;
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr; cap = 0;
+    release();
     size_t want = n + n / 8 + 256;
+    cudaGetDevice(&dev);
+    size_t got = 0;
+    if (void* q = dev_cache().take(want, dev, &got)) { p = q; cap = got; return cudaSuccess; }
     cudaError_t e = cudaMalloc(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  // Callers synchronise the streams that used the buffer before they release it (bamgpu_engine_free, bamgpu_reader_free).
+  void release() {
+    if (p && !dev_cache().give(p, cap, dev)) cudaFree(p);
+    p = nullptr; cap = 0;
+  }
   template <class T> T* as() const { return (T*)p; }
 };
 // Page-locking host memory is slow (about a second per few GB), and a Reader needs several hundred MB of it, so released
