@@ -5,8 +5,8 @@
 //
 // Mapping: a persistent grid of 8-warp CTAs, 3 CTAs per SM.  Every BGZF block is one stream, worked on by a pair of
 // lanes: lane l of decoder warp w (warps 0-3: bit reader + Huffman tables -> tokens) and lane l of copier warp w + 4
-// (tokens -> literals and LZ77 copies in the output), talking through a 16-token ring in shared memory.  So a CTA
-// advances 128 streams, an SM 384, with 24 warps resident: twice the warps per scheduler of the one-lane-per-stream
+// (tokens -> literals and LZ77 copies in the output), talking through an 8-token ring in shared memory.  So a CTA
+// advances 128 streams, an SM 384, with 24 warps resident: half as many again as the one-lane-per-stream
 // form (which was pinned to 16 warps per SM by its 128 registers and 416 B of shared memory per lane) to hide the
 // Huffman dependency chains, the shared-memory look-ups and the window-load latency behind one another.  A decoder
 // lane pulls its next block index from a global counter, so block sizes need not balance.  The per-lane logic is in
@@ -30,8 +30,8 @@ constexpr int K1_THREADS = 2 * K1_PAIR_WARPS * 32;
 constexpr int K1_CTAS_PER_SM = K1_CTAS;
 constexpr int K1_TABLE_BYTES = K1_PAIR_WARPS * 32 * LANE_WORDS * 4;                // 49152: Huffman tables
 constexpr int K1_STAGE_BYTES = K1_PAIR_WARPS * STAGE_WARP_BYTES;                   //  4096: input staging slots
-constexpr int K1_RING_BYTES = K1_PAIR_WARPS * RING_WARP_BYTES;                     // 17408: token rings
-constexpr int K1_SMEM_BYTES = K1_TABLE_BYTES + K1_STAGE_BYTES + K1_RING_BYTES;
+constexpr int K1_RING_BYTES = K1_PAIR_WARPS * RING_WARP_BYTES;                     //  8704: token rings (8 tokens)
+constexpr int K1_SMEM_BYTES = K1_TABLE_BYTES + K1_STAGE_BYTES + K1_RING_BYTES;   // 61952: 3 CTAs fit the 196 KB carve-out, leaving 60 KB of L1
 
 // The kernel is compiled for 80 registers per thread (3 CTAs x 256 threads per SM); the copier warpgroup gives 32 of
 // them back (setmaxnreg.dec) and the decoder warpgroup, whose Huffman state lives in registers, may take them.
