@@ -34,7 +34,7 @@
 //   * The DEFLATE block header / code-table build is a cold out-of-line function working on a
 //     copy of the bit reader, so the hot loop's state stays in registers.  (It also has to be
 //     out of line: with ptxas 12.9 -O1..-O3 the fully inlined form miscompiled on sm_100a —
-//     tools/debug/k1_debug2.cu reproduces it.)
+//     the harness that reproduces it, tools/debug/k1_debug2.cu, is in the history at commit 95cc6bd.)
 //
 // Everything here is __host__ __device__ so tests/host_emul.cpp can run the identical logic on
 // the CPU build box (no GPU there).  That emulation is a TEST of this code, not a fallback:
