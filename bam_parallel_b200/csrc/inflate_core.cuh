@@ -4,7 +4,7 @@
 // DeflateDecoder::read_to_end).  Every BGZF block is one independent stream, and a stream is worked on by a PAIR of
 // lanes in two different warps of one CTA:
 //   * the DECODER lane (Decoder<>) owns the bit reader and the Huffman tables, turns the bitstream into tokens
-//     (up to 3 literals + one match) and validates them (distances, output size);
+//     (up to 3 literals + one match, or 4 literals) and validates them (distances, output size);
 //   * the COPIER lane (Copier) owns the output position, writes the literals and performs the LZ77 copies.
 // They talk through a small token ring in shared memory (single producer / single consumer, no blocking waits: a lane
 // whose ring is full or empty just skips the trip).  32 streams advance side by side inside a warp either way, so
