@@ -11,13 +11,14 @@ _SRC = os.path.join(ROOT, "tests", "host_emul.cpp")
 _CORE = os.path.join(ROOT, "bam_parallel_b200", "csrc", "inflate_core.cuh")
 
 
-def _build(asan: bool) -> str:
+def _build(asan: bool, defines=()) -> str:
     os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
-    out = os.path.join(ROOT, "build", "libhostemul_asan.so" if asan else "libhostemul.so")
+    tag = "".join("_" + d.replace("=", "") for d in defines)
+    out = os.path.join(ROOT, "build", ("libhostemul_asan" if asan else "libhostemul") + tag + ".so")
     newest = max(os.path.getmtime(_SRC), os.path.getmtime(_CORE))
     if not os.path.exists(out) or os.path.getmtime(out) < newest:
         flags = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"] if asan else ["-O2"]
-        subprocess.check_call(["g++", *flags, "-fPIC", "-shared", "-std=c++17", "-o", out, _SRC])
+        subprocess.check_call(["g++", *flags, *["-D" + d for d in defines], "-fPIC", "-shared", "-std=c++17", "-o", out, _SRC])
     return out
 
 
@@ -50,13 +51,21 @@ def py_scan(data: bytes):
             np.array(isize, np.uint32), np.array(crc, np.uint32), o)
 
 
-def inflate(data: bytes, lanes: int = 32, table=None):
+def variant(defines):
+    """The emulation built with extra -D switches (kernel variants kept behind macros)."""
+    L = C.CDLL(_build(False, tuple(defines)))
+    L.host_emul_inflate.restype = C.c_int
+    L.host_emul_inflate.argtypes = [C.c_void_p] * 7 + [C.c_uint32, C.c_int]
+    return L
+
+
+def inflate(data: bytes, lanes: int = 32, table=None, library=None):
     in_off, in_len, out_off, isize, crc, total = table if table is not None else py_scan(data)
     comp = np.zeros(len(data) + 64, np.uint8)           # K1 prefetches up to 48 bytes past a payload
     comp[: len(data)] = np.frombuffer(data, np.uint8)
     outbuf = np.full(total + 64, 0xEE, np.uint8)       # 32 B lead pad (>=16), tail pad
     lead = 32 + (-outbuf.ctypes.data) % 4              # keep out[0] 4-byte aligned
     status = np.full(max(len(in_off), 1), 0xFFFFFFFF, np.uint32)
-    lib().host_emul_inflate(comp.ctypes.data, in_off.ctypes.data, in_len.ctypes.data, out_off.ctypes.data,
+    (library or lib()).host_emul_inflate(comp.ctypes.data, in_off.ctypes.data, in_len.ctypes.data, out_off.ctypes.data,
                             isize.ctypes.data, outbuf.ctypes.data + lead, status.ctypes.data, len(in_off), lanes)
     return outbuf[lead: lead + total], status[: len(in_off)], (outbuf[:lead], outbuf[lead + total:])

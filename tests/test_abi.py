@@ -34,6 +34,9 @@ def test_no_cpu_fallback_without_gpu():
         bp.Engine()
     with pytest.raises(bp.BamGpuError):
         bp.Reader.new(bc.bgzf(bc.bam_header()), 4)
+    import io
+    with pytest.raises(bp.BamGpuError):       # the sort entry point has no CPU path either
+        bp.sort_bam(0, bc.bgzf(bc.bam_header()), io.BytesIO(), sort_by=bp.SortBy.Name)
 
 
 def test_product_does_not_import_oracle():

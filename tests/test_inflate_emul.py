@@ -144,3 +144,15 @@ def test_distance_too_far_is_rejected():
     put_code(0, 7)                    # EOB
     raw = bits.to_bytes((nb + 7) // 8, "little")
     assert _status_of(bc.bgzf_block(b"aaaa", raw_deflate=raw) + bc.BGZF_EOF)[0] == 8
+
+
+@pytest.mark.parametrize("defines", [("BG_META_REGS=1",), ("BG_LITS_PER_TOKEN=2",), ("BG_RING_SHIFT=1",), ("BG_RING_SHIFT=5", "BG_LITS_PER_TOKEN=3")])
+def test_kernel_variants_behind_macros(oracle, defines):
+    """The switches DESIGN.md's experiments used (META in registers, literals per token, ring depth) stay correct."""
+    L = emul.variant(defines)
+    for shape, n, payload, level in [("pe150", 3000, 0xFF00, 6), ("long10k", 40, 4096, 1), ("longname", 1500, 7001, 9)]:
+        data = synth.generate(shape, n, level=level, payload=payload, threads=2).tobytes()
+        out, status, (lead, tail) = emul.inflate(data, 7, library=L)
+        u, _ = oracle.inflate_all(data)
+        assert status.tolist() == [0] * len(status) and out.tobytes() == u.tobytes()
+        assert (lead == 0xEE).all() and (tail == 0xEE).all()
