@@ -48,18 +48,47 @@ class Columns(C.Structure):
 class Batch(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("data_len", C.c_uint64), ("data", C.c_void_p), ("h_data", C.c_void_p),
                 ("dev", Columns), ("host", Columns), ("first_record_index", C.c_uint64), ("bad_flag_records", C.c_uint64),
-                ("chain_start", C.c_uint64), ("chain_repairs", C.c_uint64)]
+                ("chain_start", C.c_uint64), ("chain_repairs", C.c_uint64), ("data_start", C.c_uint64),
+                ("stream_offset", C.c_uint64)]
+
+
+MAX_DEVICES = 16
 
 
 class Opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("batch_bytes", C.c_uint64), ("inflate_impl", C.c_int32),
+                ("jobs_per_device", C.c_int32), ("n_devices", C.c_int32), ("devices", C.c_int32 * MAX_DEVICES),
                 ("reserved", C.c_int32)]
+
+
+def make_opts(device: int = -1, flags: int = 0, batch_bytes: int = 0, inflate_impl: int = 0, jobs_per_device: int = 0,
+              devices=None) -> Opts:
+    o = Opts()
+    o.device, o.flags, o.batch_bytes, o.inflate_impl, o.jobs_per_device = device, flags, batch_bytes, inflate_impl, jobs_per_device
+    devices = list(devices or [])
+    if len(devices) > MAX_DEVICES:
+        raise ValueError(f"at most {MAX_DEVICES} devices")
+    o.n_devices = len(devices)
+    for i, d in enumerate(devices):
+        o.devices[i] = d
+    return o
+
+
+class Digest(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("body_bytes", C.c_uint64), ("fields", C.c_uint64), ("bodies", C.c_uint64)]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class EdgeHandle(C.Structure):
+    _fields_ = [("ipc", C.c_uint8 * 64), ("ptr", C.c_uint64), ("device", C.c_int32), ("pid", C.c_int32)]
 
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("blocks", "bytes_in", "bytes_out", "records", "batches", "kernel_launches")] + \
                [(n, C.c_double) for n in ("ms_h2d", "ms_inflate", "ms_crc", "ms_records", "ms_d2h", "ms_total", "ms_sort",
-                                          "ms_gather")]
+                                          "ms_gather")] + [("p2p_bytes", C.c_uint64)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -83,6 +112,8 @@ EXPORTS = [
     "bamgpu_reader_from_memory", "bamgpu_reader_free", "bamgpu_last_error", "bamgpu_read_header", "bamgpu_next_rec",
     "bamgpu_append_record", "bamgpu_read", "bamgpu_next_batch", "bamgpu_reader_stats",
     "bamgpu_parse_reference_sequences", "bamgpu_status_str", "bamgpu_build_info", "bamgpu_engine_sort", "bamgpu_sort_bam",
+    "bamgpu_engine_digest", "bamgpu_engine_sorted_digest", "bamgpu_reader_current_engine", "bamgpu_engine_edge_open",
+    "bamgpu_engine_edge_connect", "bamgpu_engine_edge_exchange", "bamgpu_engine_edge_close",
 ]
 
 _lib = None
@@ -158,5 +189,19 @@ def load() -> C.CDLL:
     L.bamgpu_engine_sort.argtypes = [vp, C.c_int, C.c_uint32, vp, C.POINTER(Sorted)]
     L.bamgpu_sort_bam.restype = C.c_int
     L.bamgpu_sort_bam.argtypes = [READ_FN, vp, WRITE_FN, vp, sz, C.c_int, C.POINTER(Opts), C.POINTER(Stats), C.c_char_p, sz]
+    L.bamgpu_engine_digest.restype = C.c_int
+    L.bamgpu_engine_digest.argtypes = [vp, C.c_uint64, C.c_uint64, vp, C.POINTER(Digest)]
+    L.bamgpu_engine_sorted_digest.restype = C.c_int
+    L.bamgpu_engine_sorted_digest.argtypes = [vp, vp, C.POINTER(Digest)]
+    L.bamgpu_reader_current_engine.restype = vp
+    L.bamgpu_reader_current_engine.argtypes = [vp]
+    L.bamgpu_engine_edge_open.restype = C.c_int
+    L.bamgpu_engine_edge_open.argtypes = [vp, C.POINTER(EdgeHandle)]
+    L.bamgpu_engine_edge_connect.restype = C.c_int
+    L.bamgpu_engine_edge_connect.argtypes = [vp, C.POINTER(EdgeHandle), C.POINTER(EdgeHandle)]
+    L.bamgpu_engine_edge_exchange.restype = C.c_int
+    L.bamgpu_engine_edge_exchange.argtypes = [vp, C.c_uint64, vp]
+    L.bamgpu_engine_edge_close.restype = None
+    L.bamgpu_engine_edge_close.argtypes = [vp]
     _lib = L
     return L

@@ -10,6 +10,7 @@
 //   reader.rs:114-152      impl Read                                        -> bamgpu_read
 //   reader.rs:101-112      parse_reference_sequences                        -> bamgpu_parse_reference_sequences
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -49,7 +50,7 @@ struct DevCache {
   std::mutex mu;
   std::vector<Item> free_list;
   size_t bytes = 0;
-  static constexpr size_t LIMIT = (size_t)8 << 30, ITEM_LIMIT = (size_t)2 << 30;
+  static constexpr size_t LIMIT = (size_t)48 << 30, ITEM_LIMIT = (size_t)2 << 30;
   void* take(size_t n, int dev, size_t* cap) {
     std::lock_guard<std::mutex> lk(mu);
     size_t best = (size_t)-1;
@@ -100,7 +101,7 @@ struct PinnedCache {
   std::mutex mu;
   std::vector<std::pair<void*, size_t>> free_list;
   size_t bytes = 0;
-  static constexpr size_t LIMIT = (size_t)12 << 30;
+  static constexpr size_t LIMIT = (size_t)32 << 30;
   void* take(size_t n, size_t* cap) {
     std::lock_guard<std::mutex> lk(mu);
     size_t best = (size_t)-1;
@@ -173,6 +174,23 @@ struct bamgpu_engine {
   uint64_t pend_total = 0, pend_bytes_in = 0;
   bool inflate_launched = false;
   uint64_t data_len = 0;    // bytes valid in d_out (after lead pad), carry included
+  // Reader jobs ("lead mode"): a batch is inflated BEFORE the previous batch's record chain is known, so its blocks land at
+  // a fixed offset `lead` and the carried-over tail of the previous batch is copied right in front of them afterwards
+  // (engine_set_carry: a device-to-device or peer-to-peer copy): valid bytes are [data_start, data_len).
+  uint64_t lead = 0;        // 0: classic placement (carry first, blocks behind it)
+  uint64_t data_start = 0;  // first valid byte of d_out
+  DevBuf d_carry;           // this batch's unconsumed tail, saved for whoever decodes the next batch (maybe another device)
+  uint64_t carry_saved = 0;
+  cudaEvent_t ev_carry = nullptr;
+  bool own_d2h_stream = true;
+  uint64_t cols_hint = 0;   // records expected in the next batch (sizes the columns without a host round trip)
+  // shard-edge exchange (bamgpu_engine_edge_*)
+  uint8_t* edge_inbox = nullptr;
+  uint8_t* edge_left = nullptr;    // the left-hand neighbour's inbox, mapped here (peer pointer)
+  uint8_t* edge_right = nullptr;   // the right-hand neighbour's inbox (we only write its ack flag)
+  bool edge_left_ipc = false, edge_right_ipc = false, edge_has_right = false;
+  uint32_t* edge_len_scratch = nullptr;
+  bool sorted_valid = false;
   uint64_t halo_len = 0;    // bytes copied behind them from the right-hand shard (multi-GPU)
   uint64_t carry_len = 0;   // bytes at the front of the next batch kept from this one
   uint64_t keep_from = 0;   // where those bytes currently sit
@@ -305,6 +323,7 @@ extern "C" bamgpu_engine* bamgpu_engine_new(const bamgpu_opts* opts) {
   if (cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking) != cudaSuccess) { delete E; return nullptr; }
   if (cudaStreamCreateWithFlags(&E->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) { delete E; return nullptr; }
   cudaEventCreateWithFlags(&E->ev_k3_done, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&E->ev_carry, cudaEventDisableTiming);
   for (auto& M : E->mir) { cudaEventCreate(&M.ev_begin); cudaEventCreate(&M.ev_end); }
   for (auto& e : E->ev) cudaEventCreate(&e);
   E->default_flags = opts ? opts->flags : 0;
@@ -313,6 +332,7 @@ extern "C" bamgpu_engine* bamgpu_engine_new(const bamgpu_opts* opts) {
     bamgpu_engine_free(E);
     return nullptr;
   }
+  cudaMemsetAsync(E->d_misc.p, 0, 8192, E->stream);
   crc32_init_tables(E->d_crc_tables.as<uint32_t>(), E->stream);
   if (cudaStreamSynchronize(E->stream) != cudaSuccess) { bamgpu_engine_free(E); return nullptr; }
   E->crc_ready = true;
@@ -323,12 +343,17 @@ extern "C" void bamgpu_engine_free(bamgpu_engine* E) {
   if (!E) return;
   cudaSetDevice(E->device);
   if (E->stream) { cudaStreamSynchronize(E->stream); cudaStreamDestroy(E->stream); }
-  if (E->d2h_stream) { cudaStreamSynchronize(E->d2h_stream); cudaStreamDestroy(E->d2h_stream); }
+  if (E->d2h_stream) { cudaStreamSynchronize(E->d2h_stream); if (E->own_d2h_stream) cudaStreamDestroy(E->d2h_stream); }
   if (E->ev_k3_done) cudaEventDestroy(E->ev_k3_done);
+  if (E->ev_carry) cudaEventDestroy(E->ev_carry);
+  bamgpu_engine_edge_close(E);
   for (auto& M : E->mir) { if (M.ev_begin) cudaEventDestroy(M.ev_begin); if (M.ev_end) cudaEventDestroy(M.ev_end); M.d_cols.release(); M.h_data.release(); M.h_cols.release(); }
   for (auto& e : E->ev) if (e) cudaEventDestroy(e);
   E->h_tab.release(); E->d_tab.release(); E->d_status.release(); E->d_misc.release(); E->d_crc_tables.release();
   E->d_outs[0].release(); E->d_outs[1].release(); E->d_tiles.release(); E->d_k1ring.release(); E->h_res.release();
+  E->d_carry.release();
+  // the sort's scratch, permutation, offsets and gathered bodies (round 1 leaked these: ~18.7 GB per 50M-record sort)
+  E->d_sort.release(); E->d_perm.release(); E->d_soff.release(); E->d_sorted.release(); E->h_sorted.release(); E->h_perm.release();
   delete E;
 }
 
@@ -404,15 +429,23 @@ static int engine_inflate_launch(bamgpu_engine* E, const uint8_t* d_comp, const 
                                  uint32_t flags, cudaStream_t s) {
   const double t_in = now_ms();
   ECK(cudaSetDevice(E->device));
-  // 1. the destination buffer (the other one when ping-ponging) gets the carry at its front
-  const uint64_t carry = E->carry_len;
+  // 1. the destination buffer (the other one when ping-ponging) gets the carry at its front; in lead mode the blocks
+  //    land behind a fixed gap and the carry is copied into the gap later (engine_set_carry)
+  const bool lead_mode = E->lead > 0;
+  const uint64_t carry = lead_mode ? E->lead : E->carry_len;
   uint64_t total = 0, bytes_in = 0;
   for (size_t i = 0; i < n_blocks; ++i) { total += blocks[i].isize; bytes_in += blocks[i].in_len + 26; }
   const uint64_t new_len = carry + total;
-  const int src = E->cur, dst = E->pingpong ? (E->cur ^ 1) : E->cur;
+  const int src = E->cur, dst = (E->pingpong && !lead_mode) ? (E->cur ^ 1) : E->cur;
   const uint8_t* src_ptr = E->d_outs[src].p ? E->d_outs[src].as<uint8_t>() + OUT_LEAD_PAD : nullptr;
   const size_t need = OUT_LEAD_PAD + new_len + BAMGPU_MAX_HALO + OUT_TAIL_PAD;
-  if (E->d_outs[dst].cap < need) {
+  if (lead_mode) {
+    if (E->d_outs[dst].cap < need) {
+      { int w = engine_wait_d2h(E); if (w < 0) return w; }
+      ECK(E->d_outs[dst].reserve(need));
+      ECK(cudaMemsetAsync(E->d_outs[dst].p, 0, OUT_LEAD_PAD, s));
+    }
+  } else if (E->d_outs[dst].cap < need) {
     DevBuf nb;
     ECK(nb.reserve(need));
     ECK(cudaMemsetAsync(nb.p, 0, OUT_LEAD_PAD, s));
@@ -438,6 +471,7 @@ static int engine_inflate_launch(bamgpu_engine* E, const uint8_t* d_comp, const 
       tmp.release();
     }
   }
+  E->data_start = lead_mode ? E->lead : 0;
   E->cur = dst;
   E->carry_len = 0;
   E->keep_from = 0;
@@ -548,6 +582,108 @@ static int engine_wait_d2h(bamgpu_engine* E) {
   return BAMGPU_OK;
 }
 
+// ---- carry between Reader jobs -------------------------------------------------------------------------------------
+// engine_save_carry: copies this batch's unconsumed tail [keep_from, keep_from + carry_len) into the engine's small carry
+// buffer (so the big output buffer can be reused at once) and records ev_carry behind the copy.
+static int engine_save_carry(bamgpu_engine* E, cudaStream_t s) {
+  ECK(cudaSetDevice(E->device));
+  E->carry_saved = E->carry_len;
+  if (E->carry_len) {
+    ECK(E->d_carry.reserve(E->carry_len < 65536 ? 65536 : E->carry_len));
+    ECK(cudaMemcpyAsync(E->d_carry.p, E->out_ptr() + E->keep_from, E->carry_len, cudaMemcpyDeviceToDevice, s));
+  }
+  ECK(cudaEventRecord(E->ev_carry, s));
+  return BAMGPU_OK;
+}
+
+// engine_set_carry: puts `len` bytes of `from`'s saved tail right in front of this engine's freshly inflated blocks.
+// Same device: device-to-device copy; another device: cudaMemcpyPeerAsync (NVLink when peer access is on) - this is
+// the "boundary records exchanged peer-to-peer" step of the multi-GPU reader, one partial record per batch edge.
+// K1 of this batch must have finished (the caller has waited for it).  If the tail is longer than the gap in front of
+// the blocks (a record of more than `lead` bytes), the blocks move to a buffer with a larger gap first.
+static int engine_set_carry(bamgpu_engine* E, bamgpu_engine* from, cudaStream_t s) {
+  const uint64_t len = from ? from->carry_saved : 0;
+  ECK(cudaSetDevice(E->device));
+  if (len > E->lead) {
+    const uint64_t new_lead = align_up(len + 4096, 1 << 16);
+    const uint64_t total = E->data_len - E->lead;
+    DevBuf nb;
+    ECK(nb.reserve(OUT_LEAD_PAD + new_lead + total + BAMGPU_MAX_HALO + OUT_TAIL_PAD));
+    ECK(cudaMemsetAsync(nb.p, 0, OUT_LEAD_PAD, s));
+    ECK(cudaMemcpyAsync(nb.as<uint8_t>() + OUT_LEAD_PAD + new_lead, E->out_ptr() + E->lead, total + OUT_TAIL_PAD, cudaMemcpyDeviceToDevice, s));
+    ECK(cudaStreamSynchronize(s));
+    E->d_outs[E->cur].release();
+    E->d_outs[E->cur] = nb;
+    E->lead = new_lead;
+    E->data_len = new_lead + total;
+  }
+  E->data_start = E->lead - len;
+  if (len) {
+    ECK(cudaStreamWaitEvent(s, from->ev_carry, 0));
+    uint8_t* dst = E->out_ptr() + E->data_start;
+    if (from->device == E->device) ECK(cudaMemcpyAsync(dst, from->d_carry.p, len, cudaMemcpyDeviceToDevice, s));
+    else ECK(cudaMemcpyPeerAsync(dst, E->device, from->d_carry.p, from->device, len, s));
+    E->stats.p2p_bytes += from->device == E->device ? 0 : len;
+  }
+  return BAMGPU_OK;
+}
+
+// Queues the device-to-host copies `flags` ask for (bodies / offsets / all columns) on the D2H stream, behind whatever
+// is on `s` now.  Only what is not mirrored yet is copied, so a later call with more flags adds the missing pieces
+// (a caller may switch from next_batch to next_rec in mid-stream).
+static int engine_enqueue_mirrors(bamgpu_engine* E, bamgpu_engine::Mirror& M, uint32_t flags, uint64_t n_rec, bamgpu_batch* out,
+                                  cudaStream_t s, bool* queued) {
+  cudaStream_t cs = E->d2h_stream;
+  const bool want_data = (flags & BAMGPU_COPY_DATA) && !out->h_data;
+  const bool want_cols = (flags & BAMGPU_COPY_COLUMNS) && n_rec && !out->host.coord_key;
+  const bool want_offs = (flags & BAMGPU_COPY_OFFSETS) && !(flags & BAMGPU_COPY_COLUMNS) && n_rec && !out->host.rec_off;
+  const bool any_copy = want_data || want_cols || want_offs;
+  if (queued) *queued = any_copy;
+  if (!any_copy) return BAMGPU_OK;
+  ECK(cudaEventRecord(E->ev_k3_done, s));
+  ECK(cudaStreamWaitEvent(cs, E->ev_k3_done, 0));
+  if (!M.pending) ECK(cudaEventRecord(M.ev_begin, cs));
+  if (want_data) {
+    ECK(M.h_data.reserve(E->data_len + 64));
+    // lead mode: only [data_start, data_len) holds bytes; the mirror keeps the device offsets (rec_off indexes both)
+    const uint64_t from = E->data_start & ~(uint64_t)63;
+    if (E->data_len > from) ECK(cudaMemcpyAsync(M.h_data.as<uint8_t>() + from, E->out_ptr() + from, E->data_len - from, cudaMemcpyDeviceToHost, cs));
+    out->h_data = M.h_data.as<uint8_t>();
+  }
+  if (want_offs) {
+    // what next_rec() needs besides the bodies: where each one starts and how long it is
+    ECK(M.h_cols.reserve(columns_bytes(M.cols_cap)));
+    ColumnsDev hc;
+    carve_columns(M.h_cols.as<uint8_t>(), M.cols_cap, hc);
+    ECK(cudaMemcpyAsync(hc.rec_off, M.cols.rec_off, 8 * n_rec, cudaMemcpyDeviceToHost, cs));
+    ECK(cudaMemcpyAsync(hc.rec_len, M.cols.rec_len, 4 * n_rec, cudaMemcpyDeviceToHost, cs));
+    out->host.rec_off = hc.rec_off;
+    out->host.rec_len = hc.rec_len;
+  }
+  if (want_cols) {
+    size_t bytes = columns_bytes(M.cols_cap);
+    ECK(M.h_cols.reserve(bytes));
+    // copy only the used prefix of every column
+    ColumnsDev hc;
+    carve_columns(M.h_cols.as<uint8_t>(), M.cols_cap, hc);
+    auto cp = [&](void* dst, const void* src, size_t elem) {
+      return cudaMemcpyAsync(dst, src, elem * n_rec, cudaMemcpyDeviceToHost, cs);
+    };
+    ECK(cp(hc.rec_off, M.cols.rec_off, 8)); ECK(cp(hc.coord_key, M.cols.coord_key, 8));
+    ECK(cp(hc.rec_len, M.cols.rec_len, 4)); ECK(cp(hc.ref_id, M.cols.ref_id, 4)); ECK(cp(hc.pos, M.cols.pos, 4));
+    ECK(cp(hc.l_seq, M.cols.l_seq, 4)); ECK(cp(hc.next_ref_id, M.cols.next_ref_id, 4)); ECK(cp(hc.next_pos, M.cols.next_pos, 4));
+    ECK(cp(hc.tlen, M.cols.tlen, 4)); ECK(cp(hc.cigar_off, M.cols.cigar_off, 4)); ECK(cp(hc.seq_off, M.cols.seq_off, 4));
+    ECK(cp(hc.qual_off, M.cols.qual_off, 4)); ECK(cp(hc.tags_off, M.cols.tags_off, 4)); ECK(cp(hc.hi_value, M.cols.hi_value, 4));
+    ECK(cp(hc.bin, M.cols.bin, 2)); ECK(cp(hc.n_cigar_op, M.cols.n_cigar_op, 2)); ECK(cp(hc.flag, M.cols.flag, 2));
+    ECK(cp(hc.l_read_name, M.cols.l_read_name, 1)); ECK(cp(hc.mapq, M.cols.mapq, 1)); ECK(cp(hc.strand, M.cols.strand, 1));
+    ECK(cp(hc.hi_present, M.cols.hi_present, 1));
+    fill_public_columns(hc, out->host);
+  }
+  ECK(cudaEventRecord(M.ev_end, cs));
+  M.pending = true;
+  return BAMGPU_OK;
+}
+
 // Stage 2: record chain + columns over d_out[0 .. data_len).
 static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t flags, cudaStream_t s,
                           bamgpu_batch* out, uint64_t* tail_off_out, bool defer_d2h = false) {
@@ -561,6 +697,7 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
   memset(out, 0, sizeof *out);
   out->data = E->out_ptr();
   out->data_len = E->data_len;
+  out->data_start = E->data_start;
   out->first_record_index = E->first_record_index;
   out->chain_start = start;
   ChainResult* d_res = (ChainResult*)(E->d_misc.as<uint8_t>() + 64);
@@ -584,9 +721,21 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
     TileArrays t{(uint64_t*)(tb + o_entry), (uint64_t*)(tb + o_exit), (uint32_t*)(tb + o_count), (uint32_t*)(tb + o_kind),
                  (uint32_t*)(tb + o_nxt), (uint32_t*)(tb + o_jump), (uint32_t*)(tb + o_jump2), (uint8_t*)(tb + o_reach),
                  (uint64_t*)(tb + o_base), n_tiles};
+    // Columns are sized BEFORE the record count is known (from what the previous batch needed, or ~256 bytes per record the
+    // first time), so that walk -> resolve -> emit -> extract go onto the stream back to back and the host waits ONCE per
+    // batch (round 1: three waits).  If the guess was too small the last two kernels run again with room for all.
+    if (M.cols_cap == 0) {
+      uint64_t cap = E->cols_hint ? E->cols_hint : (E->data_len - start) / 256 + 4096;
+      ECK(M.d_cols.reserve(columns_bytes(cap)));
+      M.cols_cap = cap;
+      carve_columns(M.d_cols.as<uint8_t>(), cap, M.cols);
+    }
+    const bool want_hi = (flags & BAMGPU_WANT_HI) != 0;
     launch_tile_walk(p, t, s);
     ECK(launch_chain_resolve(p, t, d_res, (ResolveScratch*)(E->d_misc.as<uint8_t>() + 256), E->num_sms, s));
-    E->stats.kernel_launches += 2;
+    launch_tile_emit(p, t, M.cols.rec_off, M.cols.rec_len, M.cols_cap, s);
+    launch_extract(p, M.cols, M.cols_cap, want_hi, d_res, /*dev_count=*/true, s);
+    E->stats.kernel_launches += 4;
     launch_copy_small_to_host(h_res, d_res, sizeof(ChainResult), s);
     ECK(cudaStreamSynchronize(s));
     ECK(cudaGetLastError());
@@ -596,15 +745,16 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
     n_rec = h_res->n_records;
     tail_off = h_res->tail_off;
     tail_kind = h_res->tail_kind;
-    if (n_rec) {
-      if (n_rec > M.cols_cap) {
-        uint64_t cap = n_rec + n_rec / 8 + 1024;
-        ECK(M.d_cols.reserve(columns_bytes(cap)));
-        M.cols_cap = cap;
-        carve_columns(M.d_cols.as<uint8_t>(), cap, M.cols);
-      }
-      launch_tile_emit(p, t, M.cols.rec_off, M.cols.rec_len, s);
-      launch_extract(p, M.cols, n_rec, (flags & BAMGPU_WANT_HI) != 0, d_res, s);
+    bad_flags = h_res->bad_flags;
+    if (n_rec > M.cols_cap) {
+      { int w = engine_wait_mirror(E, E->msel); if (w < 0) return w; }
+      uint64_t cap = n_rec + n_rec / 8 + 1024;
+      ECK(M.d_cols.reserve(columns_bytes(cap)));
+      M.cols_cap = cap;
+      carve_columns(M.d_cols.as<uint8_t>(), cap, M.cols);
+      ECK(cudaMemsetAsync(&d_res->bad_flags, 0, sizeof(unsigned long long), s));
+      launch_tile_emit(p, t, M.cols.rec_off, M.cols.rec_len, cap, s);
+      launch_extract(p, M.cols, n_rec, want_hi, d_res, /*dev_count=*/false, s);
       E->stats.kernel_launches += 2;
       launch_copy_small_to_host(h_res, d_res, sizeof(ChainResult), s);
       ECK(cudaStreamSynchronize(s));
@@ -631,58 +781,16 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
   E->last_bad_flags = bad_flags;
   E->last_flags = flags;
   E->last_valid = !(flags & BAMGPU_NO_RECORDS);
+  E->sorted_valid = false;
   fill_public_columns(M.cols, out->dev);
   // host mirrors: on their own stream, behind the record kernels
-  cudaStream_t cs = E->d2h_stream;
-  const bool any_copy = (flags & BAMGPU_COPY_DATA) || ((flags & (BAMGPU_COPY_COLUMNS | BAMGPU_COPY_OFFSETS)) && n_rec);
-  if (any_copy) {
-    ECK(cudaEventRecord(E->ev_k3_done, s));
-    ECK(cudaStreamWaitEvent(cs, E->ev_k3_done, 0));
-    ECK(cudaEventRecord(M.ev_begin, cs));
-  }
-  if (flags & BAMGPU_COPY_DATA) {
-    ECK(M.h_data.reserve(E->data_len + 64));
-    if (E->data_len) ECK(cudaMemcpyAsync(M.h_data.p, E->out_ptr(), E->data_len, cudaMemcpyDeviceToHost, cs));
-    out->h_data = M.h_data.as<uint8_t>();
-  }
-  if ((flags & BAMGPU_COPY_OFFSETS) && !(flags & BAMGPU_COPY_COLUMNS) && n_rec) {
-    // what next_rec() needs besides the bodies: where each one starts and how long it is
-    ECK(M.h_cols.reserve(columns_bytes(M.cols_cap)));
-    ColumnsDev hc;
-    carve_columns(M.h_cols.as<uint8_t>(), M.cols_cap, hc);
-    ECK(cudaMemcpyAsync(hc.rec_off, M.cols.rec_off, 8 * n_rec, cudaMemcpyDeviceToHost, cs));
-    ECK(cudaMemcpyAsync(hc.rec_len, M.cols.rec_len, 4 * n_rec, cudaMemcpyDeviceToHost, cs));
-    out->host.rec_off = hc.rec_off;
-    out->host.rec_len = hc.rec_len;
-  }
-  if ((flags & BAMGPU_COPY_COLUMNS) && n_rec) {
-    size_t bytes = columns_bytes(M.cols_cap);
-    ECK(M.h_cols.reserve(bytes));
-    // copy only the used prefix of every column
-    ColumnsDev hc;
-    carve_columns(M.h_cols.as<uint8_t>(), M.cols_cap, hc);
-    auto cp = [&](void* dst, const void* src, size_t elem) {
-      return cudaMemcpyAsync(dst, src, elem * n_rec, cudaMemcpyDeviceToHost, cs);
-    };
-    ECK(cp(hc.rec_off, M.cols.rec_off, 8)); ECK(cp(hc.coord_key, M.cols.coord_key, 8));
-    ECK(cp(hc.rec_len, M.cols.rec_len, 4)); ECK(cp(hc.ref_id, M.cols.ref_id, 4)); ECK(cp(hc.pos, M.cols.pos, 4));
-    ECK(cp(hc.l_seq, M.cols.l_seq, 4)); ECK(cp(hc.next_ref_id, M.cols.next_ref_id, 4)); ECK(cp(hc.next_pos, M.cols.next_pos, 4));
-    ECK(cp(hc.tlen, M.cols.tlen, 4)); ECK(cp(hc.cigar_off, M.cols.cigar_off, 4)); ECK(cp(hc.seq_off, M.cols.seq_off, 4));
-    ECK(cp(hc.qual_off, M.cols.qual_off, 4)); ECK(cp(hc.tags_off, M.cols.tags_off, 4)); ECK(cp(hc.hi_value, M.cols.hi_value, 4));
-    ECK(cp(hc.bin, M.cols.bin, 2)); ECK(cp(hc.n_cigar_op, M.cols.n_cigar_op, 2)); ECK(cp(hc.flag, M.cols.flag, 2));
-    ECK(cp(hc.l_read_name, M.cols.l_read_name, 1)); ECK(cp(hc.mapq, M.cols.mapq, 1)); ECK(cp(hc.strand, M.cols.strand, 1));
-    ECK(cp(hc.hi_present, M.cols.hi_present, 1));
-    fill_public_columns(hc, out->host);
-  }
+  bool any_copy = false;
+  { int w = engine_enqueue_mirrors(E, M, flags, n_rec, out, s, &any_copy); if (w < 0) return w; }
   ECK(cudaStreamSynchronize(s));
   ECK(cudaGetLastError());
   float ms = 0;
   cudaEventElapsedTime(&ms, E->ev[3], E->ev[4]); E->stats.ms_records += ms;
-  if (any_copy) {
-    ECK(cudaEventRecord(M.ev_end, cs));
-    M.pending = true;
-    if (!defer_d2h) { int w = engine_wait_mirror(E, E->msel); if (w < 0) return w; }
-  }
+  if (any_copy && !defer_d2h) { int w = engine_wait_mirror(E, E->msel); if (w < 0) return w; }
   if (dbg_level() >= 2) fprintf(stderr, "[bamgpu] records host wall %.2f ms\n", now_ms() - t_in);
   E->stats.records += n_rec;
   E->stats.batches += 1;
@@ -695,6 +803,10 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
   } else {
     E->keep_from = 0;
     E->carry_len = 0;
+  }
+  if (E->lead > 0) {   // Reader job: park the tail where the next batch's engine (maybe on another GPU) can fetch it
+    int w = engine_save_carry(E, s);
+    if (w < 0) return w;
   }
   return rc;
 }
@@ -751,7 +863,6 @@ extern "C" int bamgpu_engine_stats(const bamgpu_engine* E, bamgpu_stats* out) {
 extern "C" void bamgpu_engine_reset_stats(bamgpu_engine* E) { if (E) E->stats = bamgpu_stats{}; }
 
 extern "C" void bamgpu_engine_set_n_ref(bamgpu_engine* E, int32_t n) { if (E) E->n_ref = n; }
-static void engine_set_n_ref(bamgpu_engine* E, int32_t n) { E->n_ref = n; }
 
 // -------------------------------------------------------------------------------------------------
 // Sort (sorting/sort.rs:138-178 sort_bam, the part behind the reader): stable sort of the last batch's records by the
@@ -803,6 +914,7 @@ extern "C" int bamgpu_engine_sort(bamgpu_engine* E, int sort_by, uint32_t flags,
   out->perm = E->d_perm.as<uint32_t>();
   out->body_off = E->d_soff.as<uint64_t>();
   out->bodies = E->d_sorted.as<uint8_t>();
+  E->sorted_valid = true;
   if ((flags & BAMGPU_COPY_COLUMNS) && n) {
     ECK(E->h_perm.reserve(4 * n));
     ECK(cudaMemcpyAsync(E->h_perm.p, E->d_perm.p, 4 * n, cudaMemcpyDeviceToHost, s));
@@ -822,25 +934,226 @@ extern "C" int bamgpu_engine_sort(bamgpu_engine* E, int sort_by, uint32_t flags,
   return BAMGPU_OK;
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Digests (csrc/digest.cu): size-independent parity checks (DIGEST SPEC).
+// -------------------------------------------------------------------------------------------------
+static int engine_read_digest(bamgpu_engine* E, cudaStream_t s, uint64_t n, bamgpu_digest* out) {
+  unsigned long long* acc = (unsigned long long*)(E->d_misc.as<uint8_t>() + 4096);
+  unsigned long long h[4];
+  ECK(cudaMemcpyAsync(h, acc, sizeof h, cudaMemcpyDeviceToHost, s));
+  ECK(cudaStreamSynchronize(s));
+  ECK(cudaGetLastError());
+  out->n_records = n;
+  out->body_bytes = h[1];
+  out->fields = h[2];
+  out->bodies = h[3];
+  return BAMGPU_OK;
+}
+
+extern "C" int bamgpu_engine_digest(bamgpu_engine* E, uint64_t index_base, uint64_t stream_base, void* cuda_stream, bamgpu_digest* out) {
+  if (!E || !out) return BAMGPU_ERR_ARG;
+  if (!E->last_valid) { E->err = "digest: no decoded batch on this engine"; return BAMGPU_ERR_STATE; }
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : E->stream;
+  ECK(cudaSetDevice(E->device));
+  launch_digest_records(E->out_ptr(), E->mir[E->msel].cols, E->last_n, index_base, stream_base,
+                        (unsigned long long*)(E->d_misc.as<uint8_t>() + 4096), E->num_sms, s);
+  E->stats.kernel_launches += E->last_n ? 2 : 0;
+  return engine_read_digest(E, s, E->last_n, out);
+}
+
+extern "C" int bamgpu_engine_sorted_digest(bamgpu_engine* E, void* cuda_stream, bamgpu_digest* out) {
+  if (!E || !out) return BAMGPU_ERR_ARG;
+  if (!E->sorted_valid) { E->err = "digest: no sort result on this engine"; return BAMGPU_ERR_STATE; }
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : E->stream;
+  ECK(cudaSetDevice(E->device));
+  launch_digest_sorted(E->d_sorted.as<uint8_t>(), E->d_soff.as<uint64_t>(), E->d_perm.as<uint32_t>(), E->last_n,
+                       (unsigned long long*)(E->d_misc.as<uint8_t>() + 4096), E->num_sms, s);
+  E->stats.kernel_launches += E->last_n ? 2 : 0;
+  return engine_read_digest(E, s, E->last_n, out);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Shard-edge exchange over peer memory: see include/bamgpu.h and csrc/edge.cu.
+// Inbox layout (device memory of the shard that RECEIVES):  halo[2][BAMGPU_MAX_HALO] | flags
+//   flags[0] data_step  written by the right-hand neighbour after its halo copy for `step` landed in halo[step & 1]
+//   flags[1] ack_step   written by the LEFT-hand neighbour into OUR inbox: it has consumed our halo of that step
+//   flags[2..3] halo length of each buffer (written with the data)
+// -------------------------------------------------------------------------------------------------
+namespace {
+constexpr size_t EDGE_FLAGS_OFF = 2 * (size_t)BAMGPU_MAX_HALO;
+constexpr size_t EDGE_BYTES = EDGE_FLAGS_OFF + 4096;
+}
+
+extern "C" int bamgpu_engine_edge_open(bamgpu_engine* E, bamgpu_edge_handle* mine) {
+  if (!E || !mine) return BAMGPU_ERR_ARG;
+  ECK(cudaSetDevice(E->device));
+  if (!E->edge_inbox) {
+    ECK(cudaMalloc(&E->edge_inbox, EDGE_BYTES));   // a plain allocation: cudaIpcGetMemHandle wants the base of one
+    ECK(cudaMemset(E->edge_inbox, 0, EDGE_BYTES));
+    ECK(cudaMalloc((void**)&E->edge_len_scratch, 64));
+    ECK(cudaMemset(E->edge_len_scratch, 0, 64));
+  }
+  memset(mine, 0, sizeof *mine);
+  cudaIpcMemHandle_t h;
+  ECK(cudaIpcGetMemHandle(&h, E->edge_inbox));
+  static_assert(sizeof h == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(mine->ipc, &h, 64);
+  mine->ptr = (uint64_t)(uintptr_t)E->edge_inbox;
+  mine->device = E->device;
+  mine->pid = (int32_t)getpid();
+  return BAMGPU_OK;
+}
+
+static int edge_map(bamgpu_engine* E, const bamgpu_edge_handle* h, uint8_t** out, bool* ipc) {
+  *out = nullptr;
+  *ipc = false;
+  if (!h) return BAMGPU_OK;
+  if (h->pid == (int32_t)getpid()) {   // same process: the pointer itself, with peer access switched on
+    if (h->device != E->device) {
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, E->device, h->device);
+      if (!can) { E->err = "edge: no peer access between the two GPUs"; return BAMGPU_ERR_CUDA; }
+      cudaError_t e = cudaDeviceEnablePeerAccess(h->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { E->err = cudaGetErrorString(e); return BAMGPU_ERR_CUDA; }
+      cudaGetLastError();
+    }
+    *out = (uint8_t*)(uintptr_t)h->ptr;
+    return BAMGPU_OK;
+  }
+  cudaIpcMemHandle_t ih;
+  memcpy(&ih, h->ipc, 64);
+  void* p = nullptr;
+  ECK(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+  *out = (uint8_t*)p;
+  *ipc = true;
+  return BAMGPU_OK;
+}
+
+extern "C" int bamgpu_engine_edge_connect(bamgpu_engine* E, const bamgpu_edge_handle* left, const bamgpu_edge_handle* right) {
+  if (!E) return BAMGPU_ERR_ARG;
+  if (!E->edge_inbox) { E->err = "edge_connect before edge_open"; return BAMGPU_ERR_STATE; }
+  ECK(cudaSetDevice(E->device));
+  int rc = edge_map(E, left, &E->edge_left, &E->edge_left_ipc);
+  if (rc < 0) return rc;
+  rc = edge_map(E, right, &E->edge_right, &E->edge_right_ipc);
+  if (rc < 0) return rc;
+  E->edge_has_right = right != nullptr;
+  return BAMGPU_OK;
+}
+
+extern "C" void bamgpu_engine_edge_close(bamgpu_engine* E) {
+  if (!E || !E->edge_inbox) return;
+  cudaSetDevice(E->device);
+  if (E->stream) cudaStreamSynchronize(E->stream);
+  if (E->edge_left && E->edge_left_ipc) cudaIpcCloseMemHandle(E->edge_left);
+  if (E->edge_right && E->edge_right_ipc) cudaIpcCloseMemHandle(E->edge_right);
+  cudaFree(E->edge_inbox);
+  cudaFree(E->edge_len_scratch);
+  E->edge_inbox = E->edge_left = E->edge_right = nullptr;
+  E->edge_len_scratch = nullptr;
+  cudaGetLastError();
+}
+
+extern "C" int bamgpu_engine_edge_exchange(bamgpu_engine* E, uint64_t step, void* cuda_stream) {
+  if (!E || step == 0) return BAMGPU_ERR_ARG;
+  if (!E->edge_inbox) { E->err = "edge_exchange before edge_open"; return BAMGPU_ERR_STATE; }
+  if (!E->d_outs[E->cur].p) return BAMGPU_ERR_STATE;
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : E->stream;
+  ECK(cudaSetDevice(E->device));
+  unsigned long long* my_flags = (unsigned long long*)(E->edge_inbox + EDGE_FLAGS_OFF);
+  uint32_t* timed_out = (uint32_t*)(E->d_misc.as<uint8_t>() + 4160);
+  const int buf = (int)(step & 1);
+  if (E->edge_left) {
+    // my head -> the left neighbour's inbox (peer write over NVLink), then publish the step there.
+    // Its buffer `buf` held step-2's halo: wait until the neighbour has acknowledged that one.
+    unsigned long long* left_flags = (unsigned long long*)(E->edge_left + EDGE_FLAGS_OFF);
+    if (step > 2) launch_wait_flag(&my_flags[1], step - 2, timed_out, s);
+    const size_t m = (size_t)std::min<uint64_t>(E->data_len, BAMGPU_MAX_HALO);
+    if (m) ECK(cudaMemcpyAsync(E->edge_left + (size_t)buf * BAMGPU_MAX_HALO, E->out_ptr(), m, cudaMemcpyDefault, s));
+    launch_set_flag(&left_flags[2 + buf], m, s);
+    launch_set_flag(&left_flags[0], step, s);
+    E->stats.p2p_bytes += m;
+    E->stats.kernel_launches += 2 + (step > 2 ? 1 : 0);
+  }
+  if (E->edge_has_right) {
+    // wait (on the device) for the right neighbour's halo of this step, append it, acknowledge
+    unsigned long long* right_flags = (unsigned long long*)(E->edge_right + EDGE_FLAGS_OFF);
+    launch_wait_flag(&my_flags[0], step, timed_out, s);
+    // the halo length travels with the data; it is read on the host only to size the local copy
+    ECK(cudaMemcpyAsync(E->h_res.as<uint8_t>() + 512, &my_flags[2 + buf], 8, cudaMemcpyDeviceToHost, s));
+    ECK(cudaMemcpyAsync(E->h_res.as<uint8_t>() + 520, timed_out, 4, cudaMemcpyDeviceToHost, s));
+    ECK(cudaStreamSynchronize(s));
+    if (*(uint32_t*)(E->h_res.as<uint8_t>() + 520)) { E->err = "edge: the right-hand shard never delivered its halo (20 s)"; return BAMGPU_ERR_STATE; }
+    const uint64_t m = *(uint64_t*)(E->h_res.as<uint8_t>() + 512);
+    if (m > BAMGPU_MAX_HALO) { E->err = "edge: bad halo length"; return BAMGPU_ERR_STATE; }
+    int rc = bamgpu_engine_append_halo(E, E->edge_inbox + (size_t)buf * BAMGPU_MAX_HALO, (size_t)m, s);
+    if (rc < 0) return rc;
+    launch_set_flag(&right_flags[1], step, s);
+    E->stats.kernel_launches += 2;
+  } else {
+    int rc = bamgpu_engine_append_halo(E, nullptr, 0, s);
+    if (rc < 0) return rc;
+  }
+  return BAMGPU_OK;
+}
+
 // =================================================================================================
 // Reader
 // =================================================================================================
+// The streaming drop-in for bam_tools::Reader.  Replaces readahead.rs:51-143 (reader thread + n-2 inflate workers +
+// ordering thread, n Blocks in flight) by:
+//   * a FEEDER thread (the reference's reading thread, readahead.rs:88-118): cuts the source into batches of whole BGZF
+//     blocks, scans headers AND footers, and starts each batch's host-to-device copy on the copy stream of the GPU the
+//     batch goes to (batch k -> GPU k mod D: the file is sharded by BGZF block ranges);
+//   * JOBS: every GPU owns J engines (= J batches in flight).  A batch is inflated (K1 + K2) as soon as its bytes are
+//     on the device - before the batches in front of it have been parsed, and next to the K1 of other batches, which is
+//     what fills the GPU: one 256 MiB batch is 13 k BGZF blocks, a quarter of K1's 56.8 k streams;
+//   * the record chain (reader.rs:63-81) is serial across batches: batch k can only be parsed once batch k-1 has told
+//     where its last complete record ends.  That partial record is copied in front of batch k's blocks - from whichever
+//     GPU decoded batch k-1, peer to peer (engine_set_carry) - and K3 runs; this is the only inter-GPU traffic;
+//   * device-to-host copies of one GPU go through ONE stream in batch order; up to D batches beyond the one handed out are
+//     staged, so every GPU's link is busy.
 namespace {
 
 struct Slot {
-  PinBuf host;               // compressed bytes as read from the source
+  PinBuf host;               // compressed bytes as read from the source (unused when the source itself is pinned memory)
   DevBuf dev;                // same bytes on the device
   size_t len = 0;            // bytes covered by whole blocks
   std::vector<bamgpu_block> blocks;
   bool final = false;        // no more input after this slot
-  int status = BAMGPU_OK;    // scan / io status for this slot
+  int status = BAMGPU_OK;    // scan / io status: an error here surfaces AFTER the records of the blocks scanned before it
+  uint64_t total_isize = 0;
   cudaEvent_t copied = nullptr;
 };
+
+struct DevCtx {
+  int dev = 0;
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  std::vector<Slot> slots;
+  std::deque<int> free_slots;   // guarded by the reader's mutex
+};
+
+struct Job {
+  bamgpu_engine* E = nullptr;
+  int dev_i = 0, slot = -1;
+  uint64_t seq = 0;
+  enum St { FREE, LAUNCHED, STAGED, OUT } st = FREE;
+  bamgpu_batch batch{};
+  bool final = false, carry_set = false;
+  int input_status = BAMGPU_OK;   // Slot::status
+  uint64_t stream_new = 0;        // position in the inflated stream of this batch's first new byte
+  uint64_t new_bytes = 0;
+};
+
+struct ReadyItem { uint64_t seq; int dev_i, slot; };
 
 }  // namespace
 
 struct bamgpu_reader {
-  bamgpu_engine* E = nullptr;
+  std::vector<DevCtx> devs;
+  std::vector<Job> jobs;            // devs.size() * J; batch seq -> jobs[(seq % D) * J + (seq / D) % J]
+  int J = 4;
   bamgpu_read_fn read = nullptr;
   void* ctx = nullptr;
   size_t thread_num = 3;
@@ -852,31 +1165,31 @@ struct bamgpu_reader {
   // memory source
   const uint8_t* mem = nullptr;
   size_t mem_len = 0, mem_pos = 0;
+  bool mem_pinned = false;          // the caller's buffer is page-locked: H2D straight out of it, no staging copy
   // feeder
-  static constexpr int N_SLOTS = 3;
-  Slot slots[N_SLOTS];
   std::thread feeder;
   std::mutex mu;
   std::condition_variable cv;
-  std::deque<int> ready, freeq;
+  std::deque<ReadyItem> ready;
   bool stop = false;
-  cudaStream_t copy_stream = nullptr;
   // consumer state
-  int cur_slot = -1;
-  bool header_done = false, eof = false, raw_mode = false, inflated_pending = false, input_done = false;
-  int sticky = BAMGPU_OK;
+  uint64_t n_launched = 0, n_staged = 0, n_out = 0;   // batches whose K1 is queued / whose records are parsed / handed out
+  uint64_t launched_stream = 0;     // inflated bytes of all launched batches
+  uint64_t rec_index = 0;
+  bool input_done = false, header_done = false, eof = false, raw_mode = false, no_more = false, records_mode = false;
+  int sticky = BAMGPU_OK, sticky_next = BAMGPU_OK;
   std::vector<uint8_t> header;      // without magic
   size_t off_to_refs = 0;
-  uint64_t next_start = 0;          // chain start inside the next engine_records call
+  int32_t n_ref = -1;
+  uint64_t next_start_rel = 0;      // chain start of the next staged batch, relative to its data_start (header batch only)
+  Job* cur = nullptr;               // the batch the caller holds
   bamgpu_batch batch{};
   bool batch_valid = false;
-  bamgpu_batch prep{};              // the batch staged behind `batch`: record kernels done, D2H queued
-  bool prep_valid = false, no_more = false;
-  int prep_sel = 0;
-  int sticky_next = BAMGPU_OK;
   uint64_t rec_cursor = 0;          // next record of `batch` to hand out
   uint64_t byte_cursor = 0;         // raw mode: next byte of batch.h_data
-  bool pending_final = false;
+  bamgpu_stats base_stats{};
+
+  Job& job_of(uint64_t seq) { size_t D = devs.size(); return jobs[(seq % D) * J + (seq / D) % J]; }
 };
 
 static long mem_read(void* ctx, uint8_t* dst, size_t cap) {
@@ -887,34 +1200,46 @@ static long mem_read(void* ctx, uint8_t* dst, size_t cap) {
   return (long)n;
 }
 
-// Feeder thread: readahead.rs:88-118's reading thread, but it batches whole blocks into a pinned slot,
-// scans their headers AND footers, and starts the H2D copy on its own stream.
+// Feeder thread: readahead.rs:88-118's reading thread, but it batches whole blocks, scans their headers AND footers,
+// and starts the H2D copy on the copy stream of the GPU the batch is for.
 static void feeder_main(bamgpu_reader* R) {
-  cudaSetDevice(R->E->device);
   std::vector<uint8_t> carry;  // partial block left over from the previous slot
   bool src_eof = false;
-  for (;;) {
+  const size_t D = R->devs.size();
+  for (uint64_t seq = 0;; ++seq) {
+    const int di = (int)(seq % D);
+    DevCtx& dc = R->devs[di];
     int si;
     {
       std::unique_lock<std::mutex> lk(R->mu);
-      R->cv.wait(lk, [&] { return R->stop || !R->freeq.empty(); });
+      R->cv.wait(lk, [&] { return R->stop || !dc.free_slots.empty(); });
       if (R->stop) return;
-      si = R->freeq.front();
-      R->freeq.pop_front();
+      si = dc.free_slots.front();
+      dc.free_slots.pop_front();
     }
-    Slot& S = R->slots[si];
+    cudaSetDevice(dc.dev);
+    Slot& S = dc.slots[si];
     S.blocks.clear();
     S.status = BAMGPU_OK;
     S.final = false;
-    // (Smaller first batches were tried to fill the pipeline sooner: every growth of the output buffers then costs a
-    // cudaFree, which waits for the D2H in flight - slower overall.)
+    S.len = 0;
+    S.total_isize = 0;
     const size_t bb = R->batch_bytes;
-    size_t cap = R->batch_bytes + 65536 + 64;
-    if (S.host.reserve(cap + IN_TAIL_PAD) != cudaSuccess || S.dev.reserve(cap + IN_TAIL_PAD) != cudaSuccess) {
+    const size_t cap = bb + 65536 + 64;
+    const uint8_t* src = nullptr;   // where the batch's bytes are on the host
+    size_t fill = 0;
+    if (R->mem && R->mem_pinned) {
+      // zero-copy: whole blocks straight out of the caller's page-locked buffer
+      src = R->mem + R->mem_pos;
+      fill = std::min(bb, R->mem_len - R->mem_pos);
+      if (R->mem_pos + fill >= R->mem_len) src_eof = true;
+      if (S.dev.reserve(cap + IN_TAIL_PAD) != cudaSuccess) { S.status = BAMGPU_ERR_NOMEM; S.final = true; }
+    } else if (S.host.reserve(cap + IN_TAIL_PAD) != cudaSuccess || S.dev.reserve(cap + IN_TAIL_PAD) != cudaSuccess) {
       S.status = BAMGPU_ERR_NOMEM; S.final = true;
     } else {
       uint8_t* h = S.host.as<uint8_t>();
-      size_t fill = carry.size();
+      src = h;
+      fill = carry.size();
       if (fill) memcpy(h, carry.data(), fill);
       carry.clear();
       if (R->mem && !src_eof) {
@@ -937,48 +1262,66 @@ static void feeder_main(bamgpu_reader* R) {
       }
       while (!R->mem && !src_eof && fill < bb) {
         long n = R->read(R->ctx, h + fill, std::min<size_t>(bb + 65536 - fill, 8u << 20));
-        if (n < 0) { S.status = BAMGPU_ERR_IO; src_eof = true; break; }
+        if (n < 0) { S.status = BAMGPU_ERR_IO; src_eof = true; break; }   // the blocks read so far are still decoded
         if (n == 0) { src_eof = true; break; }
         fill += (size_t)n;
         R->bytes_fed += (uint64_t)n;
       }
-      if (S.status == BAMGPU_OK) {
-        size_t nb = 0, consumed = 0;
-        uint64_t tot = 0;
-        // count, then fill
-        int rc = bamgpu_scan_blocks(h, fill, src_eof ? 1 : 0, nullptr, 0, &nb, &consumed, &tot);
-        S.blocks.resize(nb);
-        if (nb) bamgpu_scan_blocks(h, fill, src_eof ? 1 : 0, S.blocks.data(), nb, &nb, &consumed, &tot);
-        S.len = consumed;
-        if (rc < 0) { S.status = rc; S.final = true; }
-        else if (rc == BAMGPU_EOF || src_eof) S.final = true;   // silent EOF (short header / BSIZE wrap) ends the stream
-        else carry.assign(h + consumed, h + fill);
-        if (S.len) {
-          memset(h + S.len, 0, IN_TAIL_PAD);
-          cudaMemcpyAsync(S.dev.p, h, S.len + IN_TAIL_PAD, cudaMemcpyHostToDevice, R->copy_stream);
-        }
-        cudaEventRecord(S.copied, R->copy_stream);
-      } else {
-        S.final = true;
+    }
+    if (S.status != BAMGPU_ERR_NOMEM) {
+      size_t nb = 0, consumed = 0;
+      uint64_t tot = 0;
+      // count, then fill.  A scan error (block too small / truncated) keeps the whole blocks in front of it: the
+      // reference hands out their records before its reading thread dies on the bad block (readahead.rs:92).
+      int rc = bamgpu_scan_blocks(src, fill, src_eof ? 1 : 0, nullptr, 0, &nb, &consumed, &tot);
+      S.blocks.resize(nb);
+      if (nb) bamgpu_scan_blocks(src, fill, src_eof ? 1 : 0, S.blocks.data(), nb, &nb, &consumed, &tot);
+      S.len = consumed;
+      S.total_isize = tot;
+      if (rc < 0) { if (S.status == BAMGPU_OK) S.status = rc; S.final = true; }
+      else if (rc == BAMGPU_EOF || src_eof) S.final = true;   // silent EOF (short header / BSIZE wrap) ends the stream
+      else if (R->mem && R->mem_pinned) { /* the next batch starts at the first unconsumed byte */ }
+      else carry.assign(src + consumed, src + fill);
+      if (R->mem && R->mem_pinned) { R->mem_pos += consumed; R->bytes_fed += consumed; if (consumed == 0 && !S.final) S.final = true; }
+      if (S.len) {
+        cudaMemcpyAsync(S.dev.p, src, S.len, cudaMemcpyHostToDevice, dc.h2d);
+        cudaMemsetAsync(S.dev.as<uint8_t>() + S.len, 0, IN_TAIL_PAD, dc.h2d);
       }
+      cudaEventRecord(S.copied, dc.h2d);
     }
     bool fin = S.final;
     {
       std::lock_guard<std::mutex> lk(R->mu);
-      R->ready.push_back(si);
+      R->ready.push_back({seq, di, si});
     }
     R->cv.notify_all();
     if (fin) return;
   }
 }
 
+static void reader_destroy(bamgpu_reader* R);
+
 static bamgpu_reader* reader_create(bamgpu_read_fn read, void* ctx, size_t thread_num, const uint64_t* track_progress,
                                     const bamgpu_opts* opts) {
-  bamgpu_engine* E = bamgpu_engine_new(opts);
-  if (!E) return nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    fprintf(stderr, "bamgpu: no CUDA device available; this library has no CPU fallback\n");
+    return nullptr;
+  }
   bamgpu_reader* R = new bamgpu_reader();
-  R->E = E;
-  E->pingpong = true;
+  std::vector<int> devices;
+  if (opts && opts->n_devices > 0) {
+    for (int i = 0; i < opts->n_devices && i < BAMGPU_MAX_DEVICES; ++i) devices.push_back(opts->devices[i]);
+  } else {
+    int dev = opts ? opts->device : -1;
+    if (dev < 0) cudaGetDevice(&dev);
+    devices.push_back(dev);
+  }
+  for (int d : devices) if (d < 0 || d >= count) { delete R; return nullptr; }
+  const size_t D = devices.size();
+  R->J = (opts && opts->jobs_per_device > 0) ? std::min(opts->jobs_per_device, 16) : 4;
+  if (R->J < 2) R->J = 2;
+  if (const char* e = getenv("BAMGPU_JOBS")) { int v = atoi(e); if (v >= 2 && v <= 16) R->J = v; }
   R->read = read;
   R->ctx = ctx;
   unsigned hc = std::thread::hardware_concurrency();
@@ -986,14 +1329,62 @@ static bamgpu_reader* reader_create(bamgpu_read_fn read, void* ctx, size_t threa
   R->thread_num = std::max<size_t>(thread_num, 3);  // readahead.rs:53
   R->track_total = track_progress ? *track_progress : 0;
   R->flags = opts ? opts->flags : 0;
+  R->batch_bytes = D > 1 ? ((size_t)96 << 20) : ((size_t)256 << 20);
+  if (const char* e = getenv("BAMGPU_BATCH_MIB")) { long v = atol(e); if (v > 0) R->batch_bytes = (size_t)v << 20; }
   if (opts && opts->batch_bytes) R->batch_bytes = (size_t)opts->batch_bytes;
   if (R->batch_bytes < 65536) R->batch_bytes = 65536;
-  cudaStreamCreateWithFlags(&R->copy_stream, cudaStreamNonBlocking);
-  for (int i = 0; i < bamgpu_reader::N_SLOTS; ++i) {
-    cudaEventCreateWithFlags(&R->slots[i].copied, cudaEventDisableTiming);
-    R->freeq.push_back(i);
+  // peer access between every pair of GPUs (the batch-edge records travel GPU to GPU)
+  for (size_t a = 0; a < D; ++a)
+    for (size_t b = 0; b < D; ++b) {
+      if (devices[a] == devices[b]) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, devices[a], devices[b]);
+      if (can) { cudaSetDevice(devices[a]); cudaDeviceEnablePeerAccess(devices[b], 0); cudaGetLastError(); }
+    }
+  R->devs.resize(D);
+  R->jobs.resize(D * (size_t)R->J);
+  const int n_slots = 3;
+  for (size_t i = 0; i < D; ++i) {
+    DevCtx& dc = R->devs[i];
+    dc.dev = devices[i];
+    if (cudaSetDevice(dc.dev) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&dc.h2d, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&dc.d2h, cudaStreamNonBlocking) != cudaSuccess) { reader_destroy(R); return nullptr; }
+    dc.slots.resize(n_slots);
+    for (int k = 0; k < n_slots; ++k) {
+      cudaEventCreateWithFlags(&dc.slots[k].copied, cudaEventDisableTiming);
+      dc.free_slots.push_back(k);
+    }
+    for (int j = 0; j < R->J; ++j) {
+      bamgpu_opts eo{};
+      eo.device = dc.dev;
+      eo.flags = R->flags;
+      eo.inflate_impl = opts ? opts->inflate_impl : 0;
+      bamgpu_engine* E = bamgpu_engine_new(&eo);
+      if (!E) { reader_destroy(R); return nullptr; }
+      // one D2H stream per GPU: copies leave in batch order
+      cudaSetDevice(dc.dev);
+      cudaStreamDestroy(E->d2h_stream);
+      E->d2h_stream = dc.d2h;
+      E->own_d2h_stream = false;
+      E->lead = BAMGPU_MAX_HALO;
+      Job& jb = R->jobs[i * R->J + j];
+      jb.E = E;
+      jb.dev_i = (int)i;
+    }
   }
   return R;
+}
+
+static void reader_destroy(bamgpu_reader* R) {
+  for (auto& j : R->jobs) if (j.E) { bamgpu_engine_free(j.E); j.E = nullptr; }
+  for (auto& dc : R->devs) {
+    cudaSetDevice(dc.dev);
+    if (dc.h2d) { cudaStreamSynchronize(dc.h2d); cudaStreamDestroy(dc.h2d); }
+    if (dc.d2h) { cudaStreamSynchronize(dc.d2h); cudaStreamDestroy(dc.d2h); }
+    for (auto& s : dc.slots) { if (s.copied) cudaEventDestroy(s.copied); s.host.release(); s.dev.release(); }
+  }
+  delete R;
 }
 
 extern "C" bamgpu_reader* bamgpu_reader_new(bamgpu_read_fn read, void* ctx, size_t thread_num, const uint64_t* track_progress,
@@ -1011,6 +1402,14 @@ extern "C" bamgpu_reader* bamgpu_reader_from_memory(const uint8_t* buf, size_t l
   R->ctx = R;
   R->mem = buf;
   R->mem_len = len;
+  if (len) {   // page-locked by the caller (cudaHostAlloc / cudaHostRegister / bamgpu_pinned_alloc)?
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, buf) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+      cudaPointerAttributes at2{};
+      if (cudaPointerGetAttributes(&at2, buf + len - 1) == cudaSuccess && at2.type == cudaMemoryTypeHost) R->mem_pinned = true;
+    }
+    cudaGetLastError();
+  }
   R->feeder = std::thread(feeder_main, R);
   return R;
 }
@@ -1023,87 +1422,168 @@ extern "C" void bamgpu_reader_free(bamgpu_reader* R) {
   }
   R->cv.notify_all();
   if (R->feeder.joinable()) R->feeder.join();
-  cudaSetDevice(R->E->device);
-  if (R->copy_stream) { cudaStreamSynchronize(R->copy_stream); cudaStreamDestroy(R->copy_stream); }
-  for (auto& s : R->slots) { if (s.copied) cudaEventDestroy(s.copied); s.host.release(); s.dev.release(); }
-  bamgpu_engine_free(R->E);
-  delete R;
+  reader_destroy(R);
 }
 
 extern "C" const char* bamgpu_last_error(const bamgpu_reader* R) {
   if (!R) return "null reader (no CUDA device? this library has no CPU fallback)";
-  return R->err.empty() ? R->E->err.c_str() : R->err.c_str();
+  if (!R->err.empty()) return R->err.c_str();
+  for (auto& j : R->jobs) if (j.E && !j.E->err.empty()) return j.E->err.c_str();
+  return "";
 }
 
-// Returns the current slot to the feeder and takes the next one; puts its inflate on the stream (no host wait).
-// BAMGPU_EOF when input is exhausted.  With `nonblocking` it returns BAMGPU_EOF+1 (= 2) instead of waiting when the
-// feeder has no slot ready yet.
-static int reader_inflate_launch_next(bamgpu_reader* R, uint32_t flags, bool nonblocking) {
-  if (R->input_done) return BAMGPU_EOF;
-  int si;
+extern "C" bamgpu_engine* bamgpu_reader_current_engine(bamgpu_reader* R) { return (R && R->cur) ? R->cur->E : nullptr; }
+
+static void reader_release_slot(bamgpu_reader* R, Job& j) {
+  if (j.slot < 0) return;
   {
-    std::unique_lock<std::mutex> lk(R->mu);
-    if (nonblocking && R->ready.empty()) return 2;
-    if (R->cur_slot >= 0) {  // its kernels have finished (every caller synchronises the previous inflate first)
-      R->freeq.push_back(R->cur_slot);
-      R->cur_slot = -1;
-      R->cv.notify_all();
-    }
-    R->cv.wait(lk, [&] { return !R->ready.empty(); });
-    si = R->ready.front();
-    R->ready.pop_front();
+    std::lock_guard<std::mutex> lk(R->mu);
+    R->devs[j.dev_i].free_slots.push_back(j.slot);
   }
-  R->cur_slot = si;
-  Slot& S = R->slots[si];
-  if (S.final) R->input_done = true;
-  R->pending_final = S.final;
-  if (S.status < 0) {
-    R->err = std::string("input: ") + bamgpu_status_str(S.status);
-    return S.status;
-  }
-  bamgpu_engine* E = R->E;
-  cudaSetDevice(E->device);
-  if (cudaStreamWaitEvent(E->stream, S.copied, 0) != cudaSuccess) { R->err = "cudaStreamWaitEvent failed"; return BAMGPU_ERR_CUDA; }
-  int rc = engine_inflate_launch(E, S.dev.as<uint8_t>(), S.blocks.data(), S.blocks.size(), flags, E->stream);
-  if (rc != BAMGPU_OK) return rc;
-  R->inflated_pending = true;
-  return BAMGPU_OK;
+  j.slot = -1;
+  R->cv.notify_all();
 }
 
-static int reader_inflate_next(bamgpu_reader* R, uint32_t flags) {
-  int rc = reader_inflate_launch_next(R, flags, false);
-  if (rc != BAMGPU_OK) return rc;
-  return engine_inflate_finish(R->E, R->E->stream);
+// Queues K1 (+K2) for every batch the feeder has ready, as long as a job of its GPU is free.  Waits for the feeder
+// while fewer than `need_launched` batches have been launched (0: never waits).  BAMGPU_OK or an error.
+static int reader_pump(bamgpu_reader* R, uint32_t flags, uint64_t need_launched) {
+  for (;;) {
+    if (R->input_done) return BAMGPU_OK;
+    Job& j = R->job_of(R->n_launched);
+    if (j.st != Job::FREE) return BAMGPU_OK;   // every job of that GPU is busy
+    ReadyItem it;
+    {
+      std::unique_lock<std::mutex> lk(R->mu);
+      if (R->ready.empty()) {
+        if (R->n_launched >= need_launched) return BAMGPU_OK;
+        R->cv.wait(lk, [&] { return !R->ready.empty(); });
+      }
+      it = R->ready.front();
+      R->ready.pop_front();
+    }
+    DevCtx& dc = R->devs[it.dev_i];
+    Slot& S = dc.slots[it.slot];
+    j.seq = it.seq;
+    j.slot = it.slot;
+    j.final = S.final;
+    j.carry_set = false;
+    j.input_status = S.status;
+    j.stream_new = R->launched_stream;
+    j.new_bytes = S.total_isize;
+    R->launched_stream += S.total_isize;
+    if (S.final) R->input_done = true;
+    bamgpu_engine* E = j.E;
+    j.st = Job::LAUNCHED;
+    ++R->n_launched;
+    if (S.status == BAMGPU_ERR_NOMEM) continue;   // nothing on the device; the error surfaces when the batch is staged
+    cudaSetDevice(E->device);
+    if (cudaStreamWaitEvent(E->stream, S.copied, 0) != cudaSuccess) { R->err = "cudaStreamWaitEvent failed"; return BAMGPU_ERR_CUDA; }
+    int rc = engine_inflate_launch(E, S.dev.as<uint8_t>(), S.blocks.data(), S.blocks.size(), flags, E->stream);
+    if (rc != BAMGPU_OK) return rc;
+  }
+}
+
+// Waits for batch n_staged's inflate, splices the previous batch's tail in front of it and (unless `raw`) parses it; its
+// D2H is queued, not waited for.  BAMGPU_OK: the batch is staged.  BAMGPU_EOF: no more input.
+static int reader_stage(bamgpu_reader* R, uint32_t flags, bool raw) {
+  for (;;) {
+    if (R->no_more) return BAMGPU_EOF;
+    if (R->n_staged == R->n_launched) {
+      int rc = reader_pump(R, flags, R->n_staged + 1);
+      if (rc < 0) return rc;
+      if (R->n_staged == R->n_launched) {
+        if (R->input_done) { R->no_more = true; return BAMGPU_EOF; }
+        R->err = "internal: no free job for the next batch";
+        return BAMGPU_ERR_STATE;
+      }
+    }
+    Job& j = R->job_of(R->n_staged);
+    bamgpu_engine* E = j.E;
+    if (j.input_status == BAMGPU_ERR_NOMEM) { R->err = "out of memory for the input batch"; return BAMGPU_ERR_NOMEM; }
+    int rc = engine_inflate_finish(E, E->stream);
+    reader_release_slot(R, j);
+    if (rc < 0) { R->err = E->err; return rc; }
+    if (!j.carry_set) {
+      bamgpu_engine* prev = (!raw && R->n_staged > 0) ? R->job_of(R->n_staged - 1).E : nullptr;
+      rc = engine_set_carry(E, prev, E->stream);
+      if (rc < 0) { R->err = E->err; return rc; }
+      j.carry_set = true;
+    }
+    const uint64_t carry = E->lead - E->data_start;
+    // a batch that ends the input because of an error is parsed as "more would follow": its complete records are handed
+    // out, the error comes afterwards (where the reference's reading thread would have died)
+    const bool fin = j.final && j.input_status >= 0;
+    E->first_record_index = R->rec_index;
+    uint64_t tail = 0;
+    rc = engine_records(E, E->data_start + R->next_start_rel, fin ? 1 : 0, raw ? (flags | BAMGPU_NO_RECORDS | BAMGPU_COPY_DATA) : flags,
+                        E->stream, &j.batch, &tail, /*defer_d2h=*/true);
+    R->next_start_rel = 0;
+    j.batch.stream_offset = j.stream_new - carry;
+    if (rc == BAMGPU_ERR_SHORT_RECORD && j.batch.n_records) { R->sticky_next = rc; R->err = E->err; rc = BAMGPU_OK; R->no_more = true; }
+    if (rc < 0) { R->err = E->err; return rc; }
+    R->rec_index += j.batch.n_records;
+    ++R->n_staged;
+    j.st = Job::STAGED;
+    if (rc == BAMGPU_EOF || j.final) R->no_more = true;
+    if (j.input_status < 0) { R->sticky_next = j.input_status; R->err = std::string("input: ") + bamgpu_status_str(j.input_status); }
+    return BAMGPU_OK;
+  }
 }
 
 extern "C" int bamgpu_read_header(bamgpu_reader* R, const uint8_t** bytes, size_t* len, size_t* offset_to_ref_seqs) {
   if (!R) return BAMGPU_ERR_ARG;
   if (R->sticky < 0) return R->sticky;
   if (R->header_done || R->raw_mode) { R->err = "read_header called twice or after read()"; return BAMGPU_ERR_STATE; }
-  bamgpu_engine* E = R->E;
-  // Inflate batches until the whole header is on the device (normally the first batch).
+  auto fail = [&](int code, const char* what) { R->err = what; R->sticky = code; return code; };
+  // The header is read off the first batch on the device (normally a few KB of it).  If a batch ends inside the header,
+  // everything inflated so far becomes the "tail" spliced in front of the next batch, exactly like a partial record.
   std::vector<uint8_t> hb;
+  Job* hj = nullptr;
+  auto next_job = [&]() -> int {
+    const uint64_t seq = hj ? hj->seq + 1 : 0;
+    int rc = reader_pump(R, R->flags, seq + 1);
+    if (rc < 0) return rc;
+    if (R->n_launched <= seq) return BAMGPU_ERR_SHORT_HEADER;
+    Job& j = R->job_of(seq);
+    bamgpu_engine* E = j.E;
+    if (j.input_status == BAMGPU_ERR_NOMEM) return BAMGPU_ERR_NOMEM;
+    rc = engine_inflate_finish(E, E->stream);
+    reader_release_slot(R, j);
+    if (rc < 0) { R->err = E->err; return rc; }
+    rc = engine_set_carry(E, hj ? hj->E : nullptr, E->stream);
+    if (rc < 0) { R->err = E->err; return rc; }
+    j.carry_set = true;
+    if (hj) { hj->st = Job::FREE; ++R->n_staged; ++R->n_out; }   // its bytes now live in front of this batch
+    hj = &j;
+    return BAMGPU_OK;
+  };
   auto fetch = [&](uint64_t need) -> int {  // make hb hold the first `need` inflated bytes
-    while (E->data_len < need) {
-      if (R->input_done) return BAMGPU_ERR_SHORT_HEADER;
-      // keep everything inflated so far as carry for the next inflate
-      E->carry_len = E->data_len; E->keep_from = 0;
-      int rc = reader_inflate_next(R, R->flags);
-      if (rc == BAMGPU_EOF) return BAMGPU_ERR_SHORT_HEADER;
+    for (;;) {
+      bamgpu_engine* E = hj->E;
+      const uint64_t have = E->data_len - E->data_start;
+      if (have >= need) break;
+      if (hj->final) return hj->input_status < 0 ? hj->input_status : BAMGPU_ERR_SHORT_HEADER;
+      // keep everything inflated so far as the carry of the next batch
+      E->keep_from = E->data_start;
+      E->carry_len = have;
+      int rc = engine_save_carry(E, E->stream);
+      if (rc < 0) return rc;
+      rc = next_job();
       if (rc < 0) return rc;
     }
     if (hb.size() < need) {
       size_t old = hb.size();
       hb.resize(need);
-      int rc = bamgpu_memcpy_d2h(E, hb.data() + old, E->out_ptr() + old, need - old);
+      bamgpu_engine* E = hj->E;
+      int rc = bamgpu_memcpy_d2h(E, hb.data() + old, E->out_ptr() + E->data_start + old, need - old);
       if (rc < 0) return rc;
     }
     return BAMGPU_OK;
   };
-  int rc = reader_inflate_next(R, R->flags);
+  int rc = next_job();
+  if (rc == BAMGPU_ERR_SHORT_HEADER) return fail(rc, "short BAM header");
   if (rc < 0) { R->sticky = rc; return rc; }
-  auto fail = [&](int code, const char* what) { R->err = what; R->sticky = code; return code; };
-  if ((rc = fetch(4)) < 0) return fail(rc == BAMGPU_ERR_SHORT_HEADER ? BAMGPU_ERR_SHORT_HEADER : rc, "short BAM header");
+  if ((rc = fetch(4)) < 0) return fail(rc, "short BAM header");
   if (memcmp(hb.data(), "BAM\1", 4) != 0) return fail(BAMGPU_ERR_BAD_MAGIC, "invalid BAM header");   // reader.rs:90-95
   if ((rc = fetch(8)) < 0) return fail(rc, "short BAM header");
   uint64_t p = 4;
@@ -1120,77 +1600,75 @@ extern "C" int bamgpu_read_header(bamgpu_reader* R, const uint8_t** bytes, size_
   }
   R->header.assign(hb.begin() + 4, hb.begin() + p);
   R->header_done = true;
-  R->next_start = p;
-  engine_set_n_ref(E, n_ref > 0x7fffffffu ? -1 : (int32_t)n_ref);
+  R->next_start_rel = p;
+  R->n_ref = n_ref > 0x7fffffffu ? -1 : (int32_t)n_ref;
+  for (auto& j : R->jobs) j.E->n_ref = R->n_ref;
   if (bytes) *bytes = R->header.data();
   if (len) *len = R->header.size();
   if (offset_to_ref_seqs) *offset_to_ref_seqs = R->off_to_refs;
   return BAMGPU_OK;
 }
 
-// Stages the next non-empty batch: waits for its inflate (launching it first if need be), runs the record kernels and
-// queues its D2H (not waited for) -> R->prep / R->prep_sel.  BAMGPU_OK, BAMGPU_EOF (no more input) or an error.
-static int reader_stage_next(bamgpu_reader* R, uint32_t flags) {
-  bamgpu_engine* E = R->E;
-  for (;;) {
-    if (R->no_more) return BAMGPU_EOF;
-    int rc;
-    if (!R->inflated_pending) {
-      rc = reader_inflate_launch_next(R, flags, false);
-      if (rc == BAMGPU_EOF) { R->no_more = true; return BAMGPU_EOF; }   // whatever carry was left has been judged with final=1
-      if (rc < 0) return rc;
-    }
-    const double t0 = now_ms();
-    rc = engine_inflate_finish(E, E->stream);
-    if (rc < 0) return rc;
-    R->inflated_pending = false;
-    const bool fin = R->pending_final;
-    uint64_t tail = 0;
-    const double t1 = now_ms();
-    rc = engine_records(E, R->next_start, fin ? 1 : 0, flags, E->stream, &R->prep, &tail, /*defer_d2h=*/true);
-    R->next_start = 0;
-    if (rc < 0) return rc;
-    if (rc == BAMGPU_EOF || fin) R->no_more = true;
-    R->prep_sel = E->msel;
-    if (dbg_level() >= 2)
-      fprintf(stderr, "[bamgpu] stage @%.1f: wait inflate %.2f, records %.2f ms (%llu records)\n", t0, t1 - t0, now_ms() - t1,
-              (unsigned long long)R->prep.n_records);
-    if (R->prep.n_records) return BAMGPU_OK;
-    { int w = engine_wait_mirror(E, E->msel); if (w < 0) return w; }   // an empty batch: drop it
-  }
-}
-
-// Produces the next non-empty batch (or EOF). Uses the inflated-but-unparsed batch left by read_header first.
-// Pipeline per call k:  [batch k was staged by the previous call: its D2H is running]  ->  launch inflate(k+1) into the
-// device buffer the caller has just released, wait for it, K3(k+1), queue D2H(k+1) behind D2H(k) (other mirror set)  ->
-// wait D2H(k)  ->  hand out batch k.  So the copy engine goes from one batch's D2H straight into the next one's, K1/K3 of
-// batch k+1 run under D2H(k), the feeder thread's H2D of batch k+2 under both, and batch k's device and host pointers
-// stay valid until the next call.
-static int reader_next_batch(bamgpu_reader* R, uint32_t extra_flags) {
+// Produces the next non-empty batch (or EOF).  Per call: the batch the caller held goes back to its GPU; K1 is queued for
+// whatever the feeder has ready; up to D batches beyond the one about to be handed out are parsed and their D2H queued
+// (one per GPU link); then the call waits for ITS batch's D2H only.
+static int reader_next_batch(bamgpu_reader* R, uint32_t extra_flags, bool raw = false) {
   if (R->sticky < 0) return R->sticky;
   if (R->eof) return BAMGPU_EOF;
-  if (!R->header_done) { R->err = "records requested before read_header()"; return BAMGPU_ERR_STATE; }
-  bamgpu_engine* E = R->E;
   const uint32_t flags = R->flags | extra_flags;
-  if (!R->prep_valid) {
-    if (R->sticky_next < 0) { R->sticky = R->sticky_next; return R->sticky; }
-    int rc = reader_stage_next(R, flags);
-    if (rc == BAMGPU_EOF) { R->eof = true; return BAMGPU_EOF; }
-    if (rc < 0) { R->sticky = rc; return rc; }
-    R->prep_valid = true;
+  if (R->cur) { R->cur->st = Job::FREE; R->cur = nullptr; R->batch_valid = false; }
+  auto end_of_stream = [&](int rc) {
+    if (rc == BAMGPU_EOF) {
+      if (R->sticky_next < 0) { R->sticky = R->sticky_next; return R->sticky; }
+      R->eof = true;
+      return (int)BAMGPU_EOF;
+    }
+    R->sticky = rc;
+    return rc;
+  };
+  for (;;) {
+    if (R->n_out == R->n_staged) {
+      int rc = reader_stage(R, flags, raw);
+      if (rc != BAMGPU_OK) return end_of_stream(rc);
+    }
+    Job& j = R->job_of(R->n_out);
+    if (j.batch.n_records || raw) break;
+    { int w = engine_wait_mirror(j.E, j.E->msel); if (w < 0) return end_of_stream(w); }   // a batch without a record: drop it
+    j.st = Job::FREE;
+    ++R->n_out;
   }
-  const bamgpu_batch cur = R->prep;
-  const int cur_sel = R->prep_sel;
-  R->prep_valid = false;
+  {
+    int rc = reader_pump(R, flags, 0);
+    if (rc < 0) return end_of_stream(rc);
+  }
   const double t0 = now_ms();
-  const int rn = reader_stage_next(R, flags);
-  if (rn == BAMGPU_OK) R->prep_valid = true;
-  else if (rn < 0) R->sticky_next = rn;      // surfaces on the next call; this batch is still good
+  // look-ahead: parse the batches behind this one whose K1 is already queued, so that their D2H follows on
+  while (!R->no_more && R->sticky_next == BAMGPU_OK && R->n_staged - R->n_out < 1 + R->devs.size() &&
+         (R->n_staged < R->n_launched || R->n_staged == R->n_out + 1)) {
+    if (R->n_staged == R->n_launched && R->job_of(R->n_launched).st != Job::FREE) break;   // would wait for ourselves
+    int rn = reader_stage(R, flags, raw);
+    if (rn < 0) { R->sticky_next = rn; R->no_more = true; break; }
+    if (rn == BAMGPU_EOF) break;
+    int rc = reader_pump(R, flags, 0);
+    if (rc < 0) { R->sticky_next = rc; R->no_more = true; break; }
+  }
   const double t1 = now_ms();
-  int w = engine_wait_mirror(E, cur_sel);
-  if (w < 0) { R->sticky = w; return w; }
-  if (dbg_level() >= 2) fprintf(stderr, "[bamgpu] next_batch @%.1f: stage next %.2f, wait d2h %.2f ms\n", t0, t1 - t0, now_ms() - t1);
-  R->batch = cur;
+  Job& j = R->job_of(R->n_out);
+  bamgpu_engine* E = j.E;
+  // a caller that switched APIs in mid-stream (next_batch, then next_rec) may need mirrors this batch was staged without
+  {
+    cudaSetDevice(E->device);
+    bool q = false;
+    int w = engine_enqueue_mirrors(E, E->mir[E->msel], raw ? (flags | BAMGPU_COPY_DATA) : flags, j.batch.n_records, &j.batch, E->stream, &q);
+    if (w < 0) { R->sticky = w; R->err = E->err; return w; }
+  }
+  int w = engine_wait_mirror(E, E->msel);
+  if (w < 0) { R->sticky = w; R->err = E->err; return w; }
+  if (dbg_level() >= 2) fprintf(stderr, "[bamgpu] next_batch @%.1f: stage ahead %.2f, wait d2h %.2f ms\n", t0, t1 - t0, now_ms() - t1);
+  j.st = Job::OUT;
+  ++R->n_out;
+  R->cur = &j;
+  R->batch = j.batch;
   R->batch_valid = true;
   R->rec_cursor = 0;
   return BAMGPU_OK;
@@ -1199,7 +1677,9 @@ static int reader_next_batch(bamgpu_reader* R, uint32_t extra_flags) {
 extern "C" int bamgpu_next_batch(bamgpu_reader* R, bamgpu_batch* out) {
   if (!R || !out) return BAMGPU_ERR_ARG;
   if (R->raw_mode) { R->err = "next_batch after read()"; return BAMGPU_ERR_STATE; }
+  if (!R->header_done) { R->err = "records requested before read_header()"; return BAMGPU_ERR_STATE; }
   if (R->eof) return R->sticky < 0 ? R->sticky : BAMGPU_EOF;
+  R->records_mode = true;
   int rc = reader_next_batch(R, 0);
   if (rc != BAMGPU_OK) return rc;
   *out = R->batch;
@@ -1210,8 +1690,10 @@ extern "C" int bamgpu_next_batch(bamgpu_reader* R, bamgpu_batch* out) {
 extern "C" int bamgpu_next_rec(bamgpu_reader* R, const uint8_t** body, size_t* len) {
   if (!R || !body || !len) return BAMGPU_ERR_ARG;
   if (R->raw_mode) { R->err = "next_rec after read()"; return BAMGPU_ERR_STATE; }
+  if (!R->header_done) { R->err = "records requested before read_header()"; return BAMGPU_ERR_STATE; }
+  R->records_mode = true;
   while (!R->batch_valid || R->rec_cursor >= R->batch.n_records) {
-    if (R->eof) { *body = nullptr; *len = 0; return R->sticky < 0 ? R->sticky : BAMGPU_EOF; }
+    if (R->eof || R->sticky < 0) { *body = nullptr; *len = 0; return R->sticky < 0 ? R->sticky : BAMGPU_EOF; }
     int rc = reader_next_batch(R, BAMGPU_COPY_DATA | BAMGPU_COPY_OFFSETS);
     if (rc != BAMGPU_OK) { *body = nullptr; *len = 0; return rc; }
   }
@@ -1239,10 +1721,12 @@ extern "C" int bamgpu_append_record(bamgpu_reader* R, uint8_t* dst, size_t cap, 
   return BAMGPU_OK;
 }
 
+// impl Read for Reader (reader.rs:114-152).  Before read_header() it serves the inflated stream from byte 0; after it,
+// the stream continues behind the header, as in the reference (read_header consumed those bytes through the same Read).
 extern "C" long bamgpu_read(bamgpu_reader* R, uint8_t* dst, size_t cap) {
   if (!R || (!dst && cap)) return BAMGPU_ERR_ARG;
   if (R->sticky < 0) return R->sticky;
-  if (R->header_done && !R->raw_mode) { R->err = "read() after read_header(): use the record calls"; return BAMGPU_ERR_STATE; }
+  if (R->records_mode) { R->err = "read() after records were requested: use one of the two on a Reader"; return BAMGPU_ERR_STATE; }
   R->raw_mode = true;
   size_t got = 0;
   while (got < cap) {
@@ -1254,23 +1738,28 @@ extern "C" long bamgpu_read(bamgpu_reader* R, uint8_t* dst, size_t cap) {
       continue;
     }
     if (R->eof) break;
-    int rc = reader_inflate_next(R, R->flags | BAMGPU_NO_RECORDS);
-    if (rc == BAMGPU_EOF) { R->eof = true; break; }
-    if (rc < 0) { R->sticky = rc; return got ? (long)got : rc; }
-    uint64_t tail;
-    rc = engine_records(R->E, 0, R->pending_final, R->flags | BAMGPU_NO_RECORDS | BAMGPU_COPY_DATA, R->E->stream, &R->batch, &tail);
-    if (rc < 0) { R->sticky = rc; return got ? (long)got : rc; }
-    R->inflated_pending = false;
-    R->batch_valid = true;
-    R->byte_cursor = 0;
-    if (R->pending_final) R->eof = true;
+    const uint64_t skip = R->next_start_rel;   // != 0 only for the batch read_header() stopped in
+    int rc = reader_next_batch(R, BAMGPU_NO_RECORDS | BAMGPU_COPY_DATA, /*raw=*/true);
+    if (rc == BAMGPU_EOF) break;
+    if (rc < 0) return got ? (long)got : rc;
+    R->byte_cursor = R->batch.data_start + skip;
   }
   return (long)got;
 }
 
 extern "C" int bamgpu_reader_stats(const bamgpu_reader* R, bamgpu_stats* out) {
-  if (!R) return BAMGPU_ERR_ARG;
-  return bamgpu_engine_stats(R->E, out);
+  if (!R || !out) return BAMGPU_ERR_ARG;
+  bamgpu_stats t{};
+  for (auto& j : R->jobs) {
+    if (!j.E) continue;
+    const bamgpu_stats& e = j.E->stats;
+    t.blocks += e.blocks; t.bytes_in += e.bytes_in; t.bytes_out += e.bytes_out; t.records += e.records; t.batches += e.batches;
+    t.kernel_launches += e.kernel_launches; t.ms_h2d += e.ms_h2d; t.ms_inflate += e.ms_inflate; t.ms_crc += e.ms_crc;
+    t.ms_records += e.ms_records; t.ms_d2h += e.ms_d2h; t.ms_sort += e.ms_sort; t.ms_gather += e.ms_gather; t.p2p_bytes += e.p2p_bytes;
+  }
+  t.ms_total = t.ms_h2d + t.ms_inflate + t.ms_crc + t.ms_records + t.ms_d2h + t.ms_sort + t.ms_gather;
+  *out = t;
+  return BAMGPU_OK;
 }
 
 extern "C" int bamgpu_parse_reference_sequences(const uint8_t* b, size_t len, bamgpu_refseq_cb cb, void* user) {
@@ -1322,6 +1811,8 @@ extern "C" int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write
   bamgpu_opts o{};
   if (opts) o = *opts; else o.device = -1;
   o.batch_bytes = len + 65536;
+  o.n_devices = 0;            // the sort is single-GPU: the whole file is one batch on one device
+  o.jobs_per_device = 2;
   o.flags &= ~(uint32_t)(BAMGPU_COPY_DATA | BAMGPU_COPY_COLUMNS | BAMGPU_NO_RECORDS | BAMGPU_SPECULATIVE_START);
   if (sort_by == BAMGPU_SORT_NAME_AND_MATCH_MATES) o.flags |= BAMGPU_WANT_HI;
   reader_thread_num = std::max<size_t>(reader_thread_num, 1);   // sort.rs:150
@@ -1337,8 +1828,13 @@ extern "C" int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write
     rc = bamgpu_next_batch(R, &b);
     if (rc == BAMGPU_EOF) { rc = BAMGPU_OK; break; }   // no records: empty output
     if (rc != BAMGPU_OK) { msg = bamgpu_last_error(R); break; }
-    if (R->prep_valid || !R->no_more) { rc = BAMGPU_ERR_TOO_LARGE; msg = "input was split into several batches"; break; }
-    bamgpu_engine* E = R->E;
+    bamgpu_engine* E = bamgpu_reader_current_engine(R);
+    {   // the whole file must have been ONE batch: a second one means it did not fit
+      bamgpu_batch b2;
+      int r2 = bamgpu_next_batch(R, &b2);   // releases the first batch's job, whose device buffers stay untouched (no input left to launch)
+      if (r2 == BAMGPU_OK) { rc = BAMGPU_ERR_TOO_LARGE; msg = "input was split into several batches"; break; }
+      if (r2 < 0) { rc = r2; msg = bamgpu_last_error(R); break; }
+    }
     bamgpu_sorted srt;
     rc = bamgpu_engine_sort(E, sort_by, 0, nullptr, &srt);
     if (rc != BAMGPU_OK) { msg = E->err; break; }

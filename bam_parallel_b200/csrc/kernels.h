@@ -109,10 +109,24 @@ struct ResolveScratch {  // grid-wide state of k3_resolve (device memory, no ini
 cudaError_t launch_chain_resolve(const RecordParams& p, const TileArrays& t, ChainResult* d_result, ResolveScratch* d_scratch,
                                  int num_sms, cudaStream_t s);
 // Second walk: writes rec_off / rec_len for reachable tiles.
-void launch_tile_emit(const RecordParams& p, const TileArrays& t, uint64_t* rec_off, uint32_t* rec_len, cudaStream_t s);
-// Per-record fixed fields, variable offsets, keys (and HI when want_hi).
+void launch_tile_emit(const RecordParams& p, const TileArrays& t, uint64_t* rec_off, uint32_t* rec_len, uint64_t cap, cudaStream_t s);
+// Per-record fixed fields, variable offsets, keys (and HI when want_hi).  dev_count: n_records is the columns' capacity and
+// the true count is read from d_result->n_records on the device.
 void launch_extract(const RecordParams& p, const ColumnsDev& c, uint64_t n_records, bool want_hi,
-                    ChainResult* d_result, cudaStream_t s);
+                    ChainResult* d_result, bool dev_count, cudaStream_t s);
+
+// ---- digests of the decode / sort outputs (digest.cu; DIGEST SPEC in DESIGN.md) ---------------------
+// acc: 4 x u64 in device memory {n_records (unused), body_bytes, fields | perm, bodies}
+void launch_digest_records(const uint8_t* data, const ColumnsDev& c, uint64_t n, uint64_t index_base, uint64_t stream_base,
+                           unsigned long long* acc, int num_sms, cudaStream_t s);
+void launch_digest_sorted(const uint8_t* bodies, const uint64_t* body_off, const uint32_t* perm, uint64_t n,
+                          unsigned long long* acc, int num_sms, cudaStream_t s);
+
+// ---- shard-edge flags in peer memory (edge.cu) -----------------------------------------------------------------
+// Spins (with a time-out) until *flag >= want; on time-out sets *timed_out = 1 and returns.
+void launch_wait_flag(const unsigned long long* flag, unsigned long long want, uint32_t* timed_out, cudaStream_t s);
+// __threadfence_system(); *flag = value  (flag may live in a peer GPU's memory)
+void launch_set_flag(unsigned long long* flag, unsigned long long value, cudaStream_t s);
 
 // ---- sort + gather (sort.cu): the output bytes of the reference's sort_bam (sorting/sort.rs:138-178) -------------
 enum : int { SORT_NAME = 0, SORT_NAME_AND_MATCH_MATES = 1, SORT_COORDINATES_AND_STRAND = 2 };   // sort.rs:92-96 SortBy

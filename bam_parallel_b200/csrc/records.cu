@@ -110,7 +110,7 @@ struct WalkOut { uint64_t exit_off; uint32_t count; uint32_t kind; };
 // reader.rs:57-81 restricted to records STARTING before tile_end.  When EMIT, writes offsets.
 template <bool EMIT>
 __device__ WalkOut walk(const RecordParams& p, uint64_t q, uint64_t tile_end, uint64_t* rec_off, uint32_t* rec_len,
-                        uint64_t base) {
+                        uint64_t base, uint64_t cap = ~0ull) {
   WalkOut o;
   uint32_t cnt = 0;
   for (;;) {
@@ -119,7 +119,7 @@ __device__ WalkOut walk(const RecordParams& p, uint64_t q, uint64_t tile_end, ui
     uint32_t bs = ld32(p.data, q);
     if (bs == 0) { o.kind = EXIT_ZERO; break; }                       // :64-72, records.rs:25
     if (p.data_len - (q + 4) < bs) { o.kind = EXIT_INCOMPLETE; break; }  // :69-70 would panic if final
-    if (EMIT) { rec_off[base + cnt] = q + 4; rec_len[base + cnt] = bs; }
+    if (EMIT && base + cnt < cap) { rec_off[base + cnt] = q + 4; rec_len[base + cnt] = bs; }
     ++cnt;
     q += 4ull + bs;
   }
@@ -309,12 +309,14 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) k3_resolve(RecordParams p, Ti
   }
 }
 
-__global__ void __launch_bounds__(128) k3_tile_emit(RecordParams p, TileArrays t, uint64_t* rec_off, uint32_t* rec_len) {
+// `cap`: capacity of rec_off / rec_len.  The host sizes the columns from the previous batch and learns the true count
+// only after this kernel is already queued; records beyond cap are dropped here and the host re-runs with more room.
+__global__ void __launch_bounds__(128) k3_tile_emit(RecordParams p, TileArrays t, uint64_t* rec_off, uint32_t* rec_len, uint64_t cap) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= t.n_tiles || !t.reach[k] || t.entry[k] == NONE64) return;
   uint64_t te = (uint64_t)(k + 1) * TILE_BYTES;
   if (te > p.own_len) te = p.own_len;
-  walk<true>(p, t.entry[k], te, rec_off, rec_len, t.base[k]);
+  walk<true>(p, t.entry[k], te, rec_off, rec_len, t.base[k], cap);
 }
 
 // ---- HI tag: record/tags.rs:62-129 through bamrawrecord.rs:80-104 (u8-wrapping offset) -------------
@@ -384,8 +386,11 @@ __device__ int hit_count(const uint8_t* body, uint32_t len, int32_t* val) {
   return 0;
 }
 
-__global__ void __launch_bounds__(256) k3_extract(RecordParams p, ColumnsDev c, uint64_t n, bool want_hi, ChainResult* res) {
+// `n` is the record count when the host knows it; with dev_count the kernel is launched for `n` = the columns' capacity
+// and takes the count the resolve kernel left in res->n_records (no host round trip between the two).
+__global__ void __launch_bounds__(256) k3_extract(RecordParams p, ColumnsDev c, uint64_t n, bool want_hi, ChainResult* res, bool dev_count) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (dev_count) { const uint64_t m = res->n_records; if (m < n) n = m; }
   bool bad = false;
   if (i < n) {
     const uint64_t off = c.rec_off[i];
@@ -434,13 +439,13 @@ cudaError_t launch_chain_resolve(const RecordParams& p, const TileArrays& t, Cha
   return cudaLaunchCooperativeKernel((const void*)k3_resolve, dim3(grid), dim3(RESOLVE_THREADS), args, 0, s);
 }
 
-void launch_tile_emit(const RecordParams& p, const TileArrays& t, uint64_t* rec_off, uint32_t* rec_len, cudaStream_t s) {
-  if (t.n_tiles) k3_tile_emit<<<grid_for(t.n_tiles, 128), 128, 0, s>>>(p, t, rec_off, rec_len);
+void launch_tile_emit(const RecordParams& p, const TileArrays& t, uint64_t* rec_off, uint32_t* rec_len, uint64_t cap, cudaStream_t s) {
+  if (t.n_tiles) k3_tile_emit<<<grid_for(t.n_tiles, 128), 128, 0, s>>>(p, t, rec_off, rec_len, cap);
 }
 
 void launch_extract(const RecordParams& p, const ColumnsDev& c, uint64_t n_records, bool want_hi, ChainResult* d_result,
-                    cudaStream_t s) {
-  if (n_records) k3_extract<<<grid_for(n_records, 256), 256, 0, s>>>(p, c, n_records, want_hi, d_result);
+                    bool dev_count, cudaStream_t s) {
+  if (n_records) k3_extract<<<grid_for(n_records, 256), 256, 0, s>>>(p, c, n_records, want_hi, d_result, dev_count);
 }
 
 }  // namespace bamgpu

@@ -27,8 +27,8 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import (COLUMN_FIELDS, COPY_COLUMNS, COPY_DATA, NO_CRC, NO_RECORDS, WANT_HI, BamGpuError, Batch, Block, Opts,
-                   Sorted, Stats)
+from ._lib import (COLUMN_FIELDS, COPY_COLUMNS, COPY_DATA, NO_CRC, NO_RECORDS, WANT_HI, BamGpuError, Batch, Block, Digest,
+                   EdgeHandle, Opts, Sorted, Stats, make_opts)
 
 _NP = {C.c_uint64: np.uint64, C.c_uint32: np.uint32, C.c_int32: np.int32, C.c_uint16: np.uint16, C.c_uint8: np.uint8}
 
@@ -50,6 +50,8 @@ class RecordBatch:
         self.bad_flag_records = int(b.bad_flag_records)
         self.chain_start = int(b.chain_start)
         self.chain_repairs = int(b.chain_repairs)
+        self.data_start = int(b.data_start)        # Reader batches: bytes [data_start, data_len) are the inflated stream
+        self.stream_offset = int(b.stream_offset)  # position of data[data_start] in the whole inflated stream
         self.dev_data = b.data
         self.dev = {n: getattr(b.dev, n) for n, _ in COLUMN_FIELDS}
         self.data = _view(b.h_data, self.data_len, C.c_uint8) if b.h_data else None
@@ -93,10 +95,13 @@ class Records:
 
 class Reader:
     def __init__(self, inner, thread_num: int = 4, track_progress: Optional[int] = None, *, flags: int = 0,
-                 batch_bytes: int = 0, device: int = -1):
+                 batch_bytes: int = 0, device: int = -1, devices=None, jobs_per_device: int = 0, inflate_impl: int = 0):
+        """`devices`: list of CUDA ordinals - batches go to them round robin and the partial record at a batch edge moves
+        GPU to GPU (bamgpu_opts.devices).  `inner`: bytes-like / numpy array (a page-locked array is read
+        by the GPUs directly, without a staging copy) or an object with read()/readinto()."""
         self._L = L = _lib.load()
         self._inner = inner
-        opts = Opts(device, flags, batch_bytes, 0, 0)
+        opts = make_opts(device, flags, batch_bytes, inflate_impl, jobs_per_device, devices)
         tp = C.c_uint64(track_progress) if track_progress is not None else None
         self._keep = None
         if isinstance(inner, (bytes, bytearray, memoryview, np.ndarray)):
@@ -186,6 +191,16 @@ class Reader:
         self._L.bamgpu_reader_stats(self._h, C.byref(s))
         return s.asdict()
 
+    def batch_digest(self, b: "RecordBatch") -> dict:
+        """DIGEST SPEC (csrc/digest.cu) of the batch next_batch() returned last, with global record indices and stream offsets."""
+        e = self._L.bamgpu_reader_current_engine(self._h)
+        d = Digest()
+        base = (b.stream_offset - b.data_start) & 0xFFFFFFFFFFFFFFFF
+        rc = self._L.bamgpu_engine_digest(e, b.first_record_index, base, None, C.byref(d))
+        if rc < 0:
+            raise BamGpuError(rc, self._L.bamgpu_engine_last_error(e).decode())
+        return d.asdict()
+
     def close(self):
         if getattr(self, "_h", None):
             self._L.bamgpu_reader_free(self._h)
@@ -235,9 +250,9 @@ def scan_blocks(data, final: bool = True):
 class Engine:
     """Device-resident decode (bamgpu_engine_*): what Reader runs per batch and what bench.py times."""
 
-    def __init__(self, device: int = -1, flags: int = 0):
+    def __init__(self, device: int = -1, flags: int = 0, inflate_impl: int = 0):
         self._L = L = _lib.load()
-        opts = Opts(device, flags, 0, 0, 0)
+        opts = make_opts(device, flags, 0, inflate_impl)
         self._h = L.bamgpu_engine_new(C.byref(opts))
         if not self._h:
             raise BamGpuError(-2, "could not create engine: no usable CUDA device (there is no CPU fallback)")
@@ -300,6 +315,34 @@ class Engine:
         perm = (_view(srt.h_perm, n, C.c_uint32) if srt.h_perm else np.zeros(0, np.uint32)) if flags & COPY_COLUMNS else None
         bodies = (_view(srt.h_bodies, nb, C.c_uint8) if srt.h_bodies else np.zeros(0, np.uint8)) if flags & COPY_DATA else None
         return perm, bodies, srt
+
+    def digest(self, index_base: int = 0, stream_base: int = 0, cuda_stream=None) -> dict:
+        """DIGEST SPEC of the last decoded batch, from the engine's columns and inflated bytes on the device."""
+        d = Digest()
+        self._eck(self._L.bamgpu_engine_digest(self._h, index_base, stream_base & 0xFFFFFFFFFFFFFFFF, cuda_stream, C.byref(d)))
+        return d.asdict()
+
+    def sorted_digest(self, cuda_stream=None) -> dict:
+        """DIGEST SPEC of the last sort: {'perm': permutation digest, 'bodies': digest of the gathered output bytes}."""
+        d = Digest()
+        self._eck(self._L.bamgpu_engine_sorted_digest(self._h, cuda_stream, C.byref(d)))
+        r = d.asdict()
+        r["perm"] = r.pop("fields")
+        return r
+
+    # ---- shard-edge exchange over peer memory (bamgpu_engine_edge_*) ----
+    def edge_open(self) -> bytes:
+        h = EdgeHandle()
+        self._eck(self._L.bamgpu_engine_edge_open(self._h, C.byref(h)))
+        return bytes(h)
+
+    def edge_connect(self, left: Optional[bytes], right: Optional[bytes]):
+        hl = EdgeHandle.from_buffer_copy(left) if left else None
+        hr = EdgeHandle.from_buffer_copy(right) if right else None
+        self._eck(self._L.bamgpu_engine_edge_connect(self._h, C.byref(hl) if hl else None, C.byref(hr) if hr else None))
+
+    def edge_exchange(self, step: int, cuda_stream=None):
+        self._eck(self._L.bamgpu_engine_edge_exchange(self._h, step, cuda_stream))
 
     def set_n_ref(self, n_ref: int):
         """Optional hint (header n_ref) for K3's guess of record starts; results never depend on it."""

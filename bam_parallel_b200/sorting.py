@@ -20,7 +20,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import BamGpuError, Opts, Stats
+from ._lib import BamGpuError, Opts, Stats, make_opts
 
 
 class SortBy(enum.IntEnum):
@@ -69,7 +69,7 @@ def sort_bam(mem_limit: int, reader, sorted_sink, tmp_dir=None, out_compr_level:
             return -1
 
     rcb, wcb = _lib.READ_FN(_read), _lib.WRITE_FN(_write)
-    opts, st = Opts(device, flags, 0, 0, 0), Stats()
+    opts, st = make_opts(device, flags), Stats()
     err = C.create_string_buffer(512)
     rc = L.bamgpu_sort_bam(rcb, None, wcb, None, reader_thread_num, int(sort_by), C.byref(opts), C.byref(st), err, len(err))
     if rc < 0:

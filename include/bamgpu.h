@@ -123,6 +123,10 @@ typedef struct bamgpu_batch {
   uint64_t chain_start;         /* offset in `data` of record 0's block_size field (== stream_start unless
                                    BAMGPU_SPECULATIVE_START); ~0 if the batch holds no record start */
   uint64_t chain_repairs;       /* tiles whose guessed entry had to be re-walked serially (0 in practice) */
+  uint64_t data_start;          /* first valid byte of `data` / `h_data`: bytes [data_start, data_len) are the inflated stream
+                                   (Reader batches keep a gap in front so that the tail of the previous batch - copied in
+                                   from whichever GPU decoded it - and this batch's blocks are contiguous); 0 for engine calls */
+  uint64_t stream_offset;       /* Reader batches: position in the whole inflated stream of data[data_start] */
 } bamgpu_batch;
 
 enum {
@@ -138,11 +142,19 @@ enum {
                                    The caller must confirm batch.chain_start with the left-hand shard's tail_off. */
 };
 
+#define BAMGPU_MAX_DEVICES 16
 typedef struct bamgpu_opts {
-  int32_t device;               /* CUDA device ordinal; -1 = current */
+  int32_t device;               /* CUDA device ordinal; -1 = current (used when n_devices == 0) */
   uint32_t flags;               /* BAMGPU_* bits */
-  uint64_t batch_bytes;         /* compressed bytes per pipeline batch (0 = default 256 MiB) */
-  int32_t inflate_impl;         /* 0 = default; see DESIGN.md "K1 variants" */
+  uint64_t batch_bytes;         /* compressed bytes per pipeline batch (0 = default: 256 MiB on one GPU, 64 MiB on several) */
+  int32_t inflate_impl;         /* K1 variant: 0 = default (one BGZF block per lane pair), 1 = one warp per block
+                                   (the north-star's mapping, kept for comparison; DESIGN.md "K1 variants") */
+  int32_t jobs_per_device;      /* Reader: batches in flight per GPU (0 = default 4) */
+  /* Multi-GPU Reader: batches go to the listed GPUs round robin, i.e. the file is sharded by BGZF block
+   * ranges; the partial record at the end of a batch moves to the GPU that decodes the next batch peer-to-peer
+   * (cudaMemcpyPeerAsync).  n_devices == 0: one GPU (`device`). */
+  int32_t n_devices;
+  int32_t devices[BAMGPU_MAX_DEVICES];
   int32_t reserved;
 } bamgpu_opts;
 
@@ -151,6 +163,7 @@ typedef struct bamgpu_stats {
   uint64_t blocks, bytes_in, bytes_out, records, batches, kernel_launches;
   double ms_h2d, ms_inflate, ms_crc, ms_records, ms_d2h, ms_total;
   double ms_sort, ms_gather;      /* bamgpu_engine_sort: key sort / body gather */
+  uint64_t p2p_bytes;             /* bytes moved between GPUs (batch-edge records, shard halos) */
 } bamgpu_stats;
 
 /* ------------------------------------------------------------------------------------------
@@ -159,6 +172,7 @@ typedef struct bamgpu_stats {
  * `value` line.  One engine = one CUDA device + one stream.
  * ---------------------------------------------------------------------------------------- */
 typedef struct bamgpu_engine bamgpu_engine;
+typedef struct bamgpu_reader bamgpu_reader;
 
 bamgpu_engine* bamgpu_engine_new(const bamgpu_opts* opts /*nullable*/);
 void bamgpu_engine_free(bamgpu_engine*);
@@ -199,6 +213,36 @@ int bamgpu_engine_append_halo(bamgpu_engine*, const uint8_t* d_src, size_t len, 
 int bamgpu_engine_records(bamgpu_engine*, uint64_t stream_start, int final, uint32_t flags, void* cuda_stream,
                           bamgpu_batch* out, uint64_t* tail_off);
 
+/* ---- Shard-edge exchange over NVLink peer memory (one process per GPU or several GPUs in one process) ----
+ * bamgpu_engine_edge_open allocates this engine's inbox (two halo buffers + flag words) and exports it; the caller hands
+ * the 80-byte handle to the two neighbours (any transport: it is plumbing, 80 bytes once per run) and calls _connect with
+ * theirs.  bamgpu_engine_edge_exchange(step) then, on the given stream and without host synchronisation:
+ *   - writes the first min(len, BAMGPU_MAX_HALO) inflated bytes of this shard into the LEFT neighbour's inbox
+ *     (cudaMemcpyAsync to peer memory) and publishes `step` there;
+ *   - waits (on the device) until the RIGHT neighbour has published `step` here and appends that halo behind this
+ *     shard's own bytes (bamgpu_engine_append_halo), then acknowledges so the neighbour may reuse the buffer.
+ * `step` starts at 1 and increases by one per call on every shard.  No collective, no NCCL. */
+typedef struct bamgpu_edge_handle { uint8_t ipc[64]; uint64_t ptr; int32_t device; int32_t pid; } bamgpu_edge_handle;
+int bamgpu_engine_edge_open(bamgpu_engine*, bamgpu_edge_handle* mine);
+int bamgpu_engine_edge_connect(bamgpu_engine*, const bamgpu_edge_handle* left /*nullable*/, const bamgpu_edge_handle* right /*nullable*/);
+int bamgpu_engine_edge_exchange(bamgpu_engine*, uint64_t step, void* cuda_stream);
+void bamgpu_engine_edge_close(bamgpu_engine*);
+
+/* ---- Digests of the decoded batch / the sort result, computed on the device from the engine's OUTPUTS (csrc/digest.cu).
+ * A size-independent parity check: the CPU oracle folds its own results with the same published function
+ * (oracle/bam_oracle.c "DIGEST SPEC").  index_base / stream_base are added to the record index / to rec_off, so shards
+ * and batches of one file add up (all sums are mod 2^64).  Synchronises. */
+typedef struct bamgpu_digest {
+  uint64_t n_records;
+  uint64_t body_bytes;   /* sum of block_size */
+  uint64_t fields;       /* records: index, stream offset, block_size, 11 fixed fields, 4 offsets, keys, HI;  sort: the permutation */
+  uint64_t bodies;       /* every body byte, position- and order-dependent */
+} bamgpu_digest;
+int bamgpu_engine_digest(bamgpu_engine*, uint64_t index_base, uint64_t stream_base, void* cuda_stream, bamgpu_digest* out);
+int bamgpu_engine_sorted_digest(bamgpu_engine*, void* cuda_stream, bamgpu_digest* out);
+/* The engine that holds the batch bamgpu_next_batch returned last (for bamgpu_engine_digest / _sort on Reader batches). */
+bamgpu_engine* bamgpu_reader_current_engine(bamgpu_reader*);
+
 /* Number of reference sequences of the BAM header (n_ref), if the caller knows it: tightens the guess of record
  * starts inside K3 (refID must be in [-1, n_ref)).  Results never depend on it.  < 0 = unknown (default). */
 void bamgpu_engine_set_n_ref(bamgpu_engine*, int32_t n_ref);
@@ -212,8 +256,6 @@ void bamgpu_engine_reset_stats(bamgpu_engine*);
 /* std::io::Read::read: return n > 0 bytes written to dst, 0 at EOF, < 0 on error. May be called from
  * an internal thread (the reference moves `inner` to its reading thread too: readahead.rs:88). */
 typedef long (*bamgpu_read_fn)(void* ctx, uint8_t* dst, size_t cap);
-
-typedef struct bamgpu_reader bamgpu_reader;
 
 /* Reader::new (reader.rs:28-55).  thread_num is accepted for signature parity and clamped like the
  * reference ([3, num_cpus]); the GPU path needs one host feeder thread regardless.  track_progress
@@ -236,7 +278,9 @@ int bamgpu_next_rec(bamgpu_reader*, const uint8_t** body, size_t* len);
  * 0 at EOF. BAMGPU_ERR_BUFFER_TOO_SMALL leaves the record unconsumed and sets *len to the size needed. */
 int bamgpu_append_record(bamgpu_reader*, uint8_t* dst, size_t cap, size_t* len);
 /* impl Read for Reader (reader.rs:114-152): inflated byte stream; returns bytes read, 0 at EOF, <0 error.
- * Unlike the reference it never returns a short "Interrupted" read at block switches. */
+ * Unlike the reference it never returns a short "Interrupted" read at block switches.  As in the reference it may be
+ * called after read_header() and continues behind the header; mixing it with the record calls is an error here
+ * (the reference would hand out torn records). */
 long bamgpu_read(bamgpu_reader*, uint8_t* dst, size_t cap);
 /* GPU-native batch interface (no reference counterpart): all records of the next pipeline batch. */
 int bamgpu_next_batch(bamgpu_reader*, bamgpu_batch* out);

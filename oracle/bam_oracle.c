@@ -19,6 +19,7 @@
  * Each function cites the reference file:line (relative to bam_tools/src/) it restates.
  * All integers are little-endian, as byteorder::LittleEndian in the reference.
  */
+#define _GNU_SOURCE
 #include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -384,53 +385,111 @@ typedef struct {
   int err;
 } sort_ctx;
 
-static sort_ctx* g_ctx; /* qsort has no context argument; oracle sorts are single-threaded */
-
 /* comparators.rs:61-65: str::cmp == bytewise lexicographic over the name INCLUDING its
  * trailing NUL (get_range gives 32..32+l_read_name, bamrawrecord.rs:118-123). */
-static int cmp_names(uint32_t a, uint32_t b) {
-  const uint8_t* na = g_ctx->u + g_ctx->rec_off[a] + 32;
-  const uint8_t* nb = g_ctx->u + g_ctx->rec_off[b] + 32;
-  size_t la = g_ctx->c->l_read_name[a], lb = g_ctx->c->l_read_name[b];
+static int cmp_names(const sort_ctx* x, uint32_t a, uint32_t b) {
+  const uint8_t* na = x->u + x->rec_off[a] + 32;
+  const uint8_t* nb = x->u + x->rec_off[b] + 32;
+  size_t la = x->c->l_read_name[a], lb = x->c->l_read_name[b];
   size_t m = la < lb ? la : lb;
   int r = memcmp(na, nb, m);
   if (r) return r;
   return (la > lb) - (la < lb);
 }
 
-static int cmp_perm(const void* pa, const void* pb) {
+static int cmp_perm(const void* pa, const void* pb, void* vx) {
+  sort_ctx* x = (sort_ctx*)vx;
   uint32_t a = *(const uint32_t*)pa, b = *(const uint32_t*)pb;
-  const orc_columns* c = g_ctx->c;
+  const orc_columns* c = x->c;
   int r = 0;
-  if (g_ctx->mode == 0) { /* comparators.rs:117-147 */
+  if (x->mode == 0) { /* comparators.rs:117-147 */
     uint64_t ka = c->coord_key[a], kb = c->coord_key[b];
     if (ka != kb) r = ka < kb ? -1 : 1;
-    else r = (int)g_ctx->strand[a] - (int)g_ctx->strand[b];
+    else r = (int)x->strand[a] - (int)x->strand[b];
   } else {
-    r = cmp_names(a, b);
-    if (r == 0 && g_ctx->mode == 2) { /* comparators.rs:78-93 */
+    r = cmp_names(x, a, b);
+    if (r == 0 && x->mode == 2) { /* comparators.rs:78-93 */
       uint8_t pa_ = c->hi_present[a], pb_ = c->hi_present[b];
       int same = (pa_ == pb_) && (!pa_ || c->hi_value[a] == c->hi_value[b]);
       if (same) {
         r = (int)c->flag[a] - (int)c->flag[b];
       } else {
-        if (!pa_ || !pb_) { g_ctx->err = ORC_ERR_HI_MIXED; r = 0; }
+        if (!pa_ || !pb_) { x->err = ORC_ERR_HI_MIXED; r = 0; }
         else r = c->hi_value[a] < c->hi_value[b] ? -1 : 1;
       }
     }
   }
   if (r) return r;
-  return (a > b) - (a < b); /* stability */
+  return (a > b) - (a < b); /* stability: (comparator, input index) is a total order */
+}
+
+/* Since (comparator, input index) is a total order, ANY correct sorting algorithm yields the one stable order the
+ * reference's par_sort_by + chunk-index tie-break produce (sort.rs:351-371,487-510).  Large inputs are sorted as
+ * `threads` runs (qsort_r each, in parallel) that are then merged pairwise, level by level, also in parallel. */
+typedef struct { sort_ctx ctx; uint32_t* a; uint32_t* b; size_t lo, mid, hi; } sort_job;
+
+static void* sort_run_thread(void* arg) {
+  sort_job* j = (sort_job*)arg;
+  qsort_r(j->a + j->lo, j->hi - j->lo, sizeof(uint32_t), cmp_perm, &j->ctx);
+  return NULL;
+}
+static void* sort_merge_thread(void* arg) {
+  sort_job* j = (sort_job*)arg;
+  const uint32_t* a = j->a;
+  uint32_t* o = j->b;
+  size_t i = j->lo, k = j->mid, w = j->lo;
+  while (i < j->mid && k < j->hi) {
+    if (cmp_perm(&a[i], &a[k], &j->ctx) <= 0) o[w++] = a[i++];
+    else o[w++] = a[k++];
+  }
+  while (i < j->mid) o[w++] = a[i++];
+  while (k < j->hi) o[w++] = a[k++];
+  return NULL;
+}
+
+int orc_sort_perm_mt(const uint8_t* u, const uint64_t* rec_off, const orc_columns* c, const uint8_t* strand, size_t n,
+                     int mode, uint32_t* perm, int threads) {
+  sort_ctx ctx = {u, rec_off, c, strand, mode, 0};
+  for (size_t i = 0; i < n; ++i) perm[i] = (uint32_t)i;
+  if (threads < 1) threads = 1;
+  if (n < 65536) threads = 1;
+  int runs = 1;
+  while (runs < threads) runs <<= 1;
+  if (runs == 1) {
+    qsort_r(perm, n, sizeof(uint32_t), cmp_perm, &ctx);
+    return ctx.err;
+  }
+  uint32_t* tmp = (uint32_t*)malloc(sizeof(uint32_t) * n);
+  if (!tmp) return ORC_ERR_NOMEM;
+  sort_job* jobs = (sort_job*)calloc((size_t)runs, sizeof(sort_job));
+  pthread_t* th = (pthread_t*)calloc((size_t)runs, sizeof(pthread_t));
+  for (int r = 0; r < runs; ++r) {
+    jobs[r].ctx = ctx; jobs[r].a = perm; jobs[r].lo = n * (size_t)r / (size_t)runs; jobs[r].hi = n * (size_t)(r + 1) / (size_t)runs;
+    pthread_create(&th[r], NULL, sort_run_thread, &jobs[r]);
+  }
+  int err = 0;
+  for (int r = 0; r < runs; ++r) { pthread_join(th[r], NULL); if (jobs[r].ctx.err) err = jobs[r].ctx.err; }
+  uint32_t *src = perm, *dst = tmp;
+  for (int width = 1; width < runs; width <<= 1) {
+    int nj = 0;
+    for (int r = 0; r < runs; r += 2 * width) {
+      sort_job* j = &jobs[nj];
+      j->ctx = ctx; j->a = src; j->b = dst;
+      j->lo = n * (size_t)r / (size_t)runs; j->mid = n * (size_t)(r + width) / (size_t)runs; j->hi = n * (size_t)(r + 2 * width) / (size_t)runs;
+      pthread_create(&th[nj], NULL, sort_merge_thread, j);
+      ++nj;
+    }
+    for (int k = 0; k < nj; ++k) { pthread_join(th[k], NULL); if (jobs[k].ctx.err) err = jobs[k].ctx.err; }
+    uint32_t* t = src; src = dst; dst = t;
+  }
+  if (src != perm) memcpy(perm, src, sizeof(uint32_t) * n);
+  free(tmp); free(jobs); free(th);
+  return err;
 }
 
 int orc_sort_perm(const uint8_t* u, const uint64_t* rec_off, const orc_columns* c, const uint8_t* strand, size_t n,
                   int mode, uint32_t* perm) {
-  sort_ctx ctx = {u, rec_off, c, strand, mode, 0};
-  for (size_t i = 0; i < n; ++i) perm[i] = (uint32_t)i;
-  g_ctx = &ctx;
-  qsort(perm, n, sizeof(uint32_t), cmp_perm);
-  g_ctx = NULL;
-  return ctx.err;
+  return orc_sort_perm_mt(u, rec_off, c, strand, n, mode, perm, 1);
 }
 
 /* ---- CPU baseline: the reference reader's thread topology, timed -----------------------------
@@ -442,53 +501,72 @@ int orc_sort_perm(const uint8_t* u, const uint64_t* rec_off, const orc_columns* 
  * reads a u32 then copies the body out of the current block(s) into a reused buffer
  * (reader.rs:57-73, :114-152), exactly two reads + one resize per record.
  * Inflate is zlib 1.3 here vs miniz_oxide in the reference: same bytes, different speed. */
+/* Signalling: the reference hands Blocks around over flume channels (readahead.rs:54-57), i.e. every hand-over wakes
+ * exactly one peer.  Here every ring slot has its own mutex + condition variable (reader <-> consumer hand-over of
+ * that slot, worker -> consumer completion) and the inflate workers share one queue whose producer wakes ONE worker
+ * (pthread_cond_signal).  (Round 1 used one mutex and pthread_cond_broadcast for everything: every state change woke
+ * every thread, and the port got SLOWER with more cores.) */
+typedef struct {
+  pthread_mutex_t mu;
+  pthread_cond_t cv;
+  int state;           /* 0 free, 1 queued, 2 inflating, 3 done, 4 eof, 5 error */
+  uint8_t* ubuf;       /* 1 MiB */
+  uint32_t ulen;
+  const uint8_t* cptr;
+  uint32_t clen;
+} cpu_slot;
+
 typedef struct {
   const uint8_t* file;
   size_t n;
   int n_slots;
   int n_workers;
-  /* ring */
-  uint8_t** ubuf;      /* n_slots x (1 MiB) */
-  uint32_t* ulen;
-  const uint8_t** cptr;
-  uint32_t* clen;
-  int* state;          /* 0 free, 1 queued, 2 inflating, 3 done, 4 eof, 5 error */
+  cpu_slot* slots;
+  /* work queue: block indices [head_work, head_fill) wait for a worker */
+  pthread_mutex_t q_mu;
+  pthread_cond_t q_cv;
   uint64_t head_fill;  /* next block index the reader will fill */
   uint64_t head_work;  /* next block index a worker will take */
-  pthread_mutex_t mu;
-  pthread_cond_t cv;
   int reader_done;
-  int stop;            /* consumer finished early (bounded sample): everybody exits */
+  volatile int stop;   /* consumer finished early (bounded sample): everybody exits */
   int error;
 } cpu_reader;
 
 static void* cpu_reader_thread(void* arg) {
   cpu_reader* r = (cpu_reader*)arg;
   size_t pos = 0;
+  uint64_t k = 0;
   for (;;) {
-    int slot = (int)(r->head_fill % (uint64_t)r->n_slots);
-    pthread_mutex_lock(&r->mu);
-    while (r->state[slot] != 0 && !r->stop) pthread_cond_wait(&r->cv, &r->mu);
-    int stop = r->stop;
-    if (stop) { r->reader_done = 1; pthread_cond_broadcast(&r->cv); }
-    pthread_mutex_unlock(&r->mu);
-    if (stop) return NULL;
-    uint16_t bs = bgzf_block_size(r->file + pos, r->n - pos);
+    cpu_slot* s = &r->slots[k % (uint64_t)r->n_slots];
+    /* readahead.rs:90: wait until the consumer has returned this Block */
+    pthread_mutex_lock(&s->mu);
+    while (s->state != 0 && !r->stop) pthread_cond_wait(&s->cv, &s->mu);
+    pthread_mutex_unlock(&s->mu);
     int st = 1;
-    if (bs == 0) st = 4;
-    else if (bs < BGZF_HEADER_SIZE + TRAILER_SIZE || r->n - pos < bs) st = 5;
-    else {
-      r->cptr[slot] = r->file + pos + BGZF_HEADER_SIZE;
-      r->clen[slot] = (uint32_t)bs - BGZF_HEADER_SIZE - TRAILER_SIZE;
-      pos += bs;
+    if (!r->stop) {
+      uint16_t bs = bgzf_block_size(r->file + pos, r->n - pos);
+      if (bs == 0) st = 4;
+      else if (bs < BGZF_HEADER_SIZE + TRAILER_SIZE || r->n - pos < bs) st = 5;
+      else {
+        s->cptr = r->file + pos + BGZF_HEADER_SIZE;
+        s->clen = (uint32_t)bs - BGZF_HEADER_SIZE - TRAILER_SIZE;
+        pos += bs;
+      }
+      pthread_mutex_lock(&s->mu);
+      s->state = st;
+      if (st != 1) pthread_cond_broadcast(&s->cv);   /* eof / error sentinel: the consumer may be waiting for it */
+      pthread_mutex_unlock(&s->mu);
     }
-    pthread_mutex_lock(&r->mu);
-    r->state[slot] = st;
-    r->head_fill++;
-    if (st != 1) r->reader_done = 1;
-    pthread_cond_broadcast(&r->cv);
-    pthread_mutex_unlock(&r->mu);
-    if (st != 1) return NULL;
+    pthread_mutex_lock(&r->q_mu);
+    if (r->stop || st != 1) {
+      r->reader_done = 1;
+      pthread_cond_broadcast(&r->q_cv);           /* once, at the end: every worker must see it */
+      pthread_mutex_unlock(&r->q_mu);
+      return NULL;
+    }
+    r->head_fill = ++k;
+    pthread_cond_signal(&r->q_cv);                /* one task, one worker */
+    pthread_mutex_unlock(&r->q_mu);
   }
 }
 
@@ -498,24 +576,20 @@ static void* cpu_worker_thread(void* arg) {
   memset(&zs, 0, sizeof zs);
   inflateInit2(&zs, -15);
   for (;;) {
-    pthread_mutex_lock(&r->mu);
-    int slot = -1;
-    for (;;) {
-      if (r->stop) { pthread_mutex_unlock(&r->mu); inflateEnd(&zs); return NULL; }
-      if (r->head_work < r->head_fill) {
-        int s = (int)(r->head_work % (uint64_t)r->n_slots);
-        if (r->state[s] == 1) { slot = s; r->state[s] = 2; r->head_work++; break; }
-        if (r->state[s] >= 4) { pthread_mutex_unlock(&r->mu); inflateEnd(&zs); return NULL; }
-      } else if (r->reader_done) { pthread_mutex_unlock(&r->mu); inflateEnd(&zs); return NULL; }
-      pthread_cond_wait(&r->cv, &r->mu);
-    }
-    pthread_mutex_unlock(&r->mu);
-    long u = inflate_raw(&zs, r->cptr[slot], r->clen[slot], r->ubuf[slot], 1u << 20);
-    pthread_mutex_lock(&r->mu);
-    if (u < 0) { r->state[slot] = 5; } else { r->ulen[slot] = (uint32_t)u; r->state[slot] = 3; }
-    pthread_cond_broadcast(&r->cv);
-    pthread_mutex_unlock(&r->mu);
+    pthread_mutex_lock(&r->q_mu);
+    while (r->head_work >= r->head_fill && !r->reader_done && !r->stop) pthread_cond_wait(&r->q_cv, &r->q_mu);
+    if (r->stop || r->head_work >= r->head_fill) { pthread_mutex_unlock(&r->q_mu); break; }
+    uint64_t k = r->head_work++;
+    pthread_mutex_unlock(&r->q_mu);
+    cpu_slot* s = &r->slots[k % (uint64_t)r->n_slots];
+    long u = inflate_raw(&zs, s->cptr, s->clen, s->ubuf, 1u << 20);
+    pthread_mutex_lock(&s->mu);
+    if (u < 0) s->state = 5; else { s->ulen = (uint32_t)u; s->state = 3; }
+    pthread_cond_broadcast(&s->cv);               /* <= 2 waiters on a slot: the consumer (for this block) and, when the ring is full, the reader (for the slot to come back) */
+    pthread_mutex_unlock(&s->mu);
   }
+  inflateEnd(&zs);
+  return NULL;
 }
 
 typedef struct {
@@ -530,18 +604,25 @@ typedef struct {
 /* readahead.rs:128-142 get_block: give the spent Block back, wait for the next in order. */
 static int consumer_next_block(cpu_consumer* c) {
   cpu_reader* r = c->r;
-  pthread_mutex_lock(&r->mu);
-  if (c->slot >= 0) { r->state[c->slot] = 0; pthread_cond_broadcast(&r->cv); }
+  if (c->slot >= 0) {
+    cpu_slot* o = &r->slots[c->slot];
+    pthread_mutex_lock(&o->mu);
+    o->state = 0;
+    pthread_cond_broadcast(&o->cv);               /* the reader may be waiting for exactly this slot */
+    pthread_mutex_unlock(&o->mu);
+  }
   int slot = (int)(c->next_block % (uint64_t)r->n_slots);
-  while (!(r->state[slot] >= 3 && c->next_block < r->head_fill)) pthread_cond_wait(&r->cv, &r->mu);
-  int st = r->state[slot];
-  pthread_mutex_unlock(&r->mu);
+  cpu_slot* s = &r->slots[slot];
+  pthread_mutex_lock(&s->mu);
+  while (s->state < 3) pthread_cond_wait(&s->cv, &s->mu);
+  int st = s->state;
+  pthread_mutex_unlock(&s->mu);
   if (st == 4) { c->eof = 1; c->slot = -1; return 0; }
   if (st == 5) { c->eof = 1; c->slot = -1; r->error = 1; return -1; }
   c->slot = slot;
   c->cur = 0;
   c->next_block++;
-  c->ubytes += r->ulen[slot];
+  c->ubytes += s->ulen;
   return 1;
 }
 
@@ -550,13 +631,13 @@ static size_t consumer_read_exact(cpu_consumer* c, uint8_t* dst, size_t want) {
   size_t got = 0;
   while (got < want) {
     if (c->eof) break;
-    if (c->slot < 0 || c->cur == c->r->ulen[c->slot]) {
+    if (c->slot < 0 || c->cur == c->r->slots[c->slot].ulen) {
       if (consumer_next_block(c) <= 0) break;
       continue; /* ErrorKind::Interrupted -> read_exact retries */
     }
-    size_t avail = c->r->ulen[c->slot] - c->cur;
+    size_t avail = c->r->slots[c->slot].ulen - c->cur;
     size_t k = want - got < avail ? want - got : avail;
-    memcpy(dst + got, c->r->ubuf[c->slot] + c->cur, k);
+    memcpy(dst + got, c->r->slots[c->slot].ubuf + c->cur, k);
     c->cur += (uint32_t)k;
     got += k;
   }
@@ -575,14 +656,14 @@ int orc_cpu_reader_run(const uint8_t* file, size_t n, int threads, uint64_t max_
   r.n = n;
   r.n_slots = threads;
   r.n_workers = threads - 2;
-  r.ubuf = (uint8_t**)calloc((size_t)threads, sizeof(uint8_t*));
-  r.ulen = (uint32_t*)calloc((size_t)threads, sizeof(uint32_t));
-  r.cptr = (const uint8_t**)calloc((size_t)threads, sizeof(uint8_t*));
-  r.clen = (uint32_t*)calloc((size_t)threads, sizeof(uint32_t));
-  r.state = (int*)calloc((size_t)threads, sizeof(int));
-  for (int i = 0; i < threads; ++i) r.ubuf[i] = (uint8_t*)malloc(1u << 20);
-  pthread_mutex_init(&r.mu, NULL);
-  pthread_cond_init(&r.cv, NULL);
+  r.slots = (cpu_slot*)calloc((size_t)threads, sizeof(cpu_slot));
+  for (int i = 0; i < threads; ++i) {
+    r.slots[i].ubuf = (uint8_t*)malloc(1u << 20);
+    pthread_mutex_init(&r.slots[i].mu, NULL);
+    pthread_cond_init(&r.slots[i].cv, NULL);
+  }
+  pthread_mutex_init(&r.q_mu, NULL);
+  pthread_cond_init(&r.q_cv, NULL);
   struct timespec t0, t1;
   clock_gettime(CLOCK_MONOTONIC, &t0);
   pthread_t rt;
@@ -629,14 +710,19 @@ int orc_cpu_reader_run(const uint8_t* file, size_t n, int threads, uint64_t max_
   if (r.error) rc = ORC_ERR_INFLATE;
   clock_gettime(CLOCK_MONOTONIC, &t1);
   /* shut down: tell the reader and the workers to exit wherever they are */
-  pthread_mutex_lock(&r.mu);
+  pthread_mutex_lock(&r.q_mu);
   r.stop = 1;
-  pthread_cond_broadcast(&r.cv);
-  pthread_mutex_unlock(&r.mu);
+  pthread_cond_broadcast(&r.q_cv);
+  pthread_mutex_unlock(&r.q_mu);
+  for (int i = 0; i < threads; ++i) {
+    pthread_mutex_lock(&r.slots[i].mu);
+    pthread_cond_broadcast(&r.slots[i].cv);
+    pthread_mutex_unlock(&r.slots[i].mu);
+  }
   pthread_join(rt, NULL);
   for (int i = 0; i < r.n_workers; ++i) pthread_join(wt[i], NULL);
-  for (int i = 0; i < threads; ++i) free(r.ubuf[i]);
-  free(r.ubuf); free(r.ulen); free((void*)r.cptr); free(r.clen); free(r.state); free(wt); free(rec);
+  for (int i = 0; i < threads; ++i) { free(r.slots[i].ubuf); pthread_mutex_destroy(&r.slots[i].mu); pthread_cond_destroy(&r.slots[i].cv); }
+  free(r.slots); free(wt); free(rec);
   if (records) *records = nrec;
   if (ubytes) *ubytes = c.ubytes;
   if (seconds) *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
@@ -646,3 +732,209 @@ int orc_cpu_reader_run(const uint8_t* file, size_t n, int threads, uint64_t max_
 
 /* zlib's CRC-32 (what a BGZF trailer holds), exposed so tests can check the GPU CRC kernel. */
 uint32_t orc_crc32(const uint8_t* p, size_t n) { return (uint32_t)crc32(crc32(0, NULL, 0), p, (uInt)n); }
+
+/* =====================================================================================================
+ * Full-size parity helpers (tests at BASELINE.json's 50M-record sizes).  Everything below is the SAME
+ * restatement as above, run on several threads, plus a digest: 64-bit hashes of every value the reader /
+ * record accessors / sort produce, folded into a few words, so a GPU run over 50M records can be compared
+ * with the oracle without moving 20 GB of columns around.  The digest's definition (DIGEST SPEC):
+ *   mix64(z)       = splitmix64 finaliser of z + 0x9E3779B97F4A7C15
+ *   h_fields(i)    = fold of [index i, stream offset of the body, block_size, refID, pos, l_read_name, mapq, bin,
+ *                    n_cigar_op, flag, l_seq, next_refID, next_pos, tlen, cigar/seq/qual/tags offsets, coord_key,
+ *                    strand, HI present, HI value] with h = mix64(h ^ value), starting from h = 0
+ *   h_body(bytes)  = sum over 32-bit little-endian words w_k of the body (zero padded) of mix64(w_k | k << 32)
+ *   fields = sum_i h_fields(i);  bodies = sum_i mix64(h_body(body_i) + i * 0x9E3779B97F4A7C15)      (mod 2^64)
+ *   sorted: perm = sum_i mix64(perm[i] | i << 32);  bodies as above over the OUTPUT order
+ * The product computes the same function on the GPU from ITS columns and buffers (csrc/digest.cu).
+ * ===================================================================================================== */
+static inline uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+static uint64_t body_hash(const uint8_t* b, uint32_t len) {
+  uint64_t h = 0;
+  uint32_t k = 0, i = 0;
+  for (; i + 4 <= len; i += 4, ++k) h += mix64((uint64_t)rd32(b + i) | ((uint64_t)k << 32));
+  if (i < len) {
+    uint32_t w = 0;
+    for (uint32_t j = 0; i + j < len; ++j) w |= (uint32_t)b[i + j] << (8 * j);
+    h += mix64((uint64_t)w | ((uint64_t)k << 32));
+  }
+  return h;
+}
+
+typedef struct { uint64_t n_records, body_bytes, fields, bodies; } orc_digest_t;
+
+typedef struct {
+  /* parallel-for description */
+  int kind;           /* 0 inflate, 1 extract, 2 digest, 3 sorted digest */
+  size_t lo, hi;
+  /* inflate */
+  const uint8_t* file; const orc_block* blocks; const uint64_t* uoff; uint8_t* out; int err;
+  /* records */
+  const uint8_t* u; const uint64_t* rec_off; const uint32_t* rec_len; const orc_columns* c; uint8_t* strand; int want_hi;
+  const uint32_t* perm; uint64_t index_base, stream_base;
+  uint64_t bad_flags, bad_tags;
+  orc_digest_t d;
+} par_job;
+
+static void shift_columns(const orc_columns* c, size_t o, orc_columns* s) {
+  s->ref_id = c->ref_id + o; s->pos = c->pos + o; s->l_read_name = c->l_read_name + o; s->mapq = c->mapq + o;
+  s->bin = c->bin + o; s->n_cigar_op = c->n_cigar_op + o; s->flag = c->flag + o; s->l_seq = c->l_seq + o;
+  s->next_ref_id = c->next_ref_id + o; s->next_pos = c->next_pos + o; s->tlen = c->tlen + o;
+  s->cigar_off = c->cigar_off + o; s->seq_off = c->seq_off + o; s->qual_off = c->qual_off + o; s->tags_off = c->tags_off + o;
+  s->coord_key = c->coord_key + o; s->hi_present = c->hi_present ? c->hi_present + o : NULL; s->hi_value = c->hi_value ? c->hi_value + o : NULL;
+}
+
+static void* par_thread(void* arg) {
+  par_job* j = (par_job*)arg;
+  if (j->kind == 0) {
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) { j->err = ORC_ERR_NOMEM; return NULL; }
+    for (size_t b = j->lo; b < j->hi; ++b) {
+      const uint8_t* cdat = j->file + j->blocks[b].coff + BGZF_HEADER_SIZE;
+      size_t clen = j->blocks[b].bsize - BGZF_HEADER_SIZE - TRAILER_SIZE;
+      size_t cap = (size_t)(j->uoff[b + 1] - j->uoff[b]);
+      /* one spare byte would let zlib report "more output than ISIZE"; Z_FINISH with an exact-size buffer returns
+       * Z_STREAM_END only if the stream ends exactly there, which is what we verify */
+      long got = inflate_raw(&zs, cdat, clen, j->out + j->uoff[b], cap);
+      if (got < 0 || (size_t)got != cap) { j->err = ORC_ERR_INFLATE; break; }
+    }
+    inflateEnd(&zs);
+  } else if (j->kind == 1) {
+    orc_columns sc;
+    shift_columns(j->c, j->lo, &sc);
+    orc_extract(j->u, j->rec_off + j->lo, j->rec_len + j->lo, j->hi - j->lo, &sc, j->strand ? j->strand + j->lo : NULL, j->want_hi,
+                &j->bad_flags, &j->bad_tags);
+  } else if (j->kind == 2) {
+    const orc_columns* c = j->c;
+    orc_digest_t d = {0, 0, 0, 0};
+    for (size_t i = j->lo; i < j->hi; ++i) {
+      uint64_t idx = j->index_base + i, h = 0;
+#define FOLD(v) h = mix64(h ^ (uint64_t)(v))
+      FOLD(idx); FOLD(j->stream_base + j->rec_off[i]); FOLD(j->rec_len[i]);
+      FOLD((uint32_t)c->ref_id[i]); FOLD((uint32_t)c->pos[i]); FOLD(c->l_read_name[i]); FOLD(c->mapq[i]); FOLD(c->bin[i]);
+      FOLD(c->n_cigar_op[i]); FOLD(c->flag[i]); FOLD(c->l_seq[i]); FOLD((uint32_t)c->next_ref_id[i]); FOLD((uint32_t)c->next_pos[i]);
+      FOLD((uint32_t)c->tlen[i]); FOLD(c->cigar_off[i]); FOLD(c->seq_off[i]); FOLD(c->qual_off[i]); FOLD(c->tags_off[i]);
+      FOLD(c->coord_key[i]); FOLD(j->strand[i]); FOLD(c->hi_present[i] == 1 ? 1u : 0u); FOLD((uint32_t)(c->hi_present[i] == 1 ? c->hi_value[i] : 0));
+#undef FOLD
+      d.fields += h;
+      d.bodies += mix64(body_hash(j->u + j->rec_off[i], j->rec_len[i]) + idx * 0x9E3779B97F4A7C15ull);
+      d.body_bytes += j->rec_len[i];
+    }
+    d.n_records = j->hi - j->lo;
+    j->d = d;
+  } else {
+    orc_digest_t d = {0, 0, 0, 0};
+    for (size_t i = j->lo; i < j->hi; ++i) {
+      uint32_t r = j->perm[i];
+      d.fields += mix64((uint64_t)r | ((uint64_t)i << 32));
+      d.bodies += mix64(body_hash(j->u + j->rec_off[r], j->rec_len[r]) + (uint64_t)i * 0x9E3779B97F4A7C15ull);
+      d.body_bytes += j->rec_len[r];
+    }
+    d.n_records = j->hi - j->lo;
+    j->d = d;
+  }
+  return NULL;
+}
+
+static int par_run(par_job* proto, size_t n, int threads, par_job** jobs_out) {
+  if (threads < 1) threads = 1;
+  if ((size_t)threads > n) threads = n ? (int)n : 1;
+  par_job* jobs = (par_job*)calloc((size_t)threads, sizeof(par_job));
+  pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+  for (int t = 0; t < threads; ++t) {
+    jobs[t] = *proto;
+    jobs[t].lo = n * (size_t)t / (size_t)threads;
+    jobs[t].hi = n * (size_t)(t + 1) / (size_t)threads;
+    pthread_create(&th[t], NULL, par_thread, &jobs[t]);
+  }
+  for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+  free(th);
+  *jobs_out = jobs;
+  return threads;
+}
+
+/* util.rs:18-71 + :10-16 over the whole file on `threads` threads.  Output placement uses the ISIZE footers (which the
+ * reference ignores) ONLY to know where each block's bytes go; every block is then required to inflate to exactly
+ * that many bytes, otherwise ORC_ERR_INFLATE (use the serial orc_inflate_all for files with lying footers). */
+long orc_inflate_all_mt(const uint8_t* file, size_t n, uint8_t** ustream, uint64_t* ulen, int threads) {
+  long nb = orc_scan_blocks(file, n, NULL, 0);
+  if (nb < 0) return nb;
+  orc_block* blocks = (orc_block*)malloc(sizeof(orc_block) * (size_t)(nb ? nb : 1));
+  uint64_t* uoff = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(nb + 1));
+  if (!blocks || !uoff) return ORC_ERR_NOMEM;
+  orc_scan_blocks(file, n, blocks, (size_t)nb);
+  uint64_t tot = 0;
+  for (long i = 0; i < nb; ++i) { uoff[i] = tot; tot += rd32(file + blocks[i].coff + blocks[i].bsize - 4); }
+  uoff[nb] = tot;
+  uint8_t* out = (uint8_t*)malloc(tot + 64);
+  if (!out) { free(blocks); free(uoff); return ORC_ERR_NOMEM; }
+  memset(out + tot, 0, 64);
+  par_job proto;
+  memset(&proto, 0, sizeof proto);
+  proto.kind = 0; proto.file = file; proto.blocks = blocks; proto.uoff = uoff; proto.out = out;
+  par_job* jobs;
+  int nt = par_run(&proto, (size_t)nb, threads, &jobs);
+  long rc = nb;
+  for (int t = 0; t < nt; ++t) if (jobs[t].err) rc = jobs[t].err;
+  free(jobs); free(blocks); free(uoff);
+  if (rc < 0) { free(out); return rc; }
+  *ustream = out;
+  *ulen = tot;
+  return rc;
+}
+
+int orc_extract_mt(const uint8_t* u, const uint64_t* rec_off, const uint32_t* rec_len, size_t n, orc_columns* c,
+                   uint8_t* strand, int want_hi, uint64_t* bad_flags, uint64_t* bad_tags, int threads) {
+  par_job proto;
+  memset(&proto, 0, sizeof proto);
+  proto.kind = 1; proto.u = u; proto.rec_off = rec_off; proto.rec_len = rec_len; proto.c = c; proto.strand = strand; proto.want_hi = want_hi;
+  par_job* jobs;
+  int nt = par_run(&proto, n, threads, &jobs);
+  uint64_t bf = 0, bt = 0;
+  for (int t = 0; t < nt; ++t) { bf += jobs[t].bad_flags; bt += jobs[t].bad_tags; }
+  free(jobs);
+  if (bad_flags) *bad_flags = bf;
+  if (bad_tags) *bad_tags = bt;
+  return ORC_OK;
+}
+
+/* DIGEST SPEC over the oracle's own walk + columns.  stream_base is added to rec_off (records of a shard), index_base
+ * to the record index. */
+int orc_digest(const uint8_t* u, const uint64_t* rec_off, const uint32_t* rec_len, const orc_columns* c, const uint8_t* strand,
+               size_t n, uint64_t index_base, uint64_t stream_base, int threads, orc_digest_t* out) {
+  par_job proto;
+  memset(&proto, 0, sizeof proto);
+  proto.kind = 2; proto.u = u; proto.rec_off = rec_off; proto.rec_len = rec_len; proto.c = c; proto.strand = (uint8_t*)strand;
+  proto.index_base = index_base; proto.stream_base = stream_base;
+  par_job* jobs;
+  int nt = par_run(&proto, n, threads, &jobs);
+  orc_digest_t d = {0, 0, 0, 0};
+  for (int t = 0; t < nt; ++t) { d.n_records += jobs[t].d.n_records; d.body_bytes += jobs[t].d.body_bytes; d.fields += jobs[t].d.fields; d.bodies += jobs[t].d.bodies; }
+  if (n == 0) d.n_records = 0;
+  free(jobs);
+  *out = d;
+  return ORC_OK;
+}
+
+/* DIGEST SPEC of a sort result: `fields` holds the permutation digest, `bodies` the digest of the output bytes
+ * (sort.rs:643: bodies written back to back in sorted order). */
+int orc_sorted_digest(const uint8_t* u, const uint64_t* rec_off, const uint32_t* rec_len, const uint32_t* perm, size_t n,
+                      int threads, orc_digest_t* out) {
+  par_job proto;
+  memset(&proto, 0, sizeof proto);
+  proto.kind = 3; proto.u = u; proto.rec_off = rec_off; proto.rec_len = rec_len; proto.perm = perm;
+  par_job* jobs;
+  int nt = par_run(&proto, n, threads, &jobs);
+  orc_digest_t d = {0, 0, 0, 0};
+  for (int t = 0; t < nt; ++t) { d.n_records += jobs[t].d.n_records; d.body_bytes += jobs[t].d.body_bytes; d.fields += jobs[t].d.fields; d.bodies += jobs[t].d.bodies; }
+  if (n == 0) d.n_records = 0;
+  free(jobs);
+  *out = d;
+  return ORC_OK;
+}

@@ -53,6 +53,13 @@ class _Columns(C.Structure):
         "next_pos", "tlen", "cigar_off", "seq_off", "qual_off", "tags_off", "coord_key", "hi_present", "hi_value")]
 
 
+class _Digest(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("body_bytes", C.c_uint64), ("fields", C.c_uint64), ("bodies", C.c_uint64)]
+
+    def as_dict(self):
+        return {"n_records": self.n_records, "body_bytes": self.body_bytes, "fields": self.fields, "bodies": self.bodies}
+
+
 COLUMN_DTYPES = {
     "ref_id": np.int32, "pos": np.int32, "l_read_name": np.uint8, "mapq": np.uint8, "bin": np.uint16,
     "n_cigar_op": np.uint16, "flag": np.uint16, "l_seq": np.uint32, "next_ref_id": np.int32,
@@ -91,6 +98,17 @@ class COracle:
                                          C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         L.orc_crc32.restype = C.c_uint32
         L.orc_crc32.argtypes = [C.c_void_p, C.c_size_t]
+        L.orc_inflate_all_mt.restype = C.c_long
+        L.orc_inflate_all_mt.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int]
+        L.orc_extract_mt.restype = C.c_int
+        L.orc_extract_mt.argtypes = L.orc_extract.argtypes + [C.c_int]
+        L.orc_sort_perm_mt.restype = C.c_int
+        L.orc_sort_perm_mt.argtypes = L.orc_sort_perm.argtypes + [C.c_int]
+        L.orc_digest.restype = C.c_int
+        L.orc_digest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_Columns), C.c_void_p, C.c_size_t, C.c_uint64,
+                                 C.c_uint64, C.c_int, C.POINTER(_Digest)]
+        L.orc_sorted_digest.restype = C.c_int
+        L.orc_sorted_digest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(_Digest)]
 
     # -- util.rs:18-71 + readahead.rs:145-150 over the whole file --------------------------
     def inflate_all(self, data) -> tuple[np.ndarray, np.ndarray]:
@@ -173,6 +191,72 @@ class COracle:
         if rc < 0:
             raise OracleError(rc)
         return {"records": r.value, "ubytes": ub.value, "seconds": s.value, "checksum": ck.value}
+
+    # -- full-size helpers: the same restatement on several threads + the DIGEST SPEC of bam_oracle.c ------------
+    def inflate_all_mt(self, data, threads: int) -> np.ndarray:
+        """Whole-file inflate on `threads` threads; the returned array owns a C buffer (freed with the array)."""
+        buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        out, ulen = C.c_void_p(), C.c_uint64()
+        rc = self.lib.orc_inflate_all_mt(buf.ctypes.data, buf.size, C.byref(out), C.byref(ulen), threads)
+        if rc < 0:
+            raise OracleError(rc)
+        lib = self.lib
+
+        class _Owner:
+            def __init__(self, p):
+                self.p = p
+
+            def __del__(self):
+                lib.orc_free(self.p)
+
+        arr = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(ulen.value + 64,))
+        own = _Owner(out)
+        view = arr[: ulen.value]
+        self._owners = getattr(self, "_owners", {})
+        self._owners[view.ctypes.data] = own   # dropped by release()
+        return view
+
+    def release(self, u: np.ndarray):
+        getattr(self, "_owners", {}).pop(u.ctypes.data, None)
+
+    def extract_mt(self, u, rec_off, rec_len, want_hi: bool, threads: int):
+        n = rec_off.size
+        cols = {k: np.empty(max(n, 1), dtype=dt) for k, dt in COLUMN_DTYPES.items()}
+        strand = np.empty(max(n, 1), dtype=np.uint8)
+        cs = _Columns(**{k: v.ctypes.data for k, v in cols.items()})
+        bf, bt = C.c_uint64(), C.c_uint64()
+        rc = self.lib.orc_extract_mt(u.ctypes.data, rec_off.ctypes.data, rec_len.ctypes.data, n, C.byref(cs), strand.ctypes.data,
+                                     int(want_hi), C.byref(bf), C.byref(bt), threads)
+        if rc < 0:
+            raise OracleError(rc)
+        cols = {k: v[:n] for k, v in cols.items()}
+        cols["strand"] = strand[:n]
+        return cols, bf.value, bt.value
+
+    def sort_perm_mt(self, u, rec_off, cols, mode: int, threads: int) -> np.ndarray:
+        n = rec_off.size
+        perm = np.empty(max(n, 1), dtype=np.uint32)
+        cs = _Columns(**{k: cols[k].ctypes.data for k in COLUMN_DTYPES})
+        rc = self.lib.orc_sort_perm_mt(u.ctypes.data, rec_off.ctypes.data, C.byref(cs), cols["strand"].ctypes.data, n, mode,
+                                       perm.ctypes.data, threads)
+        if rc < 0:
+            raise OracleError(rc)
+        return perm[:n]
+
+    def digest(self, u, rec_off, rec_len, cols, threads: int, index_base: int = 0, stream_base: int = 0) -> dict:
+        d = _Digest()
+        cs = _Columns(**{k: cols[k].ctypes.data for k in COLUMN_DTYPES})
+        self.lib.orc_digest(u.ctypes.data, rec_off.ctypes.data, rec_len.ctypes.data, C.byref(cs), cols["strand"].ctypes.data,
+                            rec_off.size, index_base, stream_base, threads, C.byref(d))
+        return d.as_dict()
+
+    def sorted_digest(self, u, rec_off, rec_len, perm, threads: int) -> dict:
+        d = _Digest()
+        self.lib.orc_sorted_digest(u.ctypes.data, rec_off.ctypes.data, rec_len.ctypes.data, perm.ctypes.data, perm.size, threads,
+                                   C.byref(d))
+        r = d.as_dict()
+        r["perm"] = r.pop("fields")
+        return r
 
     def crc32(self, a: np.ndarray) -> int:
         a = np.ascontiguousarray(a)

@@ -200,9 +200,11 @@ size_t gen_record(int shape, uint64_t seed, uint64_t idx, uint8_t* out) {
   }
   if (shape == PE150) {
     uint64_t pair = idx >> 1;
-    int mate = (int)(idx & 1);
+    // The two mates of a pair are emitted in a seeded random order, so that the stable name sort (-n, input order
+    // inside a name group) and the mate-matching sort (-n -M, flag order inside a group) give DIFFERENT outputs.
+    int mate = (int)((idx & 1) ^ (mix(seed, pair, 8) & 1));
     Rng rp(mix(seed, pair, 2));       // shared by both mates
-    Rng r(mix(seed, idx, 3));         // private to this mate
+    Rng r(mix(seed, pair * 2 + (uint64_t)mate, 3));   // private to this mate
     Fixed f;
     bool unmapped = rp.below(50) == 0;
     int n = snprintf(name, sizeof name, "A00123:45:HXXXXDSXX:%u:%u:%u:%u", 1 + (uint32_t)((pair >> 20) & 3),
@@ -248,9 +250,14 @@ size_t gen_record(int shape, uint64_t seed, uint64_t idx, uint8_t* out) {
     // and give the other two a distinct name. Every record carries HI (reference would
     // panic on mixed None/Some within a name group, comparators.rs:90).
     uint64_t grp = idx >> 2;
-    uint32_t slot = (uint32_t)(idx & 3);
+    // the four slots of a group appear in a seeded random order (one of the 24 permutations), so hits and mates of
+    // one name are NOT pre-sorted by (HI, flag): -n keeps the input order inside a name, -n -M must reorder it
+    static const uint8_t PERM4[24][4] = {{0,1,2,3},{0,1,3,2},{0,2,1,3},{0,2,3,1},{0,3,1,2},{0,3,2,1},{1,0,2,3},{1,0,3,2},
+                                         {1,2,0,3},{1,2,3,0},{1,3,0,2},{1,3,2,0},{2,0,1,3},{2,0,3,1},{2,1,0,3},{2,1,3,0},
+                                         {2,3,0,1},{2,3,1,0},{3,0,1,2},{3,0,2,1},{3,1,0,2},{3,1,2,0},{3,2,0,1},{3,2,1,0}};
+    uint32_t slot = PERM4[mix(seed, grp, 9) % 24][idx & 3];
     Rng rg(mix(seed, grp, 4));
-    Rng r(mix(seed, idx, 5));
+    Rng r(mix(seed, grp * 4 + slot, 5));
     bool multi = rg.below(3) == 0;
     uint32_t l_name = 200 + rg.below(23);  // 200..222 incl NUL
     uint64_t name_id = (multi || slot < 2) ? grp * 2 : grp * 2 + 1;
