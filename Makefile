@@ -1,5 +1,6 @@
 # Builds every native artefact in-tree (so the .so files travel with gpurun):
 #   bam_parallel_b200/lib/libbamgpu.so   product: CUDA kernels + C-ABI host reader (sm_100a)
+#   bam_parallel_b200/lib/libbamharness.so  per-record consumer loop for bench.py (e2e_next_rec)
 #   bam_parallel_b200/lib/libbamgen.so   synthetic BAM generator (test/bench input only)
 #   bam_parallel_b200/lib/bamgen         generator CLI
 #   oracle/_build/liboracle.so           CPU oracle (test infrastructure only)
@@ -21,7 +22,7 @@ HDRS      := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 CU_OBJS   := $(patsubst $(CSRC)/%.cu,build/%.cu.o,$(CU_SRCS))
 CPP_OBJS  := $(patsubst $(CSRC)/%.cpp,build/%.cpp.o,$(CPP_SRCS))
 
-all: $(LIBDIR)/libbamgpu.so $(LIBDIR)/libbamgen.so $(LIBDIR)/bamgen oracle
+all: $(LIBDIR)/libbamgpu.so $(LIBDIR)/libbamharness.so $(LIBDIR)/libbamgen.so $(LIBDIR)/bamgen oracle
 
 build/%.cu.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build
@@ -34,6 +35,10 @@ build/%.cpp.o: $(CSRC)/%.cpp $(HDRS)
 $(LIBDIR)/libbamgpu.so: $(CU_OBJS) $(CPP_OBJS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) -Wno-deprecated-gpu-targets -shared -o $@ $^ -lpthread
+
+# bench.py's per-record consumer loop (what the Rust shim's next_rec() does), linked against the product library
+$(LIBDIR)/libbamharness.so: tools/next_rec_harness.c $(LIBDIR)/libbamgpu.so include/bamgpu.h
+	$(CC) -O2 -fPIC -Wall -shared -Iinclude -o $@ $< -L$(LIBDIR) -lbamgpu -Wl,-rpath,'$$ORIGIN'
 
 $(LIBDIR)/libbamgen.so: tools/bamgen.cpp
 	@mkdir -p $(LIBDIR)

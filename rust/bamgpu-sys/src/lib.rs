@@ -110,11 +110,31 @@ unsafe extern "C" fn write_trampoline(ctx: *mut c_void, src: *const u8, len: usi
     match sink.write_all(std::slice::from_raw_parts(src, len)) { Ok(()) => 0, Err(_) => -1 }
 }
 
-/// Drop-in for `bam_tools::sorting::sort::sort_bam` (sort.rs:138-178) without the GBAM index mode (unreachable from
-/// bam_binary, main.rs:74).  mem_limit / tmp_dir / temp_files_mode steer the reference's external merge and have no
-/// counterpart: the records stay in HBM from decode to output.  Panics where the reference's comparators panic.
-pub fn sort_bam<R: Read + Send + 'static, W: Write>(_mem_limit: usize, reader: R, sorted_sink: &mut W, reader_thread_num: usize,
-                                                   sort_by: SortBy) -> io::Result<()> {
+/// sorting/sort.rs:98-103.  Accepted for signature parity; the GPU sort keeps every record in HBM and writes no temp files.
+pub enum TempFilesMode { RegularFiles, LZ4CompressedFiles, InMemoryBlocks, InMemoryBlocksLZ4 }
+
+/// Drop-in for `bam_tools::sorting::sort::sort_bam` (sort.rs:138-149): the SAME ten arguments in the same order, so
+/// `bam_binary/src/main.rs:66-77` compiles against this crate unchanged.  `tmp_dir` is generic (the reference takes
+/// `&tempdir::TempDir`; this crate has no dependencies).  mem_limit / tmp_dir / out_compr_level / temp_files_mode steer the
+/// reference's external merge and have no counterpart here; `index_file_to_create` must be `None` (the GBAM index mode,
+/// sort.rs:106-134, is unreachable from bam_binary: main.rs:74 passes `Option::<File>::None`).  `bam_file_size` becomes
+/// the reader's `track_progress`.  Panics where the reference's comparators panic.
+#[allow(clippy::too_many_arguments)]
+pub fn sort_bam<R: Read + Send + 'static, W: Write, IndexW: Write, TmpDir>(
+    _mem_limit: usize,
+    reader: R,
+    sorted_sink: &mut W,
+    _tmp_dir: &TmpDir,
+    _out_compr_level: usize,
+    reader_thread_num: usize,
+    _temp_files_mode: TempFilesMode,
+    index_file_to_create: Option<IndexW>,
+    sort_by: SortBy,
+    _bam_file_size: Option<u64>,
+) -> io::Result<()> {
+    if index_file_to_create.is_some() {
+        return Err(io::Error::new(io::ErrorKind::Unsupported, "GBAM index sort (sort.rs:106-134) is not built"));
+    }
     let mut boxed: Box<Box<dyn Read + Send>> = Box::new(Box::new(reader));
     let mut sink: &mut dyn Write = sorted_sink;
     let mut msg = [0 as c_char; 512];

@@ -1,0 +1,286 @@
+"""The Reader's job pipeline and the multi-GPU paths behind the C ABI, against the oracle.
+
+* bamgpu_opts.devices: batches go to the listed GPUs round robin; the partial record at a batch edge is copied in front
+  of the next batch on whichever GPU decodes it (cudaMemcpyPeerAsync between different GPUs).  Listing the same GPU
+  several times exercises the identical code on a one-GPU box (the copy is then device-to-device).
+* bamgpu_engine_edge_*: block-range shards whose heads travel to the left-hand neighbour's inbox in peer memory.
+Every result is compared with the oracle's walk of the same file: bodies (md5, main.rs:83-99), record boundaries,
+columns and the DIGEST SPEC sums.
+"""
+import hashlib
+import io
+
+import numpy as np
+import pytest
+
+import bam_parallel_b200 as bp
+from bam_parallel_b200 import _lib, synth
+from bam_parallel_b200.sharding import check_edges, shard_ranges
+from oracle import oracle as orc
+from tests import bamcraft as bc
+
+pytestmark = pytest.mark.gpu
+
+COLS = [n for n in orc.COLUMN_DTYPES]
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _oracle(oracle, data):
+    u, _ = oracle.inflate_all(data)
+    hdr, off_refs, start = oracle.read_header(u)
+    off, ln = oracle.walk_records(u, start)
+    cols, bf, bt = oracle.extract(u, off, ln, True)
+    return u, start, off, ln, cols
+
+
+def _md5_bodies(u, off, ln):
+    ub = u.tobytes()
+    return hashlib.md5(b"".join(ub[o:o + l] for o, l in zip(off.tolist(), ln.tolist()))).hexdigest()
+
+
+def _reader_all(data, **kw):
+    """Everything a Reader hands out through next_batch: bodies md5, concatenated columns, summed digest, #batches."""
+    h = hashlib.md5()
+    got = {k: [] for k in COLS + ["strand", "rec_len"]}
+    stream_off = []
+    tot = {"n_records": 0, "body_bytes": 0, "fields": 0, "bodies": 0}
+    nb = 0
+    with bp.Reader.new(data, 4, flags=bp.COPY_COLUMNS | bp.COPY_DATA | bp.WANT_HI, **kw) as r:
+        r.read_header()
+        while True:
+            b = r.next_batch()
+            if b is None:
+                break
+            assert b.first_record_index == tot["n_records"]
+            d = r.batch_digest(b)
+            for k in tot:
+                tot[k] = (tot[k] + d[k]) & 0xFFFFFFFFFFFFFFFF
+            db = b.data.tobytes()
+            for o, l in zip(b.columns["rec_off"].tolist(), b.columns["rec_len"].tolist()):
+                h.update(db[o:o + l])
+            for k in got:
+                got[k].append(b.columns[k].copy())
+            stream_off.append(b.columns["rec_off"].astype(np.int64) - b.data_start + b.stream_offset)
+            nb += 1
+        st = r.stats()
+    cat = {k: (np.concatenate(v) if v else np.zeros(0)) for k, v in got.items()}
+    return h.hexdigest(), cat, (np.concatenate(stream_off) if stream_off else np.zeros(0, np.int64)), tot, nb, st
+
+
+def _assert_reader(oracle, data, **kw):
+    u, start, off, ln, cols = _oracle(oracle, data)
+    md5, cat, soff, tot, nb, st = _reader_all(data, **kw)
+    assert md5 == _md5_bodies(u, off, ln)
+    assert np.array_equal(soff, off.astype(np.int64)), "stream offsets of the bodies differ"
+    assert np.array_equal(cat["rec_len"], ln)
+    for k in COLS:
+        if k == "hi_present":
+            assert np.array_equal(cat[k] == 1, cols[k] == 1), k
+        else:
+            assert np.array_equal(cat[k], cols[k]), k
+    assert tot == oracle.digest(u, off, ln, cols, 4)
+    return nb, st
+
+
+@pytest.mark.parametrize("devices", [[0, 0], [0, 0, 0], None])
+@pytest.mark.parametrize("shape,n,payload,batch_bytes", [("pe150", 60000, 0xFF00, 1 << 20), ("long10k", 600, 4096, 200000),
+                                                         ("longname", 12000, 0xFF00, 300000), ("pe150", 4000, 300, 70000)])
+def test_reader_jobs_round_robin_one_gpu(oracle, devices, shape, n, payload, batch_bytes):
+    data = synth.generate(shape, n, payload=payload).tobytes()
+    nb, st = _assert_reader(oracle, data, devices=devices, batch_bytes=batch_bytes, jobs_per_device=2 if devices else 0)
+    assert nb > 3
+
+
+def test_reader_multi_gpu_peer_carry(oracle):
+    n = _n_gpus()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    devs = list(range(min(n, 8)))
+    for shape, cnt, payload, bb in (("pe150", 400000, 0xFF00, 4 << 20), ("long10k", 3000, 4096, 1 << 20), ("longname", 60000, 0xFF00, 2 << 20)):
+        data = synth.generate(shape, cnt, payload=payload).tobytes()
+        nb, st = _assert_reader(oracle, data, devices=devs, batch_bytes=bb)
+        assert nb >= 2 * len(devs)
+        assert st["p2p_bytes"] > 0, "no bytes moved between GPUs"
+
+
+def test_record_longer_than_the_gap_between_batches(oracle):
+    """A record larger than the 1 MiB kept free in front of a batch's blocks (round 1 refused it at shard edges):
+    the blocks move behind a larger gap and the decode goes on."""
+    hdr = bc.bam_header()
+    big = bc.bam_record(name=b"big", seq_len=1_400_000, cigar=((1_400_000, 0),))     # ~2.1 MB
+    stream = hdr + bc.bam_record(name=b"a") * 50 + big + bc.bam_record(name=b"b") * 300 + big + bc.bam_record(name=b"c") * 7
+    data = bc.bgzf(stream, level=1)
+    for kw in ({"batch_bytes": 70000}, {"batch_bytes": 70000, "devices": [0, 0], "jobs_per_device": 2}):
+        _assert_reader(oracle, data, **kw)
+
+
+def test_switching_from_batches_to_records_keeps_every_record(oracle):
+    """next_batch() (no host mirrors asked for) followed by next_rec(): the batches staged ahead get the mirrors they lack."""
+    data = synth.generate("pe150", 40000).tobytes()
+    u, start, off, ln, cols = _oracle(oracle, data)
+    with bp.Reader.new(data, 4, batch_bytes=1 << 20) as r:
+        r.read_header()
+        b = r.next_batch()
+        n0 = b.n_records
+        assert 0 < n0 < off.size
+        h = hashlib.md5()
+        ub = u.tobytes()
+        for o, l in zip(off[n0:].tolist(), ln[n0:].tolist()):
+            h.update(ub[o:o + l])
+        g = hashlib.md5()
+        recs = r.records()
+        cnt = 0
+        while True:
+            rec = recs.next_rec()
+            if rec is None:
+                break
+            g.update(rec)
+            cnt += 1
+        assert cnt == off.size - n0 and g.hexdigest() == h.hexdigest()
+
+
+def test_read_after_read_header_continues_the_stream(oracle):
+    """impl Read for Reader (reader.rs:114-152) after read_header(): the byte stream goes on behind the header."""
+    data = synth.generate("pe150", 20000).tobytes()
+    u, _ = oracle.inflate_all(data)
+    _, _, start = oracle.read_header(u)
+    for bb in (0, 300000):
+        with bp.Reader.new(data, 4, batch_bytes=bb) as r:
+            r.read_header()
+            got = r.read(777) + r.read()
+            assert got == u.tobytes()[start:]
+            with pytest.raises(bp.BamGpuError):
+                r.records().next_rec()
+
+
+def test_good_records_come_out_before_the_error(oracle):
+    """reader.rs:63-81 hands out every complete record and only then panics on the short one; a truncated BGZF block kills the
+    reference's reading thread after the blocks in front of it were delivered."""
+    recs = [bc.bam_record(name=b"r%d" % i, pos=i) for i in range(2000)]
+    good = bc.bam_header() + b"".join(recs)
+    # 1. short last record
+    data = bc.bgzf(good + bc.bam_record()[:-5], payload=4000)
+    for bb in (0, 70000):
+        with bp.Reader.new(data, 4, batch_bytes=bb) as r:
+            r.read_header()
+            it = r.records()
+            n = 0
+            with pytest.raises(bp.BamGpuError) as e:
+                while it.next_rec() is not None:
+                    n += 1
+            assert n == 2000 and e.value.code == -22
+    # 2. truncated final BGZF block
+    whole = bc.bgzf(good, payload=4000, eof=False)
+    blocks, nb, consumed, total, rc = bp.scan_blocks(whole)
+    cut = whole[:-9]
+    u, _ = oracle.inflate_all(whole[:blocks[nb - 1].in_off - 18] + bc.BGZF_EOF)
+    _, _, start = oracle.read_header(u)
+    want = 0
+    p = start
+    while len(u) - p >= 4:     # complete records inside the blocks in front of the truncated one
+        bs = int.from_bytes(u[p:p + 4].tobytes(), "little")
+        if len(u) - (p + 4) < bs:
+            break
+        want += 1
+        p += 4 + bs
+    for bb in (0, 70000):
+        with bp.Reader.new(cut, 4, batch_bytes=bb) as r:
+            r.read_header()
+            it = r.records()
+            n = 0
+            with pytest.raises(bp.BamGpuError) as e:
+                while it.next_rec() is not None:
+                    n += 1
+            assert n == want and e.value.code == -11
+
+
+def test_page_locked_source_is_read_in_place(oracle):
+    """A source buffer the caller page-locked (bamgpu_pinned_alloc) is copied to the GPUs straight from where it is."""
+    import ctypes as C
+    bam = synth.generate("pe150", 50000)
+    L = bp.load()
+    p = L.bamgpu_pinned_alloc(bam.nbytes)
+    assert p
+    try:
+        C.memmove(p, bam.array.ctypes.data, bam.nbytes)
+        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(bam.nbytes,))
+        _assert_reader(oracle, arr, batch_bytes=1 << 20)
+        _assert_reader(oracle, arr, batch_bytes=1 << 20, devices=[0, 0])
+    finally:
+        L.bamgpu_pinned_free(p)
+
+
+def test_sort_twice_does_not_leak_device_memory():
+    """bamgpu_engine_free gives the sort's scratch, permutation, offsets and gathered bodies back (round 1 leaked them)."""
+    import torch
+    data = synth.generate("pe150", 300000).tobytes()
+    free0 = None
+    for it in range(4):
+        out = io.BytesIO()
+        bp.sort_bam(0, data, out, sort_by=bp.SortBy.CoordinatesAndStrand)
+        torch.cuda.synchronize()
+        free, _ = torch.cuda.mem_get_info()
+        if it == 1:
+            free0 = free
+    assert free0 - free < (64 << 20), f"device memory shrank by {(free0 - free) >> 20} MiB over two more sorts"
+
+
+@pytest.mark.parametrize("shape,n,payload,n_shards", [("pe150", 30000, 0xFF00, 3), ("long10k", 400, 4096, 4), ("pe150", 3000, 700, 5)])
+def test_edge_exchange_in_peer_memory(oracle, shape, n, payload, n_shards):
+    """bamgpu_engine_edge_open / _connect / _exchange: shard g+1 writes its head into shard g's inbox and publishes the step;
+    shard g waits on the device, appends the halo, acknowledges.  Engines sit on as many GPUs as there are (round robin)."""
+    data = synth.generate(shape, n, level=6, payload=payload).tobytes()
+    u, start, off, ln, cols = _oracle(oracle, data)
+    blocks, nb, consumed, total, rc = bp.scan_blocks(data)
+    bv = np.frombuffer(blocks, dtype=np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("in_len", "<u4"), ("isize", "<u4"),
+                                               ("crc32", "<u4"), ("reserved", "<u4")]))[:nb]
+    ranges = shard_ranges(bv["in_off"], n_shards)
+    ng = max(_n_gpus(), 1)
+    engines, handles, shard = [], [], []
+    try:
+        for g, (b0, b1) in enumerate(ranges):
+            e = bp.Engine(device=g % ng)
+            engines.append(e)
+            handles.append(e.edge_open())
+        for g, e in enumerate(engines):
+            e.edge_connect(handles[g - 1] if g > 0 else None, handles[g + 1] if g < n_shards - 1 else None)
+        for g, (b0, b1) in enumerate(ranges):
+            e = engines[g]
+            mb = (_lib.Block * max(b1 - b0, 1))()
+            mv = np.frombuffer(mb, dtype=bv.dtype)[: b1 - b0]
+            mv[:] = bv[b0:b1]
+            c0 = int(bv["in_off"][b0]) - 18 if b1 > b0 else 0
+            c1 = int(bv["in_off"][b1 - 1]) + int(bv["in_len"][b1 - 1]) + 8 if b1 > b0 else 0
+            u0 = int(bv["out_off"][b0]) if b1 > b0 else total
+            mv["in_off"] -= np.uint64(c0)
+            mv["out_off"] -= np.uint64(u0)
+            shard.append((e.upload(data[c0:c1]), mb, b1 - b0, u0, int(mv["isize"].sum())))
+        for step in (1, 2, 3):          # three passes: the two inbox buffers and the acknowledgements are reused
+            for g, e in enumerate(engines):
+                e.inflate(shard[g][0], shard[g][1], shard[g][2])
+            for g in reversed(range(n_shards)):       # one host thread: a shard's right-hand neighbour must have sent first
+                engines[g].edge_exchange(step)
+            offs, lens, exits, starts, counts = [], [], [], [], []
+            tot = {"n_records": 0, "body_bytes": 0, "fields": 0, "bodies": 0}
+            for g, e in enumerate(engines):
+                batch, tail, rc = e.records(start if g == 0 else 0, g == n_shards - 1,
+                                            (bp.SPECULATIVE_START if g else 0) | bp.COPY_COLUMNS | bp.WANT_HI)
+                offs.append(batch.columns["rec_off"].astype(np.uint64) + np.uint64(shard[g][3]))
+                lens.append(batch.columns["rec_len"].copy())
+                exits.append(tail - shard[g][4])
+                starts.append(batch.chain_start)
+                counts.append(batch.n_records)
+                d = e.digest(index_base=sum(counts[:-1]), stream_base=shard[g][3])
+                for k in tot:
+                    tot[k] = (tot[k] + d[k]) & 0xFFFFFFFFFFFFFFFF
+            check_edges(exits, starts, counts, off.size)
+            assert np.array_equal(np.concatenate(offs), off) and np.array_equal(np.concatenate(lens), ln)
+            assert tot == oracle.digest(u, off, ln, cols, 4)
+        assert sum(e.stats()["p2p_bytes"] for e in engines) > 0
+    finally:
+        for e in engines:
+            e.close()
