@@ -155,6 +155,7 @@ struct bamgpu_engine {
   cudaStream_t stream = nullptr;
   std::string err;
   uint32_t default_flags = 0;
+  int inflate_impl = 0;     // bamgpu_opts.inflate_impl: 0 lane pairs (default), 1 one warp per block
 
   // block table (SoA) staging + device
   PinBuf h_tab;
@@ -327,6 +328,9 @@ extern "C" bamgpu_engine* bamgpu_engine_new(const bamgpu_opts* opts) {
   for (auto& M : E->mir) { cudaEventCreate(&M.ev_begin); cudaEventCreate(&M.ev_end); }
   for (auto& e : E->ev) cudaEventCreate(&e);
   E->default_flags = opts ? opts->flags : 0;
+  E->inflate_impl = opts ? opts->inflate_impl : 0;
+  if (const char* e = getenv("BAMGPU_INFLATE_IMPL")) E->inflate_impl = atoi(e);   // experiments: switch every engine of the process
+  if (E->inflate_impl < 0 || E->inflate_impl > 1) { fprintf(stderr, "bamgpu: unknown inflate_impl %d\n", E->inflate_impl); delete E; return nullptr; }
   if (E->d_misc.reserve(8192) != cudaSuccess || E->d_crc_tables.reserve(CRC_TABLE_WORDS * 4) != cudaSuccess ||
       E->h_res.reserve(4096) != cudaSuccess) {
     bamgpu_engine_free(E);
@@ -516,7 +520,8 @@ static int engine_inflate_launch(bamgpu_engine* E, const uint8_t* d_comp, const 
   ECK(cudaMemsetAsync(E->d_status.p, 0xff, 4 * nb, s));
   ECK(cudaEventRecord(E->ev[0], s));
   if (inflate_ring_bytes(E->num_sms)) ECK(E->d_k1ring.reserve(inflate_ring_bytes(E->num_sms)));
-  launch_inflate(d_comp, t, E->out_ptr(), E->d_status.as<uint32_t>(), counter, E->d_k1ring.p, E->num_sms, s);
+  if (E->inflate_impl == 1) launch_inflate_warp_per_block(d_comp, t, E->out_ptr(), E->d_status.as<uint32_t>(), counter, E->num_sms, s);
+  else launch_inflate(d_comp, t, E->out_ptr(), E->d_status.as<uint32_t>(), counter, E->d_k1ring.p, E->num_sms, s);
   ECK(cudaEventRecord(E->ev[1], s));
   E->stats.kernel_launches += 1;
   if (!(flags & BAMGPU_NO_CRC)) {

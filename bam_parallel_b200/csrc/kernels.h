@@ -20,6 +20,9 @@ struct BlockTableDev {
 // status[b] = IST_* (inflate_core.cuh).  work_counter: one zeroed u32 in device memory.
 void launch_inflate(const uint8_t* comp, const BlockTableDev& t, uint8_t* out, uint32_t* status,
                     uint32_t* work_counter, void* ring_mem, int num_sms, cudaStream_t s);
+// Variant 1 (bamgpu_opts.inflate_impl = 1): one warp per BGZF block, the north-star's mapping (inflate_warp.cu).
+void launch_inflate_warp_per_block(const uint8_t* comp, const BlockTableDev& t, uint8_t* out, uint32_t* status,
+                                   uint32_t* work_counter, int num_sms, cudaStream_t s);
 size_t inflate_smem_bytes();
 size_t inflate_ring_bytes(int num_sms);   // device scratch for the token rings when they live in global memory (else 0)
 
