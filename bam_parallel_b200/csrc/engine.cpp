@@ -346,11 +346,11 @@ extern "C" bamgpu_engine* bamgpu_engine_new(const bamgpu_opts* opts) {
 extern "C" void bamgpu_engine_free(bamgpu_engine* E) {
   if (!E) return;
   cudaSetDevice(E->device);
+  bamgpu_engine_edge_close(E);   // while the stream still exists
   if (E->stream) { cudaStreamSynchronize(E->stream); cudaStreamDestroy(E->stream); }
   if (E->d2h_stream) { cudaStreamSynchronize(E->d2h_stream); if (E->own_d2h_stream) cudaStreamDestroy(E->d2h_stream); }
   if (E->ev_k3_done) cudaEventDestroy(E->ev_k3_done);
   if (E->ev_carry) cudaEventDestroy(E->ev_carry);
-  bamgpu_engine_edge_close(E);
   for (auto& M : E->mir) { if (M.ev_begin) cudaEventDestroy(M.ev_begin); if (M.ev_end) cudaEventDestroy(M.ev_end); M.d_cols.release(); M.h_data.release(); M.h_cols.release(); }
   for (auto& e : E->ev) if (e) cudaEventDestroy(e);
   E->h_tab.release(); E->d_tab.release(); E->d_status.release(); E->d_misc.release(); E->d_crc_tables.release();
