@@ -247,10 +247,11 @@ __global__ void __launch_bounds__(WB_THREADS) k1_inflate_warp_per_block(InflateJ
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= job.n_blocks) break;
     const uint32_t isize = job.isize[b], in_len = job.in_len[b];
-    const uint8_t* in = job.comp + job.in_off[b];
+    const uint8_t* in = job.comp + job.in_off[b];   // where the bit reader was last (re)started, and what is left from there
+    uint32_t in_left = in_len;
     uint8_t* out = job.out + job.out_off[b];
     Bits br;
-    br.begin(in, in_len);
+    br.begin(in, in_left);
     uint32_t opos = 0, err = IST_OK, bfinal = 0;
     while (!err && !bfinal) {
       uint32_t btype = 0, stored = 0;
@@ -258,11 +259,13 @@ __global__ void __launch_bounds__(WB_THREADS) k1_inflate_warp_per_block(InflateJ
       if (err) break;
       if (btype == 0) {   // stored: bytes straight from the input
         const uint32_t at = br.consumed() >> 3;
-        if (at + stored > in_len) { err = IST_INPUT_OVERRUN; break; }
+        if (at + stored > in_left) { err = IST_INPUT_OVERRUN; break; }
         if (stored > isize - opos) { err = IST_OUTPUT_OVERRUN; break; }
         for (uint32_t i = lane; i < stored; i += 32) out[opos + i] = in[at + i];
         opos += stored;
-        br.begin(in + at + stored, in_len - (at + stored));
+        in += at + stored;
+        in_left -= at + stored;
+        br.begin(in, in_left);
         continue;
       }
       for (;;) {
