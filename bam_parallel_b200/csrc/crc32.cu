@@ -41,28 +41,33 @@ __global__ void k_crc_tables(uint32_t* tables) {
 __device__ __forceinline__ uint32_t z_apply(const uint32_t* t, uint32_t s) {
   return t[s & 0xff] ^ t[256 + ((s >> 8) & 0xff)] ^ t[512 + ((s >> 16) & 0xff)] ^ t[768 + (s >> 24)];
 }
-// Same on a table replicated per lane ([entry][lane]): lane l only ever touches bank l, so the four look-ups of a
-// warp are conflict free whatever the data.
-__device__ __forceinline__ uint32_t z_apply_lane(const uint32_t* t /* + lane */, uint32_t s) {
-  return t[(s & 0xff) * 32] ^ t[(256 + ((s >> 8) & 0xff)) * 32] ^ t[(512 + ((s >> 16) & 0xff)) * 32] ^ t[(768 + (s >> 24)) * 32];
+// Same on a table replicated REPL times ([entry][copy], lane l uses copy l mod REPL).  REPL = 32: lane l only ever touches
+// bank l, so the four look-ups of a warp are conflict free whatever the data.
+template <int REPL>
+__device__ __forceinline__ uint32_t z_apply_lane(const uint32_t* t /* + copy */, uint32_t s) {
+  return t[(s & 0xff) * REPL] ^ t[(256 + ((s >> 8) & 0xff)) * REPL] ^ t[(512 + ((s >> 16) & 0xff)) * REPL] ^ t[(768 + (s >> 24)) * REPL];
 }
 
-constexpr int K2_WARPS = 32;
-constexpr int K2_SMEM_BYTES = 1024 * 32 * 4 + 1024 * 4;   // Z128 per lane (128 KB) + Z4 (4 KB)
-
-__global__ void __launch_bounds__(K2_WARPS * 32, 1)
+// Two shapes of the same kernel:
+//   <32, 32>  one 32-warp CTA per SM, the table replicated per lane (132 KB): the whole file in one launch (bench.py's
+//             device-resident step), 3.5 TB/s;
+//   <4, 8>    four warps, 8 copies of the table (36 KB), <= 32 registers: small enough to sit NEXT to three resident K1
+//             CTAs (186 KB, 61 k registers) - the Reader runs the CRC of one batch while the K1 of the next batches holds
+//             every SM, and the big shape would wait for an SM to drain completely.
+template <int WARPS, int REPL>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 32 ? 1 : 16)
 k2_crc32(const uint8_t* __restrict__ out, BlockTableDev t, const uint32_t* __restrict__ g_tables,
          uint32_t* __restrict__ status) {
   extern __shared__ __align__(16) uint32_t k2_smem[];
-  uint32_t* Z128L = k2_smem;                 // [1024][32]
-  uint32_t* Z4 = k2_smem + 1024 * 32;        // [1024]
-  for (int i = threadIdx.x; i < 1024 * 32; i += blockDim.x) Z128L[i] = g_tables[1024 + (i >> 5)];
+  uint32_t* Z128L = k2_smem;                 // [1024][REPL]
+  uint32_t* Z4 = k2_smem + 1024 * REPL;      // [1024]
+  for (int i = threadIdx.x; i < 1024 * REPL; i += blockDim.x) Z128L[i] = g_tables[1024 + i / REPL];
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) Z4[i] = g_tables[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const uint32_t* Z128 = Z128L + lane;
-  const uint32_t warps_total = gridDim.x * K2_WARPS;
-  for (uint32_t b = blockIdx.x * K2_WARPS + (threadIdx.x >> 5); b < t.n_blocks; b += warps_total) {
+  const uint32_t* Z128 = Z128L + (lane % REPL);
+  const uint32_t warps_total = gridDim.x * WARPS;
+  for (uint32_t b = blockIdx.x * WARPS + (threadIdx.x >> 5); b < t.n_blocks; b += warps_total) {
     if (status[b] != 0) continue;  // warp-uniform
     const uint64_t o0 = t.out_off[b];
     const uint32_t n = t.isize[b];
@@ -83,12 +88,12 @@ k2_crc32(const uint8_t* __restrict__ out, BlockTableDev t, const uint32_t* __res
       uint32_t r = 1;
       for (; r + 4 <= rows; r += 4) {   // four rows in flight: the loads do not wait for the table walk
         uint32_t x0 = w[r * 32], x1 = w[(r + 1) * 32], x2 = w[(r + 2) * 32], x3 = w[(r + 3) * 32];
-        a = z_apply_lane(Z128, a) ^ x0;
-        a = z_apply_lane(Z128, a) ^ x1;
-        a = z_apply_lane(Z128, a) ^ x2;
-        a = z_apply_lane(Z128, a) ^ x3;
+        a = z_apply_lane<REPL>(Z128, a) ^ x0;
+        a = z_apply_lane<REPL>(Z128, a) ^ x1;
+        a = z_apply_lane<REPL>(Z128, a) ^ x2;
+        a = z_apply_lane<REPL>(Z128, a) ^ x3;
       }
-      for (; r < rows; ++r) a = z_apply_lane(Z128, a) ^ w[r * 32];
+      for (; r < rows; ++r) a = z_apply_lane<REPL>(Z128, a) ^ w[r * 32];
       // fold the 32 lanes: total = Z4(...Z4(Z4(a0) ^ a1) ...) ^ a31, then one more Z4
       uint32_t acc = 0;
       for (int i = 0; i < 32; ++i) {
@@ -111,12 +116,20 @@ k2_crc32(const uint8_t* __restrict__ out, BlockTableDev t, const uint32_t* __res
 void crc32_init_tables(uint32_t* d_tables, cudaStream_t s) { k_crc_tables<<<1, 256, 0, s>>>(d_tables); }
 
 void launch_crc32(const uint8_t* out, const BlockTableDev& t, const uint32_t* d_tables, uint32_t* status,
-                  int num_sms, cudaStream_t s) {
+                  int num_sms, bool small_footprint, cudaStream_t s) {
   if (t.n_blocks == 0) return;
-  uint32_t grid = (t.n_blocks + K2_WARPS - 1) / K2_WARPS;
+  if (small_footprint) {
+    constexpr int W = 4, R = 8, SMEM = 1024 * R * 4 + 1024 * 4;
+    uint32_t grid = (t.n_blocks + W - 1) / W;
+    if (grid > (uint32_t)num_sms * 2) grid = (uint32_t)num_sms * 2;
+    k2_crc32<W, R><<<grid, W * 32, SMEM, s>>>(out, t, d_tables, status);
+    return;
+  }
+  constexpr int W = 32, R = 32, SMEM = 1024 * R * 4 + 1024 * 4;   // Z128 per lane (128 KB) + Z4 (4 KB)
+  uint32_t grid = (t.n_blocks + W - 1) / W;
   if (grid > (uint32_t)num_sms) grid = (uint32_t)num_sms;   // one CTA per SM: the per-lane table takes 132 KB of shared memory
-  cudaFuncSetAttribute(k2_crc32, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_BYTES);
-  k2_crc32<<<grid, K2_WARPS * 32, K2_SMEM_BYTES, s>>>(out, t, d_tables, status);
+  cudaFuncSetAttribute(k2_crc32<W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  k2_crc32<W, R><<<grid, W * 32, SMEM, s>>>(out, t, d_tables, status);
 }
 
 }  // namespace bamgpu

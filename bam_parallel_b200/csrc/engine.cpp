@@ -184,6 +184,8 @@ struct bamgpu_engine {
   uint64_t carry_saved = 0;
   cudaEvent_t ev_carry = nullptr;
   bool own_d2h_stream = true;
+  cudaStream_t k1_stream = nullptr;   // low priority: K1 of a Reader job
+  cudaEvent_t ev_k1_in = nullptr;
   uint64_t cols_hint = 0;   // records expected in the next batch (sizes the columns without a host round trip)
   // shard-edge exchange (bamgpu_engine_edge_*)
   uint8_t* edge_inbox = nullptr;
@@ -321,7 +323,11 @@ extern "C" bamgpu_engine* bamgpu_engine_new(const bamgpu_opts* opts) {
   E->device = dev;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) E->num_sms = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking) != cudaSuccess) { delete E; return nullptr; }
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // numerically lower = higher priority
+  if (cudaStreamCreateWithPriority(&E->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete E; return nullptr; }
+  if (cudaStreamCreateWithPriority(&E->k1_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete E; return nullptr; }
+  cudaEventCreateWithFlags(&E->ev_k1_in, cudaEventDisableTiming);
   if (cudaStreamCreateWithFlags(&E->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) { delete E; return nullptr; }
   cudaEventCreateWithFlags(&E->ev_k3_done, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&E->ev_carry, cudaEventDisableTiming);
@@ -347,6 +353,8 @@ extern "C" void bamgpu_engine_free(bamgpu_engine* E) {
   if (!E) return;
   cudaSetDevice(E->device);
   bamgpu_engine_edge_close(E);   // while the stream still exists
+  if (E->k1_stream) { cudaStreamSynchronize(E->k1_stream); cudaStreamDestroy(E->k1_stream); }
+  if (E->ev_k1_in) cudaEventDestroy(E->ev_k1_in);
   if (E->stream) { cudaStreamSynchronize(E->stream); cudaStreamDestroy(E->stream); }
   if (E->d2h_stream) { cudaStreamSynchronize(E->d2h_stream); if (E->own_d2h_stream) cudaStreamDestroy(E->d2h_stream); }
   if (E->ev_k3_done) cudaEventDestroy(E->ev_k3_done);
@@ -518,14 +526,24 @@ static int engine_inflate_launch(bamgpu_engine* E, const uint8_t* d_comp, const 
   unsigned long long* first_bad = (unsigned long long*)(E->d_misc.as<uint8_t>() + 8);
   ECK(cudaMemsetAsync(counter, 0, 4, s));
   ECK(cudaMemsetAsync(E->d_status.p, 0xff, 4 * nb, s));
-  ECK(cudaEventRecord(E->ev[0], s));
+  // Reader jobs: K1 goes onto the engine's LOW-priority stream, everything else stays on the high-priority one.  Several
+  // batches' K1 are resident at once (persistent CTAs, ~10 ms each); when one of them ends, the CRC / record kernels
+  // of the batch in front get the freed SM slots before the next batch's K1 CTAs do.
+  cudaStream_t ks = (lead_mode && E->k1_stream && s == E->stream) ? E->k1_stream : s;
+  if (ks != s) {
+    ECK(cudaEventRecord(E->ev_k1_in, s));
+    ECK(cudaStreamWaitEvent(ks, E->ev_k1_in, 0));
+  }
+  ECK(cudaEventRecord(E->ev[0], ks));
   if (inflate_ring_bytes(E->num_sms)) ECK(E->d_k1ring.reserve(inflate_ring_bytes(E->num_sms)));
-  if (E->inflate_impl == 1) launch_inflate_warp_per_block(d_comp, t, E->out_ptr(), E->d_status.as<uint32_t>(), counter, E->num_sms, s);
-  else launch_inflate(d_comp, t, E->out_ptr(), E->d_status.as<uint32_t>(), counter, E->d_k1ring.p, E->num_sms, s);
-  ECK(cudaEventRecord(E->ev[1], s));
+  if (E->inflate_impl == 1) launch_inflate_warp_per_block(d_comp, t, E->out_ptr(), E->d_status.as<uint32_t>(), counter, E->num_sms, ks);
+  else launch_inflate(d_comp, t, E->out_ptr(), E->d_status.as<uint32_t>(), counter, E->d_k1ring.p, E->num_sms, ks);
+  ECK(cudaEventRecord(E->ev[1], ks));
+  if (ks != s) ECK(cudaStreamWaitEvent(s, E->ev[1], 0));
   E->stats.kernel_launches += 1;
+  ECK(cudaEventRecord(E->ev[6], s));
   if (!(flags & BAMGPU_NO_CRC)) {
-    launch_crc32(E->out_ptr(), t, E->d_crc_tables.as<uint32_t>(), E->d_status.as<uint32_t>(), E->num_sms, s);
+    launch_crc32(E->out_ptr(), t, E->d_crc_tables.as<uint32_t>(), E->d_status.as<uint32_t>(), E->num_sms, /*small_footprint=*/lead_mode, s);
     E->stats.kernel_launches += 1;
   }
   ECK(cudaEventRecord(E->ev[2], s));
@@ -547,7 +565,7 @@ static int engine_inflate_finish(bamgpu_engine* E, cudaStream_t s) {
   if (E->pend_nb == 0) return BAMGPU_OK;
   float ms = 0;
   cudaEventElapsedTime(&ms, E->ev[0], E->ev[1]); E->stats.ms_inflate += ms;
-  cudaEventElapsedTime(&ms, E->ev[1], E->ev[2]); E->stats.ms_crc += ms;
+  cudaEventElapsedTime(&ms, E->ev[6], E->ev[2]); E->stats.ms_crc += ms;
   E->stats.blocks += E->pend_nb;
   E->stats.bytes_out += E->pend_total;
   E->stats.bytes_in += E->pend_bytes_in;
@@ -1324,7 +1342,7 @@ static bamgpu_reader* reader_create(bamgpu_read_fn read, void* ctx, size_t threa
   }
   for (int d : devices) if (d < 0 || d >= count) { delete R; return nullptr; }
   const size_t D = devices.size();
-  R->J = (opts && opts->jobs_per_device > 0) ? std::min(opts->jobs_per_device, 16) : 4;
+  R->J = (opts && opts->jobs_per_device > 0) ? std::min(opts->jobs_per_device, 16) : 8;
   if (R->J < 2) R->J = 2;
   if (const char* e = getenv("BAMGPU_JOBS")) { int v = atoi(e); if (v >= 2 && v <= 16) R->J = v; }
   R->read = read;
@@ -1348,7 +1366,7 @@ static bamgpu_reader* reader_create(bamgpu_read_fn read, void* ctx, size_t threa
     }
   R->devs.resize(D);
   R->jobs.resize(D * (size_t)R->J);
-  const int n_slots = 3;
+  const int n_slots = R->J;   // a batch keeps its input slot until its K1 is over: as many slots as batches in flight
   for (size_t i = 0; i < D; ++i) {
     DevCtx& dc = R->devs[i];
     dc.dev = devices[i];
@@ -1621,7 +1639,16 @@ static int reader_next_batch(bamgpu_reader* R, uint32_t extra_flags, bool raw = 
   if (R->sticky < 0) return R->sticky;
   if (R->eof) return BAMGPU_EOF;
   const uint32_t flags = R->flags | extra_flags;
-  if (R->cur) { R->cur->st = Job::FREE; R->cur = nullptr; R->batch_valid = false; }
+  if (R->cur) {
+    // the pinned mirrors go back to the process-wide pool: only the batches between "parsed" and "handed out" hold some,
+    // however many jobs are inflating
+    bamgpu_engine::Mirror& M = R->cur->E->mir[R->cur->E->msel];
+    M.h_data.release();
+    M.h_cols.release();
+    R->cur->st = Job::FREE;
+    R->cur = nullptr;
+    R->batch_valid = false;
+  }
   auto end_of_stream = [&](int rc) {
     if (rc == BAMGPU_EOF) {
       if (R->sticky_next < 0) { R->sticky = R->sticky_next; return R->sticky; }

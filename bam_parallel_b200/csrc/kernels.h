@@ -31,8 +31,9 @@ size_t inflate_ring_bytes(int num_sms);   // device scratch for the token rings 
 constexpr uint32_t IST_CRC_MISMATCH = 100;
 void crc32_init_tables(uint32_t* d_tables /* CRC_TABLE_WORDS words */, cudaStream_t s);
 constexpr int CRC_TABLE_WORDS = 2 * 4 * 256;
+// small_footprint: the 4-warp / 36 KB shape that fits beside resident K1 CTAs (Reader jobs), else one 32-warp CTA per SM.
 void launch_crc32(const uint8_t* out, const BlockTableDev& t, const uint32_t* d_tables, uint32_t* status,
-                  int num_sms, cudaStream_t s);
+                  int num_sms, bool small_footprint, cudaStream_t s);
 
 // Copies `bytes` (multiple of 4, <= 4096) from device memory to PINNED HOST memory with SM stores.  Result words of a few
 // bytes must not go through cudaMemcpyAsync: the D2H copy engine serves transfers in order, so an 8-byte status read queues

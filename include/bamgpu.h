@@ -149,7 +149,7 @@ typedef struct bamgpu_opts {
   uint64_t batch_bytes;         /* compressed bytes per pipeline batch (0 = default: 256 MiB on one GPU, 64 MiB on several) */
   int32_t inflate_impl;         /* K1 variant: 0 = default (one BGZF block per lane pair), 1 = one warp per block
                                    (the north-star's mapping, kept for comparison; DESIGN.md "K1 variants") */
-  int32_t jobs_per_device;      /* Reader: batches in flight per GPU (0 = default 4) */
+  int32_t jobs_per_device;      /* Reader: batches in flight per GPU (0 = default 8) */
   /* Multi-GPU Reader: batches go to the listed GPUs round robin, i.e. the file is sharded by BGZF block
    * ranges; the partial record at the end of a batch moves to the GPU that decodes the next batch peer-to-peer
    * (cudaMemcpyPeerAsync).  n_devices == 0: one GPU (`device`). */
