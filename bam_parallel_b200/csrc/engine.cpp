@@ -50,7 +50,7 @@ struct DevCache {
   std::mutex mu;
   std::vector<Item> free_list;
   size_t bytes = 0;
-  static constexpr size_t LIMIT = (size_t)48 << 30, ITEM_LIMIT = (size_t)2 << 30;
+  static constexpr size_t LIMIT = (size_t)48 << 30, ITEM_LIMIT = (size_t)8 << 30;
   void* take(size_t n, int dev, size_t* cap) {
     std::lock_guard<std::mutex> lk(mu);
     size_t best = (size_t)-1;
@@ -161,8 +161,9 @@ struct bamgpu_engine {
   PinBuf h_tab;
   DevBuf d_tab;
   DevBuf d_status, d_misc;  // d_misc: work counter (u32 @0), first_bad (u64 @8), ChainResult @64
-  DevBuf d_crc_tables, d_k1ring;
-  bool crc_ready = false;
+  DevBuf d_k1ring;
+  const uint32_t* d_crc = nullptr;   // the GPU's CRC tables (DeviceShared)
+  cudaEvent_t ev_inflated = nullptr; // behind K1 + K2 + the status reduce of the batch in flight
   // inflated data.  The Reader runs with two buffers (pingpong): batch k+1 is inflated into one while batch k is
   // still being copied to the host out of the other.
   DevBuf d_outs[2];
@@ -309,6 +310,33 @@ extern "C" int bamgpu_scan_blocks(const uint8_t* buf, size_t len, int final, bam
   return rc;
 }
 
+// What every engine of one GPU shares and what costs milliseconds to obtain: the SM count, the stream priority range and
+// the CRC tables (one kernel + one wait).  A Reader creates 8 engines per GPU inside the caller's timed Reader::new.
+namespace {
+struct DeviceShared {
+  bool ready = false;
+  int num_sms = 148, prio_lo = 0, prio_hi = 0;
+  uint32_t* d_crc_tables = nullptr;   // never freed: lives as long as the process
+};
+DeviceShared* device_shared(int dev) {
+  static std::mutex mu;
+  static DeviceShared table[64];
+  if (dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  DeviceShared& d = table[dev];
+  if (!d.ready) {
+    if (cudaSetDevice(dev) != cudaSuccess) return nullptr;
+    cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetStreamPriorityRange(&d.prio_lo, &d.prio_hi);   // numerically lower = higher priority
+    if (cudaMalloc((void**)&d.d_crc_tables, CRC_TABLE_WORDS * 4) != cudaSuccess) return nullptr;
+    crc32_init_tables(d.d_crc_tables, 0);
+    if (cudaDeviceSynchronize() != cudaSuccess) return nullptr;
+    d.ready = true;
+  }
+  return &d;
+}
+}  // namespace
+
 extern "C" bamgpu_engine* bamgpu_engine_new(const bamgpu_opts* opts) {
   bamgpu_engine* E = new bamgpu_engine();
   int dev = opts ? opts->device : -1;
@@ -321,10 +349,11 @@ extern "C" bamgpu_engine* bamgpu_engine_new(const bamgpu_opts* opts) {
   if (dev < 0) cudaGetDevice(&dev);
   if (cudaSetDevice(dev) != cudaSuccess) { delete E; return nullptr; }
   E->device = dev;
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) E->num_sms = prop.multiProcessorCount;
-  int prio_lo = 0, prio_hi = 0;
-  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // numerically lower = higher priority
+  DeviceShared* ds = device_shared(dev);
+  if (!ds) { delete E; return nullptr; }
+  E->num_sms = ds->num_sms;
+  E->d_crc = ds->d_crc_tables;
+  const int prio_lo = ds->prio_lo, prio_hi = ds->prio_hi;
   if (cudaStreamCreateWithPriority(&E->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete E; return nullptr; }
   if (cudaStreamCreateWithPriority(&E->k1_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete E; return nullptr; }
   cudaEventCreateWithFlags(&E->ev_k1_in, cudaEventDisableTiming);
@@ -337,15 +366,12 @@ extern "C" bamgpu_engine* bamgpu_engine_new(const bamgpu_opts* opts) {
   E->inflate_impl = opts ? opts->inflate_impl : 0;
   if (const char* e = getenv("BAMGPU_INFLATE_IMPL")) E->inflate_impl = atoi(e);   // experiments: switch every engine of the process
   if (E->inflate_impl < 0 || E->inflate_impl > 1) { fprintf(stderr, "bamgpu: unknown inflate_impl %d\n", E->inflate_impl); delete E; return nullptr; }
-  if (E->d_misc.reserve(8192) != cudaSuccess || E->d_crc_tables.reserve(CRC_TABLE_WORDS * 4) != cudaSuccess ||
-      E->h_res.reserve(4096) != cudaSuccess) {
+  if (E->d_misc.reserve(8192) != cudaSuccess || E->h_res.reserve(4096) != cudaSuccess) {
     bamgpu_engine_free(E);
     return nullptr;
   }
-  cudaMemsetAsync(E->d_misc.p, 0, 8192, E->stream);
-  crc32_init_tables(E->d_crc_tables.as<uint32_t>(), E->stream);
-  if (cudaStreamSynchronize(E->stream) != cudaSuccess) { bamgpu_engine_free(E); return nullptr; }
-  E->crc_ready = true;
+  if (cudaMemsetAsync(E->d_misc.p, 0, 8192, E->stream) != cudaSuccess) { bamgpu_engine_free(E); return nullptr; }   // ordered before every use
+  cudaEventCreateWithFlags(&E->ev_inflated, cudaEventDisableTiming);
   return E;
 }
 
@@ -361,7 +387,8 @@ extern "C" void bamgpu_engine_free(bamgpu_engine* E) {
   if (E->ev_carry) cudaEventDestroy(E->ev_carry);
   for (auto& M : E->mir) { if (M.ev_begin) cudaEventDestroy(M.ev_begin); if (M.ev_end) cudaEventDestroy(M.ev_end); M.d_cols.release(); M.h_data.release(); M.h_cols.release(); }
   for (auto& e : E->ev) if (e) cudaEventDestroy(e);
-  E->h_tab.release(); E->d_tab.release(); E->d_status.release(); E->d_misc.release(); E->d_crc_tables.release();
+  E->h_tab.release(); E->d_tab.release(); E->d_status.release(); E->d_misc.release();
+  if (E->ev_inflated) cudaEventDestroy(E->ev_inflated);
   E->d_outs[0].release(); E->d_outs[1].release(); E->d_tiles.release(); E->d_k1ring.release(); E->h_res.release();
   E->d_carry.release();
   // the sort's scratch, permutation, offsets and gathered bodies (round 1 leaked these: ~18.7 GB per 50M-record sort)
@@ -543,13 +570,14 @@ static int engine_inflate_launch(bamgpu_engine* E, const uint8_t* d_comp, const 
   E->stats.kernel_launches += 1;
   ECK(cudaEventRecord(E->ev[6], s));
   if (!(flags & BAMGPU_NO_CRC)) {
-    launch_crc32(E->out_ptr(), t, E->d_crc_tables.as<uint32_t>(), E->d_status.as<uint32_t>(), E->num_sms, /*small_footprint=*/lead_mode, s);
+    launch_crc32(E->out_ptr(), t, E->d_crc, E->d_status.as<uint32_t>(), E->num_sms, /*small_footprint=*/lead_mode, s);
     E->stats.kernel_launches += 1;
   }
   ECK(cudaEventRecord(E->ev[2], s));
   launch_status_reduce(E->d_status.as<uint32_t>(), (uint32_t)nb, first_bad, s);
   E->stats.kernel_launches += 1;
   launch_copy_small_to_host(E->h_res.p, first_bad, 8, s);
+  ECK(cudaEventRecord(E->ev_inflated, s));
   if (dbg_level() >= 2) fprintf(stderr, "[bamgpu] inflate_launch host %.2f ms (%zu blocks)\n", now_ms() - t_in, n_blocks);
   return BAMGPU_OK;
 }
@@ -1184,6 +1212,7 @@ struct bamgpu_reader {
   uint64_t bytes_fed = 0;
   uint32_t flags = 0;
   size_t batch_bytes = 256u << 20;
+  size_t first_batch_bytes = 0;     // 0: like every other batch
   std::string err;
   // memory source
   const uint8_t* mem = nullptr;
@@ -1247,8 +1276,10 @@ static void feeder_main(bamgpu_reader* R) {
     S.final = false;
     S.len = 0;
     S.total_isize = 0;
-    const size_t bb = R->batch_bytes;
-    const size_t cap = bb + 65536 + 64;
+    // the first batch is small when the caller left the batch size to us: the header and the first records are there
+    // after one short copy, and the big batches' copies and K1 start that much earlier
+    const size_t bb = (seq == 0 && R->first_batch_bytes) ? R->first_batch_bytes : R->batch_bytes;
+    const size_t cap = R->batch_bytes + 65536 + 64;
     const uint8_t* src = nullptr;   // where the batch's bytes are on the host
     size_t fill = 0;
     if (R->mem && R->mem_pinned) {
@@ -1355,6 +1386,7 @@ static bamgpu_reader* reader_create(bamgpu_read_fn read, void* ctx, size_t threa
   R->batch_bytes = D > 1 ? ((size_t)96 << 20) : ((size_t)256 << 20);
   if (const char* e = getenv("BAMGPU_BATCH_MIB")) { long v = atol(e); if (v > 0) R->batch_bytes = (size_t)v << 20; }
   if (opts && opts->batch_bytes) R->batch_bytes = (size_t)opts->batch_bytes;
+  else R->first_batch_bytes = std::min(R->batch_bytes, (size_t)32 << 20);
   if (R->batch_bytes < 65536) R->batch_bytes = 65536;
   // peer access between every pair of GPUs (the batch-edge records travel GPU to GPU)
   for (size_t a = 0; a < D; ++a)
@@ -1506,6 +1538,19 @@ static int reader_pump(bamgpu_reader* R, uint32_t flags, uint64_t need_launched)
   }
 }
 
+// Waits for `ev` while keeping the pipeline fed: every batch the feeder gets ready meanwhile has its K1 queued at once,
+// not when the consumer next happens to look.
+static int reader_wait_event(bamgpu_reader* R, uint32_t flags, cudaEvent_t ev) {
+  for (;;) {
+    cudaError_t q = cudaEventQuery(ev);
+    if (q == cudaSuccess) return BAMGPU_OK;
+    if (q != cudaErrorNotReady) { R->err = cudaGetErrorString(q); return BAMGPU_ERR_CUDA; }
+    int rc = reader_pump(R, flags, 0);
+    if (rc < 0) return rc;
+    std::this_thread::sleep_for(std::chrono::microseconds(40));
+  }
+}
+
 // Waits for batch n_staged's inflate, splices the previous batch's tail in front of it and (unless `raw`) parses it; its
 // D2H is queued, not waited for.  BAMGPU_OK: the batch is staged.  BAMGPU_EOF: no more input.
 static int reader_stage(bamgpu_reader* R, uint32_t flags, bool raw) {
@@ -1523,7 +1568,9 @@ static int reader_stage(bamgpu_reader* R, uint32_t flags, bool raw) {
     Job& j = R->job_of(R->n_staged);
     bamgpu_engine* E = j.E;
     if (j.input_status == BAMGPU_ERR_NOMEM) { R->err = "out of memory for the input batch"; return BAMGPU_ERR_NOMEM; }
-    int rc = engine_inflate_finish(E, E->stream);
+    int rc = E->inflate_launched ? reader_wait_event(R, flags, E->ev_inflated) : BAMGPU_OK;
+    if (rc < 0) return rc;
+    rc = engine_inflate_finish(E, E->stream);
     reader_release_slot(R, j);
     if (rc < 0) { R->err = E->err; return rc; }
     if (!j.carry_set) {
@@ -1570,6 +1617,7 @@ extern "C" int bamgpu_read_header(bamgpu_reader* R, const uint8_t** bytes, size_
     Job& j = R->job_of(seq);
     bamgpu_engine* E = j.E;
     if (j.input_status == BAMGPU_ERR_NOMEM) return BAMGPU_ERR_NOMEM;
+    if (E->inflate_launched) { rc = reader_wait_event(R, R->flags, E->ev_inflated); if (rc < 0) return rc; }
     rc = engine_inflate_finish(E, E->stream);
     reader_release_slot(R, j);
     if (rc < 0) { R->err = E->err; return rc; }
@@ -1693,6 +1741,10 @@ static int reader_next_batch(bamgpu_reader* R, uint32_t extra_flags, bool raw = 
     bool q = false;
     int w = engine_enqueue_mirrors(E, E->mir[E->msel], raw ? (flags | BAMGPU_COPY_DATA) : flags, j.batch.n_records, &j.batch, E->stream, &q);
     if (w < 0) { R->sticky = w; R->err = E->err; return w; }
+  }
+  if (E->mir[E->msel].pending) {
+    int pw = reader_wait_event(R, flags, E->mir[E->msel].ev_end);
+    if (pw < 0) { R->sticky = pw; return pw; }
   }
   int w = engine_wait_mirror(E, E->msel);
   if (w < 0) { R->sticky = w; R->err = E->err; return w; }
