@@ -83,7 +83,7 @@ struct DevBuf {
     size_t want = n + n / 8 + 256;
     cudaGetDevice(&dev);
     size_t got = 0;
-    if (void* q = dev_cache().take(want, dev, &got)) { p = q; cap = got; return cudaSuccess; }
+    if (void* q = dev_cache().take(n, dev, &got)) { p = q; cap = got; return cudaSuccess; }
     cudaError_t e = cudaMalloc(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;
@@ -132,7 +132,7 @@ struct PinBuf {
     release();
     size_t want = n + n / 8 + 256;
     size_t got = 0;
-    if (void* q = pinned_cache().take(want, &got)) { p = q; cap = got; return cudaSuccess; }
+    if (void* q = pinned_cache().take(n, &got)) { p = q; cap = got; return cudaSuccess; }
     cudaError_t e = cudaMallocHost(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;
@@ -230,7 +230,7 @@ struct bamgpu_engine {
 };
 
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-static int dbg_level() { static int v = -1; if (v < 0) { const char* e = getenv("BAMGPU_DEBUG"); v = e ? atoi(e) : 0; } return v; }
+static int dbg_level() { const char* e = getenv("BAMGPU_DEBUG"); return e ? atoi(e) : 0; }
 
 #define ECK(call)                                                                                   \
   do {                                                                                              \
@@ -1530,6 +1530,7 @@ static int reader_pump(bamgpu_reader* R, uint32_t flags, uint64_t need_launched)
     bamgpu_engine* E = j.E;
     j.st = Job::LAUNCHED;
     ++R->n_launched;
+    if (dbg_level() >= 2) fprintf(stderr, "[bamgpu] @%.2f K1 of batch %llu queued (%zu blocks)\n", now_ms(), (unsigned long long)j.seq, S.blocks.size());
     if (S.status == BAMGPU_ERR_NOMEM) continue;   // nothing on the device; the error surfaces when the batch is staged
     cudaSetDevice(E->device);
     if (cudaStreamWaitEvent(E->stream, S.copied, 0) != cudaSuccess) { R->err = "cudaStreamWaitEvent failed"; return BAMGPU_ERR_CUDA; }
@@ -1585,6 +1586,7 @@ static int reader_stage(bamgpu_reader* R, uint32_t flags, bool raw) {
     const bool fin = j.final && j.input_status >= 0;
     E->first_record_index = R->rec_index;
     uint64_t tail = 0;
+    if (dbg_level() >= 2) fprintf(stderr, "[bamgpu] @%.2f batch %llu inflated\n", now_ms(), (unsigned long long)j.seq);
     rc = engine_records(E, E->data_start + R->next_start_rel, fin ? 1 : 0, raw ? (flags | BAMGPU_NO_RECORDS | BAMGPU_COPY_DATA) : flags,
                         E->stream, &j.batch, &tail, /*defer_d2h=*/true);
     R->next_start_rel = 0;
@@ -1594,6 +1596,10 @@ static int reader_stage(bamgpu_reader* R, uint32_t flags, bool raw) {
     R->rec_index += j.batch.n_records;
     ++R->n_staged;
     j.st = Job::STAGED;
+    if (dbg_level() >= 2)
+      fprintf(stderr, "[bamgpu] @%.2f staged batch %llu on gpu %d: %llu records, carry %llu B, launched %llu, handed out %llu\n", now_ms(),
+              (unsigned long long)j.seq, E->device, (unsigned long long)j.batch.n_records, (unsigned long long)carry,
+              (unsigned long long)R->n_launched, (unsigned long long)R->n_out);
     if (rc == BAMGPU_EOF || j.final) R->no_more = true;
     if (j.input_status < 0) { R->sticky_next = j.input_status; R->err = std::string("input: ") + bamgpu_status_str(j.input_status); }
     return BAMGPU_OK;
@@ -1748,7 +1754,7 @@ static int reader_next_batch(bamgpu_reader* R, uint32_t extra_flags, bool raw = 
   }
   int w = engine_wait_mirror(E, E->msel);
   if (w < 0) { R->sticky = w; R->err = E->err; return w; }
-  if (dbg_level() >= 2) fprintf(stderr, "[bamgpu] next_batch @%.1f: stage ahead %.2f, wait d2h %.2f ms\n", t0, t1 - t0, now_ms() - t1);
+  if (dbg_level() >= 2) fprintf(stderr, "[bamgpu] @%.2f batch %llu handed out: staging ahead took %.2f, waiting for its D2H %.2f ms\n", now_ms(), (unsigned long long)j.seq, t1 - t0, now_ms() - t1);
   j.st = Job::OUT;
   ++R->n_out;
   R->cur = &j;
