@@ -186,6 +186,7 @@ struct bamgpu_engine {
   cudaEvent_t ev_carry = nullptr;
   bool own_d2h_stream = true;
   cudaStream_t k1_stream = nullptr;   // low priority: K1 of a Reader job
+  uint32_t k1_grid = 0;               // CTAs of the K1 launch in flight (ev[1] fires when they are gone)
   cudaEvent_t ev_k1_in = nullptr;
   uint64_t cols_hint = 0;   // records expected in the next batch (sizes the columns without a host round trip)
   // shard-edge exchange (bamgpu_engine_edge_*)
@@ -561,6 +562,7 @@ static int engine_inflate_launch(bamgpu_engine* E, const uint8_t* d_comp, const 
     ECK(cudaEventRecord(E->ev_k1_in, s));
     ECK(cudaStreamWaitEvent(ks, E->ev_k1_in, 0));
   }
+  E->k1_grid = E->inflate_impl == 0 ? inflate_grid((uint32_t)nb, E->num_sms) : 0;
   ECK(cudaEventRecord(E->ev[0], ks));
   if (inflate_ring_bytes(E->num_sms)) ECK(E->d_k1ring.reserve(inflate_ring_bytes(E->num_sms)));
   if (E->inflate_impl == 1) launch_inflate_warp_per_block(d_comp, t, E->out_ptr(), E->d_status.as<uint32_t>(), counter, E->num_sms, ks);
@@ -1514,6 +1516,28 @@ static int reader_pump(bamgpu_reader* R, uint32_t flags, uint64_t need_launched)
         R->cv.wait(lk, [&] { return !R->ready.empty(); });
       }
       it = R->ready.front();
+      // K1's CTAs are persistent (~10 ms) and three of them fill an SM.  If the K1 launches in flight on this GPU filled
+      // every slot, the CRC and record kernels of the batch in FRONT would wait for a whole K1 to drain (measured: 37 ms
+      // at the start of a pass).  So K1 launches are admitted only up to a CTA budget that leaves some SM slots free.
+      {
+        const DevCtx& dcx = R->devs[it.dev_i];
+        const size_t nb_new = dcx.slots[it.slot].blocks.size();
+        bamgpu_engine* E0 = j.E;
+        const uint32_t budget = (uint32_t)E0->num_sms * 3u - 64u;
+        const uint32_t g_new = E0->inflate_impl == 0 ? inflate_grid((uint32_t)nb_new, E0->num_sms) : 0;
+        uint32_t in_flight = 0;
+        for (int k = 0; k < R->J; ++k) {
+          Job& o = R->jobs[(size_t)it.dev_i * R->J + k];
+          if (o.st == Job::LAUNCHED && o.E->inflate_launched && o.E->k1_grid && cudaEventQuery(o.E->ev[1]) == cudaErrorNotReady) in_flight += o.E->k1_grid;
+        }
+        cudaGetLastError();
+        if (in_flight && in_flight + g_new > budget) {
+          if (R->n_launched >= need_launched) return BAMGPU_OK;   // try again at the next look
+          lk.unlock();
+          std::this_thread::sleep_for(std::chrono::microseconds(50));
+          continue;
+        }
+      }
       R->ready.pop_front();
     }
     DevCtx& dc = R->devs[it.dev_i];

@@ -143,6 +143,11 @@ k1_inflate_pairs(InflateJob job, uint32_t* __restrict__ work_counter, uint8_t* _
 }
 
 size_t inflate_smem_bytes() { return K1_SMEM_BYTES; }
+uint32_t inflate_grid(uint32_t n_blocks, int num_sms) {
+  const uint32_t lanes_per_cta = K1_PAIR_WARPS * 32, max_ctas = (uint32_t)num_sms * K1_CTAS_PER_SM;
+  const uint32_t need = (n_blocks + lanes_per_cta - 1) / lanes_per_cta;
+  return need < max_ctas ? need : max_ctas;
+}
 size_t inflate_ring_bytes(int num_sms) { return BG_RING_GLOBAL ? (size_t)num_sms * K1_CTAS_PER_SM * K1_PAIR_WARPS * 32 * RING_GLOBAL_STREAM_BYTES : 0; }
 
 void launch_inflate(const uint8_t* comp, const BlockTableDev& t, uint8_t* out, uint32_t* status,

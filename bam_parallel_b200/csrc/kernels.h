@@ -23,6 +23,7 @@ void launch_inflate(const uint8_t* comp, const BlockTableDev& t, uint8_t* out, u
 // Variant 1 (bamgpu_opts.inflate_impl = 1): one warp per BGZF block, the north-star's mapping (inflate_warp.cu).
 void launch_inflate_warp_per_block(const uint8_t* comp, const BlockTableDev& t, uint8_t* out, uint32_t* status,
                                    uint32_t* work_counter, int num_sms, cudaStream_t s);
+uint32_t inflate_grid(uint32_t n_blocks, int num_sms);   // CTAs launch_inflate uses for that many blocks
 size_t inflate_smem_bytes();
 size_t inflate_ring_bytes(int num_sms);   // device scratch for the token rings when they live in global memory (else 0)
 
