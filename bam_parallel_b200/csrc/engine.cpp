@@ -10,7 +10,9 @@
 //   reader.rs:114-152      impl Read                                        -> bamgpu_read
 //   reader.rs:101-112      parse_reference_sequences                        -> bamgpu_parse_reference_sequences
 #include <cuda_runtime.h>
+#include <sched.h>
 #include <unistd.h>
+#include <cctype>
 
 #include <algorithm>
 #include <chrono>
@@ -97,48 +99,97 @@ struct DevBuf {
 };
 // Page-locking host memory is slow (about a second per few GB), and a Reader needs several hundred MB of it, so released
 // pinned buffers are parked in a small process-wide cache and handed to the next Reader instead of being unpinned.
+// Pinned buffers are tagged with the NUMA node they were allocated on (-1: wherever the calling thread ran): the
+// mirrors of a GPU's batches should sit in the memory of the socket that GPU hangs off, or eight GPUs' device-to-host
+// traffic funnels through the inter-socket link.
 struct PinnedCache {
+  struct Item { void* p; size_t cap; int node; };
   std::mutex mu;
-  std::vector<std::pair<void*, size_t>> free_list;
+  std::vector<Item> free_list;
   size_t bytes = 0;
   static constexpr size_t LIMIT = (size_t)32 << 30;
-  void* take(size_t n, size_t* cap) {
+  void* take(size_t n, int node, size_t* cap) {
     std::lock_guard<std::mutex> lk(mu);
     size_t best = (size_t)-1;
     for (size_t i = 0; i < free_list.size(); ++i)
-      if (free_list[i].second >= n && (best == (size_t)-1 || free_list[i].second < free_list[best].second)) best = i;
-    if (best == (size_t)-1 || free_list[best].second > n + n / 4 + (1 << 20)) return nullptr;   // a snug fit only: a big buffer taken for a small need is missed later
-    void* p = free_list[best].first;
-    *cap = free_list[best].second;
+      if (free_list[i].node == node && free_list[i].cap >= n && (best == (size_t)-1 || free_list[i].cap < free_list[best].cap)) best = i;
+    if (best == (size_t)-1 || free_list[best].cap > n + n / 4 + (1 << 20)) return nullptr;   // a snug fit only: a big buffer taken for a small need is missed later
+    void* p = free_list[best].p;
+    *cap = free_list[best].cap;
     bytes -= *cap;
     free_list.erase(free_list.begin() + best);
     return p;
   }
-  bool give(void* p, size_t cap) {
+  bool give(void* p, size_t cap, int node) {
     std::lock_guard<std::mutex> lk(mu);
     if (bytes + cap > LIMIT) return false;
-    free_list.emplace_back(p, cap);
+    free_list.push_back({p, cap, node});
     bytes += cap;
     return true;
   }
 };
 PinnedCache& pinned_cache() { static PinnedCache* c = new PinnedCache(); return *c; }
 
+// NUMA node of a CUDA device and the CPUs next to it, from sysfs (best effort: -1 / empty when unknown).
+struct NumaInfo { int node = -1; cpu_set_t cpus; bool have_cpus = false; };
+const NumaInfo& device_numa(int dev) {
+  static std::mutex mu;
+  static NumaInfo table[64];
+  static bool done[64];
+  static NumaInfo none;
+  if (dev < 0 || dev >= 64) return none;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!done[dev]) {
+    done[dev] = true;
+    NumaInfo& ni = table[dev];
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, dev) == cudaSuccess) {
+      for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+      std::string base = std::string("/sys/bus/pci/devices/") + bus;
+      if (FILE* f = fopen((base + "/numa_node").c_str(), "r")) { if (fscanf(f, "%d", &ni.node) != 1) ni.node = -1; fclose(f); }
+      if (FILE* f = fopen((base + "/local_cpulist").c_str(), "r")) {
+        char line[4096] = {0};
+        if (fgets(line, sizeof line, f)) {
+          CPU_ZERO(&ni.cpus);
+          for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+            int a = 0, b = 0;
+            int k = sscanf(tok, "%d-%d", &a, &b);
+            if (k == 1) b = a;
+            if (k >= 1) for (int c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET(c, &ni.cpus); ni.have_cpus = true; }
+          }
+        }
+        fclose(f);
+      }
+    }
+    cudaGetLastError();
+  }
+  return table[dev];
+}
+
 struct PinBuf {
   void* p = nullptr;
   size_t cap = 0;
-  cudaError_t reserve(size_t n) {
+  int node = -1;
+  // near_dev >= 0: allocate on the NUMA node of that GPU (the calling thread is moved next to it for the allocation:
+  // cudaMallocHost places the pages where the caller runs)
+  cudaError_t reserve(size_t n, int near_dev = -1) {
     if (n <= cap) return cudaSuccess;
     release();
     size_t want = n + n / 8 + 256;
     size_t got = 0;
-    if (void* q = pinned_cache().take(n, &got)) { p = q; cap = got; return cudaSuccess; }
+    const NumaInfo* ni = near_dev >= 0 ? &device_numa(near_dev) : nullptr;
+    node = (ni && ni->have_cpus) ? ni->node : -1;
+    if (void* q = pinned_cache().take(n, node, &got)) { p = q; cap = got; return cudaSuccess; }
+    cpu_set_t old;
+    bool moved = false;
+    if (node >= 0 && sched_getaffinity(0, sizeof old, &old) == 0 && sched_setaffinity(0, sizeof ni->cpus, &ni->cpus) == 0) moved = true;
     cudaError_t e = cudaMallocHost(&p, want);
-    if (e == cudaSuccess) cap = want;
+    if (e == cudaSuccess) cap = want;   // page-locking faults the pages in here and now, i.e. on the node the thread is on
+    if (moved) sched_setaffinity(0, sizeof old, &old);
     return e;
   }
   void release() {
-    if (p && !pinned_cache().give(p, cap)) cudaFreeHost(p);
+    if (p && !pinned_cache().give(p, cap, node)) cudaFreeHost(p);
     p = nullptr; cap = 0;
   }
   template <class T> T* as() const { return (T*)p; }
@@ -187,6 +238,7 @@ struct bamgpu_engine {
   bool own_d2h_stream = true;
   cudaStream_t k1_stream = nullptr;   // low priority: K1 of a Reader job
   uint32_t k1_grid = 0;               // CTAs of the K1 launch in flight (ev[1] fires when they are gone)
+  bool numa_aware = false;            // multi-GPU Reader: host mirrors are allocated on this GPU's NUMA node
   cudaEvent_t ev_k1_in = nullptr;
   uint64_t cols_hint = 0;   // records expected in the next batch (sizes the columns without a host round trip)
   // shard-edge exchange (bamgpu_engine_edge_*)
@@ -697,7 +749,7 @@ static int engine_enqueue_mirrors(bamgpu_engine* E, bamgpu_engine::Mirror& M, ui
   ECK(cudaStreamWaitEvent(cs, E->ev_k3_done, 0));
   if (!M.pending) ECK(cudaEventRecord(M.ev_begin, cs));
   if (want_data) {
-    ECK(M.h_data.reserve(E->data_len + 64));
+    ECK(M.h_data.reserve(E->data_len + 64, E->numa_aware ? E->device : -1));
     // lead mode: only [data_start, data_len) holds bytes; the mirror keeps the device offsets (rec_off indexes both)
     const uint64_t from = E->data_start & ~(uint64_t)63;
     if (E->data_len > from) ECK(cudaMemcpyAsync(M.h_data.as<uint8_t>() + from, E->out_ptr() + from, E->data_len - from, cudaMemcpyDeviceToHost, cs));
@@ -705,7 +757,7 @@ static int engine_enqueue_mirrors(bamgpu_engine* E, bamgpu_engine::Mirror& M, ui
   }
   if (want_offs) {
     // what next_rec() needs besides the bodies: where each one starts and how long it is
-    ECK(M.h_cols.reserve(columns_bytes(M.cols_cap)));
+    ECK(M.h_cols.reserve(columns_bytes(M.cols_cap), E->numa_aware ? E->device : -1));
     ColumnsDev hc;
     carve_columns(M.h_cols.as<uint8_t>(), M.cols_cap, hc);
     ECK(cudaMemcpyAsync(hc.rec_off, M.cols.rec_off, 8 * n_rec, cudaMemcpyDeviceToHost, cs));
@@ -715,7 +767,7 @@ static int engine_enqueue_mirrors(bamgpu_engine* E, bamgpu_engine::Mirror& M, ui
   }
   if (want_cols) {
     size_t bytes = columns_bytes(M.cols_cap);
-    ECK(M.h_cols.reserve(bytes));
+    ECK(M.h_cols.reserve(bytes, E->numa_aware ? E->device : -1));
     // copy only the used prefix of every column
     ColumnsDev hc;
     carve_columns(M.h_cols.as<uint8_t>(), M.cols_cap, hc);
@@ -1290,7 +1342,7 @@ static void feeder_main(bamgpu_reader* R) {
       fill = std::min(bb, R->mem_len - R->mem_pos);
       if (R->mem_pos + fill >= R->mem_len) src_eof = true;
       if (S.dev.reserve(cap + IN_TAIL_PAD) != cudaSuccess) { S.status = BAMGPU_ERR_NOMEM; S.final = true; }
-    } else if (S.host.reserve(cap + IN_TAIL_PAD) != cudaSuccess || S.dev.reserve(cap + IN_TAIL_PAD) != cudaSuccess) {
+    } else if (S.host.reserve(cap + IN_TAIL_PAD, D > 1 ? dc.dev : -1) != cudaSuccess || S.dev.reserve(cap + IN_TAIL_PAD) != cudaSuccess) {
       S.status = BAMGPU_ERR_NOMEM; S.final = true;
     } else {
       uint8_t* h = S.host.as<uint8_t>();
@@ -1425,6 +1477,7 @@ static bamgpu_reader* reader_create(bamgpu_read_fn read, void* ctx, size_t threa
       E->d2h_stream = dc.d2h;
       E->own_d2h_stream = false;
       E->lead = BAMGPU_MAX_HALO;
+      E->numa_aware = D > 1;
       Job& jb = R->jobs[i * R->J + j];
       jb.E = E;
       jb.dev_i = (int)i;
