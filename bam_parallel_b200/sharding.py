@@ -51,8 +51,10 @@ class _DevView:
 
 
 class EdgeExchange:
-    """Neighbour-only exchange of shard heads over torch.distributed point-to-point ops (NCCL over NVLink on GPUs;
-    gloo on CPU in the tests)."""
+    """Neighbour-only exchange of shard heads over torch.distributed point-to-point ops.  This is the HOST-LOGIC stand-in
+    the CPU tests run over gloo (tests/test_sharding.py).  On GPUs the exchange is bamgpu_engine_edge_open / _connect /
+    _exchange behind the C ABI: the head is written into the neighbour's inbox in NVLink peer memory (CUDA IPC between
+    the per-GPU processes), no torch, no NCCL on the data path (bench.py, tests/test_gpu_multi.py)."""
 
     def __init__(self, rank: int, world: int, torch, dist, halo: int = HALO, device: str = "cuda"):
         self.rank, self.world, self.torch, self.dist, self.halo, self.device = rank, world, torch, dist, halo, device

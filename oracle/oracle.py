@@ -444,3 +444,54 @@ def py_sort_perm(rows, mode: int):
             raise OracleError(-9)
         return (ha > hb) - (ha < hb)
     return sorted(range(len(rows)), key=functools.cmp_to_key(cmp))
+
+
+# ---- DIGEST SPEC, pure-Python twin (small inputs): the third statement of the same function, next to
+# oracle/bam_oracle.c (orc_digest / orc_sorted_digest) and bam_parallel_b200/csrc/digest.cu ----
+_M64 = (1 << 64) - 1
+
+
+def py_mix64(z: int) -> int:
+    z = (z + 0x9E3779B97F4A7C15) & _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+def py_body_hash(body: bytes) -> int:
+    h = 0
+    for k in range(0, (len(body) + 3) // 4):
+        w = int.from_bytes(body[4 * k:4 * k + 4].ljust(4, b"\0"), "little")
+        h = (h + py_mix64(w | (k << 32))) & _M64
+    return h
+
+
+def py_digest(u: bytes, rec_off, rec_len, cols, index_base: int = 0, stream_base: int = 0) -> dict:
+    order = ["ref_id", "pos", "l_read_name", "mapq", "bin", "n_cigar_op", "flag", "l_seq", "next_ref_id", "next_pos", "tlen",
+             "cigar_off", "seq_off", "qual_off", "tags_off"]
+    d = {"n_records": len(rec_off), "body_bytes": 0, "fields": 0, "bodies": 0}
+    for i, (o, l) in enumerate(zip(rec_off, rec_len)):
+        o, l = int(o), int(l)
+        idx = index_base + i
+        h = 0
+        vals = [idx, stream_base + o, l] + [int(cols[k][i]) & 0xFFFFFFFF for k in order]
+        vals += [int(cols["coord_key"][i]), int(cols["strand"][i])]
+        hp = int(cols["hi_present"][i]) == 1
+        vals += [1 if hp else 0, (int(cols["hi_value"][i]) & 0xFFFFFFFF) if hp else 0]
+        for v in vals:
+            h = py_mix64(h ^ (v & _M64))
+        d["fields"] = (d["fields"] + h) & _M64
+        d["bodies"] = (d["bodies"] + py_mix64((py_body_hash(u[o:o + l]) + idx * 0x9E3779B97F4A7C15) & _M64)) & _M64
+        d["body_bytes"] += l
+    return d
+
+
+def py_sorted_digest(u: bytes, rec_off, rec_len, perm) -> dict:
+    d = {"n_records": len(perm), "body_bytes": 0, "perm": 0, "bodies": 0}
+    for i, r in enumerate(perm):
+        r = int(r)
+        o, l = int(rec_off[r]), int(rec_len[r])
+        d["perm"] = (d["perm"] + py_mix64(r | (i << 32))) & _M64
+        d["bodies"] = (d["bodies"] + py_mix64((py_body_hash(u[o:o + l]) + i * 0x9E3779B97F4A7C15) & _M64)) & _M64
+        d["body_bytes"] += l
+    return d

@@ -77,6 +77,20 @@ def _worker(rank, world, port, halo, q):
         last_o, last_l = mine[-1]
         exit_rel = (last_o + last_l) - hi if rank < world - 1 else 0
         ex.verify(exit_rel, int(first), len(mine), off_all.size)
+        # the digests of the shards add up to the digest of the file (what bench.py gathers over its host-side group at N > 1)
+        cols, _, _ = orc.extract(u, off_all, len_all, True)
+        a = int(np.searchsorted(off_all, lo + 4))
+        b = a + len(mine)
+        sub = {k: np.ascontiguousarray(v[a:b]) for k, v in cols.items()}
+        d = orc.digest(buf, np.ascontiguousarray(off_all[a:b] - np.uint64(lo)), np.ascontiguousarray(len_all[a:b]), sub, 2,
+                       index_base=a, stream_base=lo)
+        alld = [None] * world
+        dist.all_gather_object(alld, d)
+        tot = {"n_records": 0, "body_bytes": 0, "fields": 0, "bodies": 0}
+        for x in alld:
+            for k in tot:
+                tot[k] = (tot[k] + x[k]) & 0xFFFFFFFFFFFFFFFF
+        assert tot == orc.digest(u, off_all, len_all, cols, 2), "shard digests do not add up"
         dist.destroy_process_group()
         q.put((rank, "ok", len(mine)))
     except Exception as e:  # pragma: no cover
