@@ -1427,7 +1427,9 @@ static bamgpu_reader* reader_create(bamgpu_read_fn read, void* ctx, size_t threa
   }
   for (int d : devices) if (d < 0 || d >= count) { delete R; return nullptr; }
   const size_t D = devices.size();
-  R->J = (opts && opts->jobs_per_device > 0) ? std::min(opts->jobs_per_device, 16) : 8;
+  // batches in flight per GPU: one GPU needs ~5 K1 launches of 256 MiB in flight to fill its 56.8 k streams; with several
+  // GPUs the host link is the limit long before that, and every job costs streams, events and buffers at open / close
+  R->J = (opts && opts->jobs_per_device > 0) ? std::min(opts->jobs_per_device, 16) : (D > 1 ? 4 : 8);
   if (R->J < 2) R->J = 2;
   if (const char* e = getenv("BAMGPU_JOBS")) { int v = atoi(e); if (v >= 2 && v <= 16) R->J = v; }
   R->read = read;
@@ -1453,12 +1455,14 @@ static bamgpu_reader* reader_create(bamgpu_read_fn read, void* ctx, size_t threa
   R->devs.resize(D);
   R->jobs.resize(D * (size_t)R->J);
   const int n_slots = R->J;   // a batch keeps its input slot until its K1 is over: as many slots as batches in flight
-  for (size_t i = 0; i < D; ++i) {
+  // per-GPU set-up (streams, events, J engines) runs on one thread per GPU: Reader::new is inside the caller's clock
+  std::vector<int> ok(D, 1);
+  auto setup = [&](size_t i) {
     DevCtx& dc = R->devs[i];
     dc.dev = devices[i];
     if (cudaSetDevice(dc.dev) != cudaSuccess ||
         cudaStreamCreateWithFlags(&dc.h2d, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&dc.d2h, cudaStreamNonBlocking) != cudaSuccess) { reader_destroy(R); return nullptr; }
+        cudaStreamCreateWithFlags(&dc.d2h, cudaStreamNonBlocking) != cudaSuccess) { ok[i] = 0; return; }
     dc.slots.resize(n_slots);
     for (int k = 0; k < n_slots; ++k) {
       cudaEventCreateWithFlags(&dc.slots[k].copied, cudaEventDisableTiming);
@@ -1470,7 +1474,7 @@ static bamgpu_reader* reader_create(bamgpu_read_fn read, void* ctx, size_t threa
       eo.flags = R->flags;
       eo.inflate_impl = opts ? opts->inflate_impl : 0;
       bamgpu_engine* E = bamgpu_engine_new(&eo);
-      if (!E) { reader_destroy(R); return nullptr; }
+      if (!E) { ok[i] = 0; return; }
       // one D2H stream per GPU: copies leave in batch order
       cudaSetDevice(dc.dev);
       cudaStreamDestroy(E->d2h_stream);
@@ -1482,17 +1486,35 @@ static bamgpu_reader* reader_create(bamgpu_read_fn read, void* ctx, size_t threa
       jb.E = E;
       jb.dev_i = (int)i;
     }
+  };
+  if (D == 1) setup(0);
+  else {
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < D; ++i) th.emplace_back(setup, i);
+    for (auto& t : th) t.join();
   }
+  for (size_t i = 0; i < D; ++i) if (!ok[i]) { reader_destroy(R); return nullptr; }
   return R;
 }
 
 static void reader_destroy(bamgpu_reader* R) {
-  for (auto& j : R->jobs) if (j.E) { bamgpu_engine_free(j.E); j.E = nullptr; }
-  for (auto& dc : R->devs) {
+  const size_t D = R->devs.size();
+  auto teardown = [&](size_t i) {
+    DevCtx& dc = R->devs[i];
+    for (int j = 0; j < R->J; ++j) {
+      Job& jb = R->jobs[i * R->J + j];
+      if (jb.E) { bamgpu_engine_free(jb.E); jb.E = nullptr; }
+    }
     cudaSetDevice(dc.dev);
     if (dc.h2d) { cudaStreamSynchronize(dc.h2d); cudaStreamDestroy(dc.h2d); }
     if (dc.d2h) { cudaStreamSynchronize(dc.d2h); cudaStreamDestroy(dc.d2h); }
     for (auto& s : dc.slots) { if (s.copied) cudaEventDestroy(s.copied); s.host.release(); s.dev.release(); }
+  };
+  if (D <= 1) { if (D) teardown(0); }
+  else {
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < D; ++i) th.emplace_back(teardown, i);
+    for (auto& t : th) t.join();
   }
   delete R;
 }

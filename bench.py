@@ -295,6 +295,8 @@ def run_b200(a, rank: int, world: int, local_rank: int, host_group=None):
                 torch.cuda.synchronize()
                 pcie[name] = round(3 * (1 << 30) / (e0.elapsed_time(e1) * 1e-3) / 1e9, 1)
             del hbuf, dbuf
+        if world > 1:
+            pcie = pcie_aggregate(torch, world)
         pin_ptr, parr = pinned_copy(L, arr[:compressed_bytes])
         devs = list(range(world)) if world > 1 else None
         e2e, reader_digest = run_e2e(a, bp, parr, torch, int(total_isize), devices=devs, want_digest=True)
@@ -493,6 +495,29 @@ def run_b200(a, rank: int, world: int, local_rank: int, host_group=None):
     eng.close()
     if keep is not None:
         keep.close()
+
+
+def pcie_aggregate(torch, n_dev, mib=512, reps=4):
+    """What the box gives N plain pinned copies running at once (one per GPU): the bound of the N-GPU e2e line.
+    On the round-2 boxes it is far below N x the single-GPU figure (the GPUs share host links)."""
+    out = {}
+    hb = [torch.empty(mib << 20, dtype=torch.uint8).pin_memory() for _ in range(n_dev)]
+    db = [torch.empty(mib << 20, dtype=torch.uint8, device=f"cuda:{d}") for d in range(n_dev)]
+    st = [torch.cuda.Stream(device=d) for d in range(n_dev)]
+    for name in ("d2h", "h2d"):
+        for rep in range(2):       # first pass warms up
+            for d in range(n_dev):
+                torch.cuda.synchronize(d)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                for d in range(n_dev):
+                    with torch.cuda.stream(st[d]):
+                        (hb[d] if name == "d2h" else db[d]).copy_(db[d] if name == "d2h" else hb[d], non_blocking=True)
+            for d in range(n_dev):
+                torch.cuda.synchronize(d)
+            dt = time.perf_counter() - t0
+        out[f"{name}_GB_per_s_all_{n_dev}_gpus_at_once"] = round(n_dev * reps * (mib << 20) / dt / 1e9, 1)
+    return out
 
 
 def verify_with_oracle(a, arr, dg):
