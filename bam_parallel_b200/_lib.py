@@ -58,12 +58,17 @@ MAX_DEVICES = 16
 class Opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("batch_bytes", C.c_uint64), ("inflate_impl", C.c_int32),
                 ("jobs_per_device", C.c_int32), ("n_devices", C.c_int32), ("devices", C.c_int32 * MAX_DEVICES),
-                ("reserved", C.c_int32)]
+                ("sort_output", C.c_int32)]
+
+
+OUT_BODIES, OUT_RECORDS, OUT_BAM = 0, 1, 2          # bamgpu_opts.sort_output
+SORT_EMIT_BLOCK_SIZE = 128
 
 
 def make_opts(device: int = -1, flags: int = 0, batch_bytes: int = 0, inflate_impl: int = 0, jobs_per_device: int = 0,
-              devices=None) -> Opts:
+              devices=None, sort_output: int = 0) -> Opts:
     o = Opts()
+    o.sort_output = sort_output
     o.device, o.flags, o.batch_bytes, o.inflate_impl, o.jobs_per_device = device, flags, batch_bytes, inflate_impl, jobs_per_device
     devices = list(devices or [])
     if len(devices) > MAX_DEVICES:
@@ -88,7 +93,7 @@ class EdgeHandle(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("blocks", "bytes_in", "bytes_out", "records", "batches", "kernel_launches")] + \
                [(n, C.c_double) for n in ("ms_h2d", "ms_inflate", "ms_crc", "ms_records", "ms_d2h", "ms_total", "ms_sort",
-                                          "ms_gather")] + [("p2p_bytes", C.c_uint64)]
+                                          "ms_gather")] + [("p2p_bytes", C.c_uint64), ("ms_bgzf_write", C.c_double)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -113,7 +118,8 @@ EXPORTS = [
     "bamgpu_append_record", "bamgpu_read", "bamgpu_next_batch", "bamgpu_reader_stats",
     "bamgpu_parse_reference_sequences", "bamgpu_status_str", "bamgpu_build_info", "bamgpu_engine_sort", "bamgpu_sort_bam",
     "bamgpu_engine_digest", "bamgpu_engine_sorted_digest", "bamgpu_reader_current_engine", "bamgpu_engine_edge_open",
-    "bamgpu_engine_edge_connect", "bamgpu_engine_edge_exchange", "bamgpu_engine_edge_close",
+    "bamgpu_engine_edge_connect", "bamgpu_engine_edge_exchange", "bamgpu_engine_edge_close", "bamgpu_bgzf_bound",
+    "bamgpu_engine_bgzf_store",
 ]
 
 _lib = None
@@ -201,6 +207,10 @@ def load() -> C.CDLL:
     L.bamgpu_engine_edge_connect.argtypes = [vp, C.POINTER(EdgeHandle), C.POINTER(EdgeHandle)]
     L.bamgpu_engine_edge_exchange.restype = C.c_int
     L.bamgpu_engine_edge_exchange.argtypes = [vp, C.c_uint64, vp]
+    L.bamgpu_bgzf_bound.restype = sz
+    L.bamgpu_bgzf_bound.argtypes = [sz]
+    L.bamgpu_engine_bgzf_store.restype = C.c_int
+    L.bamgpu_engine_bgzf_store.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), C.c_int, vp]
     L.bamgpu_engine_edge_close.restype = None
     L.bamgpu_engine_edge_close.argtypes = [vp]
     _lib = L

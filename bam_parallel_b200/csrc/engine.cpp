@@ -248,6 +248,9 @@ struct bamgpu_engine {
   bool edge_left_ipc = false, edge_right_ipc = false, edge_has_right = false;
   uint32_t* edge_len_scratch = nullptr;
   bool sorted_valid = false;
+  uint64_t sort_front = 0, sorted_front_used = 0;   // bytes kept free in front of the sorted output (bamgpu_sort_bam: the BAM header)
+  uint32_t sorted_prefix = 0;
+  DevBuf d_bgzf, d_bgzf_crc;                        // BGZF writer output + per-block CRCs
   uint64_t halo_len = 0;    // bytes copied behind them from the right-hand shard (multi-GPU)
   uint64_t carry_len = 0;   // bytes at the front of the next batch kept from this one
   uint64_t keep_from = 0;   // where those bytes currently sit
@@ -445,6 +448,7 @@ extern "C" void bamgpu_engine_free(bamgpu_engine* E) {
   E->d_outs[0].release(); E->d_outs[1].release(); E->d_tiles.release(); E->d_k1ring.release(); E->h_res.release();
   E->d_carry.release();
   // the sort's scratch, permutation, offsets and gathered bodies (round 1 leaked these: ~18.7 GB per 50M-record sort)
+  E->d_bgzf.release(); E->d_bgzf_crc.release();
   E->d_sort.release(); E->d_perm.release(); E->d_soff.release(); E->d_sorted.release(); E->h_sorted.release(); E->h_perm.release();
   delete E;
 }
@@ -820,12 +824,12 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
            o_count = align_up(o_base + 8 * nt, 256), o_kind = align_up(o_count + 4 * nt, 256),
            o_nxt = align_up(o_kind + 4 * nt, 256), o_jump = align_up(o_nxt + 4 * nt, 256),
            o_jump2 = align_up(o_jump + 4 * nt, 256), o_reach = align_up(o_jump2 + 4 * nt, 256),
-           tiles_bytes = align_up(o_reach + nt, 256);
+           o_ckpt = align_up(o_reach + nt, 256), tiles_bytes = align_up(o_ckpt + 2 * (size_t)CK_PER_TILE * nt, 256);
     ECK(E->d_tiles.reserve(tiles_bytes));
     uint8_t* tb = E->d_tiles.as<uint8_t>();
     TileArrays t{(uint64_t*)(tb + o_entry), (uint64_t*)(tb + o_exit), (uint32_t*)(tb + o_count), (uint32_t*)(tb + o_kind),
                  (uint32_t*)(tb + o_nxt), (uint32_t*)(tb + o_jump), (uint32_t*)(tb + o_jump2), (uint8_t*)(tb + o_reach),
-                 (uint64_t*)(tb + o_base), n_tiles};
+                 (uint64_t*)(tb + o_base), n_tiles, (uint16_t*)(tb + o_ckpt)};
     // Columns are sized BEFORE the record count is known (from what the previous batch needed, or ~256 bytes per record the
     // first time), so that walk -> resolve -> emit -> extract go onto the stream back to back and the host waits ONCE per
     // batch (round 1: three waits).  If the guess was too small the last two kernels run again with room for all.
@@ -1002,7 +1006,9 @@ extern "C" int bamgpu_engine_sort(bamgpu_engine* E, int sort_by, uint32_t flags,
   ECK(cudaMemcpyAsync(h_sr, d_sr, sizeof(SortResult), cudaMemcpyDeviceToHost, s));
   ECK(cudaEventRecord(E->ev[4], s));
   uint64_t total = 0;
-  ECK(sorted_offsets(E->mir[E->msel].cols, E->d_perm.as<uint32_t>(), n, E->d_sort.p, E->d_soff.as<uint64_t>(), &total, s));   // synchronises
+  const uint32_t prefix = (flags & BAMGPU_SORT_EMIT_BLOCK_SIZE) ? 4u : 0u;   // (u32 block_size, body)* instead of bodies
+  const uint64_t front = E->sort_front;                                      // room in front of the output (a BAM header)
+  ECK(sorted_offsets(E->mir[E->msel].cols, E->d_perm.as<uint32_t>(), n, E->d_sort.p, E->d_soff.as<uint64_t>(), &total, prefix, s));   // synchronises
   if (sort_by == BAMGPU_SORT_NAME_AND_MATCH_MATES) {
     if (h_sr->hi_bad_tags) { E->err = "sort: aux tags the reference's HI walk panics on"; return BAMGPU_ERR_SORT_BAD_TAGS; }
     if (h_sr->hi_mixed) {
@@ -1010,15 +1016,17 @@ extern "C" int bamgpu_engine_sort(bamgpu_engine* E, int sort_by, uint32_t flags,
       return BAMGPU_ERR_SORT_HI_MIXED;
     }
   }
-  ECK(E->d_sorted.reserve(total + 64));
+  ECK(E->d_sorted.reserve(front + total + 64));
   ECK(gather_sorted_bodies(E->out_ptr(), E->mir[E->msel].cols, E->d_perm.as<uint32_t>(), n, E->d_sort.p, E->d_soff.as<uint64_t>(),
-                           E->d_sorted.as<uint8_t>(), s));
+                           E->d_sorted.as<uint8_t>() + front, prefix, s));
+  E->sorted_prefix = prefix;
+  E->sorted_front_used = front;
   ECK(cudaEventRecord(E->ev[5], s));
   launches += 3;
   out->bodies_len = total;
   out->perm = E->d_perm.as<uint32_t>();
   out->body_off = E->d_soff.as<uint64_t>();
-  out->bodies = E->d_sorted.as<uint8_t>();
+  out->bodies = E->d_sorted.as<uint8_t>() + front;
   E->sorted_valid = true;
   if ((flags & BAMGPU_COPY_COLUMNS) && n) {
     ECK(E->h_perm.reserve(4 * n));
@@ -1027,7 +1035,7 @@ extern "C" int bamgpu_engine_sort(bamgpu_engine* E, int sort_by, uint32_t flags,
   }
   if ((flags & BAMGPU_COPY_DATA) && total) {
     ECK(E->h_sorted.reserve(total));
-    ECK(cudaMemcpyAsync(E->h_sorted.p, E->d_sorted.p, total, cudaMemcpyDeviceToHost, s));
+    ECK(cudaMemcpyAsync(E->h_sorted.p, E->d_sorted.as<uint8_t>() + front, total, cudaMemcpyDeviceToHost, s));
     out->h_bodies = E->h_sorted.as<uint8_t>();
   }
   ECK(cudaStreamSynchronize(s));
@@ -1070,9 +1078,10 @@ extern "C" int bamgpu_engine_digest(bamgpu_engine* E, uint64_t index_base, uint6
 extern "C" int bamgpu_engine_sorted_digest(bamgpu_engine* E, void* cuda_stream, bamgpu_digest* out) {
   if (!E || !out) return BAMGPU_ERR_ARG;
   if (!E->sorted_valid) { E->err = "digest: no sort result on this engine"; return BAMGPU_ERR_STATE; }
+  if (E->sorted_prefix) { E->err = "digest: the sort output carries block_size prefixes; the DIGEST SPEC is defined on bodies"; return BAMGPU_ERR_STATE; }
   cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : E->stream;
   ECK(cudaSetDevice(E->device));
-  launch_digest_sorted(E->d_sorted.as<uint8_t>(), E->d_soff.as<uint64_t>(), E->d_perm.as<uint32_t>(), E->last_n,
+  launch_digest_sorted(E->d_sorted.as<uint8_t>() + E->sorted_front_used, E->d_soff.as<uint64_t>(), E->d_perm.as<uint32_t>(), E->last_n,
                        (unsigned long long*)(E->d_misc.as<uint8_t>() + 4096), E->num_sms, s);
   E->stats.kernel_launches += E->last_n ? 2 : 0;
   return engine_read_digest(E, s, E->last_n, out);
@@ -1200,6 +1209,40 @@ extern "C" int bamgpu_engine_edge_exchange(bamgpu_engine* E, uint64_t step, void
     int rc = bamgpu_engine_append_halo(E, nullptr, 0, s);
     if (rc < 0) return rc;
   }
+  return BAMGPU_OK;
+}
+
+
+// -------------------------------------------------------------------------------------------------
+// BGZF writer with stored blocks (csrc/bgzf_write.cu)
+// -------------------------------------------------------------------------------------------------
+extern "C" size_t bamgpu_bgzf_bound(size_t len) {
+  const size_t full = len / BGZF_STORE_PAYLOAD, rem = len % BGZF_STORE_PAYLOAD;
+  return full * BGZF_STORE_BLOCK + (rem ? 18 + 5 + rem + 8 : 0) + 28;
+}
+
+extern "C" int bamgpu_engine_bgzf_store(bamgpu_engine* E, const uint8_t* d_src, size_t len, uint8_t* d_out, size_t out_cap,
+                                        size_t* out_len, int eof_marker, void* cuda_stream) {
+  if (!E || (len && !d_src) || !d_out || !out_len) return BAMGPU_ERR_ARG;
+  const size_t need = bamgpu_bgzf_bound(len) - (eof_marker ? 0 : 28);
+  if (out_cap < need) { E->err = "bgzf_store: output buffer too small"; return BAMGPU_ERR_BUFFER_TOO_SMALL; }
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : E->stream;
+  ECK(cudaSetDevice(E->device));
+  const size_t n_blocks = (len + BGZF_STORE_PAYLOAD - 1) / BGZF_STORE_PAYLOAD;
+  ECK(E->d_bgzf_crc.reserve(4 * (n_blocks + 1)));
+  cudaEvent_t& e0 = E->ev[3];
+  cudaEvent_t& e1 = E->ev[4];
+  ECK(cudaEventRecord(e0, s));
+  launch_crc32_chunks(d_src, len, BGZF_STORE_PAYLOAD, E->d_crc, E->d_bgzf_crc.as<uint32_t>(), E->num_sms, s);
+  ECK(bgzf_store_blocks(d_src, len, E->d_bgzf_crc.as<uint32_t>(), d_out, eof_marker != 0, s));
+  ECK(cudaEventRecord(e1, s));
+  ECK(cudaStreamSynchronize(s));
+  ECK(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  E->stats.ms_bgzf_write += ms;
+  E->stats.kernel_launches += 2;
+  *out_len = need;
   return BAMGPU_OK;
 }
 
@@ -1945,6 +1988,7 @@ extern "C" int bamgpu_reader_stats(const bamgpu_reader* R, bamgpu_stats* out) {
     t.blocks += e.blocks; t.bytes_in += e.bytes_in; t.bytes_out += e.bytes_out; t.records += e.records; t.batches += e.batches;
     t.kernel_launches += e.kernel_launches; t.ms_h2d += e.ms_h2d; t.ms_inflate += e.ms_inflate; t.ms_crc += e.ms_crc;
     t.ms_records += e.ms_records; t.ms_d2h += e.ms_d2h; t.ms_sort += e.ms_sort; t.ms_gather += e.ms_gather; t.p2p_bytes += e.p2p_bytes;
+    t.ms_bgzf_write += e.ms_bgzf_write;
   }
   t.ms_total = t.ms_h2d + t.ms_inflate + t.ms_crc + t.ms_records + t.ms_d2h + t.ms_sort + t.ms_gather;
   *out = t;
@@ -2024,9 +2068,33 @@ extern "C" int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write
       if (r2 == BAMGPU_OK) { rc = BAMGPU_ERR_TOO_LARGE; msg = "input was split into several batches"; break; }
       if (r2 < 0) { rc = r2; msg = bamgpu_last_error(R); break; }
     }
+    // output format (bamgpu_opts.sort_output): the reference's bodies, its spill wire format, or a complete BAM
+    const int out_fmt = opts ? opts->sort_output : BAMGPU_OUT_BODIES;
+    if (out_fmt < BAMGPU_OUT_BODIES || out_fmt > BAMGPU_OUT_BAM) { rc = BAMGPU_ERR_ARG; msg = "unknown sort_output"; break; }
+    const size_t front = out_fmt == BAMGPU_OUT_BAM ? 4 + hl : 0;
+    E->sort_front = front;
     bamgpu_sorted srt;
-    rc = bamgpu_engine_sort(E, sort_by, 0, nullptr, &srt);
+    rc = bamgpu_engine_sort(E, sort_by, out_fmt == BAMGPU_OUT_BODIES ? 0 : BAMGPU_SORT_EMIT_BLOCK_SIZE, nullptr, &srt);
+    E->sort_front = 0;
     if (rc != BAMGPU_OK) { msg = E->err; break; }
+    const uint8_t* d_result = srt.bodies;
+    uint64_t result_len = srt.bodies_len;
+    if (out_fmt == BAMGPU_OUT_BAM) {
+      // "BAM\1" + the header bytes read_header returned, in front of the sorted records; then BGZF framing
+      std::vector<uint8_t> hd(front);
+      memcpy(hd.data(), "BAM\1", 4);
+      memcpy(hd.data() + 4, hb, hl);
+      uint8_t* d_stream = E->d_sorted.as<uint8_t>();
+      if (cudaMemcpyAsync(d_stream, hd.data(), front, cudaMemcpyHostToDevice, E->stream) != cudaSuccess ||
+          cudaStreamSynchronize(E->stream) != cudaSuccess) { rc = BAMGPU_ERR_CUDA; msg = "header upload failed"; break; }
+      const size_t bound = bamgpu_bgzf_bound(front + srt.bodies_len);
+      if (E->d_bgzf.reserve(bound + 64) != cudaSuccess) { rc = BAMGPU_ERR_NOMEM; msg = "device memory for the BGZF output"; break; }
+      size_t wrote = 0;
+      rc = bamgpu_engine_bgzf_store(E, d_stream, front + srt.bodies_len, E->d_bgzf.as<uint8_t>(), bound, &wrote, 1, nullptr);
+      if (rc != BAMGPU_OK) { msg = E->err; break; }
+      d_result = E->d_bgzf.as<uint8_t>();
+      result_len = wrote;
+    }
     // 3. bodies to the sink through two pinned staging buffers (the copy of chunk k+1 overlaps write(k))
     const size_t CH = (size_t)64 << 20;
     PinBuf st[2];
@@ -2037,13 +2105,13 @@ extern "C" int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write
     cudaEvent_t t0, t1;
     cudaEventCreate(&t0); cudaEventCreate(&t1);
     cudaEventRecord(t0, E->stream);
-    const uint64_t total = srt.bodies_len;
+    const uint64_t total = result_len;
     uint64_t issued = 0, written = 0;
     int k = 0;
     size_t pending[2] = {0, 0};
     auto issue = [&](int slot) {
       size_t m = (size_t)std::min<uint64_t>(CH, total - issued);
-      cudaMemcpyAsync(st[slot].p, srt.bodies + issued, m, cudaMemcpyDeviceToHost, E->stream);
+      cudaMemcpyAsync(st[slot].p, d_result + issued, m, cudaMemcpyDeviceToHost, E->stream);
       cudaEventRecord(ev[slot], E->stream);
       pending[slot] = m;
       issued += m;

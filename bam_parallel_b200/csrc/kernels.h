@@ -69,7 +69,10 @@ struct TileArrays {
   uint8_t* reach;       // on the true chain
   uint64_t* base;       // exclusive scan of count over reachable tiles
   uint32_t n_tiles;
+  uint16_t* ckpt;       // [n_tiles][CK_PER_TILE]: tile-relative start of every CK_STRIDE-th record of the tile
 };
+constexpr uint32_t CK_STRIDE = 8;
+constexpr uint32_t CK_PER_TILE = (TILE_BYTES / 36 + CK_STRIDE) / CK_STRIDE;   // a record takes >= 36 bytes of stream: <= 1821 starts per tile
 
 struct RecordParams {
   const uint8_t* data;  // inflated bytes (carry + new); readable 16 bytes before and after
@@ -144,9 +147,18 @@ struct SortResult {
 size_t sort_scratch_bytes(uint64_t n_records);
 cudaError_t sort_permutation(const uint8_t* data, const ColumnsDev& c, uint64_t n_records, int sort_by, void* scratch, uint32_t* perm,
                              SortResult* d_res, int* launches, cudaStream_t s);
+// prefix = 4: every body is preceded by its u32 block_size (the reference's spill wire format, sort.rs:340-347); 0: bodies only (sort.rs:643)
 cudaError_t sorted_offsets(const ColumnsDev& c, const uint32_t* perm, uint64_t n_records, void* scratch, uint64_t* out_off,
-                           uint64_t* total_bytes, cudaStream_t s);
+                           uint64_t* total_bytes, uint32_t prefix, cudaStream_t s);
 cudaError_t gather_sorted_bodies(const uint8_t* data, const ColumnsDev& c, const uint32_t* perm, uint64_t n_records, void* scratch,
-                                 uint64_t* out_off, uint8_t* out, cudaStream_t s);
+                                 uint64_t* out_off, uint8_t* out, uint32_t prefix, cudaStream_t s);
+
+// ---- BGZF writer, stored blocks (bgzf_write.cu) ---------------------------------------------------
+// CRC-32 of consecutive `chunk`-byte pieces of src (the last one shorter) -> crc_out[i]   (crc32.cu, K2's warp CRC)
+void launch_crc32_chunks(const uint8_t* src, uint64_t len, uint32_t chunk, const uint32_t* d_tables, uint32_t* crc_out, int num_sms, cudaStream_t s);
+// Frames: 18-byte BGZF header + 5-byte stored-block header in front of every payload, CRC32 + ISIZE behind it, EOF marker.
+constexpr uint32_t BGZF_STORE_PAYLOAD = 0xff00;                       // bytes per block, like htslib
+constexpr uint32_t BGZF_STORE_BLOCK = 18 + 5 + BGZF_STORE_PAYLOAD + 8; // a full block on the wire
+cudaError_t bgzf_store_blocks(const uint8_t* src, uint64_t len, const uint32_t* crc, uint8_t* out, bool eof_marker, cudaStream_t s);
 
 }  // namespace bamgpu

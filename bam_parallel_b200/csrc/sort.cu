@@ -87,6 +87,24 @@ __global__ void k_assign_groups(const uint32_t* __restrict__ idx, const uint32_t
   if (i < n) seg_elem[idx[i]] = scan[i] - 1;
 }
 
+// Length of the prefix every name shares with the first record's name (<= the shortest name).  Real read names start with
+// instrument : run : flowcell; the 8-byte rounds over that prefix would sort 50 M equal keys, so they are skipped.
+__global__ void k_name_lcp(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, const uint8_t* __restrict__ l_name,
+                           uint32_t n, uint32_t* out) {
+  const uint8_t* a = data + rec_off[0] + 32;
+  const uint32_t la = l_name[0];
+  uint32_t m = 255;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint8_t* b = data + rec_off[i] + 32;
+    const uint32_t lb = l_name[i], l = la < lb ? la : lb;
+    uint32_t k = 0;
+    while (k < l && k < m && a[k] == b[k]) ++k;
+    m = k < m ? k : m;
+  }
+  for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMin(out, m);
+}
+
 __global__ void k_max_u8(const uint8_t* __restrict__ v, uint32_t n, uint32_t* out) {
   uint32_t m = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, (uint32_t)v[i]);
@@ -108,9 +126,9 @@ __global__ void k_check_hi(const uint32_t* __restrict__ idx, const uint32_t* __r
   }
 }
 
-__global__ void k_perm_len(const uint32_t* __restrict__ rec_len, const uint32_t* __restrict__ perm, uint64_t* __restrict__ len64, uint32_t n) {
+__global__ void k_perm_len(const uint32_t* __restrict__ rec_len, const uint32_t* __restrict__ perm, uint64_t* __restrict__ len64, uint32_t n, uint32_t prefix) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) len64[i] = rec_len[perm[i]];
+  if (i < n) len64[i] = (uint64_t)rec_len[perm[i]] + prefix;
 }
 
 // One warp per record: body bytes data[rec_off .. +rec_len) -> out[out_off ..).  Destination-aligned 16-byte stores;
@@ -118,14 +136,17 @@ __global__ void k_perm_len(const uint32_t* __restrict__ rec_len, const uint32_t*
 // every source byte is loaded once per warp).  HBM-bound: reads and writes every body byte once.
 __global__ void __launch_bounds__(256) k_gather_bodies(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off,
                                                        const uint32_t* __restrict__ rec_len, const uint32_t* __restrict__ perm,
-                                                       const uint64_t* __restrict__ out_off, uint8_t* __restrict__ out, uint32_t n) {
+                                                       const uint64_t* __restrict__ out_off, uint8_t* __restrict__ out, uint32_t n,
+                                                       uint32_t prefix) {
+  // prefix = 4: the record's block_size field (the 4 bytes in front of the body in the inflated stream) is copied with it:
+  // (u32 block_size, body)*, the reference's spill wire format (sort.rs:340-347) and a BAM record stream
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
     const uint32_t rec = perm[i];
-    const uint8_t* src = data + rec_off[rec];
+    const uint8_t* src = data + rec_off[rec] - prefix;
     uint8_t* dst = out + out_off[i];
-    const uint32_t len = rec_len[rec];
+    const uint32_t len = rec_len[rec] + prefix;
     // head: up to 15 bytes until dst is 16-byte aligned
     uint32_t headn = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
     if (headn > len) headn = len;
@@ -236,17 +257,23 @@ cudaError_t sort_permutation(const uint8_t* data, const ColumnsDev& c, uint64_t 
     // number of 8-byte rounds
     uint32_t* d_max = (uint32_t*)&d_res->max_name_len;
     k_max_u8<<<592, 256, 0, s>>>(c.l_read_name, n, d_max);
-    uint32_t max_len = 0;
+    uint32_t* d_lcp = flags;   // free until the first round
+    cudaMemsetAsync(d_lcp, 0xff, 4, s);
+    k_name_lcp<<<592, 256, 0, s>>>(data, c.rec_off, c.l_read_name, n, d_lcp);
+    nl += 2;
+    uint32_t max_len = 0, lcp = 0;
     cudaMemcpyAsync(&max_len, d_max, 4, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(&lcp, d_lcp, 4, cudaMemcpyDeviceToHost, s);
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return e;
     cudaMemsetAsync(seg_elem, 0, 4ull * n, s);
     const uint32_t rounds = (max_len + 7) / 8;
     uint32_t groups = 1;
-    for (uint32_t r = 0; r < rounds && groups < n; ++r) {
+    const uint32_t r0 = lcp / 8;   // bytes [0, 8 r0) are the same in every name: those rounds would leave one group
+    for (uint32_t r = r0; r < rounds && groups < n; ++r) {
       k_name_chunk<<<g, 256, 0, s>>>(data, c.rec_off, c.l_read_name, va, r, k64a, n);
       sort64();
-      if (r) {   // back into the groups of the previous rounds (stable, so the chunk order survives inside each)
+      if (r > r0) {   // back into the groups of the previous rounds (stable, so the chunk order survives inside each)
         k_gather_key<uint32_t, uint32_t><<<g, 256, 0, s>>>(seg_elem, va, k32a, n);
         int bits = 1;
         while (bits < 32 && (1u << bits) < groups) ++bits;
@@ -274,15 +301,15 @@ cudaError_t sort_permutation(const uint8_t* data, const ColumnsDev& c, uint64_t 
 // out_off[0..n] = exclusive scan of the body lengths in sorted order; bodies copied to out back to back.
 // `scratch` as above (only the front is used).  *total_bytes is read back (synchronises).
 cudaError_t gather_sorted_bodies(const uint8_t* data, const ColumnsDev& c, const uint32_t* perm, uint64_t n64, void* scratch,
-                                 uint64_t* out_off, uint8_t* out, cudaStream_t s) {
+                                 uint64_t* out_off, uint8_t* out, uint32_t prefix, cudaStream_t s) {
   const uint32_t n = (uint32_t)n64;
   if (n == 0) return cudaSuccess;
-  k_gather_bodies<<<148 * 8, 256, 0, s>>>(data, c.rec_off, c.rec_len, perm, out_off, out, n);
+  k_gather_bodies<<<148 * 8, 256, 0, s>>>(data, c.rec_off, c.rec_len, perm, out_off, out, n, prefix);
   return cudaGetLastError();
 }
 
 cudaError_t sorted_offsets(const ColumnsDev& c, const uint32_t* perm, uint64_t n64, void* scratch, uint64_t* out_off, uint64_t* total,
-                           cudaStream_t s) {
+                           uint32_t prefix, cudaStream_t s) {
   const uint32_t n = (uint32_t)n64;
   *total = 0;
   if (n == 0) return cudaMemsetAsync(out_off, 0, 8, s);
@@ -292,7 +319,7 @@ cudaError_t sorted_offsets(const ColumnsDev& c, const uint32_t* perm, uint64_t n
   for (int k = 0; k < 6; ++k) cv.take<uint32_t>(n + 1);
   void* tmp = cv.p + cv.used;
   size_t tmp_bytes = cub_temp_bytes(n);
-  k_perm_len<<<blocks_for(n), 256, 0, s>>>(c.rec_len, perm, len64, n);
+  k_perm_len<<<blocks_for(n), 256, 0, s>>>(c.rec_len, perm, len64, n, prefix);
   cudaMemsetAsync(len64 + n, 0, 8, s);
   cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (const uint64_t*)len64, out_off, (int)n + 1, s);
   cudaMemcpyAsync(total, out_off + n, 8, cudaMemcpyDeviceToHost, s);

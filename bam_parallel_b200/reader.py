@@ -344,6 +344,23 @@ class Engine:
     def edge_exchange(self, step: int, cuda_stream=None):
         self._eck(self._L.bamgpu_engine_edge_exchange(self._h, step, cuda_stream))
 
+    def bgzf_store(self, data, eof_marker: bool = True) -> bytes:
+        """bamgpu_engine_bgzf_store: `data` (bytes-like, uploaded here) wrapped into stored-block BGZF; returns the BGZF bytes."""
+        arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        d_src = self.upload(arr)
+        bound = self._L.bamgpu_bgzf_bound(arr.size)
+        d_out = self._L.bamgpu_device_alloc(self._h, bound)
+        try:
+            n = C.c_size_t()
+            self._eck(self._L.bamgpu_engine_bgzf_store(self._h, d_src, arr.size, d_out, bound, C.byref(n), int(eof_marker), None))
+            out = np.empty(n.value, dtype=np.uint8)
+            if n.value:
+                self._eck(self._L.bamgpu_memcpy_d2h(self._h, out.ctypes.data, d_out, n.value))
+            return out.tobytes()
+        finally:
+            self._L.bamgpu_device_free(self._h, d_out)
+            self.free(d_src)
+
     def set_n_ref(self, n_ref: int):
         """Optional hint (header n_ref) for K3's guess of record starts; results never depend on it."""
         self._L.bamgpu_engine_set_n_ref(self._h, n_ref)

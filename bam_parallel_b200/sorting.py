@@ -32,7 +32,7 @@ class SortBy(enum.IntEnum):
 
 def sort_bam(mem_limit: int, reader, sorted_sink, tmp_dir=None, out_compr_level: int = 0, reader_thread_num: int = 5,
              temp_files_mode=None, index_file_to_create=None, sort_by: SortBy = SortBy.CoordinatesAndStrand,
-             bam_file_size: Optional[int] = None, *, device: int = -1, flags: int = 0) -> dict:
+             bam_file_size: Optional[int] = None, *, device: int = -1, flags: int = 0, output: str = "bodies") -> dict:
     """Sorts the BAM read from `reader` (bytes-like, or an object with read()/readinto()) and writes the sorted record
     bodies to `sorted_sink` (an object with write()).  Returns the stage times (bamgpu_stats)."""
     if index_file_to_create is not None:
@@ -69,7 +69,10 @@ def sort_bam(mem_limit: int, reader, sorted_sink, tmp_dir=None, out_compr_level:
             return -1
 
     rcb, wcb = _lib.READ_FN(_read), _lib.WRITE_FN(_write)
-    opts, st = make_opts(device, flags), Stats()
+    # output: "bodies" = the reference's (sort.rs:643); "records" = (u32 block_size, body)*, its spill wire format
+    # (sort.rs:340-347); "bam" = a complete BAM (header + sorted records in stored-block BGZF + EOF marker)
+    fmt = {"bodies": _lib.OUT_BODIES, "records": _lib.OUT_RECORDS, "bam": _lib.OUT_BAM}[output]
+    opts, st = make_opts(device, flags, sort_output=fmt), Stats()
     err = C.create_string_buffer(512)
     rc = L.bamgpu_sort_bam(rcb, None, wcb, None, reader_thread_num, int(sort_by), C.byref(opts), C.byref(st), err, len(err))
     if rc < 0:

@@ -137,6 +137,7 @@ enum {
   BAMGPU_NO_RECORDS = 16,       /* inflate (+CRC) only: no record kernel (impl Read consumers) */
   BAMGPU_COPY_OFFSETS = 64,     /* D2H only rec_off + rec_len of the columns (with BAMGPU_COPY_DATA this is all that
                                    next_rec / append_record need: the reference lends bodies, nothing else) */
+  BAMGPU_SORT_EMIT_BLOCK_SIZE = 128, /* bamgpu_engine_sort: gather (u32 block_size, body)* instead of bodies (sort.rs:340-347) */
   BAMGPU_SPECULATIVE_START = 32 /* shard-edge mode (multi-GPU): stream_start is NOT a known record start; the chain
                                    begins at the first offset >= stream_start that looks like a run of records.
                                    The caller must confirm batch.chain_start with the left-hand shard's tail_off. */
@@ -155,8 +156,16 @@ typedef struct bamgpu_opts {
    * (cudaMemcpyPeerAsync).  n_devices == 0: one GPU (`device`). */
   int32_t n_devices;
   int32_t devices[BAMGPU_MAX_DEVICES];
-  int32_t reserved;
+  int32_t sort_output;          /* bamgpu_sort_bam: BAMGPU_OUT_* (0 = the reference's output) */
 } bamgpu_opts;
+
+/* What bamgpu_sort_bam writes to the sink. */
+enum {
+  BAMGPU_OUT_BODIES = 0,   /* record bodies back to back: the reference's output (sort.rs:643, README.md:5) */
+  BAMGPU_OUT_RECORDS = 1,  /* (u32 block_size, body)*: the reference's spill wire format (sort.rs:340-347) = a BAM record stream */
+  BAMGPU_OUT_BAM = 2       /* a complete BAM file: "BAM\1" + the input's header + the sorted records, in BGZF blocks whose payload is
+                              one stored DEFLATE block (0xff00 bytes, CRC32 + ISIZE footers), + the EOF marker - `samtools view -u` style */
+};
 
 /* Per-stage device times (CUDA events on the engine's stream) and counters, cumulative. */
 typedef struct bamgpu_stats {
@@ -164,6 +173,7 @@ typedef struct bamgpu_stats {
   double ms_h2d, ms_inflate, ms_crc, ms_records, ms_d2h, ms_total;
   double ms_sort, ms_gather;      /* bamgpu_engine_sort: key sort / body gather */
   uint64_t p2p_bytes;             /* bytes moved between GPUs (batch-edge records, shard halos) */
+  double ms_bgzf_write;           /* bamgpu_engine_bgzf_store: CRC + framing */
 } bamgpu_stats;
 
 /* ------------------------------------------------------------------------------------------
@@ -332,6 +342,13 @@ typedef int (*bamgpu_write_fn)(void* ctx, const uint8_t* src, size_t len);
 int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write_fn write, void* write_ctx, size_t reader_thread_num,
                     int sort_by, const bamgpu_opts* opts /*nullable*/, bamgpu_stats* stats /*nullable*/,
                     char* err_buf /*nullable*/, size_t err_cap);
+
+/* BGZF writer with stored DEFLATE blocks: wraps `len` bytes of device memory (a BAM byte stream) into BGZF
+ * blocks of 0xff00 payload bytes with CRC32 + ISIZE footers (gz.rs:9-20 framing), optionally followed by the 28-byte EOF
+ * marker.  d_out must hold bamgpu_bgzf_bound(len) bytes; *out_len gets the bytes written.  Synchronises. */
+size_t bamgpu_bgzf_bound(size_t len);
+int bamgpu_engine_bgzf_store(bamgpu_engine*, const uint8_t* d_src, size_t len, uint8_t* d_out, size_t out_cap, size_t* out_len,
+                             int eof_marker, void* cuda_stream);
 
 const char* bamgpu_status_str(int status);
 /* "sm_100a;<build id>" — lets callers assert the CUDA library (not a fallback) is loaded. */
