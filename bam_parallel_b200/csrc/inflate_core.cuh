@@ -775,7 +775,17 @@ struct Decoder {
 #endif
     if (state == ST_DECODE) {
       Tok t;
+#if BG_DIAG_NULL_DECODER   // diagnostic only (wrong output): a fixed token mix without any Huffman work -> the copiers' own pace
+      {
+        const uint32_t left = isize - produced, k = head & 7u;
+        t.lits = 0x41424344u; t.nlit = (k & 1u) ? 1u : ((k & 2u) ? 0u : 3u); t.len = 0; t.dist = 0; t.kind = 4;
+        if (k != 5u) { t.kind = 1; t.len = 3u + ((head * 7u) & 15u); t.dist = 8u + (((head * 2654435761u) >> 17) & 0x7ff0u); }
+        if (t.dist > produced + t.nlit) { t.kind = 4; t.nlit = 3; }
+        if (t.nlit + (t.kind == 1 ? t.len : 0u) >= left) { t.kind = 2; t.nlit = left > 4u ? 4u : left; if (t.nlit < left) t.kind = 4; }
+      }
+#else
       decode_token(t);
+#endif
       uint32_t w0 = (t.lits & 0xffffffu) | (t.nlit << 24), w1 = (t.lits >> 24) << 23;
       uint32_t np = produced + t.nlit, bad = 0;
       bool any = t.nlit != 0;
@@ -1018,6 +1028,17 @@ struct Copier {
   // One trip: finish the pending copy step; take the token (w0, w1) the caller peeked (`have`; never after TK_DONE)
   // unless the copy is still not done; request the source words of what is pending.
   BG_HD void trip(const InflateJob& job, bool have, uint32_t w0, uint32_t w1) {
+#if BG_DIAG_NULL_COPIER   // diagnostic only (wrong output): take tokens, move no bytes -> the decoders' own pace
+    if (have) {
+      tail += 1;
+      ring.set_tail(tail);
+      const uint32_t kind = (w0 >> 27) & 7u;
+      if (kind == TK_BEGIN) blk = w1;
+      else if (kind == TK_END) job.status[blk] = w1;
+      else if (kind == TK_DONE) done = 1;
+    }
+    return;
+#endif
     complete_copy();
     if (have && p_len == 0) {
       tail += 1;
