@@ -104,6 +104,19 @@ class Sorted(C.Structure):
                 ("bodies", C.c_void_p), ("h_perm", C.c_void_p), ("h_bodies", C.c_void_p)]
 
 
+FIELD_CIGAR, FIELD_SEQ, FIELD_QUAL = 1, 2, 4       # bamgpu_engine_decode_fields
+
+
+class Field(C.Structure):
+    _fields_ = [("total", C.c_uint64), ("bad", C.c_uint64), ("off", C.c_void_p), ("bytes", C.c_void_p), ("h_off", C.c_void_p),
+                ("h_bytes", C.c_void_p)]
+
+
+class Fields(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("cigar", Field), ("seq", Field), ("qual", Field), ("ms_measure", C.c_double),
+                ("ms_decode", C.c_double)]
+
+
 READ_FN = C.CFUNCTYPE(C.c_long, C.c_void_p, C.POINTER(C.c_uint8), C.c_size_t)
 WRITE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint8), C.c_size_t)
 REFSEQ_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p)
@@ -119,7 +132,7 @@ EXPORTS = [
     "bamgpu_parse_reference_sequences", "bamgpu_status_str", "bamgpu_build_info", "bamgpu_engine_sort", "bamgpu_sort_bam",
     "bamgpu_engine_digest", "bamgpu_engine_sorted_digest", "bamgpu_reader_current_engine", "bamgpu_engine_edge_open",
     "bamgpu_engine_edge_connect", "bamgpu_engine_edge_exchange", "bamgpu_engine_edge_close", "bamgpu_bgzf_bound",
-    "bamgpu_engine_bgzf_store",
+    "bamgpu_engine_bgzf_store", "bamgpu_engine_decode_fields", "bamgpu_engine_field_digest",
 ]
 
 _lib = None
@@ -211,6 +224,10 @@ def load() -> C.CDLL:
     L.bamgpu_bgzf_bound.argtypes = [sz]
     L.bamgpu_engine_bgzf_store.restype = C.c_int
     L.bamgpu_engine_bgzf_store.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), C.c_int, vp]
+    L.bamgpu_engine_decode_fields.restype = C.c_int
+    L.bamgpu_engine_decode_fields.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.POINTER(Fields)]
+    L.bamgpu_engine_field_digest.restype = C.c_int
+    L.bamgpu_engine_field_digest.argtypes = [vp, C.c_uint32, vp, C.POINTER(Digest)]
     L.bamgpu_engine_edge_close.restype = None
     L.bamgpu_engine_edge_close.argtypes = [vp]
     _lib = L

@@ -116,4 +116,10 @@ void launch_digest_sorted(const uint8_t* bodies, const uint64_t* body_off, const
   k_digest_bodies<<<num_sms * 8, 256, 0, s>>>(bodies, body_off, nullptr, n, 0, acc);
 }
 
+void launch_digest_ragged(const uint8_t* bytes, const uint64_t* off, uint64_t n, unsigned long long* acc, int num_sms, cudaStream_t s) {
+  cudaMemsetAsync(acc, 0, 32, s);
+  if (n == 0) return;
+  k_digest_bodies<<<num_sms * 8, 256, 0, s>>>(bytes, off, nullptr, n, 0, acc);
+}
+
 }  // namespace bamgpu

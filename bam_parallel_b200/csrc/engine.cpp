@@ -270,6 +270,12 @@ struct bamgpu_engine {
   };
   Mirror mir[2];
   int msel = 0;
+  // variable-length field decode (bamgpu_engine_decode_fields)
+  DevBuf d_fscr, d_fout[3];
+  PinBuf h_foff[3], h_fout[3];
+  FieldsDev fields{};
+  uint64_t fields_n = 0, fields_total[3] = {0, 0, 0};
+  uint32_t fields_which = 0;
   // sort (bamgpu_engine_sort)
   DevBuf d_sort, d_perm, d_soff, d_sorted;
   PinBuf h_sorted, h_perm;
@@ -450,6 +456,8 @@ extern "C" void bamgpu_engine_free(bamgpu_engine* E) {
   // the sort's scratch, permutation, offsets and gathered bodies (round 1 leaked these: ~18.7 GB per 50M-record sort)
   E->d_bgzf.release(); E->d_bgzf_crc.release();
   E->d_sort.release(); E->d_perm.release(); E->d_soff.release(); E->d_sorted.release(); E->h_sorted.release(); E->h_perm.release();
+  E->d_fscr.release();
+  for (int k = 0; k < 3; ++k) { E->d_fout[k].release(); E->h_foff[k].release(); E->h_fout[k].release(); }
   delete E;
 }
 
@@ -481,7 +489,6 @@ extern "C" int bamgpu_memcpy_d2h(bamgpu_engine* E, void* dst, const void* src, s
 
 namespace {
 
-size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Carves the SoA columns out of one allocation.
 void carve_columns(uint8_t* base, uint64_t cap, ColumnsDev& c) {
@@ -890,6 +897,7 @@ static int engine_records(bamgpu_engine* E, uint64_t start, int final, uint32_t 
   E->last_bad_flags = bad_flags;
   E->last_flags = flags;
   E->last_valid = !(flags & BAMGPU_NO_RECORDS);
+  E->fields_which = 0;   // decoded fields belong to the previous batch
   E->sorted_valid = false;
   fill_public_columns(M.cols, out->dev);
   // host mirrors: on their own stream, behind the record kernels
@@ -1047,6 +1055,73 @@ extern "C" int bamgpu_engine_sort(bamgpu_engine* E, int sort_by, uint32_t flags,
   return BAMGPU_OK;
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Variable-length field decode (csrc/fields.cu; record/bamrawrecord.rs:126-157,208-273).
+// -------------------------------------------------------------------------------------------------
+extern "C" int bamgpu_engine_decode_fields(bamgpu_engine* E, uint32_t which, uint32_t flags, void* cuda_stream, bamgpu_fields* out) {
+  if (!E || !out || !(which & 7u) || (which & ~7u)) return BAMGPU_ERR_ARG;
+  memset(out, 0, sizeof *out);
+  if (!E->last_valid) { E->err = "decode_fields: no decoded batch on this engine"; return BAMGPU_ERR_STATE; }
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : E->stream;
+  ECK(cudaSetDevice(E->device));
+  { int w = engine_wait_d2h(E); if (w < 0) return w; }
+  const uint64_t n = E->last_n;
+  if (n >= (1ull << 31)) { E->err = "decode_fields: more than 2^31 records in one batch"; return BAMGPU_ERR_TOO_LARGE; }
+  E->fields_which = 0;
+  ECK(E->d_fscr.reserve(fields_scratch_bytes(n)));
+  unsigned long long* d_bad = (unsigned long long*)(E->d_misc.as<uint8_t>() + 4096 + 64);
+  uint64_t totals[3], bad[3];
+  ECK(cudaEventRecord(E->ev[3], s));
+  ECK(fields_measure(E->out_ptr(), E->mir[E->msel].cols, n, which, E->d_fscr.p, &E->fields, d_bad, totals, bad, E->num_sms, s));
+  ECK(cudaEventRecord(E->ev[4], s));
+  for (int k = 0; k < 3; ++k) {
+    E->fields_total[k] = totals[k];
+    if (which & (1u << k)) { ECK(E->d_fout[k].reserve(totals[k] + 64)); E->fields.out[k] = E->d_fout[k].as<uint8_t>(); }
+  }
+  launch_fields_decode(E->out_ptr(), E->mir[E->msel].cols, n, which, E->fields, E->num_sms, s);
+  ECK(cudaEventRecord(E->ev[5], s));
+  bamgpu_field* fo[3] = {&out->cigar, &out->seq, &out->qual};
+  for (int k = 0; k < 3; ++k) {
+    if (!(which & (1u << k))) continue;
+    fo[k]->total = totals[k];
+    fo[k]->bad = bad[k];
+    fo[k]->off = E->fields.off[k];
+    fo[k]->bytes = E->fields.out[k];
+    if (flags & BAMGPU_COPY_DATA) {
+      ECK(E->h_foff[k].reserve(8 * (n + 1)));
+      ECK(cudaMemcpyAsync(E->h_foff[k].p, E->fields.off[k], 8 * (n + 1), cudaMemcpyDeviceToHost, s));
+      fo[k]->h_off = E->h_foff[k].as<uint64_t>();
+      ECK(E->h_fout[k].reserve(totals[k] + 1));
+      if (totals[k]) ECK(cudaMemcpyAsync(E->h_fout[k].p, E->fields.out[k], totals[k], cudaMemcpyDeviceToHost, s));
+      fo[k]->h_bytes = E->h_fout[k].as<uint8_t>();
+    }
+  }
+  ECK(cudaStreamSynchronize(s));
+  ECK(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, E->ev[3], E->ev[4]); out->ms_measure = ms;
+  cudaEventElapsedTime(&ms, E->ev[4], E->ev[5]); out->ms_decode = ms;
+  out->n_records = n;
+  E->fields_n = n;
+  E->fields_which = which;
+  E->stats.kernel_launches += n ? 2 + __builtin_popcount(which) : 0;
+  return BAMGPU_OK;
+}
+
+static int engine_read_digest(bamgpu_engine* E, cudaStream_t s, uint64_t n, bamgpu_digest* out);
+extern "C" int bamgpu_engine_field_digest(bamgpu_engine* E, uint32_t field, void* cuda_stream, bamgpu_digest* out) {
+  if (!E || !out || (field != 1 && field != 2 && field != 4)) return BAMGPU_ERR_ARG;
+  if (!(E->fields_which & field)) { E->err = "field_digest: that field has not been decoded on this engine"; return BAMGPU_ERR_STATE; }
+  const int k = field == 1 ? 0 : (field == 2 ? 1 : 2);
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : E->stream;
+  ECK(cudaSetDevice(E->device));
+  launch_digest_ragged(E->fields.out[k], E->fields.off[k], E->fields_n, (unsigned long long*)(E->d_misc.as<uint8_t>() + 4096), E->num_sms, s);
+  E->stats.kernel_launches += E->fields_n ? 1 : 0;
+  const int rc = engine_read_digest(E, s, E->fields_n, out);
+  out->body_bytes = E->fields_total[k];
+  return rc;
+}
 
 // -------------------------------------------------------------------------------------------------
 // Digests (csrc/digest.cu): size-independent parity checks (DIGEST SPEC).

@@ -6,6 +6,8 @@
 
 namespace bamgpu {
 
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
 // Device-side view of the BGZF block table of one batch (structure of arrays).
 struct BlockTableDev {
   const uint64_t* in_off;   // payload offset in the compressed buffer
@@ -123,12 +125,30 @@ void launch_tile_emit(const RecordParams& p, const TileArrays& t, uint64_t* rec_
 void launch_extract(const RecordParams& p, const ColumnsDev& c, uint64_t n_records, bool want_hi,
                     ChainResult* d_result, bool dev_count, cudaStream_t s);
 
+// ---- K5: variable-length field decode (fields.cu) ---------------------------------------------------
+// Field k = 0 CIGAR string, 1 sequence string, 2 raw quality bytes (bit 1 << k of `which` = BAMGPU_FIELD_*).
+constexpr uint32_t BAMGPU_FIELD_CIGAR_BIT = 1, BAMGPU_FIELD_SEQ_BIT = 2, BAMGPU_FIELD_QUAL_BIT = 4;
+struct FieldsDev {
+  uint64_t* off[3];       // n + 1 offsets per field (lengths before the scan)
+  uint8_t* out[3];        // the decoded bytes
+  uint32_t* cig_src;      // body-relative offset of the record's CIGAR bytes (the field, or the CG tag's value)
+  uint32_t* cig_nbytes;
+  uint8_t* flags;         // per record: bit k set = the reference would panic decoding field k (output empty)
+};
+size_t fields_scratch_bytes(uint64_t n);
+cudaError_t fields_measure(const uint8_t* data, const struct ColumnsDev& c, uint64_t n, uint32_t which, void* scratch, FieldsDev* f,
+                           unsigned long long* d_bad, uint64_t* totals, uint64_t* bad, int num_sms, cudaStream_t s);   // synchronises
+void launch_fields_decode(const uint8_t* data, const struct ColumnsDev& c, uint64_t n, uint32_t which, const FieldsDev& f, int num_sms,
+                          cudaStream_t s);
+
 // ---- digests of the decode / sort outputs (digest.cu; DIGEST SPEC in DESIGN.md) ---------------------
 // acc: 4 x u64 in device memory {n_records (unused), body_bytes, fields | perm, bodies}
 void launch_digest_records(const uint8_t* data, const ColumnsDev& c, uint64_t n, uint64_t index_base, uint64_t stream_base,
                            unsigned long long* acc, int num_sms, cudaStream_t s);
 void launch_digest_sorted(const uint8_t* bodies, const uint64_t* body_off, const uint32_t* perm, uint64_t n,
                           unsigned long long* acc, int num_sms, cudaStream_t s);
+// bodies-digest of any ragged byte array (n + 1 offsets): K5's decoded fields
+void launch_digest_ragged(const uint8_t* bytes, const uint64_t* off, uint64_t n, unsigned long long* acc, int num_sms, cudaStream_t s);
 
 // ---- shard-edge flags in peer memory (edge.cu) -----------------------------------------------------------------
 // Spins (with a time-out) until *flag >= want; on time-out sets *timed_out = 1 and returns.

@@ -26,6 +26,7 @@
 #include <cooperative_groups.h>
 
 #include "kernels.h"
+#include "tags.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -336,22 +337,7 @@ __global__ void __launch_bounds__(256) k3_tile_emit(RecordParams p, TileArrays t
   }
 }
 
-// ---- HI tag: record/tags.rs:62-129 through bamrawrecord.rs:80-104 (u8-wrapping offset) -------------
-__device__ __forceinline__ int tag_size(uint8_t c) {
-  switch (c) {
-    case 'C': case 'c': case 'A': return 1;
-    case 'S': case 's': return 2;
-    case 'I': case 'i': case 'f': return 4;
-    default: return -1;
-  }
-}
-__device__ __forceinline__ bool tag_type_ok(uint8_t c) {
-  switch (c) {
-    case 'A': case 'B': case 'C': case 'c': case 'f': case 'H': case 'i': case 'I': case 'S': case 's': case 'Z': return true;
-    default: return false;
-  }
-}
-
+// ---- HI tag: record/tags.rs:113-129 (walk: tags.cuh) through bamrawrecord.rs:80-104 (u8-wrapping offset) -------------
 // returns 0 none, 1 found (value in *val), 2 = the reference would panic
 __device__ int hit_count(const uint8_t* body, uint32_t len, int32_t* val) {
   uint32_t l_name = body[8];
@@ -360,47 +346,19 @@ __device__ int hit_count(const uint8_t* body, uint32_t len, int32_t* val) {
   uint32_t l_seq = body[16] | (body[17] << 8) | (body[18] << 16) | ((uint32_t)body[19] << 24);
   uint64_t tags = (uint64_t)cig + 4ull * n_cig + (uint64_t)((l_seq + 1u) / 2u) + l_seq;
   if (tags > len) return 2;
-  const uint8_t* data = body + tags;
-  uint64_t n = len - tags, idx = 0;
-  while (idx < n) {
-    if (idx + 2 > n) return 2;
-    const uint8_t* d = data + idx + 2;
-    uint64_t dl = n - idx - 2;
-    if (dl < 1) return 2;
-    uint8_t ty = d[0];
-    if (!tag_type_ok(ty)) return 2;
-    const uint8_t* v;
-    uint64_t used;
-    if (ty == 'B') {
-      if (dl < 2 || !tag_type_ok(d[1])) return 2;
-      int isz = tag_size(d[1]);
-      if (isz < 0 || dl < 6) return 2;
-      uint64_t cnt = d[2] | (d[3] << 8) | (d[4] << 16) | ((uint64_t)d[5] << 24);
-      uint64_t bytes = cnt * (uint64_t)isz;
-      if (dl < 6 + bytes) return 2;
-      v = d + 6; used = 6 + bytes;
-    } else if (ty == 'Z' || ty == 'H') {
-      uint64_t i = 1;
-      for (;;) { if (i >= dl) return 2; if (d[i] == 0) break; ++i; }
-      v = d + 1; used = i + 1;
-    } else {
-      int isz = tag_size(ty);
-      if (dl < 1 + (uint64_t)isz) return 2;
-      v = d + 1; used = 1 + isz;
-    }
-    if (data[idx] == 'H' && data[idx + 1] == 'I') {
-      switch (ty) {
-        case 'A': case 'C': *val = (int32_t)v[0]; return 1;
-        case 'c': *val = (int32_t)(int8_t)v[0]; return 1;
-        case 's': *val = (int32_t)(int16_t)(v[0] | (v[1] << 8)); return 1;
-        case 'S': *val = (int32_t)(v[0] | (v[1] << 8)); return 1;
-        case 'i': case 'I': *val = (int32_t)(v[0] | (v[1] << 8) | (v[2] << 16) | ((uint32_t)v[3] << 24)); return 1;
-        default: return 2;  // tags.rs:127 panic
-      }
-    }
-    idx += 2 + used;
+  uint64_t vo, vl;
+  uint8_t ty;
+  const int rc = tag_find(body + tags, len - tags, 'H', 'I', &vo, &vl, &ty);
+  if (rc != 1) return rc;
+  const uint8_t* v = body + tags + vo;
+  switch (ty) {
+    case 'A': case 'C': *val = (int32_t)v[0]; return 1;
+    case 'c': *val = (int32_t)(int8_t)v[0]; return 1;
+    case 's': *val = (int32_t)(int16_t)(v[0] | (v[1] << 8)); return 1;
+    case 'S': *val = (int32_t)(v[0] | (v[1] << 8)); return 1;
+    case 'i': case 'I': *val = (int32_t)(v[0] | (v[1] << 8) | (v[2] << 16) | ((uint32_t)v[3] << 24)); return 1;
+    default: return 2;  // tags.rs:127 panic
   }
-  return 0;
 }
 
 // `n` is the record count when the host knows it; with dev_count the kernel is launched for `n` = the columns' capacity

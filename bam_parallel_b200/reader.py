@@ -330,6 +330,34 @@ class Engine:
         r["perm"] = r.pop("fields")
         return r
 
+    def decode_fields(self, which: int = 7, flags: int = COPY_DATA, cuda_stream=None) -> dict:
+        """bamgpu_engine_decode_fields: CIGAR strings (decode_cigar over get_cigar, bamrawrecord.rs:126-157,223-236), sequence
+        strings (decode_seq, :259-270) and raw qualities (:99) of the last decoded batch.  Returns {"cigar"|"seq"|"qual":
+        {"off": uint64 numpy n+1 (host, with COPY_DATA), "bytes": uint8 numpy, "total", "bad"}, "n_records", "ms_measure", "ms_decode"}."""
+        from ._lib import Fields
+        f = Fields()
+        self._eck(self._L.bamgpu_engine_decode_fields(self._h, which, flags, cuda_stream, C.byref(f)))
+        n = int(f.n_records)
+        out = {"n_records": n, "ms_measure": f.ms_measure, "ms_decode": f.ms_decode}
+        for k, name in ((1, "cigar"), (2, "seq"), (4, "qual")):
+            if not which & k:
+                continue
+            fl = getattr(f, name)
+            d = {"total": int(fl.total), "bad": int(fl.bad), "off": None, "bytes": None}
+            if flags & COPY_DATA:
+                d["off"] = _view(fl.h_off, n + 1, C.c_uint64)
+                d["bytes"] = _view(fl.h_bytes, int(fl.total), C.c_uint8) if fl.total else np.zeros(0, np.uint8)
+            out[name] = d
+        return out
+
+    def field_digest(self, field: int, cuda_stream=None) -> dict:
+        """bodies-digest (DIGEST SPEC) of one field decode_fields produced, computed on the device."""
+        d = Digest()
+        self._eck(self._L.bamgpu_engine_field_digest(self._h, field, cuda_stream, C.byref(d)))
+        r = d.asdict()
+        r.pop("fields")
+        return r
+
     # ---- shard-edge exchange over peer memory (bamgpu_engine_edge_*) ----
     def edge_open(self) -> bytes:
         h = EdgeHandle()

@@ -253,6 +253,38 @@ int bamgpu_engine_sorted_digest(bamgpu_engine*, void* cuda_stream, bamgpu_digest
 /* The engine that holds the batch bamgpu_next_batch returned last (for bamgpu_engine_digest / _sort on Reader batches). */
 bamgpu_engine* bamgpu_reader_current_engine(bamgpu_reader*);
 
+/* ---- Variable-length fields of the batch the engine decoded last, decoded like the reference's accessors:
+ *   BAMGPU_FIELD_CIGAR  decode_cigar(get_bytes(RawCigar))   record/bamrawrecord.rs:223-236 over get_cigar :126-157:
+ *                       "<len><op>" per operation ("" for refID < 0, pos < 0 or n_cigar_op == 0); a two-operation CIGAR whose
+ *                       first operation is `<x>S` with x == (l_seq + 1) / 2 (sic: the reference compares with the packed
+ *                       sequence's BYTE length) is replaced by the value of the CG tag if there is one;
+ *   BAMGPU_FIELD_SEQ    decode_seq(get_bytes(RawSequence))  :259-270: "=ACMGRSVTWYHKDBN"[nibble]; every low nibble equal to 0
+ *                       is dropped (the reference's stated assumption), not only the padding of an odd-length read;
+ *   BAMGPU_FIELD_QUAL   get_bytes(RawQual)                  :99: the l_seq raw phred bytes.
+ * Each field comes back as n_records + 1 offsets and the concatenated bytes, in device memory; with BAMGPU_COPY_DATA also in
+ * pinned host memory (h_*).  Records for which the reference would panic (slice beyond the record, CIGAR bytes not a multiple
+ * of 4, operation code > 8, malformed tag in front of CG) get an empty field and are counted in bad[].  Offsets use the
+ * get_bytes closures' u8 arithmetic (`32 + l_read_name` wraps for l_read_name >= 224, :80-84).  Valid until the next decode or
+ * decode_fields call on the engine.  Synchronises. */
+enum { BAMGPU_FIELD_CIGAR = 1, BAMGPU_FIELD_SEQ = 2, BAMGPU_FIELD_QUAL = 4 };
+typedef struct bamgpu_field {
+  uint64_t total;               /* bytes in `bytes` */
+  uint64_t bad;                 /* records whose field the reference would panic on (empty here) */
+  const uint64_t* off;          /* device: n_records + 1 offsets */
+  const uint8_t* bytes;         /* device */
+  const uint64_t* h_off;        /* pinned host mirrors (BAMGPU_COPY_DATA), else NULL */
+  const uint8_t* h_bytes;
+} bamgpu_field;
+typedef struct bamgpu_fields {
+  uint64_t n_records;
+  bamgpu_field cigar, seq, qual;
+  double ms_measure, ms_decode;  /* device time of the two passes */
+} bamgpu_fields;
+int bamgpu_engine_decode_fields(bamgpu_engine*, uint32_t which /* BAMGPU_FIELD_* */, uint32_t flags /* BAMGPU_COPY_DATA */,
+                                void* cuda_stream, bamgpu_fields* out);
+/* bodies-digest (DIGEST SPEC) of one decoded field: n_records, body_bytes = total, bodies = sum_i mix64(h_body(field_i) + i * K). */
+int bamgpu_engine_field_digest(bamgpu_engine*, uint32_t field /* one BAMGPU_FIELD_* bit */, void* cuda_stream, bamgpu_digest* out);
+
 /* Number of reference sequences of the BAM header (n_ref), if the caller knows it: tightens the guess of record
  * starts inside K3 (refID must be in [-1, n_ref)).  Results never depend on it.  < 0 = unknown (default). */
 void bamgpu_engine_set_n_ref(bamgpu_engine*, int32_t n_ref);

@@ -22,6 +22,7 @@
 #define _GNU_SOURCE
 #include <pthread.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -734,6 +735,116 @@ int orc_cpu_reader_run(const uint8_t* file, size_t n, int threads, uint64_t max_
 uint32_t orc_crc32(const uint8_t* p, size_t n) { return (uint32_t)crc32(crc32(0, NULL, 0), p, (uInt)n); }
 
 /* =====================================================================================================
+ * Variable-length field decode: record/bamrawrecord.rs:80-104 get_bytes, :126-157 get_cigar,
+ * :208-236 get_cig_op / decode_cigar, :238-270 get_seq_base / decode_seq.  Test infrastructure like the rest of this file.
+ * A "panic" of the reference (slice out of range, unwrap on a short chunk, unsupported op) is ORC_ERR_PANIC for that record.
+ * ===================================================================================================== */
+#define ORC_ERR_PANIC (-40)
+typedef struct { int32_t ref, pos; uint32_t n_cig, l_seq, nseq; uint64_t cig, seq, qual, tags; } var_geom;
+
+/* the closures of get_bytes (:80-84): `32 + self.l_read_name()` is u8 + u8 (wraps in a release build), the rest usize;
+ * ((l_seq + 1) / 2) is u32 arithmetic */
+static void var_geometry(const uint8_t* body, var_geom* g) {
+  g->ref = (int32_t)rd32(body); g->pos = (int32_t)rd32(body + 4);
+  g->n_cig = rd16(body + 12); g->l_seq = rd32(body + 16);
+  g->nseq = (uint32_t)(g->l_seq + 1u) / 2u;
+  g->cig = (uint8_t)(32u + body[8]);
+  g->seq = g->cig + 4ull * g->n_cig;
+  g->qual = g->seq + g->nseq;
+  g->tags = g->qual + g->l_seq;
+}
+
+/* get_cigar (:126-157) */
+static int get_cigar(const uint8_t* body, uint32_t len, const var_geom* g, const uint8_t** src, size_t* nb) {
+  *src = body; *nb = 0;
+  if (g->ref < 0 || g->pos < 0 || g->n_cig == 0) return ORC_OK;               /* return &[] */
+  size_t fb = 4 * (size_t)g->n_cig;
+  if (g->cig + fb > len) return ORC_ERR_PANIC;                                 /* get_slice */
+  *src = body + g->cig; *nb = fb;
+  uint32_t first = rd32(body + g->cig);                                        /* &cigar_field_data[..4] */
+  if ((first & 0xf) != 4 || (size_t)(first >> 4) != (size_t)g->nseq || g->n_cig != 2) return ORC_OK;
+  if (g->tags > len) return ORC_ERR_PANIC;                                     /* self.0.len() - get_tags_offset() */
+  const uint8_t* v; uint8_t t;
+  size_t tl = (size_t)(len - g->tags);
+  int rc = get_tag(body + g->tags, tl, "CG", &v, &t);
+  if (rc < 0) return ORC_ERR_PANIC;
+  if (rc == 1) {   /* tag_val.0: the value slice get_tag_data returns (tags.rs:62-93) */
+    size_t vl;
+    if (t == 'B') vl = (size_t)rd32(v - 4) * (size_t)tag_size(*(v - 5));
+    else if (t == 'Z' || t == 'H') { vl = 0; while (v[vl] != 0) ++vl; }
+    else vl = (size_t)tag_size(t);
+    *src = v; *nb = vl;
+  }
+  return ORC_OK;
+}
+
+/* decode_cigar (:223-236); dst NULL = length only */
+static long decode_cigar(const uint8_t* src, size_t nb, uint8_t* dst) {
+  static const char OPS[] = "MIDNSHP=X";
+  long o = 0;
+  for (size_t i = 0; i < nb; i += 4) {
+    if (nb - i < 4) return ORC_ERR_PANIC;              /* slice.read_u32().unwrap() on a short chunk */
+    uint32_t cig = rd32(src + i), op = cig & 0xf, n = cig >> 4;
+    char tmp[16];
+    int d = snprintf(tmp, sizeof tmp, "%u", n);        /* op_len.to_string() */
+    if (op > 8) return ORC_ERR_PANIC;                  /* get_cig_op */
+    if (dst) { memcpy(dst + o, tmp, (size_t)d); dst[o + d] = (uint8_t)OPS[op]; }
+    o += d + 1;
+  }
+  return o;
+}
+
+/* decode_seq (:259-270) */
+static long decode_seq(const uint8_t* src, size_t nb, uint8_t* dst) {
+  static const char BASES[] = "=ACMGRSVTWYHKDBN";
+  long o = 0;
+  for (size_t i = 0; i < nb; ++i) {
+    uint32_t first = src[i] >> 4, second = src[i] & 0xf;
+    if (dst) dst[o] = (uint8_t)BASES[first];
+    ++o;
+    if (second != 0) { if (dst) dst[o] = (uint8_t)BASES[second]; ++o; }
+  }
+  return o;
+}
+
+/* One record's field: 1 CIGAR string, 2 sequence string, 4 raw quality bytes.  Returns its length or ORC_ERR_PANIC. */
+static long decode_one_field(const uint8_t* body, uint32_t len, int field, uint8_t* dst) {
+  if (len < 32) return ORC_ERR_PANIC;                   /* get_slice of a fixed field */
+  var_geom g;
+  var_geometry(body, &g);
+  if (field == 1) {
+    const uint8_t* src; size_t nb;
+    int rc = get_cigar(body, len, &g, &src, &nb);
+    if (rc < 0) return rc;
+    return decode_cigar(src, nb, dst);
+  }
+  if (field == 2) {
+    if (g.seq + g.nseq > len) return ORC_ERR_PANIC;
+    return decode_seq(body + g.seq, g.nseq, dst);
+  }
+  if (g.qual + g.l_seq > len) return ORC_ERR_PANIC;
+  if (dst) memcpy(dst, body + g.qual, g.l_seq);
+  return (long)g.l_seq;
+}
+
+/* All records.  Call with out == NULL first: off[0..n] gets the offsets (a panicking record contributes nothing and is
+ * counted in *bad); then again with `out` of off[n] bytes. */
+int orc_decode_field(const uint8_t* u, const uint64_t* rec_off, const uint32_t* rec_len, size_t n, int field, uint64_t* off,
+                     uint8_t* out, uint64_t* bad) {
+  uint64_t o = 0, nb = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (!out) off[i] = o;
+    long l = decode_one_field(u + rec_off[i], rec_len[i], field, NULL);
+    if (l < 0) { ++nb; continue; }
+    if (out) decode_one_field(u + rec_off[i], rec_len[i], field, out + off[i]);
+    o += (uint64_t)l;
+  }
+  if (!out) off[n] = o;
+  if (bad) *bad = nb;
+  return ORC_OK;
+}
+
+/* =====================================================================================================
  * Full-size parity helpers (tests at BASELINE.json's 50M-record sizes).  Everything below is the SAME
  * restatement as above, run on several threads, plus a digest: 64-bit hashes of every value the reader /
  * record accessors / sort produce, folded into a few words, so a GPU run over 50M records can be compared
@@ -770,7 +881,8 @@ typedef struct { uint64_t n_records, body_bytes, fields, bodies; } orc_digest_t;
 
 typedef struct {
   /* parallel-for description */
-  int kind;           /* 0 inflate, 1 extract, 2 digest, 3 sorted digest */
+  int kind;           /* 0 inflate, 1 extract, 2 digest, 3 sorted digest, 4 field digest */
+  int field;
   size_t lo, hi;
   /* inflate */
   const uint8_t* file; const orc_block* blocks; const uint64_t* uoff; uint8_t* out; int err;
@@ -826,6 +938,22 @@ static void* par_thread(void* arg) {
       d.bodies += mix64(body_hash(j->u + j->rec_off[i], j->rec_len[i]) + idx * 0x9E3779B97F4A7C15ull);
       d.body_bytes += j->rec_len[i];
     }
+    d.n_records = j->hi - j->lo;
+    j->d = d;
+  } else if (j->kind == 4) {
+    orc_digest_t d = {0, 0, 0, 0};
+    size_t cap = 1 << 16;
+    uint8_t* buf = (uint8_t*)malloc(cap);
+    for (size_t i = j->lo; i < j->hi; ++i) {
+      const uint8_t* body = j->u + j->rec_off[i];
+      long l = decode_one_field(body, j->rec_len[i], j->field, NULL);
+      if (l < 0) { l = 0; d.fields += 1; }               /* `fields` counts the panicking records here */
+      if ((size_t)l + 8 > cap) { cap = (size_t)l * 2 + 8; buf = (uint8_t*)realloc(buf, cap); }
+      if (l) decode_one_field(body, j->rec_len[i], j->field, buf);
+      d.bodies += mix64(body_hash(buf, (uint32_t)l) + (j->index_base + i) * 0x9E3779B97F4A7C15ull);
+      d.body_bytes += (uint64_t)l;
+    }
+    free(buf);
     d.n_records = j->hi - j->lo;
     j->d = d;
   } else {
@@ -929,6 +1057,23 @@ int orc_sorted_digest(const uint8_t* u, const uint64_t* rec_off, const uint32_t*
   par_job proto;
   memset(&proto, 0, sizeof proto);
   proto.kind = 3; proto.u = u; proto.rec_off = rec_off; proto.rec_len = rec_len; proto.perm = perm;
+  par_job* jobs;
+  int nt = par_run(&proto, n, threads, &jobs);
+  orc_digest_t d = {0, 0, 0, 0};
+  for (int t = 0; t < nt; ++t) { d.n_records += jobs[t].d.n_records; d.body_bytes += jobs[t].d.body_bytes; d.fields += jobs[t].d.fields; d.bodies += jobs[t].d.bodies; }
+  if (n == 0) d.n_records = 0;
+  free(jobs);
+  *out = d;
+  return ORC_OK;
+}
+
+/* bodies-digest (DIGEST SPEC) of one decoded field without materialising it: body_bytes = total length,
+ * bodies = sum_i mix64(h_body(field_i) + i * K), fields = number of records the reference would panic on. */
+int orc_field_digest(const uint8_t* u, const uint64_t* rec_off, const uint32_t* rec_len, size_t n, int field, int threads,
+                     orc_digest_t* out) {
+  par_job proto;
+  memset(&proto, 0, sizeof proto);
+  proto.kind = 4; proto.field = field; proto.u = u; proto.rec_off = rec_off; proto.rec_len = rec_len;
   par_job* jobs;
   int nt = par_run(&proto, n, threads, &jobs);
   orc_digest_t d = {0, 0, 0, 0};

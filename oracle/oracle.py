@@ -109,6 +109,10 @@ class COracle:
                                  C.c_uint64, C.c_int, C.POINTER(_Digest)]
         L.orc_sorted_digest.restype = C.c_int
         L.orc_sorted_digest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(_Digest)]
+        L.orc_decode_field.restype = C.c_int
+        L.orc_decode_field.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.orc_field_digest.restype = C.c_int
+        L.orc_field_digest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(_Digest)]
 
     # -- util.rs:18-71 + readahead.rs:145-150 over the whole file --------------------------
     def inflate_all(self, data) -> tuple[np.ndarray, np.ndarray]:
@@ -258,6 +262,25 @@ class COracle:
         r["perm"] = r.pop("fields")
         return r
 
+    # -- bamrawrecord.rs:126-157 get_cigar, :223-236 decode_cigar, :259-270 decode_seq, :99 RawQual ----------
+    def decode_field(self, u, rec_off, rec_len, field: int):
+        """field: 1 CIGAR string, 2 sequence string, 4 raw quality.  Returns (offsets u64[n+1], bytes u8[], records the
+        reference would panic on)."""
+        n = rec_off.size
+        off = np.zeros(n + 1, dtype=np.uint64)
+        bad = C.c_uint64()
+        self.lib.orc_decode_field(u.ctypes.data, rec_off.ctypes.data, rec_len.ctypes.data, n, field, off.ctypes.data, None, C.byref(bad))
+        out = np.zeros(max(int(off[n]), 1), dtype=np.uint8)
+        self.lib.orc_decode_field(u.ctypes.data, rec_off.ctypes.data, rec_len.ctypes.data, n, field, off.ctypes.data, out.ctypes.data, C.byref(bad))
+        return off, out[: int(off[n])], bad.value
+
+    def field_digest(self, u, rec_off, rec_len, field: int, threads: int) -> dict:
+        d = _Digest()
+        self.lib.orc_field_digest(u.ctypes.data, rec_off.ctypes.data, rec_len.ctypes.data, rec_off.size, field, threads, C.byref(d))
+        r = d.as_dict()
+        r["bad"] = r.pop("fields")
+        return r
+
     def crc32(self, a: np.ndarray) -> int:
         a = np.ascontiguousarray(a)
         return self.lib.orc_crc32(a.ctypes.data, a.size)
@@ -397,6 +420,65 @@ def py_hit_count(body: bytes):
     if fmt is None:
         raise OracleError(-10)
     return struct.unpack_from(fmt, val, 0)[0]
+
+
+_CIG_OPS = "MIDNSHP=X"
+_SEQ_BASES = "=ACMGRSVTWYHKDBN"
+
+
+def py_decode_field(body: bytes, field: int) -> bytes:
+    """One record's field the way the reference's accessors produce it: 1 decode_cigar(get_bytes(RawCigar))
+    (bamrawrecord.rs:223-236 over :126-157), 2 decode_seq(get_bytes(RawSequence)) (:259-270), 4 get_bytes(RawQual) (:99).
+    Raises OracleError(-40) where the reference panics."""
+    if len(body) < 32:
+        raise OracleError(-40)
+    ref, pos = struct.unpack_from("<ii", body, 0)
+    n_cig = struct.unpack_from("<H", body, 12)[0]
+    l_seq = struct.unpack_from("<I", body, 16)[0]
+    nseq = ((l_seq + 1) & 0xFFFFFFFF) // 2
+    cig = (32 + body[8]) & 0xFF                      # u8 arithmetic in the get_bytes closures (:80)
+    seq = cig + 4 * n_cig
+    qual = seq + nseq
+    tags = qual + l_seq
+    if field == 2:
+        if seq + nseq > len(body):
+            raise OracleError(-40)
+        out = []
+        for b in body[seq:seq + nseq]:
+            out.append(_SEQ_BASES[b >> 4])
+            if b & 15:
+                out.append(_SEQ_BASES[b & 15])
+        return "".join(out).encode()
+    if field == 4:
+        if qual + l_seq > len(body):
+            raise OracleError(-40)
+        return body[qual:qual + l_seq]
+    # get_cigar
+    if ref < 0 or pos < 0 or n_cig == 0:
+        data = b""
+    else:
+        if cig + 4 * n_cig > len(body):
+            raise OracleError(-40)
+        data = body[cig:cig + 4 * n_cig]
+        first = struct.unpack_from("<I", data, 0)[0]
+        if (first & 0xF) == 4 and (first >> 4) == nseq and n_cig == 2:
+            if tags > len(body):
+                raise OracleError(-40)
+            try:
+                r = py_get_tag(body[tags:], b"CG")
+            except OracleError:
+                raise OracleError(-40)
+            if r is not None:
+                data = r[0]
+    out = []
+    for i in range(0, len(data), 4):
+        if len(data) - i < 4:
+            raise OracleError(-40)
+        v = struct.unpack_from("<I", data, i)[0]
+        if (v & 15) > 8:
+            raise OracleError(-40)
+        out.append(str(v >> 4) + _CIG_OPS[v & 15])
+    return "".join(out).encode()
 
 
 def py_extract(u: bytes, offs, lens, want_hi=True):

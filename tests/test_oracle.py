@@ -324,3 +324,51 @@ def test_sorted_output_format_matches_sort_rs(oracle):
     assert oracle.sort_perm(u, off, cols, 0).tolist() == list(range(len(recs)))
     ub = u.tobytes()
     assert b"".join(ub[int(o):int(o) + int(l)] for o, l in zip(off, ln)) == b"".join(r[4:] for r in recs)
+
+
+# ---- variable-length field decode: C restatement vs the independent pure-Python one --------------------
+
+def test_field_decoders_c_vs_python(oracle):
+    from oracle.oracle import OracleError, py_decode_field
+    for shape, n in (("pe150", 1500), ("longname", 600), ("long10k", 30)):
+        data = synth.generate(shape, n, level=6, threads=2).tobytes()
+        u, _ = oracle.inflate_all(data)
+        _, _, start = oracle.read_header(u)
+        off, ln = oracle.walk_records(u, start)
+        ub = u.tobytes()
+        for field in (1, 2, 4):
+            fo, fb, bad = oracle.decode_field(u, off, ln, field)
+            assert bad == 0
+            for i in range(off.size):
+                assert fb[int(fo[i]):int(fo[i + 1])].tobytes() == py_decode_field(ub[int(off[i]):int(off[i]) + int(ln[i])], field)
+            d = oracle.field_digest(u, off, ln, field, 3)
+            want = sum(orc.py_mix64(orc.py_body_hash(fb[int(fo[i]):int(fo[i + 1])].tobytes()) + i * 0x9E3779B97F4A7C15) for i in range(off.size)) & (2 ** 64 - 1)
+            assert d["bodies"] == want and d["body_bytes"] == int(fo[-1]) and d["bad"] == 0
+
+
+def test_field_decoder_known_answers(oracle):
+    """Values worked out by hand from bamrawrecord.rs: decode_cigar :223-236, decode_seq :259-270 (zero low nibbles dropped),
+    get_cigar :126-157 (CG substitution keyed on (l_seq + 1) / 2), the u8 wrap of `32 + l_read_name` (:80)."""
+    from oracle.oracle import OracleError, py_decode_field
+    import struct as st
+
+    def rec(ref=0, pos=1, name=b"r", cigar=b"", seq=b"", l_seq=0, qual=b"", tags=b""):
+        nb = name + b"\0"
+        return st.pack("<iiBBHHHIiii", ref, pos, len(nb) & 0xFF, 0, 0, len(cigar) // 4, 0, l_seq, -1, -1, 0) + nb + cigar + seq + qual + tags
+
+    ops = lambda *o: b"".join(st.pack("<I", (n << 4) | op) for n, op in o)
+    r = rec(cigar=ops((10, 0), (2, 1), (268435455, 8)), seq=bytes([0x12, 0x40, 0x8F]), l_seq=6, qual=b"abcdef")
+    assert py_decode_field(r, 1) == b"10M2I268435455X"
+    assert py_decode_field(r, 2) == b"ACGTN"            # 0x40: the low nibble 0 is dropped although it is not padding
+    assert py_decode_field(r, 4) == b"abcdef"
+    assert py_decode_field(rec(ref=-1, cigar=ops((5, 0))), 1) == b""
+    cg = b"CGBI" + st.pack("<I", 2) + ops((7, 0), (9, 2))
+    assert py_decode_field(rec(cigar=ops((3, 4), (1, 3)), seq=b"\x11\x11\x10", l_seq=5, qual=b"!" * 5, tags=cg), 1) == b"7M9D"
+    assert py_decode_field(rec(cigar=ops((5, 4), (1, 3)), seq=b"\x11\x11\x10", l_seq=5, qual=b"!" * 5, tags=cg), 1) == b"5S1N"
+    with pytest.raises(OracleError):
+        py_decode_field(rec(cigar=ops((1, 9))), 1)
+    # the C restatement gives the same answers
+    body = rec(cigar=ops((3, 4), (1, 3)), seq=b"\x11\x11\x10", l_seq=5, qual=b"!" * 5, tags=cg)
+    u = np.frombuffer(st.pack("<I", len(body)) + body + bytes(64), dtype=np.uint8)
+    fo, fb, bad = oracle.decode_field(u, np.array([4], np.uint64), np.array([len(body)], np.uint32), 1)
+    assert fb.tobytes() == b"7M9D" and bad == 0
