@@ -454,6 +454,19 @@ def run_b200(a, rank: int, world: int, local_rank: int, host_group=None):
                              "order, sort.rs:643); parity vs the oracle in tests/test_gpu_sort.py and tests/test_gpu_fullsize.py; gather GB/s "
                              "counts bodies read + written")
 
+    # ---- K5: variable-length field decode of the same batch, reported beside the headline ----
+    fields_info = None
+    if world == 1 and not a.no_sort:
+        for rep in range(2):
+            fd = eng.decode_fields(7, 0, cuda_stream=sptr)
+        out_bytes = sum(fd[k]["total"] for k in ("cigar", "seq", "qual"))
+        ms = fd["ms_measure"] + fd["ms_decode"]
+        fields_info = {"ms_measure": round(fd["ms_measure"], 2), "ms_decode": round(fd["ms_decode"], 2), "records_per_s": a.records / (ms * 1e-3),
+                       "decoded_bytes": out_bytes, "decoded_GB_per_s": out_bytes / (ms * 1e-3) / 1e9,
+                       "bad": {k: fd[k]["bad"] for k in ("cigar", "seq", "qual")},
+                       "note": "bamgpu_engine_decode_fields on the batch just decoded: CIGAR strings (decode_cigar over get_cigar), sequence "
+                               "strings (decode_seq), raw qualities; parity vs the oracle in tests/test_gpu_fields.py and tests/test_gpu_fullsize.py"}
+
     # ---- CPU baseline (rank 0, N=1 only): the whole file, min(num_cpus, 20) threads as bam_binary's hash mode ----
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -488,7 +501,7 @@ def run_b200(a, rank: int, world: int, local_rank: int, host_group=None):
                        "generator_seconds": round(gen_s, 1), "k3_chain_repairs": chain_repairs, "p2p_bytes_per_step": p2p // max(a.steps, 1)},
             "records_per_s": n_rec_all / (ms_step * 1e-3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_with_columns": e2e_all, "e2e_columns_only": e2e_cols,
-            "e2e_next_rec": e2e_rec, "pcie_pinned_copy": pcie, "sort": sort_info, "gpu_launches": launches,
+            "e2e_next_rec": e2e_rec, "pcie_pinned_copy": pcie, "sort": sort_info, "fields": fields_info, "gpu_launches": launches,
             "verify": verify, "scaling_limiter": limiter, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

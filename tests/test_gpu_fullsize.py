@@ -23,6 +23,7 @@ pytestmark = pytest.mark.gpu
 
 SCALE = float(os.environ.get("BAMGPU_FULLSIZE_SCALE", "1.0"))
 THREADS = min(os.cpu_count() or 4, 32)
+FIELDS = {"cigar": 1, "seq": 2, "qual": 4}
 MODES = {"coord": (bp.SortBy.CoordinatesAndStrand, 0), "name": (bp.SortBy.Name, 1), "name_mates": (bp.SortBy.NameAndMatchMates, 2)}
 
 
@@ -39,6 +40,8 @@ def _oracle_side(oracle, arr, sort_modes):
     cols, bad_flags, bad_tags = oracle.extract_mt(u, off, ln, True, THREADS)
     assert bad_flags == 0 and bad_tags == 0
     out = {"start": start, "ulen": int(u.size), "decode": oracle.digest(u, off, ln, cols, THREADS)}
+    for name, fid in FIELDS.items():       # decode_cigar / decode_seq / RawQual over every record (bamrawrecord.rs:126-157,208-273)
+        out["field_" + name] = oracle.field_digest(u, off, ln, fid, THREADS)
     for m in sort_modes:
         perm = oracle.sort_perm_mt(u, off, cols, MODES[m][1], THREADS)
         out[m] = oracle.sorted_digest(u, off, ln, perm, THREADS)
@@ -59,6 +62,9 @@ def _gpu_engine_side(arr, start, sort_modes):
         batch, tail, rc = eng.decode(d, blocks, nb, start, True, bp.WANT_HI)
         assert tail == total
         out = {"decode": eng.digest(), "n": batch.n_records, "ulen": total}
+        fd = eng.decode_fields(7, 0)
+        for name, fid in FIELDS.items():
+            out["field_" + name] = dict(eng.field_digest(fid), bad=fd[name]["bad"])
         for m in sort_modes:
             eng.sort(int(MODES[m][0]), flags=0)
             out[m] = eng.sorted_digest()
@@ -92,6 +98,8 @@ def _check(oracle, shape, n, level, payload, sort_modes, reader_kw=None):
     assert got["ulen"] == ref["ulen"]
     assert got["decode"] == ref["decode"], "decode digest differs from the oracle"
     assert got["n"] == n
+    for name in FIELDS:
+        assert got["field_" + name] == ref["field_" + name], f"{name} field digest differs from the oracle"
     for m in sort_modes:
         assert got[m] == ref[m], f"{m} sort digest differs from the oracle"
     if reader_kw is not None:
