@@ -58,7 +58,7 @@ MAX_DEVICES = 16
 class Opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("batch_bytes", C.c_uint64), ("inflate_impl", C.c_int32),
                 ("jobs_per_device", C.c_int32), ("n_devices", C.c_int32), ("devices", C.c_int32 * MAX_DEVICES),
-                ("sort_output", C.c_int32)]
+                ("sort_output", C.c_int32), ("reserved0", C.c_int32), ("sort_mem_limit", C.c_uint64)]
 
 
 OUT_BODIES, OUT_RECORDS, OUT_BAM = 0, 1, 2          # bamgpu_opts.sort_output
@@ -66,9 +66,10 @@ SORT_EMIT_BLOCK_SIZE = 128
 
 
 def make_opts(device: int = -1, flags: int = 0, batch_bytes: int = 0, inflate_impl: int = 0, jobs_per_device: int = 0,
-              devices=None, sort_output: int = 0) -> Opts:
+              devices=None, sort_output: int = 0, sort_mem_limit: int = 0) -> Opts:
     o = Opts()
     o.sort_output = sort_output
+    o.sort_mem_limit = sort_mem_limit
     o.device, o.flags, o.batch_bytes, o.inflate_impl, o.jobs_per_device = device, flags, batch_bytes, inflate_impl, jobs_per_device
     devices = list(devices or [])
     if len(devices) > MAX_DEVICES:

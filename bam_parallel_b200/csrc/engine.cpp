@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -72,8 +73,20 @@ struct DevCache {
     bytes += cap;
     return true;
   }
+  // Out of device memory: hand everything parked for `dev` back to the driver (the caller retries its allocation).
+  size_t flush(int dev) {
+    std::lock_guard<std::mutex> lk(mu);
+    size_t freed = 0;
+    for (size_t i = 0; i < free_list.size();) {
+      if (free_list[i].dev == dev) { cudaFree(free_list[i].p); freed += free_list[i].cap; bytes -= free_list[i].cap; free_list.erase(free_list.begin() + i); }
+      else ++i;
+    }
+    return freed;
+  }
+  size_t parked() { std::lock_guard<std::mutex> lk(mu); return bytes; }
 };
 DevCache& dev_cache() { static DevCache* c = new DevCache(); return *c; }
+static size_t dev_cache_bytes() { return dev_cache().parked(); }
 
 struct DevBuf {
   void* p = nullptr;
@@ -87,7 +100,11 @@ struct DevBuf {
     size_t got = 0;
     if (void* q = dev_cache().take(n, dev, &got)) { p = q; cap = got; return cudaSuccess; }
     cudaError_t e = cudaMalloc(&p, want);
-    if (e == cudaSuccess) cap = want;
+    if (e == cudaErrorMemoryAllocation && dev_cache().flush(dev)) {   // parked buffers are memory too
+      cudaGetLastError();
+      e = cudaMalloc(&p, want);
+    }
+    if (e == cudaSuccess) cap = want; else p = nullptr;
     return e;
   }
   // Callers synchronise the streams that used the buffer before they release it (bamgpu_engine_free, bamgpu_reader_free).
@@ -2092,6 +2109,242 @@ extern "C" int bamgpu_parse_reference_sequences(const uint8_t* b, size_t len, ba
 // =================================================================================================
 // sort_bam (sorting/sort.rs:138-178): reader -> records -> stable sort -> bodies to the sink
 // =================================================================================================
+// -------------------------------------------------------------------------------------------------
+// Streamed sort: inputs whose inflated records do not fit in HBM (sort.rs:185-308 read_split_sort_dump_chunks +
+// :590-652 merge_sorted_chunks_and_write, i.e. what `mem_limit` is for).  The file goes through the Reader batch by batch;
+// of every batch only what the comparator looks at stays on the device — coord_key + strand, or l_read_name / flag / HI and
+// the read names packed into a compact store — while the bodies are kept in host memory (the reference writes them to chunk
+// files).  One global stable sort of the keys then gives the permutation (the result of the reference's per-chunk sorts +
+// N-way merge, ties to the lower chunk = input order), and the bodies are gathered on the host in that order.
+// -------------------------------------------------------------------------------------------------
+namespace {
+struct GrowBuf {   // device array that keeps its contents when it grows
+  DevBuf b;
+  size_t used = 0;
+  cudaError_t ensure(size_t need, cudaStream_t s) {
+    if (need <= b.cap) return cudaSuccess;
+    DevBuf nb;
+    cudaError_t e = nb.reserve(std::max(need, b.cap + b.cap / 2));
+    if (e != cudaSuccess) return e;
+    if (used) {
+      e = cudaMemcpyAsync(nb.p, b.p, used, cudaMemcpyDeviceToDevice, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) { nb.release(); return e; }
+    }
+    b.release();
+    b = nb;
+    return cudaSuccess;
+  }
+  cudaError_t append(const void* d_src, size_t bytes, cudaStream_t s) {
+    cudaError_t e = ensure(used + bytes + 64, s);
+    if (e != cudaSuccess) return e;
+    if (bytes) e = cudaMemcpyAsync((uint8_t*)b.p + used, d_src, bytes, cudaMemcpyDeviceToDevice, s);
+    used += bytes;
+    return e;
+  }
+};
+struct HostRun {   // one batch's inflated bytes and where its records are
+  uint8_t* mem = nullptr;
+  uint64_t first = 0, n = 0;
+  std::vector<uint64_t> off;
+  std::vector<uint32_t> len;
+};
+struct MemSrc { const uint8_t* p; size_t n, pos; };
+long memsrc_read(void* ctx, uint8_t* dst, size_t cap) {
+  MemSrc* m = (MemSrc*)ctx;
+  const size_t k = std::min(cap, m->n - m->pos);
+  memcpy(dst, m->p + m->pos, k);
+  m->pos += k;
+  return (long)k;
+}
+void par_memcpy(uint8_t* dst, const uint8_t* src, size_t n, size_t threads) {
+  if (n < ((size_t)8 << 20) || threads < 2) { memcpy(dst, src, n); return; }
+  threads = std::min<size_t>(threads, 16);
+  std::vector<std::thread> th;
+  for (size_t t = 0; t < threads; ++t) {
+    const size_t a = n * t / threads, b = n * (t + 1) / threads;
+    th.emplace_back([=] { memcpy(dst + a, src + a, b - a); });
+  }
+  for (auto& x : th) x.join();
+}
+}  // namespace
+
+static int sort_bam_streamed(bamgpu_read_fn read, void* read_ctx, bamgpu_write_fn write, void* write_ctx, size_t threads, int sort_by,
+                             const bamgpu_opts* opts, bamgpu_stats* stats, std::string& msg) {
+  bamgpu_opts o{};
+  if (opts) o = *opts; else o.device = -1;
+  const int out_fmt = o.sort_output;
+  if (out_fmt < BAMGPU_OUT_BODIES || out_fmt > BAMGPU_OUT_BAM) { msg = "unknown sort_output"; return BAMGPU_ERR_ARG; }
+  o.n_devices = 0;
+  o.jobs_per_device = 0;
+  if (o.sort_mem_limit) o.batch_bytes = std::min<uint64_t>(std::max<uint64_t>(o.sort_mem_limit / 8, 64 << 10), (uint64_t)256 << 20);
+  o.flags &= ~(uint32_t)(BAMGPU_COPY_COLUMNS | BAMGPU_NO_RECORDS | BAMGPU_SPECULATIVE_START);
+  o.flags |= BAMGPU_COPY_DATA | BAMGPU_COPY_OFFSETS;
+  if (sort_by == BAMGPU_SORT_NAME_AND_MATCH_MATES) o.flags |= BAMGPU_WANT_HI;
+  threads = std::max<size_t>(threads, 1);
+  bamgpu_reader* R = bamgpu_reader_new(read, read_ctx, threads, nullptr, &o);
+  if (!R) { msg = "no usable CUDA device (this library has no CPU fallback)"; return BAMGPU_ERR_CUDA; }
+  int rc = BAMGPU_OK;
+  std::vector<HostRun> runs;
+  GrowBuf g_key, g_strand, g_lname, g_flag, g_hip, g_hiv, g_voff, g_names;
+  bamgpu_engine* E = nullptr;
+  std::vector<uint8_t> header;
+  uint64_t total = 0, bad_flags = 0, out_bytes = 0;
+  const bool by_name = sort_by != BAMGPU_SORT_COORDINATES_AND_STRAND;
+  do {
+    const uint8_t* hb; size_t hl, ho;
+    rc = bamgpu_read_header(R, &hb, &hl, &ho);   // read and discarded by the reference (sort.rs:152-153); BAMGPU_OUT_BAM re-emits it
+    if (rc != BAMGPU_OK) { msg = bamgpu_last_error(R); break; }
+    header.assign(hb, hb + hl);
+    // 1. batches: keys stay on the device, bodies go to host memory
+    for (;;) {
+      bamgpu_batch b;
+      rc = bamgpu_next_batch(R, &b);
+      if (rc == BAMGPU_EOF) { rc = BAMGPU_OK; break; }
+      if (rc != BAMGPU_OK) { msg = bamgpu_last_error(R); break; }
+      E = bamgpu_reader_current_engine(R);
+      const uint64_t nb = b.n_records;
+      if (nb == 0) continue;
+      if (total + nb >= (1ull << 31)) { rc = BAMGPU_ERR_TOO_LARGE; msg = "sort: more than 2^31 records"; break; }
+      cudaSetDevice(E->device);
+      cudaStream_t s = E->stream;
+      bad_flags += b.bad_flag_records;
+      cudaError_t e = cudaSuccess;
+      if (!by_name) {
+        e = g_key.append(b.dev.coord_key, 8 * nb, s);
+        if (e == cudaSuccess) e = g_strand.append(b.dev.strand, nb, s);
+      } else {
+        e = g_lname.append(b.dev.l_read_name, nb, s);
+        if (e == cudaSuccess && sort_by == BAMGPU_SORT_NAME_AND_MATCH_MATES) {
+          e = g_flag.append(b.dev.flag, 2 * nb, s);
+          if (e == cudaSuccess) e = g_hip.append(b.dev.hi_present, nb, s);
+          if (e == cudaSuccess) e = g_hiv.append(b.dev.hi_value, 4 * nb, s);
+        }
+        uint64_t name_bytes = 0;
+        ColumnsDev bc{};
+        bc.rec_off = (uint64_t*)b.dev.rec_off;
+        bc.l_read_name = (uint8_t*)b.dev.l_read_name;
+        if (e == cudaSuccess) e = E->d_sort.reserve(sort_scratch_bytes(nb));
+        if (e == cudaSuccess) e = names_total(bc, nb, E->d_sort.p, &name_bytes, s);
+        if (e == cudaSuccess) e = g_names.ensure(g_names.used + name_bytes + 64, s);
+        if (e == cudaSuccess) e = g_voff.ensure(g_voff.used + 8 * nb + 64, s);
+        if (e == cudaSuccess) e = pack_names(b.data, bc, nb, E->d_sort.p, (uint8_t*)g_names.b.p, g_names.used, (uint64_t*)((uint8_t*)g_voff.b.p + g_voff.used), s);
+        g_names.used += name_bytes;
+        g_voff.used += 8 * nb;
+        E->stats.kernel_launches += 3;
+      }
+      if (e != cudaSuccess) { rc = e == cudaErrorMemoryAllocation ? BAMGPU_ERR_TOO_LARGE : BAMGPU_ERR_CUDA; msg = std::string("streamed sort: ") + cudaGetErrorString(e); break; }
+      // the bodies: the batch's valid bytes as they are, plus the records' offsets in them
+      HostRun r;
+      r.first = total; r.n = nb;
+      const uint64_t span = b.data_len - b.data_start;
+      r.mem = (uint8_t*)malloc(span + 8);
+      if (!r.mem) { rc = BAMGPU_ERR_NOMEM; msg = "streamed sort: out of host memory for the record bodies"; break; }
+      par_memcpy(r.mem, b.h_data + b.data_start, span, threads);
+      r.off.resize(nb); r.len.assign(b.host.rec_len, b.host.rec_len + nb);
+      for (uint64_t i = 0; i < nb; ++i) r.off[i] = b.host.rec_off[i] - b.data_start;
+      runs.push_back(std::move(r));
+      total += nb;
+      if (cudaStreamSynchronize(s) != cudaSuccess) { rc = BAMGPU_ERR_CUDA; msg = "streamed sort: key copy failed"; break; }   // before the batch's buffers are reused
+    }
+    if (rc != BAMGPU_OK) break;
+    const uint32_t prefix = out_fmt == BAMGPU_OUT_BODIES ? 0u : 4u;
+    // 2. one stable sort of all keys
+    std::vector<uint32_t> perm(total);
+    if (total) {
+      if (sort_by == BAMGPU_SORT_COORDINATES_AND_STRAND && bad_flags) {
+        rc = BAMGPU_ERR_SORT_BAD_FLAGS;
+        msg = "sort: " + std::to_string(bad_flags) + " record(s) with flag bits >= 0x1000 (Flags::from_bits().unwrap() panics, comparators.rs:178)";
+        break;
+      }
+      cudaSetDevice(E->device);
+      cudaStream_t s = E->stream;
+      ColumnsDev gc{};
+      gc.coord_key = (uint64_t*)g_key.b.p; gc.strand = (uint8_t*)g_strand.b.p; gc.l_read_name = (uint8_t*)g_lname.b.p;
+      gc.flag = (uint16_t*)g_flag.b.p; gc.hi_present = (uint8_t*)g_hip.b.p; gc.hi_value = (int32_t*)g_hiv.b.p; gc.rec_off = (uint64_t*)g_voff.b.p;
+      SortResult* d_sr = (SortResult*)(E->d_misc.as<uint8_t>() + 192);
+      SortResult h_sr{};
+      int launches = 0;
+      cudaError_t e = E->d_sort.reserve(sort_scratch_bytes(total));
+      if (e == cudaSuccess) e = E->d_perm.reserve(4 * (total + 1));
+      cudaEvent_t t0, t1;
+      cudaEventCreate(&t0); cudaEventCreate(&t1);
+      cudaEventRecord(t0, s);
+      if (e == cudaSuccess) e = sort_permutation((const uint8_t*)g_names.b.p, gc, total, sort_by, E->d_sort.p, E->d_perm.as<uint32_t>(), d_sr, &launches, s);
+      cudaEventRecord(t1, s);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(&h_sr, d_sr, sizeof h_sr, cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(perm.data(), E->d_perm.p, 4 * total, cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, t0, t1);
+      cudaEventDestroy(t0); cudaEventDestroy(t1);
+      E->stats.ms_sort += ms;
+      E->stats.kernel_launches += launches;
+      if (e != cudaSuccess) { rc = e == cudaErrorMemoryAllocation ? BAMGPU_ERR_TOO_LARGE : BAMGPU_ERR_CUDA; msg = std::string("streamed sort: ") + cudaGetErrorString(e); break; }
+      if (sort_by == BAMGPU_SORT_NAME_AND_MATCH_MATES) {
+        if (h_sr.hi_bad_tags) { rc = BAMGPU_ERR_SORT_BAD_TAGS; msg = "sort: aux tags the reference's HI walk panics on"; break; }
+        if (h_sr.hi_mixed) {
+          rc = BAMGPU_ERR_SORT_HI_MIXED;
+          msg = "sort: " + std::to_string(h_sr.hi_mixed) + " pair(s) of equal read names with HI on one record only (Option::unwrap() panics, comparators.rs:90)";
+          break;
+        }
+      }
+    }
+    // 3. gather on the host in sorted order, in pieces of a whole number of BGZF payloads
+    const size_t PIECE = (size_t)1024 * 0xff00;
+    std::vector<uint8_t> stage;
+    stage.reserve(PIECE + (1 << 20));
+    if (out_fmt == BAMGPU_OUT_BAM) { stage.insert(stage.end(), {'B', 'A', 'M', 1}); stage.insert(stage.end(), header.begin(), header.end()); }
+    auto flush = [&](size_t nbytes, bool last) -> int {   // the first nbytes of `stage` go out
+      if (out_fmt != BAMGPU_OUT_BAM) { out_bytes += nbytes; return nbytes ? write(write_ctx, stage.data(), nbytes) : 0; }
+      bamgpu_engine* W = E;
+      std::unique_ptr<bamgpu_engine, void (*)(bamgpu_engine*)> own(nullptr, bamgpu_engine_free);
+      if (!W) { own.reset(bamgpu_engine_new(&o)); W = own.get(); if (!W) return BAMGPU_ERR_CUDA; }   // a BAM without records: header + EOF marker
+      const size_t bound = bamgpu_bgzf_bound(nbytes);
+      if (W->d_sorted.reserve(nbytes + 64) != cudaSuccess || W->d_bgzf.reserve(bound + 64) != cudaSuccess) return BAMGPU_ERR_NOMEM;
+      std::vector<uint8_t> framed(bound);
+      size_t wrote = 0;
+      int r = nbytes ? bamgpu_memcpy_h2d(W, W->d_sorted.p, stage.data(), nbytes) : BAMGPU_OK;
+      if (r == BAMGPU_OK) r = bamgpu_engine_bgzf_store(W, W->d_sorted.as<uint8_t>(), nbytes, W->d_bgzf.as<uint8_t>(), bound, &wrote, last ? 1 : 0, nullptr);
+      if (r == BAMGPU_OK && wrote) r = bamgpu_memcpy_d2h(W, framed.data(), W->d_bgzf.p, wrote);
+      if (r != BAMGPU_OK) return r;
+      out_bytes += wrote;
+      return wrote ? write(write_ctx, framed.data(), wrote) : 0;
+    };
+    size_t run_hint = 0;
+    for (uint64_t i = 0; i < total && rc == BAMGPU_OK; ++i) {
+      const uint64_t gidx = perm[i];
+      if (!(run_hint < runs.size() && gidx >= runs[run_hint].first && gidx < runs[run_hint].first + runs[run_hint].n)) {
+        size_t lo = 0, hi = runs.size();
+        while (hi - lo > 1) { const size_t m = (lo + hi) / 2; if (runs[m].first <= gidx) lo = m; else hi = m; }
+        run_hint = lo;
+      }
+      const HostRun& r = runs[run_hint];
+      const uint64_t k = gidx - r.first;
+      const uint32_t len = r.len[k];
+      if (prefix) { const uint8_t* q = (const uint8_t*)&len; stage.insert(stage.end(), q, q + 4); }   // little-endian host (x86-64 / aarch64)
+      stage.insert(stage.end(), r.mem + r.off[k], r.mem + r.off[k] + len);
+      if (stage.size() >= PIECE) {
+        const size_t whole = stage.size() / 0xff00 * 0xff00;
+        const int w = flush(whole, false);
+        if (w < 0) { rc = w == BAMGPU_ERR_CUDA || w == BAMGPU_ERR_NOMEM ? w : BAMGPU_ERR_IO; msg = "streamed sort: writing the output failed"; break; }
+        stage.erase(stage.begin(), stage.begin() + whole);
+      }
+    }
+    if (rc != BAMGPU_OK) break;
+    if (!stage.empty() || out_fmt == BAMGPU_OUT_BAM) {
+      const int w = flush(stage.size(), true);
+      if (w < 0) { rc = w == BAMGPU_ERR_CUDA || w == BAMGPU_ERR_NOMEM ? w : BAMGPU_ERR_IO; msg = "streamed sort: writing the output failed"; }
+    }
+  } while (0);
+  if (stats) bamgpu_reader_stats(R, stats);
+  if (E) { cudaSetDevice(E->device); cudaStreamSynchronize(E->stream); }
+  for (GrowBuf* g : {&g_key, &g_strand, &g_lname, &g_flag, &g_hip, &g_hiv, &g_voff, &g_names}) g->b.release();
+  bamgpu_reader_free(R);
+  for (auto& r : runs) free(r.mem);
+  return rc;
+}
+
 extern "C" int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write_fn write, void* write_ctx, size_t reader_thread_num,
                                int sort_by, const bamgpu_opts* opts, bamgpu_stats* stats, char* err_buf, size_t err_cap) {
   auto fail = [&](int rc, const std::string& msg) {
@@ -2099,6 +2352,11 @@ extern "C" int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write
     return rc;
   };
   if (!read || !write || sort_by < BAMGPU_SORT_NAME || sort_by > BAMGPU_SORT_COORDINATES_AND_STRAND) return fail(BAMGPU_ERR_ARG, "bad argument");
+  if (opts && opts->sort_mem_limit) {   // sort.rs:138 mem_limit: the streamed form, straight from the caller's source
+    std::string m;
+    const int r = sort_bam_streamed(read, read_ctx, write, write_ctx, reader_thread_num, sort_by, opts, stats, m);
+    return r == BAMGPU_OK ? r : fail(r, m.empty() ? bamgpu_status_str(r) : m);
+  }
   // 1. the whole input (its size decides the batch size; the reference's reading thread streams it instead, readahead.rs:88-118)
   size_t cap = (size_t)64 << 20, len = 0;
   uint8_t* buf = (uint8_t*)malloc(cap);
@@ -2114,6 +2372,22 @@ extern "C" int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write
     if (got < 0) { free(buf); return fail(BAMGPU_ERR_IO, "read callback failed"); }
     if (got == 0) break;
     len += (size_t)got;
+  }
+  {   // does it fit in HBM as one batch?  compressed + inflated + gathered output + columns and sort scratch (~110 B per record)
+    uint64_t isize_total = 0;
+    size_t nblk = 0, consumed = 0;
+    bamgpu_scan_blocks(buf, len, 1, nullptr, 0, &nblk, &consumed, &isize_total);
+    size_t free_b = 0, total_b = 0;
+    if (opts && opts->device >= 0) cudaSetDevice(opts->device);
+    const bool have_dev = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess;
+    const uint64_t need = (uint64_t)len + 2 * isize_total + isize_total / 3 + ((uint64_t)1 << 30);
+    if (have_dev && need > (uint64_t)free_b + dev_cache_bytes()) {
+      MemSrc src{buf, len, 0};
+      std::string m;
+      const int r = sort_bam_streamed(memsrc_read, &src, write, write_ctx, reader_thread_num, sort_by, opts, stats, m);
+      free(buf);
+      return r == BAMGPU_OK ? r : fail(r, m.empty() ? bamgpu_status_str(r) : m);
+    }
   }
   // 2. one batch = the whole file
   bamgpu_opts o{};

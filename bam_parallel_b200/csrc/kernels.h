@@ -173,6 +173,11 @@ cudaError_t sorted_offsets(const ColumnsDev& c, const uint32_t* perm, uint64_t n
 cudaError_t gather_sorted_bodies(const uint8_t* data, const ColumnsDev& c, const uint32_t* perm, uint64_t n_records, void* scratch,
                                  uint64_t* out_off, uint8_t* out, uint32_t prefix, cudaStream_t s);
 
+// streamed sort (bodies on the host, keys on the device): the names of a batch -> compact store + virtual record offsets
+cudaError_t names_total(const ColumnsDev& c, uint64_t n_records, void* scratch, uint64_t* name_bytes, cudaStream_t s);   // synchronises
+cudaError_t pack_names(const uint8_t* data, const ColumnsDev& c, uint64_t n_records, void* scratch, uint8_t* store, uint64_t store_base,
+                       uint64_t* voff, cudaStream_t s);
+
 // ---- BGZF writer, stored blocks (bgzf_write.cu) ---------------------------------------------------
 // CRC-32 of consecutive `chunk`-byte pieces of src (the last one shorter) -> crc_out[i]   (crc32.cu, K2's warp CRC)
 void launch_crc32_chunks(const uint8_t* src, uint64_t len, uint32_t chunk, const uint32_t* d_tables, uint32_t* crc_out, int num_sms, cudaStream_t s);

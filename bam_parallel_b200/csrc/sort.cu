@@ -171,6 +171,25 @@ __global__ void __launch_bounds__(256) k_gather_bodies(const uint8_t* __restrict
   }
 }
 
+// ---- streamed sort (inputs whose bodies do not fit in HBM): only the keys stay on the device ----
+__global__ void k_name_len64(const uint8_t* __restrict__ l_name, uint32_t n, uint64_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= n) out[i] = i < n ? l_name[i] : 0;
+}
+// The names of a batch, back to back behind store[store_base]; voff[i] = "record offset" that makes data + voff + 32 the name.
+__global__ void k_pack_names(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, const uint8_t* __restrict__ l_name,
+                             const uint64_t* __restrict__ local_off, uint32_t n, uint8_t* __restrict__ store, uint64_t store_base,
+                             uint64_t* __restrict__ voff) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const uint64_t o = store_base + local_off[i];
+    const uint8_t* src = data + rec_off[i] + 32;
+    const uint32_t len = l_name[i];
+    for (uint32_t k = 0; k < len; ++k) store[o + k] = src[k];
+    voff[i] = o - 32;
+  }
+}
+
 inline uint32_t blocks_for(uint32_t n, uint32_t threads = 256) { return (n + threads - 1) / threads; }
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -295,6 +314,35 @@ cudaError_t sort_permutation(const uint8_t* data, const ColumnsDev& c, uint64_t 
   }
   cudaMemcpyAsync(perm, va, 4ull * n, cudaMemcpyDeviceToDevice, s);
   if (launches) *launches += nl;
+  return cudaGetLastError();
+}
+
+// Streamed sort: appends the read names of `n` records (a decoded batch) to the compact name store and writes the virtual
+// record offsets sort_permutation needs to find them there.  `scratch` >= sort_scratch_bytes(n).  *name_bytes (host) gets
+// the bytes appended; synchronises.  The caller makes sure the store holds store_base + 255 * n more bytes... or calls
+// names_total first (cheap) — here the store must hold store_base + *name_bytes, checked by the caller through names_total.
+cudaError_t names_total(const ColumnsDev& c, uint64_t n64, void* scratch, uint64_t* name_bytes, cudaStream_t s) {
+  const uint32_t n = (uint32_t)n64;
+  *name_bytes = 0;
+  if (n == 0) return cudaSuccess;
+  Carve cv{(uint8_t*)scratch};
+  uint64_t* len64 = cv.take<uint64_t>(n + 1);
+  cv.take<uint64_t>(n + 1);
+  for (int k = 0; k < 6; ++k) cv.take<uint32_t>(n + 1);
+  void* tmp = cv.p + cv.used;
+  size_t tmp_bytes = cub_temp_bytes(n);
+  k_name_len64<<<blocks_for(n + 1), 256, 0, s>>>(c.l_read_name, n, len64);
+  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (const uint64_t*)len64, len64, (int)n + 1, s);
+  cudaMemcpyAsync(name_bytes, len64 + n, 8, cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+// After names_total on the same scratch: copies the names and writes voff[0..n).
+cudaError_t pack_names(const uint8_t* data, const ColumnsDev& c, uint64_t n64, void* scratch, uint8_t* store, uint64_t store_base,
+                       uint64_t* voff, cudaStream_t s) {
+  const uint32_t n = (uint32_t)n64;
+  if (n == 0) return cudaSuccess;
+  k_pack_names<<<blocks_for(n), 256, 0, s>>>(data, c.rec_off, c.l_read_name, (const uint64_t*)scratch, n, store, store_base, voff);
   return cudaGetLastError();
 }
 

@@ -7,8 +7,11 @@
 The reference reads with its Reader, sorts chunks of records with rayon, spills them and merges; the output is the
 record bodies in globally stable sorted order (sort.rs:643).  Here the Reader's CUDA path decodes the whole file into
 HBM, the keys K3 extracted are radix-sorted on the device and the bodies gathered in that order: same bytes, no chunks,
-no temp files.  Arguments that only steer the external merge (mem_limit, tmp_dir, temp_files_mode, out_compr_level)
-are accepted for signature parity and ignored; the unreachable GBAM index mode (main.rs:74 passes None) is not built.
+no temp files.  A file that does not fit in HBM — or any file, with device_mem_limit — takes the streamed form
+(sort.rs:185-308,590-652 without the chunk files): batches through the Reader, sort keys and read names on the device, bodies
+in host memory, gathered there in sorted order.  Arguments that only steer the reference's external merge (mem_limit — a
+HOST memory bound of 2 GB in bam_binary, main.rs:72 —, tmp_dir, temp_files_mode, out_compr_level) are accepted for signature
+parity and ignored; the unreachable GBAM index mode (main.rs:74 passes None) is not built.
 Where the reference panics (HI on one mate only, flag bits >= 0x1000 under coordinate sort) this raises BamGpuError.
 """
 from __future__ import annotations
@@ -32,7 +35,8 @@ class SortBy(enum.IntEnum):
 
 def sort_bam(mem_limit: int, reader, sorted_sink, tmp_dir=None, out_compr_level: int = 0, reader_thread_num: int = 5,
              temp_files_mode=None, index_file_to_create=None, sort_by: SortBy = SortBy.CoordinatesAndStrand,
-             bam_file_size: Optional[int] = None, *, device: int = -1, flags: int = 0, output: str = "bodies") -> dict:
+             bam_file_size: Optional[int] = None, *, device: int = -1, flags: int = 0, output: str = "bodies",
+             device_mem_limit: int = 0, batch_bytes: int = 0) -> dict:
     """Sorts the BAM read from `reader` (bytes-like, or an object with read()/readinto()) and writes the sorted record
     bodies to `sorted_sink` (an object with write()).  Returns the stage times (bamgpu_stats)."""
     if index_file_to_create is not None:
@@ -72,7 +76,8 @@ def sort_bam(mem_limit: int, reader, sorted_sink, tmp_dir=None, out_compr_level:
     # output: "bodies" = the reference's (sort.rs:643); "records" = (u32 block_size, body)*, its spill wire format
     # (sort.rs:340-347); "bam" = a complete BAM (header + sorted records in stored-block BGZF + EOF marker)
     fmt = {"bodies": _lib.OUT_BODIES, "records": _lib.OUT_RECORDS, "bam": _lib.OUT_BAM}[output]
-    opts, st = make_opts(device, flags, sort_output=fmt), Stats()
+    # device_mem_limit > 0 (bamgpu_opts.sort_mem_limit): the streamed form, with batches of about device_mem_limit / 8 compressed bytes
+    opts, st = make_opts(device, flags, sort_output=fmt, sort_mem_limit=device_mem_limit, batch_bytes=batch_bytes), Stats()
     err = C.create_string_buffer(512)
     rc = L.bamgpu_sort_bam(rcb, None, wcb, None, reader_thread_num, int(sort_by), C.byref(opts), C.byref(st), err, len(err))
     if rc < 0:

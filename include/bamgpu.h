@@ -53,7 +53,7 @@ typedef enum bamgpu_status {
   BAMGPU_ERR_SORT_HI_MIXED = -30,   /* sorting/comparators.rs:90 unwrap(): equal names, HI on one record only -> the reference panics */
   BAMGPU_ERR_SORT_BAD_FLAGS = -31,  /* comparators.rs:178 Flags::from_bits().unwrap(): flag bits >= 0x1000 -> the reference panics */
   BAMGPU_ERR_SORT_BAD_TAGS = -32,   /* record/tags.rs:64-129: the aux walk for HI hits a type it panics on */
-  BAMGPU_ERR_TOO_LARGE = -33        /* sort: the whole BAM must fit in device memory as one batch */
+  BAMGPU_ERR_TOO_LARGE = -33        /* sort: more than 2^31 records, or the sort keys alone do not fit in device memory */
 } bamgpu_status;
 
 /* ------------------------------------------------------------------------------------------
@@ -157,6 +157,13 @@ typedef struct bamgpu_opts {
   int32_t n_devices;
   int32_t devices[BAMGPU_MAX_DEVICES];
   int32_t sort_output;          /* bamgpu_sort_bam: BAMGPU_OUT_* (0 = the reference's output) */
+  int32_t reserved0;
+  uint64_t sort_mem_limit;      /* bamgpu_sort_bam: sort.rs:138 `mem_limit` — bytes of DEVICE memory the record bodies may take.
+                                   0 = the whole file is decoded and sorted in HBM if it fits there, else the streamed form below;
+                                   > 0 = always the streamed form: the file goes through the Reader in batches of about
+                                   mem_limit / 8 compressed bytes, only the sort keys (and, for the name orders, the read names)
+                                   stay on the device, the bodies wait in host memory and are gathered there in sorted order
+                                   (the reference's chunk files + N-way merge, sort.rs:185-308,590-652, without the files) */
 } bamgpu_opts;
 
 /* What bamgpu_sort_bam writes to the sink. */
@@ -370,7 +377,8 @@ int bamgpu_engine_sort(bamgpu_engine*, int sort_by, uint32_t flags /* BAMGPU_COP
 typedef int (*bamgpu_write_fn)(void* ctx, const uint8_t* src, size_t len);
 /* sort_bam (sort.rs:138-178): reads the whole BGZF stream from `read`, decodes and sorts it on the device and writes
  * the sorted bodies to `write`.  The header is read and discarded like the reference does (sort.rs:152-153).
- * The whole file must fit in device memory (BAMGPU_ERR_TOO_LARGE otherwise). *stats (nullable) gets the stage times. */
+ * A file that does not fit in device memory as one batch (or any file, with bamgpu_opts.sort_mem_limit) is sorted in the
+ * streamed form: batches through the Reader, keys on the device, bodies in host memory.  *stats (nullable) gets the stage times. */
 int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write_fn write, void* write_ctx, size_t reader_thread_num,
                     int sort_by, const bamgpu_opts* opts /*nullable*/, bamgpu_stats* stats /*nullable*/,
                     char* err_buf /*nullable*/, size_t err_cap);

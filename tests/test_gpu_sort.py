@@ -228,6 +228,58 @@ def test_sort_output_formats_and_bgzf_writer(oracle, shape, n, payload, sort_by)
     assert st["ms_bgzf_write"] > 0
 
 
+@pytest.mark.parametrize("sort_by", list(SortBy))
+@pytest.mark.parametrize("shape,n,payload,limit", [("pe150", 60000, 0xFF00, 8 << 20), ("long10k", 400, 4096, 4 << 20), ("longname", 6000, 0xFF00, 1 << 20)])
+def test_streamed_sort_matches_the_resident_one(oracle, shape, n, payload, limit, sort_by):
+    """bamgpu_opts.sort_mem_limit (sort.rs:138 mem_limit): the file goes through the Reader in many small batches, keys and
+    names stay on the device, bodies on the host — the output bytes must be those of the one-batch sort and of the oracle,
+    in all three output formats."""
+    import gzip
+    data = synth.generate(shape, n, level=6, payload=payload).tobytes()
+    start, perm, out = _oracle_sorted(oracle, data, sort_by)
+    u, _ = oracle.inflate_all(data)
+    off, ln = oracle.walk_records(u, start)
+    sink = io.BytesIO()
+    st = sort_bam(0, io.BytesIO(data), sink, sort_by=sort_by, device_mem_limit=limit)
+    assert st["batches"] > 3, st["batches"]                          # really streamed
+    assert hashlib.md5(sink.getvalue()).hexdigest() == hashlib.md5(out).hexdigest()
+    assert st["records"] == n and st["ms_sort"] > 0
+    want_records = _records_stream(out, [int(ln[i]) for i in perm.tolist()])
+    sink = io.BytesIO()
+    sort_bam(0, data, sink, sort_by=sort_by, output="records", device_mem_limit=limit)
+    assert sink.getvalue() == want_records
+    sink = io.BytesIO()
+    sort_bam(0, data, sink, sort_by=sort_by, output="bam", device_mem_limit=limit)
+    bam = sink.getvalue()
+    assert gzip.decompress(bam) == u.tobytes()[:start] + want_records and bam.endswith(bc.BGZF_EOF)
+    resident = io.BytesIO()
+    sort_bam(0, data, resident, sort_by=sort_by, output="bam")
+    assert resident.getvalue() == bam                                 # byte-identical files either way
+
+
+def test_streamed_sort_edge_cases(oracle):
+    for recs in ([], [_rec(b"only", 3, 9, 16)]):
+        data = _bam(recs)
+        for sb in SortBy:
+            sink = io.BytesIO()
+            sort_bam(0, data, sink, sort_by=sb, device_mem_limit=1 << 20)
+            assert sink.getvalue() == b"".join(r[4:] for r in recs)
+            sink = io.BytesIO()
+            sort_bam(0, data, sink, sort_by=sb, device_mem_limit=1 << 20, output="bam")
+            u, _ = oracle.inflate_all(sink.getvalue())
+            _, _, start = oracle.read_header(u)
+            assert u.tobytes()[start:] == b"".join(recs)
+    # the reference's panics are errors here too
+    data = _bam([_rec(b"q", 0, 1, 0, tags=b"HIi" + struct.pack("<i", 1)), _rec(b"q", 0, 2, 0)])
+    with pytest.raises(bp.BamGpuError) as e:
+        sort_bam(0, data, io.BytesIO(), sort_by=SortBy.NameAndMatchMates, device_mem_limit=1 << 20)
+    assert e.value.code == -30
+    data = _bam([_rec(b"q", 0, 1, 0x1000)])
+    with pytest.raises(bp.BamGpuError) as e:
+        sort_bam(0, data, io.BytesIO(), sort_by=SortBy.CoordinatesAndStrand, device_mem_limit=1 << 20)
+    assert e.value.code == -31
+
+
 def test_bgzf_store_edge_sizes(oracle, engine):
     import gzip
     rnd = random.Random(5)
