@@ -5,8 +5,38 @@ use std::io::{self, Read, Write};
 use std::os::raw::{c_char, c_int, c_long, c_void};
 
 #[repr(C)] pub struct bamgpu_reader { _p: [u8; 0] }
-#[repr(C)] #[derive(Default, Clone, Copy)]
-pub struct bamgpu_opts { pub device: i32, pub flags: u32, pub batch_bytes: u64, pub inflate_impl: i32, pub reserved: i32 }
+pub const BAMGPU_MAX_DEVICES: usize = 16;
+/// include/bamgpu.h `bamgpu_opts`, field for field (the layout is part of the ABI).
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct bamgpu_opts {
+    pub device: i32, pub flags: u32, pub batch_bytes: u64, pub inflate_impl: i32, pub jobs_per_device: i32,
+    pub n_devices: i32, pub devices: [i32; BAMGPU_MAX_DEVICES], pub sort_output: i32, pub reserved0: i32, pub sort_mem_limit: u64,
+}
+impl Default for bamgpu_opts {
+    fn default() -> Self {
+        bamgpu_opts { device: -1, flags: 0, batch_bytes: 0, inflate_impl: 0, jobs_per_device: 0, n_devices: 0,
+                      devices: [0; BAMGPU_MAX_DEVICES], sort_output: 0, reserved0: 0, sort_mem_limit: 0 }
+    }
+}
+impl bamgpu_opts {
+    /// One Reader over several GPUs of the box: batches (= BGZF block ranges) go to them round robin.
+    pub fn with_devices(devs: &[i32]) -> Self {
+        let mut o = Self::default();
+        o.n_devices = devs.len().min(BAMGPU_MAX_DEVICES) as i32;
+        for (i, d) in devs.iter().take(BAMGPU_MAX_DEVICES).enumerate() { o.devices[i] = *d; }
+        o
+    }
+}
+#[repr(C)] pub struct bamgpu_engine { _p: [u8; 0] }
+/// include/bamgpu.h `bamgpu_field` / `bamgpu_fields` (bamgpu_engine_decode_fields: decode_cigar / decode_seq / RawQual of a batch).
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct bamgpu_field { pub total: u64, pub bad: u64, pub off: *const u64, pub bytes: *const u8, pub h_off: *const u64, pub h_bytes: *const u8 }
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct bamgpu_fields { pub n_records: u64, pub cigar: bamgpu_field, pub seq: bamgpu_field, pub qual: bamgpu_field, pub ms_measure: f64, pub ms_decode: f64 }
+pub const BAMGPU_FIELD_CIGAR: u32 = 1;
+pub const BAMGPU_FIELD_SEQ: u32 = 2;
+pub const BAMGPU_FIELD_QUAL: u32 = 4;
+pub const BAMGPU_COPY_DATA: u32 = 1;
 pub type bamgpu_read_fn = unsafe extern "C" fn(ctx: *mut c_void, dst: *mut u8, cap: usize) -> c_long;
 pub const BAMGPU_OK: c_int = 0;
 pub const BAMGPU_EOF: c_int = 1;
@@ -20,6 +50,8 @@ extern "C" {
     pub fn bamgpu_next_rec(r: *mut bamgpu_reader, body: *mut *const u8, len: *mut usize) -> c_int;
     pub fn bamgpu_append_record(r: *mut bamgpu_reader, dst: *mut u8, cap: usize, len: *mut usize) -> c_int;
     pub fn bamgpu_read(r: *mut bamgpu_reader, dst: *mut u8, cap: usize) -> c_long;
+    pub fn bamgpu_reader_current_engine(r: *mut bamgpu_reader) -> *mut bamgpu_engine;
+    pub fn bamgpu_engine_decode_fields(e: *mut bamgpu_engine, which: u32, flags: u32, cuda_stream: *mut c_void, out: *mut bamgpu_fields) -> c_int;
     pub fn bamgpu_sort_bam(read: bamgpu_read_fn, rctx: *mut c_void, write: bamgpu_write_fn, wctx: *mut c_void, reader_thread_num: usize,
                            sort_by: c_int, opts: *const bamgpu_opts, stats: *mut c_void, err: *mut c_char, err_cap: usize) -> c_int;
 }
@@ -118,7 +150,9 @@ pub enum TempFilesMode { RegularFiles, LZ4CompressedFiles, InMemoryBlocks, InMem
 /// `&tempdir::TempDir`; this crate has no dependencies).  mem_limit / tmp_dir / out_compr_level / temp_files_mode steer the
 /// reference's external merge and have no counterpart here; `index_file_to_create` must be `None` (the GBAM index mode,
 /// sort.rs:106-134, is unreachable from bam_binary: main.rs:74 passes `Option::<File>::None`).  `bam_file_size` becomes
-/// the reader's `track_progress`.  Panics where the reference's comparators panic.
+/// the reader's `track_progress`.  Panics where the reference's comparators panic.  A file that does not fit in HBM is
+/// sorted in the streamed form automatically (keys on the device, bodies in host memory); `sort_bam_with` exposes
+/// `bamgpu_opts` (device list, output format, `sort_mem_limit` to force the streamed form).
 #[allow(clippy::too_many_arguments)]
 pub fn sort_bam<R: Read + Send + 'static, W: Write, IndexW: Write, TmpDir>(
     _mem_limit: usize,
@@ -135,12 +169,19 @@ pub fn sort_bam<R: Read + Send + 'static, W: Write, IndexW: Write, TmpDir>(
     if index_file_to_create.is_some() {
         return Err(io::Error::new(io::ErrorKind::Unsupported, "GBAM index sort (sort.rs:106-134) is not built"));
     }
+    sort_bam_with(reader, sorted_sink, reader_thread_num, sort_by, &bamgpu_opts::default())
+}
+
+/// `sort_bam` with explicit options (bamgpu_opts.sort_output: 0 bodies = the reference's output, 1 (u32 block_size, body)*,
+/// 2 a complete BAM in stored-block BGZF; bamgpu_opts.sort_mem_limit: device bytes for record bodies, 0 = whatever fits).
+pub fn sort_bam_with<R: Read + Send + 'static, W: Write>(reader: R, sorted_sink: &mut W, reader_thread_num: usize, sort_by: SortBy,
+                                                       opts: &bamgpu_opts) -> io::Result<()> {
     let mut boxed: Box<Box<dyn Read + Send>> = Box::new(Box::new(reader));
     let mut sink: &mut dyn Write = sorted_sink;
     let mut msg = [0 as c_char; 512];
     let rc = unsafe {
         bamgpu_sort_bam(trampoline, &mut *boxed as *mut _ as *mut c_void, write_trampoline, &mut sink as *mut _ as *mut c_void,
-                        reader_thread_num, sort_by as c_int, std::ptr::null(), std::ptr::null_mut(), msg.as_mut_ptr(), msg.len())
+                        reader_thread_num, sort_by as c_int, opts as *const bamgpu_opts, std::ptr::null_mut(), msg.as_mut_ptr(), msg.len())
     };
     let text = unsafe { std::ffi::CStr::from_ptr(msg.as_ptr()) }.to_string_lossy().into_owned();
     match rc {

@@ -93,3 +93,20 @@ def test_parse_reference_sequences(oracle):
         bp.parse_reference_sequences(bad)
     with pytest.raises(bp.BamGpuError):
         bp.parse_reference_sequences(hb[off:-2])
+
+
+def test_opts_layout_is_the_same_in_every_binding():
+    """bamgpu_opts crosses the ABI by pointer: the ctypes mirror and the Rust source must list the header's fields in order."""
+    import re
+    from bam_parallel_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "bamgpu.h")).read()
+    body = re.search(r"typedef struct bamgpu_opts \{(.*?)\} bamgpu_opts;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    c_fields = [re.sub(r"\[.*\]", "", d.split()[-1]) for d in body.split(";") if d.strip()]
+    assert c_fields == [n for n, _ in _lib.Opts._fields_]
+    rs = open(os.path.join(root, "rust", "bamgpu-sys", "src", "lib.rs")).read()
+    rbody = re.search(r"pub struct bamgpu_opts \{(.*?)\n\}", rs, re.S).group(1)
+    assert re.findall(r"pub (\w+):", rbody) == c_fields
+    import ctypes as C
+    assert C.sizeof(_lib.Opts) == 4 + 4 + 8 + 4 + 4 + 4 + 4 * 16 + 4 + 4 + 8
