@@ -58,7 +58,7 @@ MAX_DEVICES = 16
 class Opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("batch_bytes", C.c_uint64), ("inflate_impl", C.c_int32),
                 ("jobs_per_device", C.c_int32), ("n_devices", C.c_int32), ("devices", C.c_int32 * MAX_DEVICES),
-                ("sort_output", C.c_int32), ("reserved0", C.c_int32), ("sort_mem_limit", C.c_uint64)]
+                ("sort_output", C.c_int32), ("sort_mem_limit", C.c_uint64)]
 
 
 OUT_BODIES, OUT_RECORDS, OUT_BAM = 0, 1, 2          # bamgpu_opts.sort_output

@@ -157,7 +157,6 @@ typedef struct bamgpu_opts {
   int32_t n_devices;
   int32_t devices[BAMGPU_MAX_DEVICES];
   int32_t sort_output;          /* bamgpu_sort_bam: BAMGPU_OUT_* (0 = the reference's output) */
-  int32_t reserved0;
   uint64_t sort_mem_limit;      /* bamgpu_sort_bam: sort.rs:138 `mem_limit` — bytes of DEVICE memory the record bodies may take.
                                    0 = the whole file is decoded and sorted in HBM if it fits there, else the streamed form below;
                                    > 0 = always the streamed form: the file goes through the Reader in batches of about
