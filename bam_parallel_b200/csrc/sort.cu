@@ -11,10 +11,10 @@
 //     K3 already wrote coord_key (both i32 biased to unsigned, refID in the high word) and strand; the order is a
 //     stable LSD radix sort: 1 bit of strand, then the 64 bits of coord_key.
 //   Name (comparators.rs:61-65): str::cmp of the read names INCLUDING their NUL (bamrawrecord.rs:118-123) = bytewise
-//     lexicographic, a proper prefix first.  Variable-length keys: MSD refinement, 8 name bytes per round (big-endian
-//     u64, zero-padded past l_read_name), each round a stable sort of (group, chunk); groups = runs of records equal
-//     so far.  Zero padding alone would tie "A\0" with "A\0\0"; sorting by l_read_name BEFORE the rounds (stable sorts
-//     keep it as the order inside fully tied groups) makes the result exact for arbitrary name bytes.
+//     lexicographic, a proper prefix first.  Variable-length keys: stable LSD passes over 8 name bytes each (big-endian
+//     u64, zero-padded past l_read_name), last chunk first; the chunks inside the prefix all names share are skipped.
+//     Zero padding alone would tie "A\0" with "A\0\0"; sorting by l_read_name BEFORE the passes (stable sorts keep it
+//     as the order among names that tie on every chunk) makes the result exact for arbitrary name bytes.
 //   NameAndMatchMates (comparators.rs:78-93): name, then HI (Option<i32>; None == None; None vs Some panics in the
 //     reference -> reported in SortResult.hi_mixed), then the full u16 flag: the same, with flag and HI sorted first.
 // The radix sort primitive is CUB's DeviceRadixSort (stable, onesweep); key construction, group refinement and the
@@ -67,26 +67,6 @@ __global__ void k_name_chunk(const uint8_t* __restrict__ data, const uint64_t* _
   }
 }
 
-// After a round: position i starts a new group iff its (group, chunk) differs from position i-1's.
-__global__ void k_boundaries(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, const uint8_t* __restrict__ l_name,
-                             const uint32_t* __restrict__ idx, const uint32_t* __restrict__ seg_elem, uint32_t r,
-                             uint32_t* __restrict__ flag, uint32_t n) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    uint32_t f = 1;
-    if (i) {
-      uint32_t a = idx[i - 1], b = idx[i];
-      f = seg_elem[a] != seg_elem[b] || name_chunk(data, rec_off[a], l_name[a], r) != name_chunk(data, rec_off[b], l_name[b], r);
-    }
-    flag[i] = f;
-  }
-}
-// flag has been inclusive-scanned: group id of position i = scan[i] - 1; hand it to the element.
-__global__ void k_assign_groups(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ scan, uint32_t* __restrict__ seg_elem, uint32_t n) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) seg_elem[idx[i]] = scan[i] - 1;
-}
-
 // Length of the prefix every name shares with the first record's name (<= the shortest name).  Real read names start with
 // instrument : run : flowcell; the 8-byte rounds over that prefix would sort 50 M equal keys, so they are skipped.
 __global__ void k_name_lcp(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, const uint8_t* __restrict__ l_name,
@@ -112,16 +92,24 @@ __global__ void k_max_u8(const uint8_t* __restrict__ v, uint32_t n, uint32_t* ou
   if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
-// NameAndMatchMates: neighbours with the same full name must agree on HI being present (comparators.rs:90 unwrap).
-__global__ void k_check_hi(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ seg_elem, const uint8_t* __restrict__ l_name,
-                           const uint8_t* __restrict__ present, uint32_t n, SortResult* res) {
+// NameAndMatchMates: neighbours in the sorted order whose names are equal byte for byte must agree on HI being present
+// (comparators.rs:90 unwrap).
+__global__ void k_check_hi_names(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, const uint32_t* __restrict__ idx,
+                                 const uint8_t* __restrict__ l_name, const uint8_t* __restrict__ present, uint32_t n, SortResult* res) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    uint32_t b = idx[i];
+    const uint32_t b = idx[i];
     if (present[b] == 2) atomicAdd(&res->hi_bad_tags, 1ull);
     if (i) {
-      uint32_t a = idx[i - 1];
-      if (seg_elem[a] == seg_elem[b] && l_name[a] == l_name[b] && (present[a] == 1) != (present[b] == 1)) atomicAdd(&res->hi_mixed, 1ull);
+      const uint32_t a = idx[i - 1];
+      if (l_name[a] == l_name[b] && (present[a] == 1) != (present[b] == 1)) {
+        const uint8_t* pa = data + rec_off[a] + 32;
+        const uint8_t* pb = data + rec_off[b] + 32;
+        const uint32_t len = l_name[a];
+        uint32_t k = 0;
+        while (k < len && pa[k] == pb[k]) ++k;
+        if (k == len) atomicAdd(&res->hi_mixed, 1ull);
+      }
     }
   }
 }
@@ -285,30 +273,19 @@ cudaError_t sort_permutation(const uint8_t* data, const ColumnsDev& c, uint64_t 
     cudaMemcpyAsync(&lcp, d_lcp, 4, cudaMemcpyDeviceToHost, s);
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return e;
-    cudaMemsetAsync(seg_elem, 0, 4ull * n, s);
+    // Least-significant chunk first: every pass is a stable sort, so after the pass over chunk r0 the order is
+    // (chunk r0, chunk r0 + 1, ..., last chunk, l_read_name, [HI, flag], input order) — the lexicographic order of the names,
+    // ties as the comparator breaks them.  No group bookkeeping and no host round trip between the passes (the MSD form,
+    // which re-sorted by group id and rebuilt the groups after every chunk, took 8 ms per chunk against 5 here).
     const uint32_t rounds = (max_len + 7) / 8;
-    uint32_t groups = 1;
-    const uint32_t r0 = lcp / 8;   // bytes [0, 8 r0) are the same in every name: those rounds would leave one group
-    for (uint32_t r = r0; r < rounds && groups < n; ++r) {
+    const uint32_t r0 = lcp / 8;   // bytes [0, 8 r0) are the same in every name: those passes would not move anything
+    for (uint32_t r = rounds; r-- > r0;) {
       k_name_chunk<<<g, 256, 0, s>>>(data, c.rec_off, c.l_read_name, va, r, k64a, n);
       sort64();
-      if (r > r0) {   // back into the groups of the previous rounds (stable, so the chunk order survives inside each)
-        k_gather_key<uint32_t, uint32_t><<<g, 256, 0, s>>>(seg_elem, va, k32a, n);
-        int bits = 1;
-        while (bits < 32 && (1u << bits) < groups) ++bits;
-        sort32(bits);
-        ++nl;
-      }
-      k_boundaries<<<g, 256, 0, s>>>(data, c.rec_off, c.l_read_name, va, seg_elem, r, flags, n);
-      cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, (const uint32_t*)flags, k32a, (int)n, s);
-      k_assign_groups<<<g, 256, 0, s>>>(va, k32a, seg_elem, n);
-      cudaMemcpyAsync(&groups, k32a + (n - 1), 4, cudaMemcpyDeviceToHost, s);
-      nl += 5;
-      e = cudaStreamSynchronize(s);
-      if (e != cudaSuccess) return e;
+      ++nl;
     }
     if (sort_by == SORT_NAME_AND_MATCH_MATES) {
-      k_check_hi<<<g, 256, 0, s>>>(va, seg_elem, c.l_read_name, c.hi_present, n, d_res);
+      k_check_hi_names<<<g, 256, 0, s>>>(data, c.rec_off, va, c.l_read_name, c.hi_present, n, d_res);
       ++nl;
     }
   }
