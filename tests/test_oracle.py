@@ -372,3 +372,18 @@ def test_field_decoder_known_answers(oracle):
     u = np.frombuffer(st.pack("<I", len(body)) + body + bytes(64), dtype=np.uint8)
     fo, fb, bad = oracle.decode_field(u, np.array([4], np.uint64), np.array([len(body)], np.uint32), 1)
     assert fb.tobytes() == b"7M9D" and bad == 0
+
+
+def test_reference_flags_known_answers(oracle):
+    """The reference's own unit tests for Flags (sorting/flags.rs:207-251: READ_1 == 0x40, twelve flags, default empty) pin
+    what the coordinate comparator reads from the flag word (comparators.rs:173-180): strand = REVERSE_COMPLEMENTED = 0x10,
+    and Flags::from_bits(..).unwrap() panics exactly for bits >= 0x1000 (flags.rs:2-31 defines bits 0..11)."""
+    flags = [0x0, 0x40, 0x10, 0x10 | 0x40, 0x1, 0x2, 0x4, 0x8, 0x20, 0x80, 0x100, 0x200, 0x400, 0x800, 0xFFF, 0x1000, 0x8010]
+    recs = [bc.bam_record(name=b"f%d" % i, flag=f) for i, f in enumerate(flags)]
+    u, _ = oracle.inflate_all(bc.bgzf(bc.bam_header() + b"".join(recs)))
+    _, _, start = oracle.read_header(u)
+    off, ln = oracle.walk_records(u, start)
+    cols, bad_flags, _ = oracle.extract(u, off, ln, True)
+    assert cols["flag"].tolist() == flags
+    assert cols["strand"].tolist() == [1 if f & 0x10 else 0 for f in flags]        # is_reverse_complemented
+    assert bad_flags == 2                                                          # 0x1000 and 0x8010 only
