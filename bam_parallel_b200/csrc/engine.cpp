@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -2118,10 +2119,10 @@ extern "C" int bamgpu_parse_reference_sequences(const uint8_t* b, size_t len, ba
 // N-way merge, ties to the lower chunk = input order), and the bodies are gathered on the host in that order.
 // -------------------------------------------------------------------------------------------------
 namespace {
-struct GrowBuf {   // device array that keeps its contents when it grows
+struct GrowBuf {   // device array (on the device that is current when it first grows) that keeps its contents when it grows
   DevBuf b;
   size_t used = 0;
-  cudaError_t ensure(size_t need, cudaStream_t s) {
+  cudaError_t ensure(size_t need, cudaStream_t s) {   // s: a stream of the array's device, with nothing of ours in flight elsewhere
     if (need <= b.cap) return cudaSuccess;
     DevBuf nb;
     cudaError_t e = nb.reserve(std::max(need, b.cap + b.cap / 2));
@@ -2135,10 +2136,14 @@ struct GrowBuf {   // device array that keeps its contents when it grows
     b = nb;
     return cudaSuccess;
   }
-  cudaError_t append(const void* d_src, size_t bytes, cudaStream_t s) {
-    cudaError_t e = ensure(used + bytes + 64, s);
+  // Appends `bytes` from src_dev's memory; home / hs: the array's device and a stream on it, ss: a stream of src_dev.
+  cudaError_t append(const void* d_src, size_t bytes, int home, cudaStream_t hs, int src_dev, cudaStream_t ss) {
+    cudaSetDevice(home);
+    cudaError_t e = ensure(used + bytes + 64, hs);
+    cudaSetDevice(src_dev);
     if (e != cudaSuccess) return e;
-    if (bytes) e = cudaMemcpyAsync((uint8_t*)b.p + used, d_src, bytes, cudaMemcpyDeviceToDevice, s);
+    if (bytes) e = src_dev == home ? cudaMemcpyAsync((uint8_t*)b.p + used, d_src, bytes, cudaMemcpyDeviceToDevice, ss)
+                                   : cudaMemcpyPeerAsync((uint8_t*)b.p + used, home, d_src, src_dev, bytes, ss);
     used += bytes;
     return e;
   }
@@ -2175,8 +2180,7 @@ static int sort_bam_streamed(bamgpu_read_fn read, void* read_ctx, bamgpu_write_f
   if (opts) o = *opts; else o.device = -1;
   const int out_fmt = o.sort_output;
   if (out_fmt < BAMGPU_OUT_BODIES || out_fmt > BAMGPU_OUT_BAM) { msg = "unknown sort_output"; return BAMGPU_ERR_ARG; }
-  o.n_devices = 0;
-  o.jobs_per_device = 0;
+  o.jobs_per_device = 0;     // (n_devices stays: the batches are decoded on every listed GPU, the keys collect on the first one used)
   if (o.sort_mem_limit) o.batch_bytes = std::min<uint64_t>(std::max<uint64_t>(o.sort_mem_limit / 8, 64 << 10), (uint64_t)256 << 20);
   o.flags &= ~(uint32_t)(BAMGPU_COPY_COLUMNS | BAMGPU_NO_RECORDS | BAMGPU_SPECULATIVE_START);
   o.flags |= BAMGPU_COPY_DATA | BAMGPU_COPY_OFFSETS;
@@ -2187,7 +2191,10 @@ static int sort_bam_streamed(bamgpu_read_fn read, void* read_ctx, bamgpu_write_f
   int rc = BAMGPU_OK;
   std::vector<HostRun> runs;
   GrowBuf g_key, g_strand, g_lname, g_flag, g_hip, g_hiv, g_voff, g_names;
-  bamgpu_engine* E = nullptr;
+  std::map<int, std::pair<DevBuf, DevBuf>> tmp;   // per source device: packed names / their offsets before they move to the home device
+  bamgpu_engine* E = nullptr;      // the engine that holds the current batch
+  bamgpu_engine* H = nullptr;      // "home": the first engine used; its device keeps the keys and sorts them
+  uint64_t p2p_bytes = 0;
   std::vector<uint8_t> header;
   uint64_t total = 0, bad_flags = 0, out_bytes = 0;
   const bool by_name = sort_by != BAMGPU_SORT_COORDINATES_AND_STRAND;
@@ -2203,34 +2210,42 @@ static int sort_bam_streamed(bamgpu_read_fn read, void* read_ctx, bamgpu_write_f
       if (rc == BAMGPU_EOF) { rc = BAMGPU_OK; break; }
       if (rc != BAMGPU_OK) { msg = bamgpu_last_error(R); break; }
       E = bamgpu_reader_current_engine(R);
+      if (!H) H = E;
       const uint64_t nb = b.n_records;
       if (nb == 0) continue;
       if (total + nb >= (1ull << 31)) { rc = BAMGPU_ERR_TOO_LARGE; msg = "sort: more than 2^31 records"; break; }
-      cudaSetDevice(E->device);
-      cudaStream_t s = E->stream;
+      const int home = H->device, dev = E->device;
+      cudaStream_t hs = H->stream, s = E->stream;
+      cudaSetDevice(dev);
       bad_flags += b.bad_flag_records;
       cudaError_t e = cudaSuccess;
+      auto app = [&](GrowBuf& g, const void* src, size_t bytes) {
+        if (dev != home) p2p_bytes += bytes;
+        return g.append(src, bytes, home, hs, dev, s);
+      };
       if (!by_name) {
-        e = g_key.append(b.dev.coord_key, 8 * nb, s);
-        if (e == cudaSuccess) e = g_strand.append(b.dev.strand, nb, s);
+        e = app(g_key, b.dev.coord_key, 8 * nb);
+        if (e == cudaSuccess) e = app(g_strand, b.dev.strand, nb);
       } else {
-        e = g_lname.append(b.dev.l_read_name, nb, s);
+        e = app(g_lname, b.dev.l_read_name, nb);
         if (e == cudaSuccess && sort_by == BAMGPU_SORT_NAME_AND_MATCH_MATES) {
-          e = g_flag.append(b.dev.flag, 2 * nb, s);
-          if (e == cudaSuccess) e = g_hip.append(b.dev.hi_present, nb, s);
-          if (e == cudaSuccess) e = g_hiv.append(b.dev.hi_value, 4 * nb, s);
+          e = app(g_flag, b.dev.flag, 2 * nb);
+          if (e == cudaSuccess) e = app(g_hip, b.dev.hi_present, nb);
+          if (e == cudaSuccess) e = app(g_hiv, b.dev.hi_value, 4 * nb);
         }
+        // the names: packed on the GPU that decoded the batch, then appended to the store on the home GPU
         uint64_t name_bytes = 0;
         ColumnsDev bc{};
         bc.rec_off = (uint64_t*)b.dev.rec_off;
         bc.l_read_name = (uint8_t*)b.dev.l_read_name;
+        auto& t = tmp[dev];
         if (e == cudaSuccess) e = E->d_sort.reserve(sort_scratch_bytes(nb));
         if (e == cudaSuccess) e = names_total(bc, nb, E->d_sort.p, &name_bytes, s);
-        if (e == cudaSuccess) e = g_names.ensure(g_names.used + name_bytes + 64, s);
-        if (e == cudaSuccess) e = g_voff.ensure(g_voff.used + 8 * nb + 64, s);
-        if (e == cudaSuccess) e = pack_names(b.data, bc, nb, E->d_sort.p, (uint8_t*)g_names.b.p, g_names.used, (uint64_t*)((uint8_t*)g_voff.b.p + g_voff.used), s);
-        g_names.used += name_bytes;
-        g_voff.used += 8 * nb;
+        if (e == cudaSuccess) e = t.first.reserve(name_bytes + 64);
+        if (e == cudaSuccess) e = t.second.reserve(8 * nb + 64);
+        if (e == cudaSuccess) e = pack_names(b.data, bc, nb, E->d_sort.p, t.first.as<uint8_t>(), g_names.used, t.second.as<uint64_t>(), s);
+        if (e == cudaSuccess) e = app(g_names, t.first.p, name_bytes);
+        if (e == cudaSuccess) e = app(g_voff, t.second.p, 8 * nb);
         E->stats.kernel_launches += 3;
       }
       if (e != cudaSuccess) { rc = e == cudaErrorMemoryAllocation ? BAMGPU_ERR_TOO_LARGE : BAMGPU_ERR_CUDA; msg = std::string("streamed sort: ") + cudaGetErrorString(e); break; }
@@ -2257,6 +2272,7 @@ static int sort_bam_streamed(bamgpu_read_fn read, void* read_ctx, bamgpu_write_f
         msg = "sort: " + std::to_string(bad_flags) + " record(s) with flag bits >= 0x1000 (Flags::from_bits().unwrap() panics, comparators.rs:178)";
         break;
       }
+      E = H;                       // the keys are on the home device
       cudaSetDevice(E->device);
       cudaStream_t s = E->stream;
       ColumnsDev gc{};
@@ -2337,8 +2353,10 @@ static int sort_bam_streamed(bamgpu_read_fn read, void* read_ctx, bamgpu_write_f
       if (w < 0) { rc = w == BAMGPU_ERR_CUDA || w == BAMGPU_ERR_NOMEM ? w : BAMGPU_ERR_IO; msg = "streamed sort: writing the output failed"; }
     }
   } while (0);
+  if (H) H->stats.p2p_bytes += p2p_bytes;
   if (stats) bamgpu_reader_stats(R, stats);
-  if (E) { cudaSetDevice(E->device); cudaStreamSynchronize(E->stream); }
+  for (auto& kv : tmp) { cudaSetDevice(kv.first); cudaDeviceSynchronize(); kv.second.first.release(); kv.second.second.release(); }
+  if (H) { cudaSetDevice(H->device); cudaStreamSynchronize(H->stream); }
   for (GrowBuf* g : {&g_key, &g_strand, &g_lname, &g_flag, &g_hip, &g_hiv, &g_voff, &g_names}) g->b.release();
   bamgpu_reader_free(R);
   for (auto& r : runs) free(r.mem);

@@ -175,7 +175,7 @@ cudaError_t gather_sorted_bodies(const uint8_t* data, const ColumnsDev& c, const
 
 // streamed sort (bodies on the host, keys on the device): the names of a batch -> compact store + virtual record offsets
 cudaError_t names_total(const ColumnsDev& c, uint64_t n_records, void* scratch, uint64_t* name_bytes, cudaStream_t s);   // synchronises
-cudaError_t pack_names(const uint8_t* data, const ColumnsDev& c, uint64_t n_records, void* scratch, uint8_t* store, uint64_t store_base,
+cudaError_t pack_names(const uint8_t* data, const ColumnsDev& c, uint64_t n_records, void* scratch, uint8_t* dst, uint64_t store_base,
                        uint64_t* voff, cudaStream_t s);
 
 // ---- BGZF writer, stored blocks (bgzf_write.cu) ---------------------------------------------------

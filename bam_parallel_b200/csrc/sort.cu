@@ -164,17 +164,18 @@ __global__ void k_name_len64(const uint8_t* __restrict__ l_name, uint32_t n, uin
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i <= n) out[i] = i < n ? l_name[i] : 0;
 }
-// The names of a batch, back to back behind store[store_base]; voff[i] = "record offset" that makes data + voff + 32 the name.
+// The names of a batch, back to back in dst (which becomes store[store_base ..) — on this or, after a peer copy, on another
+// device); voff[i] = the "record offset" that makes store + voff + 32 the name.
 __global__ void k_pack_names(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, const uint8_t* __restrict__ l_name,
-                             const uint64_t* __restrict__ local_off, uint32_t n, uint8_t* __restrict__ store, uint64_t store_base,
+                             const uint64_t* __restrict__ local_off, uint32_t n, uint8_t* __restrict__ dst, uint64_t store_base,
                              uint64_t* __restrict__ voff) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    const uint64_t o = store_base + local_off[i];
+    const uint64_t o = local_off[i];
     const uint8_t* src = data + rec_off[i] + 32;
     const uint32_t len = l_name[i];
-    for (uint32_t k = 0; k < len; ++k) store[o + k] = src[k];
-    voff[i] = o - 32;
+    for (uint32_t k = 0; k < len; ++k) dst[o + k] = src[k];
+    voff[i] = store_base + o - 32;
   }
 }
 
@@ -314,12 +315,13 @@ cudaError_t names_total(const ColumnsDev& c, uint64_t n64, void* scratch, uint64
   cudaError_t e = cudaStreamSynchronize(s);
   return e != cudaSuccess ? e : cudaGetLastError();
 }
-// After names_total on the same scratch: copies the names and writes voff[0..n).
-cudaError_t pack_names(const uint8_t* data, const ColumnsDev& c, uint64_t n64, void* scratch, uint8_t* store, uint64_t store_base,
+// After names_total on the same scratch: copies the names to dst[0 .. name_bytes) and writes voff[0..n) for a store in which
+// they will sit at store_base.
+cudaError_t pack_names(const uint8_t* data, const ColumnsDev& c, uint64_t n64, void* scratch, uint8_t* dst, uint64_t store_base,
                        uint64_t* voff, cudaStream_t s) {
   const uint32_t n = (uint32_t)n64;
   if (n == 0) return cudaSuccess;
-  k_pack_names<<<blocks_for(n), 256, 0, s>>>(data, c.rec_off, c.l_read_name, (const uint64_t*)scratch, n, store, store_base, voff);
+  k_pack_names<<<blocks_for(n), 256, 0, s>>>(data, c.rec_off, c.l_read_name, (const uint64_t*)scratch, n, dst, store_base, voff);
   return cudaGetLastError();
 }
 

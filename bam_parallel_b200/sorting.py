@@ -36,7 +36,7 @@ class SortBy(enum.IntEnum):
 def sort_bam(mem_limit: int, reader, sorted_sink, tmp_dir=None, out_compr_level: int = 0, reader_thread_num: int = 5,
              temp_files_mode=None, index_file_to_create=None, sort_by: SortBy = SortBy.CoordinatesAndStrand,
              bam_file_size: Optional[int] = None, *, device: int = -1, flags: int = 0, output: str = "bodies",
-             device_mem_limit: int = 0, batch_bytes: int = 0) -> dict:
+             device_mem_limit: int = 0, batch_bytes: int = 0, devices=None) -> dict:
     """Sorts the BAM read from `reader` (bytes-like, or an object with read()/readinto()) and writes the sorted record
     bodies to `sorted_sink` (an object with write()).  Returns the stage times (bamgpu_stats)."""
     if index_file_to_create is not None:
@@ -77,7 +77,8 @@ def sort_bam(mem_limit: int, reader, sorted_sink, tmp_dir=None, out_compr_level:
     # (sort.rs:340-347); "bam" = a complete BAM (header + sorted records in stored-block BGZF + EOF marker)
     fmt = {"bodies": _lib.OUT_BODIES, "records": _lib.OUT_RECORDS, "bam": _lib.OUT_BAM}[output]
     # device_mem_limit > 0 (bamgpu_opts.sort_mem_limit): the streamed form, with batches of about device_mem_limit / 8 compressed bytes
-    opts, st = make_opts(device, flags, sort_output=fmt, sort_mem_limit=device_mem_limit, batch_bytes=batch_bytes), Stats()
+    # devices (bamgpu_opts.devices[]): the streamed form decodes its batches on all of them; the keys collect on the first one used
+    opts, st = make_opts(device, flags, sort_output=fmt, sort_mem_limit=device_mem_limit, batch_bytes=batch_bytes, devices=devices), Stats()
     err = C.create_string_buffer(512)
     rc = L.bamgpu_sort_bam(rcb, None, wcb, None, reader_thread_num, int(sort_by), C.byref(opts), C.byref(st), err, len(err))
     if rc < 0:

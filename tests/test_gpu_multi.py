@@ -285,3 +285,25 @@ def test_edge_exchange_in_peer_memory(oracle, shape, n, payload, n_shards):
     finally:
         for e in engines:
             e.close()
+
+
+@pytest.mark.parametrize("sort_by", ["CoordinatesAndStrand", "Name", "NameAndMatchMates"])
+def test_streamed_sort_over_several_gpus(oracle, sort_by):
+    """bamgpu_sort_bam with sort_mem_limit and a device list: the batches are decoded on every listed GPU, the sort keys
+    (and packed read names) collect on the first one — peer copies between different GPUs —, one stable key sort there, the
+    bodies gathered on the host.  Output = the oracle's (sort.rs:138-178, comparators.rs:61-147)."""
+    from bam_parallel_b200.sorting import SortBy, sort_bam
+    sb = SortBy[sort_by]
+    ng = _n_gpus()
+    devices = list(range(ng)) if ng > 1 else [0, 0, 0]
+    data = synth.generate("pe150", 80000, level=6).tobytes()
+    u, start, off, ln, cols = _oracle(oracle, data)
+    perm = oracle.sort_perm(u, off, cols, {"Name": 1, "NameAndMatchMates": 2, "CoordinatesAndStrand": 0}[sort_by])
+    ub = u.tobytes()
+    want = b"".join(ub[int(off[i]):int(off[i]) + int(ln[i])] for i in perm.tolist())
+    sink = io.BytesIO()
+    st = sort_bam(0, data, sink, sort_by=sb, device_mem_limit=8 << 20, devices=devices)
+    assert st["batches"] > 3
+    assert hashlib.md5(sink.getvalue()).hexdigest() == hashlib.md5(want).hexdigest()
+    if ng > 1:
+        assert st["p2p_bytes"] > 0            # keys really crossed GPUs
