@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <array>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -2363,6 +2364,474 @@ static int sort_bam_streamed(bamgpu_read_fn read, void* read_ctx, bamgpu_write_f
   return rc;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Sort over several GPUs ("multi-GPU => sample sort"): bamgpu_sort_bam with bamgpu_opts.devices[].
+//   1. the file is cut into G contiguous BGZF block ranges of about equal compressed size; every GPU inflates its range
+//      (K1 + K2) at the same time; the head of the ranges to the right is copied behind each range (peer copy, <= 1 MiB) so
+//      that the record across the cut is whole; the record chain (reader.rs:63-81) then runs range by range — K3 is a few
+//      milliseconds, and the start of range g + 1 is simply where range g's last record ended (no guessing);
+//   2. a few hundred evenly spaced keys per GPU go to the host, which picks G - 1 splitters; records that compare equal to a
+//      splitter all fall into the bucket above it, so a bucket holds whole groups of equal keys;
+//   3. every GPU partitions its records by bucket (stable), gathers them as a (u32 block_size, body)* stream and writes
+//      bucket d's piece into GPU d's memory (cudaMemcpyPeerAsync, NVLink): pieces sit there in range order;
+//   4. GPU d parses what it received (K3 again: keys come from the records themselves) and sorts it with the single-GPU
+//      sort — stable, so ties keep range order = input order; the output is bucket 0, bucket 1, ... back to back, byte for
+//      byte what the single-GPU sort writes (for the BAM format the 0xff00-byte pieces that cross a bucket edge are
+//      completed by copying the odd tail of bucket d in front of bucket d + 1).
+// No collective; the exchange is G x G independent peer copies.  Anything unusual (a record longer than the halo, fewer blocks
+// than GPUs, a header that does not fit the first range, a scan error) leaves the job to the single-GPU path.
+// -------------------------------------------------------------------------------------------------
+namespace {
+constexpr int SORT_MULTI_NOT_APPLICABLE = 1000;
+
+struct SortShard {
+  int dev = 0;
+  bamgpu_engine* A = nullptr;   // decodes the block range
+  bamgpu_engine* B = nullptr;   // holds and sorts bucket g
+  DevBuf d_comp, d_samples, d_split, d_bounds, d_send, d_soff;
+  size_t b0 = 0, b1 = 0;
+  std::vector<bamgpu_block> blocks;
+  uint64_t own_len = 0, n = 0, bad_flags = 0;
+  std::vector<SplitKey> samples;
+  std::vector<uint32_t> bounds;   // [G + 1] where each bucket starts in the partitioned order
+  std::vector<uint64_t> seg;      // [G + 1] ... and in d_send
+  uint64_t recv_bytes = 0, recv_records = 0, out_len = 0, front = 0;
+  uint8_t* stream = nullptr;      // front bytes + sorted output (device)
+  uint64_t framed = 0;            // BAM: bytes of `stream` this GPU frames
+  size_t bgzf_len = 0;
+  int rc = BAMGPU_OK;
+  std::string msg;
+  void fail(int code, const std::string& m) { if (rc == BAMGPU_OK) { rc = code; msg = m; } }
+};
+
+template <class F> static void for_each_shard(std::vector<SortShard>& sh, F f) {
+  std::vector<std::thread> th;
+  for (size_t g = 0; g < sh.size(); ++g)
+    th.emplace_back([&sh, &f, g] { if (sh[g].rc == BAMGPU_OK) { cudaSetDevice(sh[g].dev); f(sh[g], g); } });
+  for (auto& t : th) t.join();
+}
+static bool shard_failed(const std::vector<SortShard>& sh, int* rc, std::string* msg) {
+  for (auto& s : sh) if (s.rc != BAMGPU_OK) { *rc = s.rc; *msg = s.msg; return true; }
+  return false;
+}
+
+// The inflated bytes of `len` bytes follow: makes the engine's buffer ready to receive them (no inflate).
+static int engine_adopt_stream(bamgpu_engine* E, uint64_t len, cudaStream_t s) {
+  ECK(cudaSetDevice(E->device));
+  { int w = engine_wait_d2h(E); if (w < 0) return w; }
+  ECK(E->d_outs[E->cur].reserve(OUT_LEAD_PAD + len + OUT_TAIL_PAD));
+  ECK(cudaMemsetAsync(E->d_outs[E->cur].p, 0, OUT_LEAD_PAD, s));
+  ECK(cudaMemsetAsync(E->out_ptr() + len, 0, OUT_TAIL_PAD, s));
+  E->lead = 0; E->data_start = 0; E->carry_len = 0; E->keep_from = 0; E->data_len = len; E->halo_len = 0;
+  E->inflate_launched = false; E->pend_nb = 0;
+  return BAMGPU_OK;
+}
+
+// reader.rs:87-98,154-200 over inflated bytes that sit in device memory: header bytes without the magic, where the records begin.
+static int header_from_device(bamgpu_engine* E, uint64_t avail, std::vector<uint8_t>& header, uint64_t* end, int32_t* n_ref_out) {
+  std::vector<uint8_t> hb;
+  uint64_t want = std::min<uint64_t>(avail, 1 << 16);
+  for (;;) {
+    if (hb.size() < want) {
+      const size_t old = hb.size();
+      hb.resize(want);
+      int rc = bamgpu_memcpy_d2h(E, hb.data() + old, E->out_ptr() + old, want - old);
+      if (rc < 0) return rc;
+    }
+    uint64_t need = 0, p = 4;
+    do {
+      if (hb.size() < 8) { need = 8; break; }
+      if (memcmp(hb.data(), "BAM\1", 4) != 0) return BAMGPU_ERR_BAD_MAGIC;
+      const uint64_t l_text = rd32(hb.data() + p); p += 4;
+      if (hb.size() < p + l_text + 4) { need = p + l_text + 4; break; }
+      p += l_text;
+      const uint32_t n_ref = rd32(hb.data() + p); p += 4;
+      for (uint32_t i = 0; i < n_ref && !need; ++i) {
+        if (hb.size() < p + 4) { need = p + 4 + 4096; break; }
+        const uint64_t l_name = rd32(hb.data() + p); p += 4;
+        if (hb.size() < p + l_name + 4) { need = p + l_name + 4 + 4096; break; }
+        p += l_name + 4;
+      }
+      if (!need) {
+        header.assign(hb.begin() + 4, hb.begin() + p);
+        *end = p;
+        *n_ref_out = n_ref > 0x7fffffffu ? -1 : (int32_t)n_ref;
+        return BAMGPU_OK;
+      }
+    } while (0);
+    if (hb.size() >= avail) return BAMGPU_ERR_SHORT_HEADER;
+    want = std::min<uint64_t>(avail, std::max<uint64_t>(need, hb.size() * 2));
+  }
+}
+
+static bool split_less(const SplitKey& a, const SplitKey& b, bool by_name) {
+  if (!by_name) return a.key != b.key ? a.key < b.key : a.strand < b.strand;
+  const uint32_t l = std::min(a.name_len, b.name_len);
+  const int c = memcmp(a.name, b.name, l);
+  return c != 0 ? c < 0 : a.name_len < b.name_len;
+}
+
+struct OutSeg { int dev; cudaStream_t s; const uint8_t* p; uint64_t len; };
+// The segments, one after the other, to the sink through two pinned staging buffers (the copy of piece k + 1 overlaps write(k)).
+static int write_segments(const std::vector<OutSeg>& segs, bamgpu_write_fn write, void* write_ctx, uint64_t* out_bytes, double* ms, std::string& msg) {
+  const size_t CH = (size_t)64 << 20;
+  struct Piece { size_t seg; uint64_t off; size_t len; };
+  std::vector<Piece> pieces;
+  for (size_t i = 0; i < segs.size(); ++i)
+    for (uint64_t o = 0; o < segs[i].len; o += CH) pieces.push_back({i, o, (size_t)std::min<uint64_t>(CH, segs[i].len - o)});
+  if (pieces.empty()) return BAMGPU_OK;
+  PinBuf st[2];
+  if (st[0].reserve(CH) != cudaSuccess || st[1].reserve(CH) != cudaSuccess) { msg = "pinned staging"; return BAMGPU_ERR_NOMEM; }
+  std::map<int, std::array<cudaEvent_t, 2>> evs;
+  for (auto& sg : segs)
+    if (!evs.count(sg.dev)) {
+      cudaSetDevice(sg.dev);
+      std::array<cudaEvent_t, 2> e{};
+      cudaEventCreateWithFlags(&e[0], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&e[1], cudaEventDisableTiming);
+      evs[sg.dev] = e;
+    }
+  const double t0 = now_ms();
+  int rc = BAMGPU_OK;
+  auto issue = [&](size_t k) {
+    const Piece& pc = pieces[k];
+    const OutSeg& sg = segs[pc.seg];
+    cudaSetDevice(sg.dev);
+    cudaMemcpyAsync(st[k & 1].p, sg.p + pc.off, pc.len, cudaMemcpyDeviceToHost, sg.s);
+    cudaEventRecord(evs[sg.dev][k & 1], sg.s);
+  };
+  issue(0);
+  for (size_t k = 0; k < pieces.size(); ++k) {
+    if (k + 1 < pieces.size()) issue(k + 1);
+    const OutSeg& sg = segs[pieces[k].seg];
+    if (cudaEventSynchronize(evs[sg.dev][k & 1]) != cudaSuccess) { rc = BAMGPU_ERR_CUDA; msg = "D2H of the sorted output failed"; break; }
+    if (write(write_ctx, st[k & 1].as<uint8_t>(), pieces[k].len) < 0) { rc = BAMGPU_ERR_IO; msg = "write callback failed"; break; }
+    *out_bytes += pieces[k].len;
+  }
+  for (auto& sg : segs) { cudaSetDevice(sg.dev); cudaStreamSynchronize(sg.s); }
+  *ms += now_ms() - t0;
+  for (auto& kv : evs) { cudaSetDevice(kv.first); cudaEventDestroy(kv.second[0]); cudaEventDestroy(kv.second[1]); }
+  st[0].release(); st[1].release();
+  return rc;
+}
+
+static void add_stats(bamgpu_stats& acc, const bamgpu_stats& s) {
+  acc.blocks += s.blocks; acc.bytes_in += s.bytes_in; acc.bytes_out += s.bytes_out; acc.records += s.records; acc.batches += s.batches;
+  acc.kernel_launches += s.kernel_launches; acc.p2p_bytes += s.p2p_bytes;
+  // the GPUs work side by side: the stage times are those of the slowest one
+  acc.ms_h2d = std::max(acc.ms_h2d, s.ms_h2d); acc.ms_inflate = std::max(acc.ms_inflate, s.ms_inflate); acc.ms_crc = std::max(acc.ms_crc, s.ms_crc);
+  acc.ms_records = std::max(acc.ms_records, s.ms_records); acc.ms_sort = std::max(acc.ms_sort, s.ms_sort);
+  acc.ms_gather = std::max(acc.ms_gather, s.ms_gather); acc.ms_bgzf_write = std::max(acc.ms_bgzf_write, s.ms_bgzf_write);
+}
+}  // namespace
+
+// buf[0..len): the whole BGZF file in host memory.  Returns BAMGPU_OK / an error, or SORT_MULTI_NOT_APPLICABLE (nothing written).
+static int sort_bam_multi(const uint8_t* buf, size_t len, bamgpu_write_fn write, void* write_ctx, int sort_by, const bamgpu_opts& opts,
+                          bamgpu_stats* stats, std::string& msg) {
+  const int G = opts.n_devices;
+  const int out_fmt = opts.sort_output;
+  if (out_fmt < BAMGPU_OUT_BODIES || out_fmt > BAMGPU_OUT_BAM) { msg = "unknown sort_output"; return BAMGPU_ERR_ARG; }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { msg = "no usable CUDA device (this library has no CPU fallback)"; return BAMGPU_ERR_CUDA; }
+  for (int g = 0; g < G; ++g) if (opts.devices[g] < 0 || opts.devices[g] >= count) { msg = "bamgpu_opts.devices: no such device"; return BAMGPU_ERR_ARG; }
+  // 0. the block table, cut into G ranges
+  size_t nblk = 0, consumed = 0;
+  uint64_t isize_total = 0;
+  int sc = bamgpu_scan_blocks(buf, len, 1, nullptr, 0, &nblk, &consumed, &isize_total);
+  if (sc < 0 || nblk < (size_t)G * 2) return SORT_MULTI_NOT_APPLICABLE;
+  std::vector<bamgpu_block> all(nblk);
+  sc = bamgpu_scan_blocks(buf, len, 1, all.data(), nblk, &nblk, &consumed, &isize_total);
+  if (sc < 0) return SORT_MULTI_NOT_APPLICABLE;
+  {   // room on every GPU for its range, what it sends, its bucket and the bucket's sorted output (buckets are about even)?
+    std::map<int, uint64_t> need;
+    for (int g = 0; g < G; ++g) need[opts.devices[g]] += ((uint64_t)len + 4 * isize_total + isize_total / 2) / G + ((uint64_t)1 << 30);
+    for (auto& kv : need) {
+      size_t free_b = 0, total_b = 0;
+      if (cudaSetDevice(kv.first) != cudaSuccess || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { msg = "no usable CUDA device (this library has no CPU fallback)"; return BAMGPU_ERR_CUDA; }
+      if (kv.second > (uint64_t)free_b + dev_cache_bytes()) return SORT_MULTI_NOT_APPLICABLE;
+    }
+  }
+  for (int a = 0; a < G; ++a)
+    for (int b = a + 1; b < G; ++b)
+      if (opts.devices[a] != opts.devices[b]) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, opts.devices[a], opts.devices[b]);
+        if (can) {
+          cudaSetDevice(opts.devices[a]); cudaDeviceEnablePeerAccess(opts.devices[b], 0);
+          cudaSetDevice(opts.devices[b]); cudaDeviceEnablePeerAccess(opts.devices[a], 0);
+          cudaGetLastError();   // "already enabled" is fine; without peer access the copies are staged by the driver
+        }
+      }
+  std::vector<SortShard> sh(G);
+  {
+    size_t b = 0;
+    for (int g = 0; g < G; ++g) {
+      sh[g].dev = opts.devices[g];
+      sh[g].b0 = b;
+      const uint64_t want = (uint64_t)consumed * (g + 1) / G;
+      while (b < nblk && (g == G - 1 || all[b].in_off - 18 < want || b == sh[g].b0)) ++b;
+      if (g == G - 1) b = nblk;
+      sh[g].b1 = b;
+      if (sh[g].b1 == sh[g].b0) return SORT_MULTI_NOT_APPLICABLE;
+    }
+  }
+  const bool by_name = sort_by != BAMGPU_SORT_COORDINATES_AND_STRAND;
+  const uint32_t rec_flags = (opts.flags & BAMGPU_NO_CRC) | (sort_by == BAMGPU_SORT_NAME_AND_MATCH_MATES ? BAMGPU_WANT_HI : 0u);
+  int rc = BAMGPU_OK;
+  uint64_t p2p_bytes = 0, out_bytes = 0;
+  double ms_d2h = 0;
+  bamgpu_stats acc{};
+  std::vector<uint8_t> header;
+  auto cleanup = [&]() {
+    for (auto& s : sh) {
+      cudaSetDevice(s.dev);
+      if (s.A) { cudaStreamSynchronize(s.A->stream); bamgpu_stats st; bamgpu_engine_stats(s.A, &st); add_stats(acc, st); bamgpu_engine_free(s.A); s.A = nullptr; }
+      if (s.B) { cudaStreamSynchronize(s.B->stream); bamgpu_stats st; bamgpu_engine_stats(s.B, &st); add_stats(acc, st); bamgpu_engine_free(s.B); s.B = nullptr; }
+      for (DevBuf* d : {&s.d_comp, &s.d_samples, &s.d_split, &s.d_bounds, &s.d_send, &s.d_soff}) d->release();
+    }
+    if (stats) { acc.p2p_bytes += p2p_bytes; acc.ms_d2h += ms_d2h; acc.ms_total = acc.ms_h2d + acc.ms_inflate + acc.ms_crc + acc.ms_records + acc.ms_d2h + acc.ms_sort + acc.ms_gather; *stats = acc; }
+  };
+#define SHCK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { s.fail(_e == cudaErrorMemoryAllocation ? BAMGPU_ERR_NOMEM : BAMGPU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); return; } } while (0)
+  // 1. every GPU: its range to the device, K1 + K2
+  for_each_shard(sh, [&](SortShard& s, size_t) {
+    bamgpu_opts eo{};
+    eo.device = s.dev;
+    eo.flags = opts.flags & BAMGPU_NO_CRC;
+    eo.inflate_impl = opts.inflate_impl;
+    s.A = bamgpu_engine_new(&eo);
+    if (!s.A) { s.fail(BAMGPU_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)"); return; }
+    const uint64_t c0 = all[s.b0].in_off - 18, c1 = all[s.b1 - 1].in_off + all[s.b1 - 1].in_len + 8;
+    s.blocks.assign(all.begin() + s.b0, all.begin() + s.b1);
+    for (auto& b : s.blocks) b.in_off -= c0;
+    SHCK(s.d_comp.reserve(c1 - c0 + IN_TAIL_PAD));
+    SHCK(cudaMemsetAsync(s.d_comp.as<uint8_t>() + (c1 - c0), 0, IN_TAIL_PAD, s.A->stream));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, s.A->stream);
+    SHCK(cudaMemcpyAsync(s.d_comp.p, buf + c0, c1 - c0, cudaMemcpyHostToDevice, s.A->stream));
+    cudaEventRecord(e1, s.A->stream);
+    int r = engine_inflate(s.A, s.d_comp.as<uint8_t>(), s.blocks.data(), s.blocks.size(), eo.flags, s.A->stream);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    s.A->stats.ms_h2d += ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (r < 0) { s.fail(r, s.A->err); return; }
+    s.own_len = s.A->data_len;
+  });
+  do {
+    if (shard_failed(sh, &rc, &msg)) break;
+    // 2. halos: the first bytes to the right of every range, from as many ranges as it takes (<= BAMGPU_MAX_HALO)
+    for (int g = 0; g + 1 < G; ++g) {
+      SortShard& s = sh[g];
+      cudaSetDevice(s.dev);
+      uint64_t have = 0;
+      for (int h = g + 1; h < G && have < BAMGPU_MAX_HALO; ++h) {
+        const uint64_t m = std::min<uint64_t>(sh[h].own_len, BAMGPU_MAX_HALO - have);
+        if (m && cudaMemcpyPeerAsync(s.A->out_ptr() + s.own_len + have, s.dev, sh[h].A->out_ptr(), sh[h].dev, m, s.A->stream) != cudaSuccess) {
+          rc = BAMGPU_ERR_CUDA; msg = "halo copy failed"; break;
+        }
+        if (sh[h].dev != s.dev) p2p_bytes += m;
+        have += m;
+      }
+      if (rc != BAMGPU_OK) break;
+      cudaMemsetAsync(s.A->out_ptr() + s.own_len + have, 0, OUT_TAIL_PAD, s.A->stream);
+      s.A->halo_len = have;
+      if (cudaStreamSynchronize(s.A->stream) != cudaSuccess) { rc = BAMGPU_ERR_CUDA; msg = "halo copy failed"; break; }
+    }
+    if (rc != BAMGPU_OK) break;
+    // 3. the header, then the record chain range by range (reader.rs:63-81)
+    uint64_t start = 0;
+    int32_t n_ref = -1;
+    {
+      int r = header_from_device(sh[0].A, sh[0].own_len + sh[0].A->halo_len, header, &start, &n_ref);
+      if (r == BAMGPU_ERR_BAD_MAGIC) { rc = r; msg = "invalid BAM header"; break; }
+      if (r == BAMGPU_ERR_SHORT_HEADER) { rc = SORT_MULTI_NOT_APPLICABLE; break; }
+      if (r < 0) { rc = r; msg = sh[0].A->err; break; }
+    }
+    uint64_t total = 0, bad_flags = 0;
+    bool ended = false;
+    for (int g = 0; g < G && rc == BAMGPU_OK; ++g) {
+      SortShard& s = sh[g];
+      if (ended) { s.n = 0; continue; }
+      s.A->n_ref = n_ref;
+      bamgpu_batch b;
+      uint64_t tail = 0;
+      const int final = g == G - 1;
+      int r = engine_records(s.A, start, final, rec_flags, s.A->stream, &b, &tail);
+      if (r < 0) { rc = r; msg = s.A->err; break; }
+      s.n = b.n_records;
+      bad_flags += b.bad_flag_records;
+      total += s.n;
+      if (r == BAMGPU_EOF) { ended = true; continue; }
+      if (!final) {
+        if (tail < s.own_len || tail > s.own_len + s.A->halo_len) { rc = SORT_MULTI_NOT_APPLICABLE; break; }   // a record longer than the halo
+        start = tail - s.own_len;
+      }
+    }
+    if (rc != BAMGPU_OK) break;
+    if (total == 0) { rc = SORT_MULTI_NOT_APPLICABLE; break; }
+    if (!by_name && bad_flags) {
+      rc = BAMGPU_ERR_SORT_BAD_FLAGS;
+      msg = "sort: " + std::to_string(bad_flags) + " record(s) with flag bits >= 0x1000 (Flags::from_bits().unwrap() panics, comparators.rs:178)";
+      break;
+    }
+    // 4. splitters from evenly spaced samples
+    for_each_shard(sh, [&](SortShard& s, size_t) {
+      const uint32_t ns = (uint32_t)std::min<uint64_t>(s.n, 512);
+      if (!ns) return;
+      SHCK(s.d_samples.reserve(ns * sizeof(SplitKey)));
+      SHCK(sample_keys(s.A->out_ptr(), s.A->mir[s.A->msel].cols, s.n, sort_by, ns, s.d_samples.as<SplitKey>(), s.A->stream));
+      s.samples.resize(ns);
+      SHCK(cudaMemcpyAsync(s.samples.data(), s.d_samples.p, ns * sizeof(SplitKey), cudaMemcpyDeviceToHost, s.A->stream));
+      SHCK(cudaStreamSynchronize(s.A->stream));
+      s.A->stats.kernel_launches += 1;
+    });
+    if (shard_failed(sh, &rc, &msg)) break;
+    std::vector<SplitKey> split;
+    {
+      std::vector<SplitKey> pool;
+      for (auto& s : sh) pool.insert(pool.end(), s.samples.begin(), s.samples.end());
+      std::stable_sort(pool.begin(), pool.end(), [&](const SplitKey& a, const SplitKey& b) { return split_less(a, b, by_name); });
+      for (int k = 1; k < G; ++k) split.push_back(pool[std::min(pool.size() - 1, pool.size() * k / G)]);
+    }
+    // 5. partition by bucket, gather (u32 block_size, body)* in that order
+    for_each_shard(sh, [&](SortShard& s, size_t) {
+      s.bounds.assign(G + 1, 0);
+      s.seg.assign(G + 1, 0);
+      if (!s.n) return;
+      cudaStream_t st = s.A->stream;
+      const ColumnsDev& cols = s.A->mir[s.A->msel].cols;
+      SHCK(s.d_split.reserve(sizeof(SplitKey) * (G - 1) + 64));
+      SHCK(cudaMemcpyAsync(s.d_split.p, split.data(), sizeof(SplitKey) * (G - 1), cudaMemcpyHostToDevice, st));
+      SHCK(s.d_bounds.reserve(4 * (G + 2)));
+      SHCK(s.A->d_sort.reserve(sort_scratch_bytes(s.n)));
+      SHCK(s.A->d_perm.reserve(4 * (s.n + 1)));
+      SHCK(s.d_soff.reserve(8 * (s.n + 2)));
+      int launches = 0;
+      cudaEventRecord(s.A->ev[3], st);
+      SHCK(partition_by_splitters(s.A->out_ptr(), cols, s.n, sort_by, s.d_split.as<SplitKey>(), (uint32_t)(G - 1), s.A->d_sort.p,
+                                  s.A->d_perm.as<uint32_t>(), s.d_bounds.as<uint32_t>(), &launches, st));
+      cudaEventRecord(s.A->ev[4], st);
+      SHCK(cudaMemcpyAsync(s.bounds.data(), s.d_bounds.p, 4 * (G + 1), cudaMemcpyDeviceToHost, st));
+      uint64_t total_bytes = 0;
+      SHCK(sorted_offsets(cols, s.A->d_perm.as<uint32_t>(), s.n, s.A->d_sort.p, s.d_soff.as<uint64_t>(), &total_bytes, 4, st));   // synchronises
+      for (int d = 0; d <= G; ++d) SHCK(cudaMemcpyAsync(&s.seg[d], s.d_soff.as<uint64_t>() + s.bounds[d], 8, cudaMemcpyDeviceToHost, st));
+      SHCK(s.d_send.reserve(total_bytes + 64));
+      SHCK(gather_sorted_bodies(s.A->out_ptr(), cols, s.A->d_perm.as<uint32_t>(), s.n, s.A->d_sort.p, s.d_soff.as<uint64_t>(), s.d_send.as<uint8_t>(), 4, st));
+      cudaEventRecord(s.A->ev[5], st);
+      SHCK(cudaStreamSynchronize(st));
+      float ms = 0;
+      cudaEventElapsedTime(&ms, s.A->ev[3], s.A->ev[4]); s.A->stats.ms_sort += ms;
+      cudaEventElapsedTime(&ms, s.A->ev[4], s.A->ev[5]); s.A->stats.ms_gather += ms;
+      s.A->stats.kernel_launches += launches + 3;
+    });
+    if (shard_failed(sh, &rc, &msg)) break;
+    // 6. the exchange: bucket d's piece of every range into GPU d's memory, in range order
+    std::vector<std::vector<uint64_t>> roff(G, std::vector<uint64_t>(G, 0));
+    for (int d = 0; d < G; ++d) {
+      uint64_t o = 0, cnt = 0;
+      for (int g = 0; g < G; ++g) { roff[g][d] = o; o += sh[g].seg[d + 1] - sh[g].seg[d]; cnt += sh[g].bounds[d + 1] - sh[g].bounds[d]; }
+      sh[d].recv_bytes = o;
+      sh[d].recv_records = cnt;
+    }
+    for_each_shard(sh, [&](SortShard& s, size_t) {
+      bamgpu_opts eo{};
+      eo.device = s.dev;
+      eo.flags = opts.flags & BAMGPU_NO_CRC;
+      s.B = bamgpu_engine_new(&eo);
+      if (!s.B) { s.fail(BAMGPU_ERR_CUDA, "engine for the bucket"); return; }
+      s.B->n_ref = n_ref;
+      int r = engine_adopt_stream(s.B, s.recv_bytes, s.B->stream);
+      if (r < 0) { s.fail(r, s.B->err); return; }
+      SHCK(cudaStreamSynchronize(s.B->stream));
+    });
+    if (shard_failed(sh, &rc, &msg)) break;
+    for_each_shard(sh, [&](SortShard& s, size_t g) {
+      for (int d = 0; d < G; ++d) {
+        const uint64_t m = s.seg[d + 1] - s.seg[d];
+        if (m) SHCK(cudaMemcpyPeerAsync(sh[d].B->out_ptr() + roff[g][d], sh[d].dev, s.d_send.as<uint8_t>() + s.seg[d], s.dev, m, s.A->stream));
+      }
+      SHCK(cudaStreamSynchronize(s.A->stream));
+    });
+    if (shard_failed(sh, &rc, &msg)) break;
+    for (int g = 0; g < G; ++g)
+      for (int d = 0; d < G; ++d) if (sh[g].dev != sh[d].dev) p2p_bytes += sh[g].seg[d + 1] - sh[g].seg[d];
+    // the ranges are no longer needed: their memory goes back before the buckets are sorted
+    for (auto& s : sh) {
+      cudaSetDevice(s.dev);
+      bamgpu_stats st; bamgpu_engine_stats(s.A, &st); add_stats(acc, st);
+      bamgpu_engine_free(s.A); s.A = nullptr;
+      s.d_comp.release(); s.d_send.release(); s.d_soff.release();
+    }
+    // 7. every GPU parses and sorts its bucket
+    const uint32_t prefix = out_fmt == BAMGPU_OUT_BODIES ? 0u : 4u;
+    {
+      uint64_t carry = out_fmt == BAMGPU_OUT_BAM ? 4 + header.size() : 0;
+      for (int d = 0; d < G; ++d) {
+        sh[d].front = carry;
+        sh[d].out_len = sh[d].recv_bytes - (prefix ? 0 : 4 * sh[d].recv_records);
+        const uint64_t L = carry + sh[d].out_len;
+        sh[d].framed = (out_fmt == BAMGPU_OUT_BAM && d < G - 1) ? L / BGZF_STORE_PAYLOAD * BGZF_STORE_PAYLOAD : L;
+        carry = L - sh[d].framed;
+      }
+    }
+    for_each_shard(sh, [&](SortShard& s, size_t) {
+      bamgpu_engine* E = s.B;
+      if (s.recv_records == 0) {
+        SHCK(E->d_sorted.reserve(s.front + 64));
+        s.stream = E->d_sorted.as<uint8_t>();
+        return;
+      }
+      bamgpu_batch b;
+      uint64_t tail = 0;
+      int r = engine_records(E, 0, 1, rec_flags, E->stream, &b, &tail);
+      if (r < 0) { s.fail(r, E->err); return; }
+      if (b.n_records != s.recv_records || tail != s.recv_bytes) { s.fail(BAMGPU_ERR_STATE, "internal: the exchanged bucket does not parse back to its records"); return; }
+      E->sort_front = s.front;
+      bamgpu_sorted srt;
+      r = bamgpu_engine_sort(E, sort_by, prefix ? BAMGPU_SORT_EMIT_BLOCK_SIZE : 0, nullptr, &srt);
+      E->sort_front = 0;
+      if (r < 0) { s.fail(r, E->err); return; }
+      if (srt.bodies_len != s.out_len) { s.fail(BAMGPU_ERR_STATE, "internal: bucket output size"); return; }
+      s.stream = E->d_sorted.as<uint8_t>();
+    });
+    if (shard_failed(sh, &rc, &msg)) break;
+    // 8. output
+    std::vector<OutSeg> segs;
+    if (out_fmt == BAMGPU_OUT_BAM) {
+      {   // "BAM\1" + header in front of bucket 0; the odd tail of bucket d in front of bucket d + 1
+        std::vector<uint8_t> hd(4 + header.size());
+        memcpy(hd.data(), "BAM\1", 4);
+        memcpy(hd.data() + 4, header.data(), header.size());
+        cudaSetDevice(sh[0].dev);
+        if (cudaMemcpy(sh[0].stream, hd.data(), hd.size(), cudaMemcpyHostToDevice) != cudaSuccess) { rc = BAMGPU_ERR_CUDA; msg = "header upload failed"; break; }
+      }
+      for (int d = 1; d < G && rc == BAMGPU_OK; ++d) {
+        const uint64_t c = sh[d].front;
+        if (c && cudaMemcpyPeer(sh[d].stream, sh[d].dev, sh[d - 1].stream + sh[d - 1].framed, sh[d - 1].dev, c) != cudaSuccess) { rc = BAMGPU_ERR_CUDA; msg = "bucket edge copy failed"; }
+        if (sh[d].dev != sh[d - 1].dev) p2p_bytes += c;
+      }
+      if (rc != BAMGPU_OK) break;
+      for_each_shard(sh, [&](SortShard& s, size_t g) {
+        const bool last = (int)g == G - 1;
+        if (s.framed == 0 && !last) return;
+        const size_t bound = bamgpu_bgzf_bound(s.framed);
+        SHCK(s.B->d_bgzf.reserve(bound + 64));
+        int r = bamgpu_engine_bgzf_store(s.B, s.stream, s.framed, s.B->d_bgzf.as<uint8_t>(), bound, &s.bgzf_len, last ? 1 : 0, nullptr);
+        if (r < 0) s.fail(r, s.B->err);
+      });
+      if (shard_failed(sh, &rc, &msg)) break;
+      for (auto& s : sh) if (s.bgzf_len) segs.push_back({s.dev, s.B->stream, s.B->d_bgzf.as<uint8_t>(), s.bgzf_len});
+    } else {
+      for (auto& s : sh) if (s.out_len) segs.push_back({s.dev, s.B->stream, s.stream, s.out_len});
+    }
+    rc = write_segments(segs, write, write_ctx, &out_bytes, &ms_d2h, msg);
+  } while (0);
+#undef SHCK
+  cleanup();
+  return rc;
+}
+
 extern "C" int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write_fn write, void* write_ctx, size_t reader_thread_num,
                                int sort_by, const bamgpu_opts* opts, bamgpu_stats* stats, char* err_buf, size_t err_cap) {
   auto fail = [&](int rc, const std::string& msg) {
@@ -2390,6 +2859,16 @@ extern "C" int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write
     if (got < 0) { free(buf); return fail(BAMGPU_ERR_IO, "read callback failed"); }
     if (got == 0) break;
     len += (size_t)got;
+  }
+  // several GPUs: the sample sort over them (falls through to one GPU when it does not apply)
+  if (opts && opts->n_devices > 1) {
+    if (opts->n_devices > BAMGPU_MAX_DEVICES) { free(buf); return fail(BAMGPU_ERR_ARG, "too many devices"); }
+    std::string m;
+    const int r = sort_bam_multi(buf, len, write, write_ctx, sort_by, *opts, stats, m);
+    if (r != SORT_MULTI_NOT_APPLICABLE) {
+      free(buf);
+      return r == BAMGPU_OK ? r : fail(r, m.empty() ? bamgpu_status_str(r) : m);
+    }
   }
   {   // does it fit in HBM as one batch?  compressed + inflated + gathered output + columns and sort scratch (~110 B per record)
     uint64_t isize_total = 0;

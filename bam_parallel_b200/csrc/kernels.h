@@ -173,6 +173,17 @@ cudaError_t sorted_offsets(const ColumnsDev& c, const uint32_t* perm, uint64_t n
 cudaError_t gather_sorted_bodies(const uint8_t* data, const ColumnsDev& c, const uint32_t* perm, uint64_t n_records, void* scratch,
                                  uint64_t* out_off, uint8_t* out, uint32_t prefix, cudaStream_t s);
 
+// sample sort over several GPUs (bamgpu_sort_bam with a device list): one sampled key / one splitter
+struct SplitKey {
+  uint64_t key;          // coord_key          (CoordinatesAndStrand)
+  uint32_t strand;
+  uint32_t name_len;     // l_read_name        (Name, NameAndMatchMates: buckets are cut by the name alone)
+  uint8_t name[256];
+};
+cudaError_t sample_keys(const uint8_t* data, const ColumnsDev& c, uint64_t n_records, int sort_by, uint32_t n_samples, SplitKey* d_out, cudaStream_t s);
+cudaError_t partition_by_splitters(const uint8_t* data, const ColumnsDev& c, uint64_t n_records, int sort_by, const SplitKey* d_split,
+                                   uint32_t n_split, void* scratch, uint32_t* perm, uint32_t* d_bounds, int* launches, cudaStream_t s);
+
 // streamed sort (bodies on the host, keys on the device): the names of a batch -> compact store + virtual record offsets
 cudaError_t names_total(const ColumnsDev& c, uint64_t n_records, void* scratch, uint64_t* name_bytes, cudaStream_t s);   // synchronises
 cudaError_t pack_names(const uint8_t* data, const ColumnsDev& c, uint64_t n_records, void* scratch, uint8_t* dst, uint64_t store_base,

@@ -179,6 +179,59 @@ __global__ void k_pack_names(const uint8_t* __restrict__ data, const uint64_t* _
   }
 }
 
+
+// ---- sample sort over several GPUs (bamgpu_sort_bam with a device list): splitters and the stable partition by them ----
+// a <= b in the order the buckets are cut by: (coord_key, strand), or the read names bytewise (a proper prefix first).
+// Records that compare equal here land in ONE bucket, so HI / flag / input order are settled by the bucket's own stable sort.
+__device__ __forceinline__ bool split_le_name(const uint8_t* __restrict__ a, uint32_t la, const uint8_t* __restrict__ b, uint32_t lb) {
+  const uint32_t l = la < lb ? la : lb;
+  for (uint32_t k = 0; k < l; ++k) {
+    const uint32_t x = a[k], y = b[k];
+    if (x != y) return x < y;
+  }
+  return la <= lb;
+}
+__global__ void k_sample_keys(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, const uint8_t* __restrict__ l_name,
+                              const uint64_t* __restrict__ coord_key, const uint8_t* __restrict__ strand, uint32_t n, uint32_t n_samples,
+                              int by_name, SplitKey* __restrict__ out) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_samples) return;
+  const uint32_t i = (uint32_t)(((uint64_t)j * n + n / 2) / n_samples);   // evenly spaced over the (unsorted) input
+  SplitKey& o = out[j];
+  o.key = by_name ? 0 : coord_key[i];
+  o.strand = by_name ? 0 : strand[i];
+  o.name_len = by_name ? l_name[i] : 0;
+  if (by_name) {
+    const uint8_t* src = data + rec_off[i] + 32;
+    for (uint32_t k = 0; k < o.name_len; ++k) o.name[k] = src[k];
+  }
+}
+__global__ void k_bucket_of(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, const uint8_t* __restrict__ l_name,
+                            const uint64_t* __restrict__ coord_key, const uint8_t* __restrict__ strand, uint32_t n, int by_name,
+                            const SplitKey* __restrict__ sp, uint32_t n_split, uint32_t* __restrict__ bucket) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t b = 0;
+  if (by_name) {
+    const uint8_t* nm = data + rec_off[i] + 32;
+    const uint32_t ln = l_name[i];
+    for (uint32_t d = 0; d < n_split; ++d) b += split_le_name(sp[d].name, sp[d].name_len, nm, ln) ? 1u : 0u;
+  } else {
+    const uint64_t k = coord_key[i];
+    const uint32_t st = strand[i];
+    for (uint32_t d = 0; d < n_split; ++d) b += (sp[d].key < k || (sp[d].key == k && sp[d].strand <= st)) ? 1u : 0u;
+  }
+  bucket[i] = b;   // splitters are sorted, so this is the index of the bucket
+}
+// bounds[b] = first position of the partitioned order whose bucket is >= b, for b = 0 .. n_buckets (bounds[n_buckets] = n)
+__global__ void k_bucket_bounds(const uint32_t* __restrict__ sorted_bucket, uint32_t n, uint32_t n_buckets, uint32_t* __restrict__ bounds) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const uint32_t prev = i ? sorted_bucket[i - 1] : 0u, cur = i < n ? sorted_bucket[i] : n_buckets;
+  if (i == 0) bounds[0] = 0;
+  for (uint32_t b = prev + 1; b <= cur; ++b) bounds[b] = i;
+}
+
 inline uint32_t blocks_for(uint32_t n, uint32_t threads = 256) { return (n + threads - 1) / threads; }
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -322,6 +375,45 @@ cudaError_t pack_names(const uint8_t* data, const ColumnsDev& c, uint64_t n64, v
   const uint32_t n = (uint32_t)n64;
   if (n == 0) return cudaSuccess;
   k_pack_names<<<blocks_for(n), 256, 0, s>>>(data, c.rec_off, c.l_read_name, (const uint64_t*)scratch, n, dst, store_base, voff);
+  return cudaGetLastError();
+}
+
+
+// Sample sort over several GPUs, step 1: n_samples keys of this shard, evenly spaced, to `d_out` (device).
+cudaError_t sample_keys(const uint8_t* data, const ColumnsDev& c, uint64_t n64, int sort_by, uint32_t n_samples, SplitKey* d_out, cudaStream_t s) {
+  const uint32_t n = (uint32_t)n64;
+  if (n == 0 || n_samples == 0) return cudaSuccess;
+  k_sample_keys<<<blocks_for(n_samples), 256, 0, s>>>(data, c.rec_off, c.l_read_name, c.coord_key, c.strand, n, n_samples,
+                                                     sort_by != SORT_COORDINATES_AND_STRAND, d_out);
+  return cudaGetLastError();
+}
+// Step 2: perm[0..n) = the shard's records grouped by bucket (bucket b = records with splitter[b-1] <= key < splitter[b]), input
+// order kept inside a bucket; d_bounds[0..n_split+1] = where each bucket starts in perm.  `scratch` >= sort_scratch_bytes(n).
+cudaError_t partition_by_splitters(const uint8_t* data, const ColumnsDev& c, uint64_t n64, int sort_by, const SplitKey* d_split, uint32_t n_split,
+                                   void* scratch, uint32_t* perm, uint32_t* d_bounds, int* launches, cudaStream_t s) {
+  const uint32_t n = (uint32_t)n64, n_buckets = n_split + 1;
+  if (n == 0) return cudaMemsetAsync(d_bounds, 0, 4 * (n_buckets + 1), s);
+  Carve cv{(uint8_t*)scratch};
+  cv.take<uint64_t>(n + 1);
+  cv.take<uint64_t>(n + 1);
+  uint32_t* va = cv.take<uint32_t>(n + 1);
+  uint32_t* vb = cv.take<uint32_t>(n + 1);
+  uint32_t* k32a = cv.take<uint32_t>(n + 1);
+  uint32_t* k32b = cv.take<uint32_t>(n + 1);
+  cv.take<uint32_t>(n + 1);
+  cv.take<uint32_t>(n + 1);
+  void* tmp = cv.p + cv.used;
+  size_t tmp_bytes = cub_temp_bytes(n);
+  const uint32_t g = blocks_for(n);
+  k_iota<<<g, 256, 0, s>>>(va, n);
+  k_bucket_of<<<g, 256, 0, s>>>(data, c.rec_off, c.l_read_name, c.coord_key, c.strand, n, sort_by != SORT_COORDINATES_AND_STRAND, d_split,
+                               n_split, k32a);
+  int bits = 1;
+  while ((1u << bits) < n_buckets) ++bits;
+  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const uint32_t*)k32a, k32b, (const uint32_t*)va, vb, (int)n, 0, bits, s);
+  k_bucket_bounds<<<blocks_for(n + 1), 256, 0, s>>>(k32b, n, n_buckets, d_bounds);
+  cudaMemcpyAsync(perm, vb, 4ull * n, cudaMemcpyDeviceToDevice, s);
+  if (launches) *launches += 6;
   return cudaGetLastError();
 }
 

@@ -307,3 +307,74 @@ def test_streamed_sort_over_several_gpus(oracle, sort_by):
     assert hashlib.md5(sink.getvalue()).hexdigest() == hashlib.md5(want).hexdigest()
     if ng > 1:
         assert st["p2p_bytes"] > 0            # keys really crossed GPUs
+
+
+def _n_sort_devices(k):
+    ng = _n_gpus()
+    return list(range(ng)) if ng > 1 else [0] * k
+
+
+@pytest.mark.parametrize("sort_by", ["CoordinatesAndStrand", "Name", "NameAndMatchMates"])
+@pytest.mark.parametrize("shape,n,payload,k", [("pe150", 90000, 0xFF00, 3), ("long10k", 500, 4096, 4), ("longname", 9000, 0xFF00, 2),
+                                               ("pe150", 4000, 700, 5)])
+def test_sample_sort_over_several_gpus(oracle, shape, n, payload, k, sort_by):
+    """bamgpu_sort_bam with a device list and no memory limit ("multi-GPU => sample sort"): contiguous block ranges are
+    decoded side by side, cut into buckets by sampled splitters, exchanged with peer copies and sorted bucket by bucket.  The three
+    output formats must be byte-identical to the single-GPU sort's and the bodies to the oracle's (sort.rs:138-178, :643,
+    comparators.rs:61-147)."""
+    from bam_parallel_b200.sorting import SortBy, sort_bam
+    sb = SortBy[sort_by]
+    devices = _n_sort_devices(k)
+    data = synth.generate(shape, n, level=6, payload=payload).tobytes()
+    u, start, off, ln, cols = _oracle(oracle, data)
+    perm = oracle.sort_perm(u, off, cols, {"Name": 1, "NameAndMatchMates": 2, "CoordinatesAndStrand": 0}[sort_by])
+    ub = u.tobytes()
+    want = b"".join(ub[int(off[i]):int(off[i]) + int(ln[i])] for i in perm.tolist())
+    sink = io.BytesIO()
+    st = sort_bam(0, data, sink, sort_by=sb, devices=devices)
+    assert hashlib.md5(sink.getvalue()).hexdigest() == hashlib.md5(want).hexdigest()
+    assert st["records"] >= n and st["batches"] >= len(devices)          # every range and every bucket went through K3
+    if len(set(devices)) > 1:
+        assert st["p2p_bytes"] > len(want) // 4                            # the buckets really crossed GPUs
+    for fmt in ("records", "bam"):
+        one, many = io.BytesIO(), io.BytesIO()
+        sort_bam(0, data, one, sort_by=sb, output=fmt)
+        sort_bam(0, data, many, sort_by=sb, output=fmt, devices=devices)
+        assert one.getvalue() == many.getvalue(), fmt
+
+
+def test_sample_sort_skewed_keys_and_fallbacks(oracle):
+    """Every record with the same key (one bucket takes all, the others are empty), records longer than the halo between ranges
+    and inputs with fewer blocks than GPUs (the single-GPU path takes over) - same bytes as the single-GPU sort; the reference's
+    panics stay errors."""
+    import struct
+    from bam_parallel_b200.sorting import SortBy, sort_bam
+    from tests import bamcraft as bc
+    devices = _n_sort_devices(3)
+
+    def rec(name, ref_id=0, pos=0, flag=0, tags=b"", seq_len=4):
+        body = struct.pack("<iiBBHHHIiii", ref_id, pos, len(name) + 1, 0, 0, 0, flag, seq_len, -1, -1, 0) + name + b"\0" + \
+            b"\x11" * ((seq_len + 1) // 2) + b"\x20" * seq_len + tags
+        return struct.pack("<I", len(body)) + body
+
+    def bam(recs, payload=0xFF00):
+        return bc.bgzf(b"BAM\x01" + struct.pack("<I", 0) + struct.pack("<I", 1) + struct.pack("<I", 4) + b"ch1\0" + struct.pack("<I", 1000)
+                       + b"".join(recs), payload=payload)
+
+    same = [rec(b"r%05d" % (i % 7), 0, 5, 0, seq_len=40 + (i % 50)) for i in range(20000)]
+    for data in (bam(same, 3000), bam([rec(b"big%d" % i, 0, 9 - i, 0, seq_len=1500000) for i in range(3)], 0xFF00),
+                 bam([rec(b"a", 0, 2), rec(b"b", 0, 1)])):
+        for sb in SortBy:
+            for fmt in ("bodies", "bam"):
+                one, many = io.BytesIO(), io.BytesIO()
+                sort_bam(0, data, one, sort_by=sb, output=fmt)
+                sort_bam(0, data, many, sort_by=sb, output=fmt, devices=devices)
+                assert one.getvalue() == many.getvalue(), (sb, fmt, len(data))
+    data = bam([rec(b"q%d" % (i % 3), 0, i, 0x1000 if i == 7777 else 0) for i in range(20000)], 2000)
+    with pytest.raises(bp.BamGpuError) as e:
+        sort_bam(0, data, io.BytesIO(), sort_by=SortBy.CoordinatesAndStrand, devices=devices)
+    assert e.value.code == -31
+    data = bam([rec(b"q%d" % (i % 3), 0, i, 0, tags=(b"HIi" + struct.pack("<i", 1)) if i != 7777 else b"") for i in range(20000)], 2000)
+    with pytest.raises(bp.BamGpuError) as e:
+        sort_bam(0, data, io.BytesIO(), sort_by=SortBy.NameAndMatchMates, devices=devices)
+    assert e.value.code == -30
