@@ -130,7 +130,7 @@ EXPORTS = [
     "bamgpu_engine_records", "bamgpu_engine_set_n_ref", "bamgpu_engine_stats", "bamgpu_engine_reset_stats", "bamgpu_reader_new",
     "bamgpu_reader_from_memory", "bamgpu_reader_free", "bamgpu_last_error", "bamgpu_read_header", "bamgpu_next_rec",
     "bamgpu_append_record", "bamgpu_read", "bamgpu_next_batch", "bamgpu_reader_stats",
-    "bamgpu_parse_reference_sequences", "bamgpu_status_str", "bamgpu_build_info", "bamgpu_engine_sort", "bamgpu_sort_bam",
+    "bamgpu_parse_reference_sequences", "bamgpu_status_str", "bamgpu_build_info", "bamgpu_engine_sort", "bamgpu_sort_bam", "bamgpu_sort_bam_from_memory",
     "bamgpu_engine_digest", "bamgpu_engine_sorted_digest", "bamgpu_reader_current_engine", "bamgpu_engine_edge_open",
     "bamgpu_engine_edge_connect", "bamgpu_engine_edge_exchange", "bamgpu_engine_edge_close", "bamgpu_bgzf_bound",
     "bamgpu_engine_bgzf_store", "bamgpu_engine_decode_fields", "bamgpu_engine_field_digest",
@@ -209,6 +209,8 @@ def load() -> C.CDLL:
     L.bamgpu_engine_sort.argtypes = [vp, C.c_int, C.c_uint32, vp, C.POINTER(Sorted)]
     L.bamgpu_sort_bam.restype = C.c_int
     L.bamgpu_sort_bam.argtypes = [READ_FN, vp, WRITE_FN, vp, sz, C.c_int, C.POINTER(Opts), C.POINTER(Stats), C.c_char_p, sz]
+    L.bamgpu_sort_bam_from_memory.restype = C.c_int
+    L.bamgpu_sort_bam_from_memory.argtypes = [vp, sz, WRITE_FN, vp, sz, C.c_int, C.POINTER(Opts), C.POINTER(Stats), C.c_char_p, sz]
     L.bamgpu_engine_digest.restype = C.c_int
     L.bamgpu_engine_digest.argtypes = [vp, C.c_uint64, C.c_uint64, vp, C.POINTER(Digest)]
     L.bamgpu_engine_sorted_digest.restype = C.c_int

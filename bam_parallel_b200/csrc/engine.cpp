@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <array>
 #include <map>
 #include <memory>
@@ -1469,7 +1470,10 @@ static void feeder_main(bamgpu_reader* R) {
     S.total_isize = 0;
     // the first batch is small when the caller left the batch size to us: the header and the first records are there
     // after one short copy, and the big batches' copies and K1 start that much earlier
-    const size_t bb = (seq == 0 && R->first_batch_bytes) ? R->first_batch_bytes : R->batch_bytes;
+    // ... and the following ones double up to the full size (32, 64, 128, 256 MiB): each is inflated and parsed by the time the
+    // device-to-host copy of the one in front ends, so that link - the bound of the whole pass - has work from the first
+    // ~13 ms on (with a full-size second batch it idled until that batch's 13 k blocks were through K1 + K3: ~35 ms)
+    const size_t bb = (R->first_batch_bytes && seq < 8) ? std::min(R->batch_bytes, R->first_batch_bytes << seq) : R->batch_bytes;
     const size_t cap = R->batch_bytes + 65536 + 64;
     const uint8_t* src = nullptr;   // where the batch's bytes are on the host
     size_t fill = 0;
@@ -2328,19 +2332,54 @@ static int sort_bam_streamed(bamgpu_read_fn read, void* read_ctx, bamgpu_write_f
       out_bytes += wrote;
       return wrote ? write(write_ctx, framed.data(), wrote) : 0;
     };
-    size_t run_hint = 0;
-    for (uint64_t i = 0; i < total && rc == BAMGPU_OK; ++i) {
-      const uint64_t gidx = perm[i];
-      if (!(run_hint < runs.size() && gidx >= runs[run_hint].first && gidx < runs[run_hint].first + runs[run_hint].n)) {
-        size_t lo = 0, hi = runs.size();
-        while (hi - lo > 1) { const size_t m = (lo + hi) / 2; if (runs[m].first <= gidx) lo = m; else hi = m; }
-        run_hint = lo;
-      }
-      const HostRun& r = runs[run_hint];
-      const uint64_t k = gidx - r.first;
-      const uint32_t len = r.len[k];
-      if (prefix) { const uint8_t* q = (const uint8_t*)&len; stage.insert(stage.end(), q, q + 4); }   // little-endian host (x86-64 / aarch64)
-      stage.insert(stage.end(), r.mem + r.off[k], r.mem + r.off[k] + len);
+    // The records of a piece are looked up (which batch, where, how long), placed by a prefix sum over their lengths and copied
+    // by `threads` workers: perm is a random walk through the batches, so both the look-ups and the copies are cache misses that
+    // only several threads in flight can hide (one thread: about 2 GB/s).
+    const size_t nt = std::min<size_t>(std::max<size_t>(threads, 1), 16);
+    std::vector<const uint8_t*> src;
+    std::vector<uint32_t> slen;
+    std::vector<uint64_t> dpos;
+    uint64_t group = 4096;                        // records looked up per round; follows what a piece turns out to hold
+    auto parallel_over = [&](uint64_t n, const std::function<void(uint64_t, uint64_t)>& f) {
+      const size_t k = n < 2048 ? 1 : nt;
+      if (k == 1) { f(0, n); return; }
+      std::vector<std::thread> th;
+      for (size_t t = 0; t < k; ++t) th.emplace_back([&f, n, t, k] { f(n * t / k, n * (t + 1) / k); });
+      for (auto& x : th) x.join();
+    };
+    for (uint64_t i = 0; i < total && rc == BAMGPU_OK;) {
+      const uint64_t cnt = std::min<uint64_t>(group, total - i);
+      src.resize(cnt); slen.resize(cnt); dpos.resize(cnt + 1);
+      parallel_over(cnt, [&](uint64_t a, uint64_t b) {
+        size_t hint = 0;
+        for (uint64_t j = a; j < b; ++j) {
+          const uint64_t gidx = perm[i + j];
+          if (!(hint < runs.size() && gidx >= runs[hint].first && gidx < runs[hint].first + runs[hint].n)) {
+            size_t lo = 0, hi = runs.size();
+            while (hi - lo > 1) { const size_t m = (lo + hi) / 2; if (runs[m].first <= gidx) lo = m; else hi = m; }
+            hint = lo;
+          }
+          const HostRun& r = runs[hint];
+          const uint64_t k = gidx - r.first;
+          src[j] = r.mem + r.off[k];
+          slen[j] = r.len[k];
+        }
+      });
+      // how many of them fill the piece
+      uint64_t take = 0, pos = stage.size();
+      while (take < cnt && pos < PIECE) { dpos[take] = pos; pos += prefix + slen[take]; ++take; }
+      dpos[take] = pos;
+      stage.resize(pos);
+      uint8_t* out = stage.data();
+      parallel_over(take, [&](uint64_t a, uint64_t b) {
+        for (uint64_t j = a; j < b; ++j) {
+          uint8_t* d = out + dpos[j];
+          if (prefix) memcpy(d, &slen[j], 4);     // little-endian host (x86-64 / aarch64)
+          memcpy(d + prefix, src[j], slen[j]);
+        }
+      });
+      i += take;
+      group = std::min<uint64_t>(std::max<uint64_t>(2 * take, 4096), (uint64_t)1 << 20);
       if (stage.size() >= PIECE) {
         const size_t whole = stage.size() / 0xff00 * 0xff00;
         const int w = flush(whole, false);
@@ -2578,6 +2617,10 @@ static int sort_bam_multi(const uint8_t* buf, size_t len, bamgpu_write_fn write,
   const bool by_name = sort_by != BAMGPU_SORT_COORDINATES_AND_STRAND;
   const uint32_t rec_flags = (opts.flags & BAMGPU_NO_CRC) | (sort_by == BAMGPU_SORT_NAME_AND_MATCH_MATES ? BAMGPU_WANT_HI : 0u);
   int rc = BAMGPU_OK;
+  double t_phase = now_ms();
+  auto phase = [&](const char* what) {
+    if (dbg_level() >= 1) { const double t = now_ms(); fprintf(stderr, "[bamgpu] sort over %d GPUs: %-28s %8.2f ms\n", G, what, t - t_phase); t_phase = t; }
+  };
   uint64_t p2p_bytes = 0, out_bytes = 0;
   double ms_d2h = 0;
   bamgpu_stats acc{};
@@ -2620,6 +2663,7 @@ static int sort_bam_multi(const uint8_t* buf, size_t len, bamgpu_write_fn write,
   });
   do {
     if (shard_failed(sh, &rc, &msg)) break;
+    phase("upload + K1 + K2");
     // 2. halos: the first bytes to the right of every range, from as many ranges as it takes (<= BAMGPU_MAX_HALO)
     for (int g = 0; g + 1 < G; ++g) {
       SortShard& s = sh[g];
@@ -2669,6 +2713,7 @@ static int sort_bam_multi(const uint8_t* buf, size_t len, bamgpu_write_fn write,
       }
     }
     if (rc != BAMGPU_OK) break;
+    phase("halos + header + K3 chain");
     if (total == 0) { rc = SORT_MULTI_NOT_APPLICABLE; break; }
     if (!by_name && bad_flags) {
       rc = BAMGPU_ERR_SORT_BAD_FLAGS;
@@ -2726,6 +2771,7 @@ static int sort_bam_multi(const uint8_t* buf, size_t len, bamgpu_write_fn write,
       s.A->stats.kernel_launches += launches + 3;
     });
     if (shard_failed(sh, &rc, &msg)) break;
+    phase("splitters + partition + gather");
     // 6. the exchange: bucket d's piece of every range into GPU d's memory, in range order
     std::vector<std::vector<uint64_t>> roff(G, std::vector<uint64_t>(G, 0));
     for (int d = 0; d < G; ++d) {
@@ -2763,6 +2809,7 @@ static int sort_bam_multi(const uint8_t* buf, size_t len, bamgpu_write_fn write,
       bamgpu_engine_free(s.A); s.A = nullptr;
       s.d_comp.release(); s.d_send.release(); s.d_soff.release();
     }
+    phase("exchange");
     // 7. every GPU parses and sorts its bucket
     const uint32_t prefix = out_fmt == BAMGPU_OUT_BODIES ? 0u : 4u;
     {
@@ -2796,6 +2843,7 @@ static int sort_bam_multi(const uint8_t* buf, size_t len, bamgpu_write_fn write,
       s.stream = E->d_sorted.as<uint8_t>();
     });
     if (shard_failed(sh, &rc, &msg)) break;
+    phase("K3 + sort of the buckets");
     // 8. output
     std::vector<OutSeg> segs;
     if (out_fmt == BAMGPU_OUT_BAM) {
@@ -2826,49 +2874,26 @@ static int sort_bam_multi(const uint8_t* buf, size_t len, bamgpu_write_fn write,
       for (auto& s : sh) if (s.out_len) segs.push_back({s.dev, s.B->stream, s.stream, s.out_len});
     }
     rc = write_segments(segs, write, write_ctx, &out_bytes, &ms_d2h, msg);
+    phase("output to the sink");
   } while (0);
 #undef SHCK
   cleanup();
   return rc;
 }
 
-extern "C" int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write_fn write, void* write_ctx, size_t reader_thread_num,
-                               int sort_by, const bamgpu_opts* opts, bamgpu_stats* stats, char* err_buf, size_t err_cap) {
+// The whole BGZF file sits in host memory at buf[0..len) (not copied, not freed here).
+static int sort_bam_buffer(const uint8_t* buf, size_t len, bamgpu_write_fn write, void* write_ctx, size_t reader_thread_num,
+                           int sort_by, const bamgpu_opts* opts, bamgpu_stats* stats, char* err_buf, size_t err_cap) {
   auto fail = [&](int rc, const std::string& msg) {
     if (err_buf && err_cap) snprintf(err_buf, err_cap, "%s", msg.c_str());
     return rc;
   };
-  if (!read || !write || sort_by < BAMGPU_SORT_NAME || sort_by > BAMGPU_SORT_COORDINATES_AND_STRAND) return fail(BAMGPU_ERR_ARG, "bad argument");
-  if (opts && opts->sort_mem_limit) {   // sort.rs:138 mem_limit: the streamed form, straight from the caller's source
-    std::string m;
-    const int r = sort_bam_streamed(read, read_ctx, write, write_ctx, reader_thread_num, sort_by, opts, stats, m);
-    return r == BAMGPU_OK ? r : fail(r, m.empty() ? bamgpu_status_str(r) : m);
-  }
-  // 1. the whole input (its size decides the batch size; the reference's reading thread streams it instead, readahead.rs:88-118)
-  size_t cap = (size_t)64 << 20, len = 0;
-  uint8_t* buf = (uint8_t*)malloc(cap);
-  if (!buf) return fail(BAMGPU_ERR_NOMEM, "out of host memory");
-  for (;;) {
-    if (len == cap) {
-      cap *= 2;
-      uint8_t* nb = (uint8_t*)realloc(buf, cap);
-      if (!nb) { free(buf); return fail(BAMGPU_ERR_NOMEM, "out of host memory"); }
-      buf = nb;
-    }
-    long got = read(read_ctx, buf + len, std::min(cap - len, (size_t)256 << 20));
-    if (got < 0) { free(buf); return fail(BAMGPU_ERR_IO, "read callback failed"); }
-    if (got == 0) break;
-    len += (size_t)got;
-  }
   // several GPUs: the sample sort over them (falls through to one GPU when it does not apply)
   if (opts && opts->n_devices > 1) {
-    if (opts->n_devices > BAMGPU_MAX_DEVICES) { free(buf); return fail(BAMGPU_ERR_ARG, "too many devices"); }
+    if (opts->n_devices > BAMGPU_MAX_DEVICES) return fail(BAMGPU_ERR_ARG, "too many devices");
     std::string m;
     const int r = sort_bam_multi(buf, len, write, write_ctx, sort_by, *opts, stats, m);
-    if (r != SORT_MULTI_NOT_APPLICABLE) {
-      free(buf);
-      return r == BAMGPU_OK ? r : fail(r, m.empty() ? bamgpu_status_str(r) : m);
-    }
+    if (r != SORT_MULTI_NOT_APPLICABLE) return r == BAMGPU_OK ? r : fail(r, m.empty() ? bamgpu_status_str(r) : m);
   }
   {   // does it fit in HBM as one batch?  compressed + inflated + gathered output + columns and sort scratch (~110 B per record)
     uint64_t isize_total = 0;
@@ -2876,13 +2901,13 @@ extern "C" int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write
     bamgpu_scan_blocks(buf, len, 1, nullptr, 0, &nblk, &consumed, &isize_total);
     size_t free_b = 0, total_b = 0;
     if (opts && opts->device >= 0) cudaSetDevice(opts->device);
+    else if (opts && opts->n_devices > 0) cudaSetDevice(opts->devices[0]);
     const bool have_dev = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess;
     const uint64_t need = (uint64_t)len + 2 * isize_total + isize_total / 3 + ((uint64_t)1 << 30);
     if (have_dev && need > (uint64_t)free_b + dev_cache_bytes()) {
       MemSrc src{buf, len, 0};
       std::string m;
       const int r = sort_bam_streamed(memsrc_read, &src, write, write_ctx, reader_thread_num, sort_by, opts, stats, m);
-      free(buf);
       return r == BAMGPU_OK ? r : fail(r, m.empty() ? bamgpu_status_str(r) : m);
     }
   }
@@ -2890,13 +2915,14 @@ extern "C" int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write
   bamgpu_opts o{};
   if (opts) o = *opts; else o.device = -1;
   o.batch_bytes = len + 65536;
-  o.n_devices = 0;            // the sort is single-GPU: the whole file is one batch on one device
+  if (o.n_devices > 0 && o.device < 0) o.device = o.devices[0];
+  o.n_devices = 0;            // one batch on one device (a device list is served by sort_bam_multi above when it applies)
   o.jobs_per_device = 2;
   o.flags &= ~(uint32_t)(BAMGPU_COPY_DATA | BAMGPU_COPY_COLUMNS | BAMGPU_NO_RECORDS | BAMGPU_SPECULATIVE_START);
   if (sort_by == BAMGPU_SORT_NAME_AND_MATCH_MATES) o.flags |= BAMGPU_WANT_HI;
   reader_thread_num = std::max<size_t>(reader_thread_num, 1);   // sort.rs:150
   bamgpu_reader* R = bamgpu_reader_from_memory(buf, len, reader_thread_num, &o);
-  if (!R) { free(buf); return fail(BAMGPU_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)"); }
+  if (!R) return fail(BAMGPU_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)");
   int rc = BAMGPU_OK;
   std::string msg;
   do {
@@ -2981,7 +3007,55 @@ extern "C" int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write
   } while (0);
   if (stats) bamgpu_reader_stats(R, stats);
   bamgpu_reader_free(R);
-  free(buf);
   if (rc != BAMGPU_OK) return fail(rc, msg.empty() ? bamgpu_status_str(rc) : msg);
   return BAMGPU_OK;
+}
+
+extern "C" int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write_fn write, void* write_ctx, size_t reader_thread_num,
+                               int sort_by, const bamgpu_opts* opts, bamgpu_stats* stats, char* err_buf, size_t err_cap) {
+  auto fail = [&](int rc, const std::string& msg) {
+    if (err_buf && err_cap) snprintf(err_buf, err_cap, "%s", msg.c_str());
+    return rc;
+  };
+  if (!read || !write || sort_by < BAMGPU_SORT_NAME || sort_by > BAMGPU_SORT_COORDINATES_AND_STRAND) return fail(BAMGPU_ERR_ARG, "bad argument");
+  if (opts && opts->sort_mem_limit) {   // sort.rs:138 mem_limit: the streamed form, straight from the caller's source
+    std::string m;
+    const int r = sort_bam_streamed(read, read_ctx, write, write_ctx, reader_thread_num, sort_by, opts, stats, m);
+    return r == BAMGPU_OK ? r : fail(r, m.empty() ? bamgpu_status_str(r) : m);
+  }
+  // the whole input (its size decides how it is sorted; the reference's reading thread streams it instead, readahead.rs:88-118)
+  size_t cap = (size_t)64 << 20, len = 0;
+  uint8_t* buf = (uint8_t*)malloc(cap);
+  if (!buf) return fail(BAMGPU_ERR_NOMEM, "out of host memory");
+  for (;;) {
+    if (len == cap) {
+      cap *= 2;
+      uint8_t* nb = (uint8_t*)realloc(buf, cap);
+      if (!nb) { free(buf); return fail(BAMGPU_ERR_NOMEM, "out of host memory"); }
+      buf = nb;
+    }
+    long got = read(read_ctx, buf + len, std::min(cap - len, (size_t)256 << 20));
+    if (got < 0) { free(buf); return fail(BAMGPU_ERR_IO, "read callback failed"); }
+    if (got == 0) break;
+    len += (size_t)got;
+  }
+  const int rc = sort_bam_buffer(buf, len, write, write_ctx, reader_thread_num, sort_by, opts, stats, err_buf, err_cap);
+  free(buf);
+  return rc;
+}
+
+extern "C" int bamgpu_sort_bam_from_memory(const uint8_t* buf, size_t len, bamgpu_write_fn write, void* write_ctx, size_t reader_thread_num,
+                                           int sort_by, const bamgpu_opts* opts, bamgpu_stats* stats, char* err_buf, size_t err_cap) {
+  if ((len && !buf) || !write || sort_by < BAMGPU_SORT_NAME || sort_by > BAMGPU_SORT_COORDINATES_AND_STRAND) {
+    if (err_buf && err_cap) snprintf(err_buf, err_cap, "bad argument");
+    return BAMGPU_ERR_ARG;
+  }
+  if (opts && opts->sort_mem_limit) {
+    MemSrc src{buf, len, 0};
+    std::string m;
+    const int r = sort_bam_streamed(memsrc_read, &src, write, write_ctx, reader_thread_num, sort_by, opts, stats, m);
+    if (r != BAMGPU_OK && err_buf && err_cap) snprintf(err_buf, err_cap, "%s", m.empty() ? bamgpu_status_str(r) : m.c_str());
+    return r;
+  }
+  return sort_bam_buffer(buf, len, write, write_ctx, reader_thread_num, sort_by, opts, stats, err_buf, err_cap);
 }

@@ -42,16 +42,11 @@ def sort_bam(mem_limit: int, reader, sorted_sink, tmp_dir=None, out_compr_level:
     if index_file_to_create is not None:
         raise NotImplementedError("GBAM index sort (sort.rs:106-134) is unreachable from bam_binary and not built")
     L = _lib.load()
+    arr = None
     if isinstance(reader, (bytes, bytearray, memoryview, np.ndarray)):
-        arr = np.frombuffer(reader, dtype=np.uint8) if not isinstance(reader, np.ndarray) else reader
-        pos = [0]
-
-        def _read(_ctx, dst, cap):
-            n = min(cap, arr.size - pos[0])
-            if n:
-                C.memmove(dst, arr.ctypes.data + pos[0], n)
-                pos[0] += n
-            return n
+        # already in memory: bamgpu_sort_bam_from_memory reads it in place (no copy through the read callback)
+        arr = np.ascontiguousarray(np.frombuffer(reader, dtype=np.uint8) if not isinstance(reader, np.ndarray) else reader)
+        _read = None
     else:
         readinto = getattr(reader, "readinto", None)
 
@@ -67,20 +62,28 @@ def sort_bam(mem_limit: int, reader, sorted_sink, tmp_dir=None, out_compr_level:
 
     def _write(_ctx, src, n):
         try:
-            sorted_sink.write(C.string_at(src, n))
+            if sorted_sink is not None:          # None: the output is produced and dropped (timing runs)
+                sorted_sink.write(C.string_at(src, n))
             return 0
         except Exception:
             return -1
 
-    rcb, wcb = _lib.READ_FN(_read), _lib.WRITE_FN(_write)
+    wcb = _lib.WRITE_FN(_write)
     # output: "bodies" = the reference's (sort.rs:643); "records" = (u32 block_size, body)*, its spill wire format
     # (sort.rs:340-347); "bam" = a complete BAM (header + sorted records in stored-block BGZF + EOF marker)
     fmt = {"bodies": _lib.OUT_BODIES, "records": _lib.OUT_RECORDS, "bam": _lib.OUT_BAM}[output]
     # device_mem_limit > 0 (bamgpu_opts.sort_mem_limit): the streamed form, with batches of about device_mem_limit / 8 compressed bytes
-    # devices (bamgpu_opts.devices[]): the streamed form decodes its batches on all of them; the keys collect on the first one used
+    # devices (bamgpu_opts.devices[]): without a memory limit the sample sort over those GPUs (contiguous block ranges decoded side by
+    # side, buckets exchanged with peer copies, each GPU sorts one bucket); the streamed form decodes its batches on all of them and
+    # collects the keys on the first one used
     opts, st = make_opts(device, flags, sort_output=fmt, sort_mem_limit=device_mem_limit, batch_bytes=batch_bytes, devices=devices), Stats()
     err = C.create_string_buffer(512)
-    rc = L.bamgpu_sort_bam(rcb, None, wcb, None, reader_thread_num, int(sort_by), C.byref(opts), C.byref(st), err, len(err))
+    if arr is not None:
+        rc = L.bamgpu_sort_bam_from_memory(arr.ctypes.data, arr.size, wcb, None, reader_thread_num, int(sort_by), C.byref(opts), C.byref(st),
+                                           err, len(err))
+    else:
+        rcb = _lib.READ_FN(_read)
+        rc = L.bamgpu_sort_bam(rcb, None, wcb, None, reader_thread_num, int(sort_by), C.byref(opts), C.byref(st), err, len(err))
     if rc < 0:
         raise BamGpuError(rc, err.value.decode(errors="replace"))
     return st.asdict()

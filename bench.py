@@ -277,7 +277,7 @@ def run_b200(a, rank: int, world: int, local_rank: int, host_group=None):
     # holds nothing else on the device (the same loop run after the device-resident phase, with its 45 GB of buffers alive,
     # was measured 15-20 % slower on the D2H side).  N > 1: rank 0 drives all N GPUs through ONE Reader
     # (bamgpu_opts.devices), the other ranks wait on the host. ----
-    e2e = e2e_cols = e2e_all = e2e_rec = pcie = None
+    e2e = e2e_cols = e2e_all = e2e_rec = pcie = sort_multi = None
     reader_digest = None
     if not a.no_e2e and rank == 0:
         if world == 1:
@@ -306,6 +306,22 @@ def run_b200(a, rank: int, world: int, local_rank: int, host_group=None):
             e2e_cols, _ = run_e2e(a, bp, parr, torch, int(total_isize), flags=bp.COPY_COLUMNS,
                                   api="only the SoA columns + sort keys come back (what a host-side sort of keys needs); bodies stay in HBM")
             e2e_rec = run_e2e_next_rec(a, bp, parr, int(total_isize))
+        if world > 1 and not a.no_sort:
+            # the sort over all N GPUs behind bamgpu_sort_bam (sample sort, peer-copy exchange): host buffer in,
+            # sorted bodies out (written to a sink that drops them); device stage times are the slowest GPU's
+            from bam_parallel_b200.sorting import SortBy, sort_bam
+            sort_multi = {}
+            for sb in (SortBy.CoordinatesAndStrand, SortBy.Name):
+                for rep in range(2):
+                    t0 = time.perf_counter()
+                    stt = sort_bam(0, parr, None, sort_by=sb, devices=devs)
+                    wall = time.perf_counter() - t0
+                sort_multi[sb.name] = {"wall_s": round(wall, 3), "ms_inflate": round(stt["ms_inflate"], 2), "ms_records": round(stt["ms_records"], 2),
+                                       "ms_partition_and_key_sort": round(stt["ms_sort"], 2), "ms_gathers": round(stt["ms_gather"], 2),
+                                       "ms_d2h_to_sink": round(stt["ms_d2h"], 1), "p2p_bytes": int(stt["p2p_bytes"]), "records": a.records}
+            sort_multi["note"] = ("bamgpu_sort_bam(devices = all N GPUs) on rank 0: N block ranges decoded side by side, sampled splitters, stable "
+                                  "partition, N x N peer copies of (block_size, body) streams, K3 + stable sort per bucket; output bytes = the "
+                                  "single-GPU sort's (tests/test_gpu_multi.py::test_sample_sort_over_several_gpus)")
         L.bamgpu_pinned_free(pin_ptr)
         del parr
     if dist is not None:
@@ -501,7 +517,7 @@ def run_b200(a, rank: int, world: int, local_rank: int, host_group=None):
                        "generator_seconds": round(gen_s, 1), "k3_chain_repairs": chain_repairs, "p2p_bytes_per_step": p2p // max(a.steps, 1)},
             "records_per_s": n_rec_all / (ms_step * 1e-3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_with_columns": e2e_all, "e2e_columns_only": e2e_cols,
-            "e2e_next_rec": e2e_rec, "pcie_pinned_copy": pcie, "sort": sort_info, "fields": fields_info, "gpu_launches": launches,
+            "e2e_next_rec": e2e_rec, "pcie_pinned_copy": pcie, "sort": sort_info, "sort_multi_gpu": sort_multi, "fields": fields_info, "gpu_launches": launches,
             "verify": verify, "scaling_limiter": limiter, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -381,6 +381,17 @@ typedef int (*bamgpu_write_fn)(void* ctx, const uint8_t* src, size_t len);
 int bamgpu_sort_bam(bamgpu_read_fn read, void* read_ctx, bamgpu_write_fn write, void* write_ctx, size_t reader_thread_num,
                     int sort_by, const bamgpu_opts* opts /*nullable*/, bamgpu_stats* stats /*nullable*/,
                     char* err_buf /*nullable*/, size_t err_cap);
+/* The same over a BGZF file that is already in host memory (not copied; like bamgpu_reader_from_memory a page-locked buffer is
+ * read by the GPUs straight from where it is).
+ * Several GPUs (bamgpu_opts.devices[], both entry points; SURVEY.md 8 f1 "multi-GPU => sample sort"): without sort_mem_limit the
+ * file is cut into one contiguous BGZF block range per GPU, the ranges are decoded side by side, sampled keys give n - 1 splitters,
+ * every GPU partitions its records by bucket and writes bucket d's (u32 block_size, body)* stream into GPU d's memory
+ * (cudaMemcpyPeerAsync), and GPU d parses and sorts what it received; the buckets go to the sink in order.  Output bytes are those of
+ * the single-GPU sort in every format.  Inputs this does not apply to (fewer blocks than GPUs, a record longer than
+ * BAMGPU_MAX_HALO across a range edge, too little device memory) are sorted by the single-GPU / streamed path instead. */
+int bamgpu_sort_bam_from_memory(const uint8_t* buf, size_t len, bamgpu_write_fn write, void* write_ctx, size_t reader_thread_num,
+                                int sort_by, const bamgpu_opts* opts /*nullable*/, bamgpu_stats* stats /*nullable*/,
+                                char* err_buf /*nullable*/, size_t err_cap);
 
 /* BGZF writer with stored DEFLATE blocks: wraps `len` bytes of device memory (a BAM byte stream) into BGZF
  * blocks of 0xff00 payload bytes with CRC32 + ISIZE footers (gz.rs:9-20 framing), optionally followed by the 28-byte EOF

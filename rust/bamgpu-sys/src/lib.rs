@@ -54,6 +54,8 @@ extern "C" {
     pub fn bamgpu_engine_decode_fields(e: *mut bamgpu_engine, which: u32, flags: u32, cuda_stream: *mut c_void, out: *mut bamgpu_fields) -> c_int;
     pub fn bamgpu_sort_bam(read: bamgpu_read_fn, rctx: *mut c_void, write: bamgpu_write_fn, wctx: *mut c_void, reader_thread_num: usize,
                            sort_by: c_int, opts: *const bamgpu_opts, stats: *mut c_void, err: *mut c_char, err_cap: usize) -> c_int;
+    pub fn bamgpu_sort_bam_from_memory(buf: *const u8, len: usize, write: bamgpu_write_fn, wctx: *mut c_void, reader_thread_num: usize,
+                                       sort_by: c_int, opts: *const bamgpu_opts, stats: *mut c_void, err: *mut c_char, err_cap: usize) -> c_int;
 }
 pub type bamgpu_write_fn = unsafe extern "C" fn(ctx: *mut c_void, src: *const u8, len: usize) -> c_int;
 
