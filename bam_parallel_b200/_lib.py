@@ -58,7 +58,7 @@ MAX_DEVICES = 16
 class Opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("batch_bytes", C.c_uint64), ("inflate_impl", C.c_int32),
                 ("jobs_per_device", C.c_int32), ("n_devices", C.c_int32), ("devices", C.c_int32 * MAX_DEVICES),
-                ("sort_output", C.c_int32), ("sort_mem_limit", C.c_uint64)]
+                ("sort_output", C.c_int32), ("sort_mem_limit", C.c_uint64), ("out_compr_level", C.c_int32), ("reserved", C.c_int32)]
 
 
 OUT_BODIES, OUT_RECORDS, OUT_BAM = 0, 1, 2          # bamgpu_opts.sort_output
@@ -66,8 +66,9 @@ SORT_EMIT_BLOCK_SIZE = 128
 
 
 def make_opts(device: int = -1, flags: int = 0, batch_bytes: int = 0, inflate_impl: int = 0, jobs_per_device: int = 0,
-              devices=None, sort_output: int = 0, sort_mem_limit: int = 0) -> Opts:
+              devices=None, sort_output: int = 0, sort_mem_limit: int = 0, out_compr_level: int = 0) -> Opts:
     o = Opts()
+    o.out_compr_level = out_compr_level
     o.sort_output = sort_output
     o.sort_mem_limit = sort_mem_limit
     o.device, o.flags, o.batch_bytes, o.inflate_impl, o.jobs_per_device = device, flags, batch_bytes, inflate_impl, jobs_per_device
@@ -133,7 +134,7 @@ EXPORTS = [
     "bamgpu_parse_reference_sequences", "bamgpu_status_str", "bamgpu_build_info", "bamgpu_engine_sort", "bamgpu_sort_bam", "bamgpu_sort_bam_from_memory",
     "bamgpu_engine_digest", "bamgpu_engine_sorted_digest", "bamgpu_reader_current_engine", "bamgpu_engine_edge_open",
     "bamgpu_engine_edge_connect", "bamgpu_engine_edge_exchange", "bamgpu_engine_edge_close", "bamgpu_bgzf_bound",
-    "bamgpu_engine_bgzf_store", "bamgpu_engine_decode_fields", "bamgpu_engine_field_digest",
+    "bamgpu_engine_bgzf_store", "bamgpu_engine_bgzf_write", "bamgpu_engine_decode_fields", "bamgpu_engine_field_digest",
 ]
 
 _lib = None
@@ -227,6 +228,8 @@ def load() -> C.CDLL:
     L.bamgpu_bgzf_bound.argtypes = [sz]
     L.bamgpu_engine_bgzf_store.restype = C.c_int
     L.bamgpu_engine_bgzf_store.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), C.c_int, vp]
+    L.bamgpu_engine_bgzf_write.restype = C.c_int
+    L.bamgpu_engine_bgzf_write.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), C.c_int, C.c_int, vp]
     L.bamgpu_engine_decode_fields.restype = C.c_int
     L.bamgpu_engine_decode_fields.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.POINTER(Fields)]
     L.bamgpu_engine_field_digest.restype = C.c_int

@@ -270,7 +270,7 @@ struct bamgpu_engine {
   bool sorted_valid = false;
   uint64_t sort_front = 0, sorted_front_used = 0;   // bytes kept free in front of the sorted output (bamgpu_sort_bam: the BAM header)
   uint32_t sorted_prefix = 0;
-  DevBuf d_bgzf, d_bgzf_crc;                        // BGZF writer output + per-block CRCs
+  DevBuf d_bgzf, d_bgzf_crc, d_bgzf_tmp;            // BGZF writer output + per-block CRCs + the compressor's slots
   uint64_t halo_len = 0;    // bytes copied behind them from the right-hand shard (multi-GPU)
   uint64_t carry_len = 0;   // bytes at the front of the next batch kept from this one
   uint64_t keep_from = 0;   // where those bytes currently sit
@@ -474,7 +474,7 @@ extern "C" void bamgpu_engine_free(bamgpu_engine* E) {
   E->d_outs[0].release(); E->d_outs[1].release(); E->d_tiles.release(); E->d_k1ring.release(); E->h_res.release();
   E->d_carry.release();
   // the sort's scratch, permutation, offsets and gathered bodies (round 1 leaked these: ~18.7 GB per 50M-record sort)
-  E->d_bgzf.release(); E->d_bgzf_crc.release();
+  E->d_bgzf.release(); E->d_bgzf_crc.release(); E->d_bgzf_tmp.release();
   E->d_sort.release(); E->d_perm.release(); E->d_soff.release(); E->d_sorted.release(); E->h_sorted.release(); E->h_perm.release();
   E->d_fscr.release();
   for (int k = 0; k < 3; ++k) { E->d_fout[k].release(); E->h_foff[k].release(); E->h_fout[k].release(); }
@@ -1338,6 +1338,34 @@ extern "C" int bamgpu_engine_bgzf_store(bamgpu_engine* E, const uint8_t* d_src, 
   E->stats.ms_bgzf_write += ms;
   E->stats.kernel_launches += 2;
   *out_len = need;
+  return BAMGPU_OK;
+}
+
+// K6 (csrc/deflate.cu): the same framing with COMPRESSED payloads.  level <= 0: stored blocks (bamgpu_engine_bgzf_store).
+extern "C" int bamgpu_engine_bgzf_write(bamgpu_engine* E, const uint8_t* d_src, size_t len, uint8_t* d_out, size_t out_cap,
+                                        size_t* out_len, int eof_marker, int level, void* cuda_stream) {
+  if (level <= 0) return bamgpu_engine_bgzf_store(E, d_src, len, d_out, out_cap, out_len, eof_marker, cuda_stream);
+  if (!E || (len && !d_src) || !d_out || !out_len) return BAMGPU_ERR_ARG;
+  if (out_cap < bamgpu_bgzf_bound(len) - (eof_marker ? 0 : 28)) { E->err = "bgzf_write: output buffer too small"; return BAMGPU_ERR_BUFFER_TOO_SMALL; }
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : E->stream;
+  ECK(cudaSetDevice(E->device));
+  const size_t n_blocks = (len + BGZF_STORE_PAYLOAD - 1) / BGZF_STORE_PAYLOAD;
+  ECK(E->d_bgzf_crc.reserve(4 * (n_blocks + 1)));
+  ECK(E->d_bgzf_tmp.reserve(bgzf_deflate_scratch_bytes(len, E->num_sms)));
+  cudaEvent_t& e0 = E->ev[3];
+  cudaEvent_t& e1 = E->ev[4];
+  ECK(cudaEventRecord(e0, s));
+  launch_crc32_chunks(d_src, len, BGZF_STORE_PAYLOAD, E->d_crc, E->d_bgzf_crc.as<uint32_t>(), E->num_sms, s);
+  uint64_t total = 0;
+  ECK(bgzf_deflate_blocks(d_src, len, E->d_bgzf_crc.as<uint32_t>(), E->d_bgzf_tmp.p, d_out, eof_marker != 0, level, &total, E->num_sms, s));
+  ECK(cudaEventRecord(e1, s));
+  ECK(cudaStreamSynchronize(s));
+  ECK(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  E->stats.ms_bgzf_write += ms;
+  E->stats.kernel_launches += 5;
+  *out_len = (size_t)total;
   return BAMGPU_OK;
 }
 
@@ -2326,7 +2354,7 @@ static int sort_bam_streamed(bamgpu_read_fn read, void* read_ctx, bamgpu_write_f
       std::vector<uint8_t> framed(bound);
       size_t wrote = 0;
       int r = nbytes ? bamgpu_memcpy_h2d(W, W->d_sorted.p, stage.data(), nbytes) : BAMGPU_OK;
-      if (r == BAMGPU_OK) r = bamgpu_engine_bgzf_store(W, W->d_sorted.as<uint8_t>(), nbytes, W->d_bgzf.as<uint8_t>(), bound, &wrote, last ? 1 : 0, nullptr);
+      if (r == BAMGPU_OK) r = bamgpu_engine_bgzf_write(W, W->d_sorted.as<uint8_t>(), nbytes, W->d_bgzf.as<uint8_t>(), bound, &wrote, last ? 1 : 0, o.out_compr_level, nullptr);
       if (r == BAMGPU_OK && wrote) r = bamgpu_memcpy_d2h(W, framed.data(), W->d_bgzf.p, wrote);
       if (r != BAMGPU_OK) return r;
       out_bytes += wrote;
@@ -2865,7 +2893,7 @@ static int sort_bam_multi(const uint8_t* buf, size_t len, bamgpu_write_fn write,
         if (s.framed == 0 && !last) return;
         const size_t bound = bamgpu_bgzf_bound(s.framed);
         SHCK(s.B->d_bgzf.reserve(bound + 64));
-        int r = bamgpu_engine_bgzf_store(s.B, s.stream, s.framed, s.B->d_bgzf.as<uint8_t>(), bound, &s.bgzf_len, last ? 1 : 0, nullptr);
+        int r = bamgpu_engine_bgzf_write(s.B, s.stream, s.framed, s.B->d_bgzf.as<uint8_t>(), bound, &s.bgzf_len, last ? 1 : 0, opts.out_compr_level, nullptr);
         if (r < 0) s.fail(r, s.B->err);
       });
       if (shard_failed(sh, &rc, &msg)) break;
@@ -2962,7 +2990,7 @@ static int sort_bam_buffer(const uint8_t* buf, size_t len, bamgpu_write_fn write
       const size_t bound = bamgpu_bgzf_bound(front + srt.bodies_len);
       if (E->d_bgzf.reserve(bound + 64) != cudaSuccess) { rc = BAMGPU_ERR_NOMEM; msg = "device memory for the BGZF output"; break; }
       size_t wrote = 0;
-      rc = bamgpu_engine_bgzf_store(E, d_stream, front + srt.bodies_len, E->d_bgzf.as<uint8_t>(), bound, &wrote, 1, nullptr);
+      rc = bamgpu_engine_bgzf_write(E, d_stream, front + srt.bodies_len, E->d_bgzf.as<uint8_t>(), bound, &wrote, 1, opts ? opts->out_compr_level : 0, nullptr);
       if (rc != BAMGPU_OK) { msg = E->err; break; }
       d_result = E->d_bgzf.as<uint8_t>();
       result_len = wrote;

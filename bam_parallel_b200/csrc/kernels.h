@@ -197,4 +197,12 @@ constexpr uint32_t BGZF_STORE_PAYLOAD = 0xff00;                       // bytes p
 constexpr uint32_t BGZF_STORE_BLOCK = 18 + 5 + BGZF_STORE_PAYLOAD + 8; // a full block on the wire
 cudaError_t bgzf_store_blocks(const uint8_t* src, uint64_t len, const uint32_t* crc, uint8_t* out, bool eof_marker, cudaStream_t s);
 
+
+// ---- K6: BGZF writer, compressed blocks (deflate.cu) -----------------------------------------------
+// Every 0xff00-byte payload -> one DEFLATE block: level 1 the fixed Huffman code, level >= 2 a code built for the block (or
+// the fixed one if that is smaller); a stored block when neither is smaller than the payload.
+size_t bgzf_deflate_scratch_bytes(uint64_t len, int num_sms);
+cudaError_t bgzf_deflate_blocks(const uint8_t* src, uint64_t len, const uint32_t* crc, void* scratch, uint8_t* out, bool eof_marker, int level,
+                                uint64_t* out_len, int num_sms, cudaStream_t s);   // synchronises
+
 }  // namespace bamgpu

@@ -389,6 +389,23 @@ class Engine:
             self._L.bamgpu_device_free(self._h, d_out)
             self.free(d_src)
 
+    def bgzf_write(self, data, level: int = 1, eof_marker: bool = True) -> bytes:
+        """bamgpu_engine_bgzf_write: `data` wrapped into BGZF with compressed payloads (K6; level 0 = stored); returns the BGZF bytes."""
+        arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        d_src = self.upload(arr)
+        bound = self._L.bamgpu_bgzf_bound(arr.size)
+        d_out = self._L.bamgpu_device_alloc(self._h, bound)
+        try:
+            n = C.c_size_t()
+            self._eck(self._L.bamgpu_engine_bgzf_write(self._h, d_src, arr.size, d_out, bound, C.byref(n), int(eof_marker), int(level), None))
+            out = np.empty(n.value, dtype=np.uint8)
+            if n.value:
+                self._eck(self._L.bamgpu_memcpy_d2h(self._h, out.ctypes.data, d_out, n.value))
+            return out.tobytes()
+        finally:
+            self._L.bamgpu_device_free(self._h, d_out)
+            self.free(d_src)
+
     def set_n_ref(self, n_ref: int):
         """Optional hint (header n_ref) for K3's guess of record starts; results never depend on it."""
         self._L.bamgpu_engine_set_n_ref(self._h, n_ref)

@@ -70,13 +70,15 @@ def sort_bam(mem_limit: int, reader, sorted_sink, tmp_dir=None, out_compr_level:
 
     wcb = _lib.WRITE_FN(_write)
     # output: "bodies" = the reference's (sort.rs:643); "records" = (u32 block_size, body)*, its spill wire format
-    # (sort.rs:340-347); "bam" = a complete BAM (header + sorted records in stored-block BGZF + EOF marker)
+    # (sort.rs:340-347); "bam" = a complete BAM (header + sorted records in BGZF + EOF marker): stored blocks, or with
+    # out_compr_level >= 1 (sort.rs:143, unused by the reference) blocks compressed on the GPU (K6)
     fmt = {"bodies": _lib.OUT_BODIES, "records": _lib.OUT_RECORDS, "bam": _lib.OUT_BAM}[output]
     # device_mem_limit > 0 (bamgpu_opts.sort_mem_limit): the streamed form, with batches of about device_mem_limit / 8 compressed bytes
     # devices (bamgpu_opts.devices[]): without a memory limit the sample sort over those GPUs (contiguous block ranges decoded side by
     # side, buckets exchanged with peer copies, each GPU sorts one bucket); the streamed form decodes its batches on all of them and
     # collects the keys on the first one used
-    opts, st = make_opts(device, flags, sort_output=fmt, sort_mem_limit=device_mem_limit, batch_bytes=batch_bytes, devices=devices), Stats()
+    opts, st = make_opts(device, flags, sort_output=fmt, sort_mem_limit=device_mem_limit, batch_bytes=batch_bytes, devices=devices,
+                          out_compr_level=out_compr_level), Stats()
     err = C.create_string_buffer(512)
     if arr is not None:
         rc = L.bamgpu_sort_bam_from_memory(arr.ctypes.data, arr.size, wcb, None, reader_thread_num, int(sort_by), C.byref(opts), C.byref(st),

@@ -466,6 +466,28 @@ def run_b200(a, rank: int, world: int, local_rank: int, host_group=None):
                                   "records_per_s": a.records / ((stt["ms_sort"] + stt["ms_gather"]) * 1e-3),
                                   "gather_GB_per_s": 2 * nb_out / (stt["ms_gather"] * 1e-3) / 1e9 if stt["ms_gather"] > 0 else None,
                                   "output_bytes": nb_out}
+        # K6: the sorted bodies (still in HBM) through the BGZF writers: stored blocks, fixed-Huffman blocks, per-block Huffman codes
+        try:
+            bound = int(L.bamgpu_bgzf_bound(nb_out))
+            d_bg = L.bamgpu_device_alloc(eng._h, bound)
+            writer = {}
+            if d_bg:
+                for level, name in ((0, "stored"), (1, "fixed_huffman"), (2, "per_block_huffman")):
+                    for rep in range(2):
+                        eng.reset_stats()
+                        wrote = C.c_size_t()
+                        rcw = L.bamgpu_engine_bgzf_write(eng._h, srt.bodies, nb_out, d_bg, bound, C.byref(wrote), 1, level, sptr)
+                        assert rcw == 0, rcw
+                        stt = eng.stats()
+                    writer[name] = {"ms": round(stt["ms_bgzf_write"], 2), "input_GB_per_s": nb_out / (stt["ms_bgzf_write"] * 1e-3) / 1e9,
+                                    "output_bytes": int(wrote.value), "ratio": round(nb_out / max(wrote.value, 1), 3)}
+                L.bamgpu_device_free(eng._h, d_bg)
+                writer["note"] = ("bamgpu_engine_bgzf_write over the name-sorted record bodies in HBM (0xff00-byte payloads, CRC32 by K2's warp CRC): "
+                                  "level 0 stored blocks, 1 fixed Huffman code, 2 a Huffman code built per block (K6, csrc/deflate.cu); "
+                                  "read back by zlib, the oracle and K1 in tests/test_gpu_deflate.py")
+                sort_info["bgzf_writer"] = writer
+        except Exception as ex:   # reported, never fatal for the headline
+            sort_info["bgzf_writer"] = {"error": repr(ex)}
         sort_info["note"] = ("bamgpu_engine_sort on the batch just decoded: output bytes = bam_binary's (record bodies in stable sorted "
                              "order, sort.rs:643); parity vs the oracle in tests/test_gpu_sort.py and tests/test_gpu_fullsize.py; gather GB/s "
                              "counts bodies read + written")

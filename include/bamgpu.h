@@ -163,6 +163,9 @@ typedef struct bamgpu_opts {
                                    mem_limit / 8 compressed bytes, only the sort keys (and, for the name orders, the read names)
                                    stay on the device, the bodies wait in host memory and are gathered there in sorted order
                                    (the reference's chunk files + N-way merge, sort.rs:185-308,590-652, without the files) */
+  int32_t out_compr_level;      /* bamgpu_sort_bam with BAMGPU_OUT_BAM: sort.rs:143 `_out_compr_level` (which the reference accepts and never
+                                   uses).  0 = stored DEFLATE blocks (copy speed); >= 1 = compressed blocks (K6: fixed-Huffman DEFLATE) */
+  int32_t reserved;
 } bamgpu_opts;
 
 /* What bamgpu_sort_bam writes to the sink. */
@@ -399,6 +402,12 @@ int bamgpu_sort_bam_from_memory(const uint8_t* buf, size_t len, bamgpu_write_fn 
 size_t bamgpu_bgzf_bound(size_t len);
 int bamgpu_engine_bgzf_store(bamgpu_engine*, const uint8_t* d_src, size_t len, uint8_t* d_out, size_t out_cap, size_t* out_len,
                              int eof_marker, void* cuda_stream);
+
+/* The same framing with COMPRESSED payloads (K6, csrc/deflate.cu): level <= 0 = bamgpu_engine_bgzf_store; level >= 1 = every payload becomes
+ * one DEFLATE block with the fixed Huffman code (RFC 1951 3.2.6; LZ77 matches from a hash of 4-byte sequences and a distance-1 probe,
+ * greedy parse), or a stored block when that is not smaller.  The same bytes on every run.  d_out must hold bamgpu_bgzf_bound(len). */
+int bamgpu_engine_bgzf_write(bamgpu_engine*, const uint8_t* d_src, size_t len, uint8_t* d_out, size_t out_cap, size_t* out_len,
+                             int eof_marker, int level, void* cuda_stream);
 
 const char* bamgpu_status_str(int status);
 /* "sm_100a;<build id>" — lets callers assert the CUDA library (not a fallback) is loaded. */

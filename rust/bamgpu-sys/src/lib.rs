@@ -11,11 +11,12 @@ pub const BAMGPU_MAX_DEVICES: usize = 16;
 pub struct bamgpu_opts {
     pub device: i32, pub flags: u32, pub batch_bytes: u64, pub inflate_impl: i32, pub jobs_per_device: i32,
     pub n_devices: i32, pub devices: [i32; BAMGPU_MAX_DEVICES], pub sort_output: i32, pub sort_mem_limit: u64,
+    pub out_compr_level: i32, pub reserved: i32,
 }
 impl Default for bamgpu_opts {
     fn default() -> Self {
         bamgpu_opts { device: -1, flags: 0, batch_bytes: 0, inflate_impl: 0, jobs_per_device: 0, n_devices: 0,
-                      devices: [0; BAMGPU_MAX_DEVICES], sort_output: 0, sort_mem_limit: 0 }
+                      devices: [0; BAMGPU_MAX_DEVICES], sort_output: 0, sort_mem_limit: 0, out_compr_level: 0, reserved: 0 }
     }
 }
 impl bamgpu_opts {

@@ -109,4 +109,4 @@ def test_opts_layout_is_the_same_in_every_binding():
     rbody = re.search(r"pub struct bamgpu_opts \{(.*?)\n\}", rs, re.S).group(1)
     assert re.findall(r"pub (\w+):", rbody) == c_fields
     import ctypes as C
-    assert C.sizeof(_lib.Opts) == 4 + 4 + 8 + 4 + 4 + 4 + 4 * 16 + 4 + 8   # no implicit padding
+    assert C.sizeof(_lib.Opts) == 4 + 4 + 8 + 4 + 4 + 4 + 4 * 16 + 4 + 8 + 4 + 4   # no implicit padding
