@@ -101,7 +101,34 @@ __device__ __forceinline__ void token_bits(uint32_t lit, uint32_t len, uint32_t 
 
 // Phases A - C for the chunk [c0, c0 + clen) of an n-byte payload at raw + mis: on return mark[i] != 0 for the positions of the
 // greedy parse, mlen / mdist hold their matches (mlen 0: a literal).  `entry`: where the chain enters the chunk.
-__device__ __forceinline__ void parse_chunk(DfShared& S, uint32_t mis, uint32_t c0, uint32_t clen, uint32_t n, uint32_t entry, uint32_t tid) {
+using DfScan = cub::BlockScan<uint32_t, DF_THREADS>;
+__device__ __forceinline__ void parse_chunk(DfShared& S, DfScan::TempStorage& scan_tmp, uint32_t mis, uint32_t c0, uint32_t clen, uint32_t n,
+                                            uint32_t entry, uint32_t tid) {
+  // runs: nz[i] = the first chunk position q >= i whose byte differs from the byte in front of it (clen: none), by a reverse
+  // min-scan.  The distance-1 match at i is then nz[i] - i bytes long: no position of a long run (binned base qualities) loops
+  // over it - with a compare loop per position a warp waited for its longest run at every one of them (6x the time).
+  uint16_t* nz = S.jmp[1];
+  {
+    const uint8_t* rb = reinterpret_cast<const uint8_t*>(S.raw) + mis + c0;
+    uint32_t v[DF_ITEMS];
+#pragma unroll
+    for (int k = 0; k < DF_ITEMS; ++k) {
+      const uint32_t r = tid * DF_ITEMS + k;
+      v[k] = clen;
+      if (r < clen) {
+        const uint32_t i = clen - 1 - r;
+        const bool same = c0 + i > 0 && rb[i] == rb[(int)i - 1];
+        v[k] = same ? clen : i;
+      }
+    }
+    DfScan(scan_tmp).InclusiveScan(v, v, cub::Min());
+#pragma unroll
+    for (int k = 0; k < DF_ITEMS; ++k) {
+      const uint32_t r = tid * DF_ITEMS + k;
+      if (r < clen) nz[clen - 1 - r] = (uint16_t)v[k];
+    }
+  }
+  __syncthreads();
   // A. candidates
   for (uint32_t s0 = 0; s0 < clen; s0 += DF_SUB) {
     uint32_t h = 0;
@@ -139,16 +166,18 @@ __device__ __forceinline__ void parse_chunk(DfShared& S, uint32_t mis, uint32_t 
       uint32_t best = 0, bdist = 0;
       if (pos + DF_MIN_MATCH <= n) {
         const uint32_t maxl = n - pos < DF_MAX_MATCH ? n - pos : DF_MAX_MATCH;
-        const uint32_t v = ld32u(S.raw, mis + pos);
+        uint32_t l1 = nz[i] - i;              // bytes from pos on that repeat the byte in front of them
+        if (l1 && i + l1 == clen && l1 < maxl) {   // the run reaches the end of the chunk: follow it (few positions per chunk)
+          const uint8_t* rb = reinterpret_cast<const uint8_t*>(S.raw) + mis + pos;
+          while (l1 < maxl && rb[l1] == rb[l1 - 1]) ++l1;
+        }
+        l1 = l1 < maxl ? l1 : maxl;
         const uint32_t c1 = S.mlen[i];        // candidate position + 1 (same thread overwrites it below)
-        if (c1 && pos - (c1 - 1) <= 32768u && ld32u(S.raw, mis + c1 - 1) == v) {   // the DEFLATE window is 32 KiB
+        if (l1 < 64 && c1 && pos - (c1 - 1) <= 32768u && ld32u(S.raw, mis + c1 - 1) == ld32u(S.raw, mis + pos)) {   // the DEFLATE window is 32 KiB
           best = extend_match(S.raw, mis + c1 - 1, mis + pos, maxl);
           bdist = pos - (c1 - 1);
         }
-        if (pos >= 1 && best < maxl && ld32u(S.raw, mis + pos - 1) == v) {
-          const uint32_t l1 = extend_match(S.raw, mis + pos - 1, mis + pos, maxl);
-          if (l1 >= best) { best = l1; bdist = 1; }
-        }
+        if (l1 >= DF_MIN_MATCH && l1 >= best) { best = l1; bdist = 1; }
       }
       S.mlen[i] = (uint16_t)best;
       S.mdist[i] = (uint16_t)bdist;
@@ -211,7 +240,7 @@ k6_deflate_fixed(const uint8_t* __restrict__ src, unsigned long long len, uint8_
     uint32_t entry = 0;             // where the chain enters the chunk (relative)
     for (uint32_t c0 = 0; c0 < n; c0 += DF_CHUNK) {
       const uint32_t clen = n - c0 < DF_CHUNK ? n - c0 : DF_CHUNK;
-      parse_chunk(S, mis, c0, clen, n, entry, tid);
+      parse_chunk(S, scan_tmp, mis, c0, clen, n, entry, tid);
       // D. tokens -> bits
       uint32_t bits[DF_ITEMS], nb[DF_ITEMS], off[DF_ITEMS];
       const uint8_t* rb = reinterpret_cast<const uint8_t*>(S.raw) + mis + c0;
@@ -464,7 +493,7 @@ k6_deflate_dynamic(const uint8_t* __restrict__ src, unsigned long long len, uint
     uint32_t ntok = 0, entry = 0;
     for (uint32_t c0 = 0; c0 < n; c0 += DF_CHUNK) {
       const uint32_t clen = n - c0 < DF_CHUNK ? n - c0 : DF_CHUNK;
-      parse_chunk(S, mis, c0, clen, n, entry, tid);
+      parse_chunk(S, scan_tmp, mis, c0, clen, n, entry, tid);
       const uint8_t* rb = reinterpret_cast<const uint8_t*>(S.raw) + mis + c0;
       uint32_t tok[DF_ITEMS], flag[DF_ITEMS], idx[DF_ITEMS], cnt = 0;
 #pragma unroll
