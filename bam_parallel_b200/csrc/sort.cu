@@ -21,6 +21,9 @@
 // body gather — the HBM-heavy part — are the kernels below.
 #include <cub/cub.cuh>
 
+#include <utility>
+#include <vector>
+
 #include "kernels.h"
 
 namespace bamgpu {
@@ -65,6 +68,58 @@ __global__ void k_name_chunk(const uint8_t* __restrict__ data, const uint64_t* _
     uint32_t rec = idx[i];
     key[i] = name_chunk(data, rec_off[rec], l_name[rec], r);
   }
+}
+
+// ---- name keys without their constant bits ----------------------------------------------------------------------
+// Byte j of a name, zero past l_read_name ("virtual byte": what the zero-padded comparison sees).
+__device__ __forceinline__ uint32_t name_vbyte(const uint8_t* __restrict__ nm, uint32_t len, uint32_t j) { return j < len ? nm[j] : 0u; }
+
+// masks[j] = OR over all records of (virtual byte j XOR record 0's virtual byte j), j < max_len: the bits of position j that are
+// not the same in every name.  Real read names are mostly digits and fixed separators behind a common prefix: 3 - 4 varying bits
+// per byte, none at all in many positions.  One thread per record and tile of 16 positions, OR-reduced per warp.
+constexpr uint32_t NAME_TILE = 16;
+__global__ void k_name_masks(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, const uint8_t* __restrict__ l_name,
+                             uint32_t n, uint32_t first_pos, uint32_t* __restrict__ masks /* one u32 per position */) {
+  const uint32_t tile = blockIdx.y, j0 = first_pos + tile * NAME_TILE;
+  const uint8_t* ref = data + rec_off[0] + 32;
+  const uint32_t lref = l_name[0];
+  uint32_t rb[NAME_TILE], m[NAME_TILE];
+#pragma unroll
+  for (uint32_t k = 0; k < NAME_TILE; ++k) { rb[k] = name_vbyte(ref, lref, j0 + k); m[k] = 0; }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint8_t* nm = data + rec_off[i] + 32;
+    const uint32_t len = l_name[i];
+#pragma unroll
+    for (uint32_t k = 0; k < NAME_TILE; ++k) m[k] |= name_vbyte(nm, len, j0 + k) ^ rb[k];
+  }
+#pragma unroll
+  for (uint32_t k = 0; k < NAME_TILE; ++k) {
+    const uint32_t w = __reduce_or_sync(0xffffffffu, m[k]);
+    if ((threadIdx.x & 31) == 0 && w) atomicOr(&masks[j0 + k], w);
+  }
+}
+
+// One LSD pass sorts by a GROUP of positions: the low width[e] bits of the virtual bytes at pos[e], most significant position
+// first, optionally l_read_name in the low 8 bits (the last tie-break of the zero-padded comparison: "A\0" before "A\0\0").
+struct NameGroup {
+  uint8_t pos[64], width[64];
+  uint32_t count, with_len;
+};
+template <typename K>
+__global__ void k_name_group_key(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, const uint8_t* __restrict__ l_name,
+                                 const uint32_t* __restrict__ idx, NameGroup g, K* __restrict__ key, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t rec = idx[i];
+  const uint8_t* nm = data + rec_off[rec] + 32;
+  const uint32_t len = l_name[rec];
+  uint64_t k = 0;
+  for (uint32_t e = 0; e < g.count; ++e) {
+    const uint32_t w = g.width[e];
+    k = (k << w) | (name_vbyte(nm, len, g.pos[e]) & ((1u << w) - 1u));
+  }
+  if (g.with_len) k = (k << 8) | len;
+  key[i] = (K)k;
 }
 
 // Length of the prefix every name shares with the first record's name (<= the shortest name).  Real read names start with
@@ -290,8 +345,8 @@ cudaError_t sort_permutation(const uint8_t* data, const ColumnsDev& c, uint64_t 
     std::swap(k32a, k32b);
     nl += 3;
   };
-  auto sort64 = [&]() {
-    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const uint64_t*)k64a, k64b, (const uint32_t*)va, vb, (int)n, 0, 64, s);
+  auto sort64 = [&](int bits = 64) {
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const uint64_t*)k64a, k64b, (const uint32_t*)va, vb, (int)n, 0, bits, s);
     std::swap(va, vb);
     std::swap(k64a, k64b);
     nl += 5;
@@ -312,14 +367,19 @@ cudaError_t sort_permutation(const uint8_t* data, const ColumnsDev& c, uint64_t 
       sort32(32);
       nl += 2;
     }
-    k_gather_key<uint8_t, uint32_t><<<g, 256, 0, s>>>(c.l_read_name, va, k32a, n);
-    sort32(8);
-    ++nl;
-    // number of 8-byte rounds
+    // The comparison is bytewise over the names zero-padded to the longest, then by l_read_name.  Stable LSD passes, least
+    // significant first - but only over the bits that differ between names: one pass over all names ORs, per byte position, the
+    // XOR against the first name (k_name_masks); positions that are the same everywhere (the instrument : run : flowcell prefix,
+    // separators) drop out, a digit position keeps 4 bits.  The remaining bits are packed, most significant position first,
+    // into groups of <= 64 bits; every group is one key gather + one radix sort over just its bits, and l_read_name rides in the
+    // low 8 bits of the least significant group.  50 M Illumina-style names: ~80 varying bits = 2 groups, 11 radix passes and 2
+    // gathers, where whole 8-byte chunks took 3 groups, 25 passes and 3 gathers (20.0 ms).
     uint32_t* d_max = (uint32_t*)&d_res->max_name_len;
     k_max_u8<<<592, 256, 0, s>>>(c.l_read_name, n, d_max);
-    uint32_t* d_lcp = flags;   // free until the first round
+    uint32_t* d_lcp = (uint32_t*)((uint8_t*)scratch + sort_scratch_bytes(n64) - 2048);   // the slack at the end of the scratch
+    uint32_t* d_masks = d_lcp + 64;      // 256 positions
     cudaMemsetAsync(d_lcp, 0xff, 4, s);
+    cudaMemsetAsync(d_masks, 0, 256 * 4, s);
     k_name_lcp<<<592, 256, 0, s>>>(data, c.rec_off, c.l_read_name, n, d_lcp);
     nl += 2;
     uint32_t max_len = 0, lcp = 0;
@@ -327,15 +387,54 @@ cudaError_t sort_permutation(const uint8_t* data, const ColumnsDev& c, uint64_t 
     cudaMemcpyAsync(&lcp, d_lcp, 4, cudaMemcpyDeviceToHost, s);
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return e;
-    // Least-significant chunk first: every pass is a stable sort, so after the pass over chunk r0 the order is
-    // (chunk r0, chunk r0 + 1, ..., last chunk, l_read_name, [HI, flag], input order) — the lexicographic order of the names,
-    // ties as the comparator breaks them.  No group bookkeeping and no host round trip between the passes (the MSD form,
-    // which re-sorted by group id and rebuilt the groups after every chunk, took 8 ms per chunk against 5 here).
-    const uint32_t rounds = (max_len + 7) / 8;
-    const uint32_t r0 = lcp / 8;   // bytes [0, 8 r0) are the same in every name: those passes would not move anything
-    for (uint32_t r = rounds; r-- > r0;) {
-      k_name_chunk<<<g, 256, 0, s>>>(data, c.rec_off, c.l_read_name, va, r, k64a, n);
-      sort64();
+    uint32_t masks[256] = {0};
+    if (lcp < max_len) {
+      const uint32_t tiles = (max_len - lcp + NAME_TILE - 1) / NAME_TILE;
+      uint32_t gx = (n + 255) / 256;
+      const uint32_t cap = 592u * 4 / tiles + 1;
+      if (gx > cap) gx = cap;
+      k_name_masks<<<dim3(gx, tiles), 256, 0, s>>>(data, c.rec_off, c.l_read_name, n, lcp, d_masks);
+      ++nl;
+      cudaMemcpyAsync(masks, d_masks, 256 * 4, cudaMemcpyDeviceToHost, s);
+      e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) return e;
+    }
+    // groups, least significant (highest positions) first
+    std::vector<NameGroup> groups;
+    {
+      NameGroup cur{};
+      uint32_t bits = 8;                 // the first group carries l_read_name
+      cur.with_len = 1;
+      std::vector<std::pair<uint8_t, uint8_t>> rev;   // (pos, width) of the current group, highest position first
+      auto close = [&]() {
+        cur.count = (uint32_t)rev.size();
+        for (uint32_t k2 = 0; k2 < cur.count; ++k2) { cur.pos[k2] = rev[cur.count - 1 - k2].first; cur.width[k2] = rev[cur.count - 1 - k2].second; }
+        groups.push_back(cur);
+        cur = NameGroup{};
+        rev.clear();
+        bits = 0;
+      };
+      for (uint32_t j = max_len; j-- > lcp;) {
+        const uint32_t m = masks[j] & 0xffu;
+        if (!m) continue;
+        const uint32_t w = 32u - (uint32_t)__builtin_clz(m);
+        if (bits + w > 64 || rev.size() == 64) close();
+        rev.push_back({(uint8_t)j, (uint8_t)w});
+        bits += w;
+      }
+      close();                           // (also when no position varies: l_read_name alone)
+    }
+    for (const NameGroup& grp : groups) {
+      uint32_t bits = grp.with_len ? 8u : 0u;
+      for (uint32_t k2 = 0; k2 < grp.count; ++k2) bits += grp.width[k2];
+      if (bits == 0) continue;
+      if (bits <= 32) {
+        k_name_group_key<uint32_t><<<g, 256, 0, s>>>(data, c.rec_off, c.l_read_name, va, grp, k32a, n);
+        sort32((int)bits);
+      } else {
+        k_name_group_key<uint64_t><<<g, 256, 0, s>>>(data, c.rec_off, c.l_read_name, va, grp, k64a, n);
+        sort64((int)bits);
+      }
       ++nl;
     }
     if (sort_by == SORT_NAME_AND_MATCH_MATES) {

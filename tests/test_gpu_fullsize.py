@@ -129,3 +129,49 @@ def test_config5_longname_5m(oracle, level):
 def test_config5_long10k(oracle, n, level, payload):
     """configs[4]: ~15 KB records spanning 1-4+ BGZF blocks (payload 4096 and 0xff00), levels 1/6/9; -n -M sort."""
     _check(oracle, "long10k", _n(n), level, payload, ("name_mates",), reader_kw={"batch_bytes": 128 << 20})
+
+
+class _CrcSink:
+    """io.Write for sort_bam that keeps a CRC-32 and a length instead of 17 GB of output."""
+    def __init__(self):
+        import zlib
+        self._crc32, self.crc, self.n = zlib.crc32, 0, 0
+
+    def write(self, b):
+        self.crc = self._crc32(b, self.crc)
+        self.n += len(b)
+
+
+def test_sort_over_several_gpus_50m():
+    """configs[3] through bamgpu_sort_bam: the sample sort over the box's GPUs (on one GPU: two block ranges and two buckets on it)
+    must write the bytes of the single-GPU sort, whose order and bytes test_config2_and_4_pe150_50m compares with the oracle."""
+    import torch
+    from bam_parallel_b200.sorting import SortBy, sort_bam
+    bam = synth.generate("pe150", _n(50_000_000), level=6)
+    ng = torch.cuda.device_count()
+    devices = list(range(ng)) if ng > 1 else [0, 0]
+    for sb in (SortBy.CoordinatesAndStrand, SortBy.NameAndMatchMates):
+        one, many = _CrcSink(), _CrcSink()
+        sort_bam(0, bam.array, one, sort_by=sb)
+        st = sort_bam(0, bam.array, many, sort_by=sb, devices=devices)
+        assert st["batches"] >= len(devices), "the multi-GPU path did not run"
+        assert (one.n, one.crc) == (many.n, many.crc), sb
+    bam.close()
+
+
+def test_compressed_bam_at_scale():
+    """K6 on 10 M records: the name-sorted BAM written with per-block Huffman codes reads back (K1 + CRC check, batched Reader) to
+    the digest of the same BAM written with stored blocks, and is about a third of its size."""
+    from bam_parallel_b200.sorting import SortBy, sort_bam
+    import io
+    bam = synth.generate("pe150", _n(10_000_000), level=6)
+    files = {}
+    for level in (0, 2):
+        sink = io.BytesIO()
+        sort_bam(0, bam.array, sink, None, level, sort_by=SortBy.Name, output="bam")
+        files[level] = np.frombuffer(sink.getbuffer(), dtype=np.uint8)
+    bam.close()
+    assert files[2].size < 0.4 * files[0].size, (files[2].size, files[0].size)
+    d0, _ = _gpu_reader_side(files[0])
+    d2, nb = _gpu_reader_side(files[2], batch_bytes=64 << 20)
+    assert d0["n_records"] == _n(10_000_000) and d2 == d0 and nb > 3
