@@ -11,10 +11,11 @@
 //     K3 already wrote coord_key (both i32 biased to unsigned, refID in the high word) and strand; the order is a
 //     stable LSD radix sort: 1 bit of strand, then the 64 bits of coord_key.
 //   Name (comparators.rs:61-65): str::cmp of the read names INCLUDING their NUL (bamrawrecord.rs:118-123) = bytewise
-//     lexicographic, a proper prefix first.  Variable-length keys: stable LSD passes over 8 name bytes each (big-endian
-//     u64, zero-padded past l_read_name), last chunk first; the chunks inside the prefix all names share are skipped.
-//     Zero padding alone would tie "A\0" with "A\0\0"; sorting by l_read_name BEFORE the passes (stable sorts keep it
-//     as the order among names that tie on every chunk) makes the result exact for arbitrary name bytes.
+//     lexicographic, a proper prefix first.  Variable-length keys: stable LSD passes from the last bytes to the first over
+//     the names zero-padded past l_read_name - packed so that only the bits that differ between names are sorted
+//     (k_name_masks / k_name_group_key).  Zero padding alone would tie "A\0" with "A\0\0"; l_read_name as the LEAST
+//     significant key (stable sorts keep it as the order among names that tie on every byte) makes the result exact for
+//     arbitrary name bytes.
 //   NameAndMatchMates (comparators.rs:78-93): name, then HI (Option<i32>; None == None; None vs Some panics in the
 //     reference -> reported in SortResult.hi_mixed), then the full u16 flag: the same, with flag and HI sorted first.
 // The radix sort primitive is CUB's DeviceRadixSort (stable, onesweep); key construction, group refinement and the
@@ -47,26 +48,6 @@ __global__ void k_hi_key(const uint8_t* __restrict__ present, const int32_t* __r
   if (i < n) {
     uint32_t r = idx[i];
     key[i] = present[r] == 1 ? ((uint32_t)value[r] ^ 0x80000000u) : 0u;
-  }
-}
-
-// Bytes [8r, 8r+8) of the name of record idx[i], big-endian, zero past l_read_name.
-__device__ __forceinline__ uint64_t name_chunk(const uint8_t* __restrict__ data, uint64_t off, uint32_t len, uint32_t r) {
-  const uint32_t b = 8 * r;
-  uint64_t k = 0;
-  if (b < len) {
-    const uint8_t* p = data + off + 32 + b;
-    const uint32_t m = len - b < 8 ? len - b : 8;
-    for (uint32_t j = 0; j < m; ++j) k |= (uint64_t)p[j] << (56 - 8 * j);
-  }
-  return k;
-}
-__global__ void k_name_chunk(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, const uint8_t* __restrict__ l_name,
-                             const uint32_t* __restrict__ idx, uint32_t r, uint64_t* __restrict__ key, uint32_t n) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    uint32_t rec = idx[i];
-    key[i] = name_chunk(data, rec_off[rec], l_name[rec], r);
   }
 }
 
