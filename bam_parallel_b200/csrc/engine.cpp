@@ -2696,7 +2696,15 @@ static int sort_bam_multi(const uint8_t* buf, size_t len, bamgpu_write_fn write,
     cudaEventRecord(e0, s.A->stream);
     SHCK(cudaMemcpyAsync(s.d_comp.p, buf + c0, c1 - c0, cudaMemcpyHostToDevice, s.A->stream));
     cudaEventRecord(e1, s.A->stream);
-    int r = engine_inflate(s.A, s.d_comp.as<uint8_t>(), s.blocks.data(), s.blocks.size(), eo.flags, s.A->stream);
+    int r = engine_inflate_launch(s.A, s.d_comp.as<uint8_t>(), s.blocks.data(), s.blocks.size(), eo.flags, s.A->stream);
+    if (r == BAMGPU_OK) {
+      // while K1 runs: the buffer this GPU will gather its (u32 block_size, body)* stream into (a cudaMalloc of several GB takes
+      // tens of milliseconds, and the host has nothing else to do now); 4 bytes per record on top of the inflated bytes
+      uint64_t isz = 0;
+      for (auto& b : s.blocks) isz += b.isize;
+      s.d_send.reserve(isz + isz / 16 + (1 << 20));   // (too small for very short records: reserved again later, then)
+      r = engine_inflate_finish(s.A, s.A->stream);
+    }
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     s.A->stats.ms_h2d += ms;
@@ -2799,17 +2807,18 @@ static int sort_bam_multi(const uint8_t* buf, size_t len, bamgpu_write_fn write,
       cudaEventRecord(s.A->ev[3], st);
       SHCK(partition_by_splitters(s.A->out_ptr(), cols, s.n, sort_by, s.d_split.as<SplitKey>(), (uint32_t)(G - 1), s.A->d_sort.p,
                                   s.A->d_perm.as<uint32_t>(), s.d_bounds.as<uint32_t>(), &launches, st));
-      cudaEventRecord(s.A->ev[4], st);
+      cudaEventRecord(s.A->ev[6], st);
       SHCK(cudaMemcpyAsync(s.bounds.data(), s.d_bounds.p, 4 * (G + 1), cudaMemcpyDeviceToHost, st));
       uint64_t total_bytes = 0;
       SHCK(sorted_offsets(cols, s.A->d_perm.as<uint32_t>(), s.n, s.A->d_sort.p, s.d_soff.as<uint64_t>(), &total_bytes, 4, st));   // synchronises
       for (int d = 0; d <= G; ++d) SHCK(cudaMemcpyAsync(&s.seg[d], s.d_soff.as<uint64_t>() + s.bounds[d], 8, cudaMemcpyDeviceToHost, st));
       SHCK(s.d_send.reserve(total_bytes + 64));
+      cudaEventRecord(s.A->ev[4], st);
       SHCK(gather_sorted_bodies(s.A->out_ptr(), cols, s.A->d_perm.as<uint32_t>(), s.n, s.A->d_sort.p, s.d_soff.as<uint64_t>(), s.d_send.as<uint8_t>(), 4, st));
       cudaEventRecord(s.A->ev[5], st);
       SHCK(cudaStreamSynchronize(st));
       float ms = 0;
-      cudaEventElapsedTime(&ms, s.A->ev[3], s.A->ev[4]); s.A->stats.ms_sort += ms;
+      cudaEventElapsedTime(&ms, s.A->ev[3], s.A->ev[6]); s.A->stats.ms_sort += ms;
       cudaEventElapsedTime(&ms, s.A->ev[4], s.A->ev[5]); s.A->stats.ms_gather += ms;
       s.A->stats.kernel_launches += launches + 3;
     });

@@ -371,6 +371,19 @@ def test_sample_sort_skewed_keys_and_fallbacks(oracle):
                 sort_bam(0, data, one, sort_by=sb, output=fmt)
                 sort_bam(0, data, many, sort_by=sb, output=fmt, devices=devices)
                 assert one.getvalue() == many.getvalue(), (sb, fmt, len(data))
+    # a block whose CRC32 footer is wrong / whose DEFLATE bytes are damaged, in the middle of the file: the same error either way
+    good = bytearray(bam(same, 3000))
+    blocks, nb, _, _, _ = bp.scan_blocks(bytes(good))
+    mid = blocks[nb // 2]
+    for where, code in ((int(mid.in_off + mid.in_len), -14), (int(mid.in_off + 5), None)):
+        bad = bytearray(good)
+        bad[where] ^= 0x5A
+        codes = []
+        for kw in ({}, {"devices": devices}):
+            with pytest.raises(bp.BamGpuError) as e:
+                sort_bam(0, bytes(bad), io.BytesIO(), sort_by=SortBy.Name, **kw)
+            codes.append(e.value.code)
+        assert codes[0] == codes[1] and (code is None or codes[0] == code), codes
     data = bam([rec(b"q%d" % (i % 3), 0, i, 0x1000 if i == 7777 else 0) for i in range(20000)], 2000)
     with pytest.raises(bp.BamGpuError) as e:
         sort_bam(0, data, io.BytesIO(), sort_by=SortBy.CoordinatesAndStrand, devices=devices)
