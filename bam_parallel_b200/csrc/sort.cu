@@ -55,28 +55,41 @@ __global__ void k_hi_key(const uint8_t* __restrict__ present, const int32_t* __r
 // Byte j of a name, zero past l_read_name ("virtual byte": what the zero-padded comparison sees).
 __device__ __forceinline__ uint32_t name_vbyte(const uint8_t* __restrict__ nm, uint32_t len, uint32_t j) { return j < len ? nm[j] : 0u; }
 
-// masks[j] = OR over all records of (virtual byte j XOR record 0's virtual byte j), j < max_len: the bits of position j that are
-// not the same in every name.  Real read names are mostly digits and fixed separators behind a common prefix: 3 - 4 varying bits
-// per byte, none at all in many positions.  One thread per record and tile of 16 positions, OR-reduced per warp.
-constexpr uint32_t NAME_TILE = 16;
+// masks: byte j = OR over all records of (virtual byte j XOR record 0's virtual byte j), j < max_len: the bits of position j that
+// are not the same in every name.  Real read names are mostly digits and fixed separators behind a common prefix: 3 - 4 varying
+// bits per byte, none at all in many positions (the whole instrument : run : flowcell prefix).  One thread per record and tile of
+// 64 positions (16 packed words), OR-reduced per warp; names up to 64 bytes take ONE pass over the records, and no separate
+// common-prefix scan is needed.
+constexpr uint32_t NAME_TILE = 64;
 __global__ void k_name_masks(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, const uint8_t* __restrict__ l_name,
-                             uint32_t n, uint32_t first_pos, uint32_t* __restrict__ masks /* one u32 per position */) {
-  const uint32_t tile = blockIdx.y, j0 = first_pos + tile * NAME_TILE;
+                             uint32_t n, uint32_t* __restrict__ masks /* 4 positions per word */) {
+  const uint32_t tile = blockIdx.y, j0 = tile * NAME_TILE;
   const uint8_t* ref = data + rec_off[0] + 32;
   const uint32_t lref = l_name[0];
-  uint32_t rb[NAME_TILE], m[NAME_TILE];
+  uint32_t rw[NAME_TILE / 4], m[NAME_TILE / 4];
 #pragma unroll
-  for (uint32_t k = 0; k < NAME_TILE; ++k) { rb[k] = name_vbyte(ref, lref, j0 + k); m[k] = 0; }
+  for (uint32_t w = 0; w < NAME_TILE / 4; ++w) {
+    rw[w] = 0; m[w] = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) rw[w] |= name_vbyte(ref, lref, j0 + 4 * w + k) << (8 * k);
+  }
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint8_t* nm = data + rec_off[i] + 32;
     const uint32_t len = l_name[i];
 #pragma unroll
-    for (uint32_t k = 0; k < NAME_TILE; ++k) m[k] |= name_vbyte(nm, len, j0 + k) ^ rb[k];
+    for (uint32_t w = 0; w < NAME_TILE / 4; ++w) {
+      uint32_t v = 0;
+      if (j0 + 4 * w < len) {
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) v |= name_vbyte(nm, len, j0 + 4 * w + k) << (8 * k);
+      }
+      m[w] |= v ^ rw[w];
+    }
   }
 #pragma unroll
-  for (uint32_t k = 0; k < NAME_TILE; ++k) {
-    const uint32_t w = __reduce_or_sync(0xffffffffu, m[k]);
-    if ((threadIdx.x & 31) == 0 && w) atomicOr(&masks[j0 + k], w);
+  for (uint32_t w = 0; w < NAME_TILE / 4; ++w) {
+    const uint32_t r = __reduce_or_sync(0xffffffffu, m[w]);
+    if ((threadIdx.x & 31) == 0 && r) atomicOr(&masks[j0 / 4 + w], r);
   }
 }
 
@@ -101,24 +114,6 @@ __global__ void k_name_group_key(const uint8_t* __restrict__ data, const uint64_
   }
   if (g.with_len) k = (k << 8) | len;
   key[i] = (K)k;
-}
-
-// Length of the prefix every name shares with the first record's name (<= the shortest name).  Real read names start with
-// instrument : run : flowcell; the 8-byte rounds over that prefix would sort 50 M equal keys, so they are skipped.
-__global__ void k_name_lcp(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, const uint8_t* __restrict__ l_name,
-                           uint32_t n, uint32_t* out) {
-  const uint8_t* a = data + rec_off[0] + 32;
-  const uint32_t la = l_name[0];
-  uint32_t m = 255;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint8_t* b = data + rec_off[i] + 32;
-    const uint32_t lb = l_name[i], l = la < lb ? la : lb;
-    uint32_t k = 0;
-    while (k < l && k < m && a[k] == b[k]) ++k;
-    m = k < m ? k : m;
-  }
-  for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMin(out, m);
 }
 
 __global__ void k_max_u8(const uint8_t* __restrict__ v, uint32_t n, uint32_t* out) {
@@ -357,26 +352,23 @@ cudaError_t sort_permutation(const uint8_t* data, const ColumnsDev& c, uint64_t 
     // gathers, where whole 8-byte chunks took 3 groups, 25 passes and 3 gathers (20.0 ms).
     uint32_t* d_max = (uint32_t*)&d_res->max_name_len;
     k_max_u8<<<592, 256, 0, s>>>(c.l_read_name, n, d_max);
-    uint32_t* d_lcp = (uint32_t*)((uint8_t*)scratch + sort_scratch_bytes(n64) - 2048);   // the slack at the end of the scratch
-    uint32_t* d_masks = d_lcp + 64;      // 256 positions
-    cudaMemsetAsync(d_lcp, 0xff, 4, s);
-    cudaMemsetAsync(d_masks, 0, 256 * 4, s);
-    k_name_lcp<<<592, 256, 0, s>>>(data, c.rec_off, c.l_read_name, n, d_lcp);
-    nl += 2;
-    uint32_t max_len = 0, lcp = 0;
+    uint32_t* d_masks = (uint32_t*)((uint8_t*)scratch + sort_scratch_bytes(n64) - 2048);   // the slack at the end of the scratch: 256 positions, 4 per word
+    cudaMemsetAsync(d_masks, 0, 256, s);
+    ++nl;
+    uint32_t max_len = 0;
     cudaMemcpyAsync(&max_len, d_max, 4, cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(&lcp, d_lcp, 4, cudaMemcpyDeviceToHost, s);
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return e;
-    uint32_t masks[256] = {0};
-    if (lcp < max_len) {
-      const uint32_t tiles = (max_len - lcp + NAME_TILE - 1) / NAME_TILE;
+    uint8_t masks[256] = {0};
+    const uint32_t lcp = 0;
+    if (max_len) {
+      const uint32_t tiles = (max_len + NAME_TILE - 1) / NAME_TILE;
       uint32_t gx = (n + 255) / 256;
       const uint32_t cap = 592u * 4 / tiles + 1;
       if (gx > cap) gx = cap;
-      k_name_masks<<<dim3(gx, tiles), 256, 0, s>>>(data, c.rec_off, c.l_read_name, n, lcp, d_masks);
+      k_name_masks<<<dim3(gx, tiles), 256, 0, s>>>(data, c.rec_off, c.l_read_name, n, d_masks);
       ++nl;
-      cudaMemcpyAsync(masks, d_masks, 256 * 4, cudaMemcpyDeviceToHost, s);
+      cudaMemcpyAsync(masks, d_masks, 256, cudaMemcpyDeviceToHost, s);   // little-endian host: byte j of the array = position j
       e = cudaStreamSynchronize(s);
       if (e != cudaSuccess) return e;
     }
@@ -396,7 +388,7 @@ cudaError_t sort_permutation(const uint8_t* data, const ColumnsDev& c, uint64_t 
         bits = 0;
       };
       for (uint32_t j = max_len; j-- > lcp;) {
-        const uint32_t m = masks[j] & 0xffu;
+        const uint32_t m = masks[j];
         if (!m) continue;
         const uint32_t w = 32u - (uint32_t)__builtin_clz(m);
         if (bits + w > 64 || rev.size() == 64) close();
