@@ -17,6 +17,7 @@ ERR_NAMES = {
 }
 SORT_NAME, SORT_NAME_AND_MATCH_MATES, SORT_COORDINATES_AND_STRAND = 0, 1, 2   # sorting/sort.rs:92-96 SortBy
 COPY_DATA, COPY_COLUMNS, WANT_HI, NO_CRC, NO_RECORDS, SPECULATIVE_START, COPY_OFFSETS = 1, 2, 4, 8, 16, 32, 64
+DEFER_CRC = 256
 MAX_HALO = 1 << 20
 
 

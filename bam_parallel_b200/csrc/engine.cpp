@@ -246,6 +246,7 @@ struct bamgpu_engine {
   size_t pend_nb = 0;
   uint64_t pend_total = 0, pend_bytes_in = 0;
   bool inflate_launched = false;
+  bool inflate_deferred = false;      // BAMGPU_DEFER_CRC: K2 and the status read run on k3_stream; engine_records collects the verdict
   uint64_t data_len = 0;    // bytes valid in d_out (after lead pad), carry included
   // Reader jobs ("lead mode"): a batch is inflated BEFORE the previous batch's record chain is known, so its blocks land at
   // a fixed offset `lead` and the carried-over tail of the previous batch is copied right in front of them afterwards
@@ -551,10 +552,17 @@ int map_block_status(uint32_t st) {
 //   engine_inflate_launch  enqueues carry move, block table upload, K1, K2, status reduce; no host wait
 //   engine_inflate_finish  waits, reads the first failing block (if any), books the stage times
 static int engine_wait_d2h(bamgpu_engine* E);
+static int engine_inflate_finish(bamgpu_engine* E, cudaStream_t s);
 static int engine_inflate_launch(bamgpu_engine* E, const uint8_t* d_comp, const bamgpu_block* blocks, size_t n_blocks,
                                  uint32_t flags, cudaStream_t s) {
   const double t_in = now_ms();
   ECK(cudaSetDevice(E->device));
+  if (E->inflate_deferred) {   // a deferred verdict nobody asked for (no records call in between): collect it now
+    E->inflate_deferred = false;
+    ECK(cudaStreamSynchronize(s));
+    int w = engine_inflate_finish(E, E->k3_stream);
+    if (w < 0) return w;
+  }
   // 1. the destination buffer (the other one when ping-ponging) gets the carry at its front; in lead mode the blocks
   //    land behind a fixed gap and the carry is copied into the gap later (engine_set_carry)
   const bool lead_mode = E->lead > 0;
@@ -656,16 +664,24 @@ static int engine_inflate_launch(bamgpu_engine* E, const uint8_t* d_comp, const 
   ECK(cudaEventRecord(E->ev[1], ks));
   if (ks != s) ECK(cudaStreamWaitEvent(s, E->ev[1], 0));
   E->stats.kernel_launches += 1;
-  ECK(cudaEventRecord(E->ev[6], s));
+  // BAMGPU_DEFER_CRC: everything behind K1 that only concerns the blocks' verdict goes onto the side stream
+  cudaStream_t vs = s;
+  E->inflate_deferred = false;
+  if ((flags & BAMGPU_DEFER_CRC) && !lead_mode && E->k3_stream) {
+    vs = E->k3_stream;
+    ECK(cudaStreamWaitEvent(vs, E->ev[1], 0));
+    E->inflate_deferred = true;
+  }
+  ECK(cudaEventRecord(E->ev[6], vs));
   if (!(flags & BAMGPU_NO_CRC)) {
-    launch_crc32(E->out_ptr(), t, E->d_crc, E->d_status.as<uint32_t>(), E->num_sms, /*small_footprint=*/lead_mode, s);
+    launch_crc32(E->out_ptr(), t, E->d_crc, E->d_status.as<uint32_t>(), E->num_sms, /*small_footprint=*/lead_mode, vs);
     E->stats.kernel_launches += 1;
   }
-  ECK(cudaEventRecord(E->ev[2], s));
-  launch_status_reduce(E->d_status.as<uint32_t>(), (uint32_t)nb, first_bad, s);
+  ECK(cudaEventRecord(E->ev[2], vs));
+  launch_status_reduce(E->d_status.as<uint32_t>(), (uint32_t)nb, first_bad, vs);
   E->stats.kernel_launches += 1;
-  launch_copy_small_to_host(E->h_res.p, first_bad, 8, s);
-  ECK(cudaEventRecord(E->ev_inflated, s));
+  launch_copy_small_to_host(E->h_res.p, first_bad, 8, vs);
+  ECK(cudaEventRecord(E->ev_inflated, vs));
   if (dbg_level() >= 2) fprintf(stderr, "[bamgpu] inflate_launch host %.2f ms (%zu blocks)\n", now_ms() - t_in, n_blocks);
   return BAMGPU_OK;
 }
@@ -979,7 +995,14 @@ extern "C" int bamgpu_engine_inflate(bamgpu_engine* E, const uint8_t* d_comp, co
   if (!E || (n_blocks && (!blocks || !d_comp))) return BAMGPU_ERR_ARG;
   E->carry_len = 0;
   E->keep_from = 0;
-  return engine_inflate(E, d_comp, blocks, n_blocks, flags | E->default_flags, cuda_stream ? (cudaStream_t)cuda_stream : E->stream);
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : E->stream;
+  flags |= E->default_flags;
+  if (flags & BAMGPU_DEFER_CRC) {
+    int rc = engine_inflate_launch(E, d_comp, blocks, n_blocks, flags, s);
+    if (rc != BAMGPU_OK || E->inflate_deferred) return rc;   // deferred: bamgpu_engine_records collects the verdict
+    return engine_inflate_finish(E, s);
+  }
+  return engine_inflate(E, d_comp, blocks, n_blocks, flags, s);
 }
 
 extern "C" int bamgpu_engine_data(const bamgpu_engine* E, const uint8_t** d_data, uint64_t* len) {
@@ -1003,7 +1026,13 @@ extern "C" int bamgpu_engine_append_halo(bamgpu_engine* E, const uint8_t* d_src,
 extern "C" int bamgpu_engine_records(bamgpu_engine* E, uint64_t stream_start, int final, uint32_t flags, void* cuda_stream,
                                      bamgpu_batch* out, uint64_t* tail_off) {
   if (!E || !out) return BAMGPU_ERR_ARG;
-  return engine_records(E, stream_start, final, flags | E->default_flags, cuda_stream ? (cudaStream_t)cuda_stream : E->stream, out, tail_off);
+  const int rc = engine_records(E, stream_start, final, flags | E->default_flags, cuda_stream ? (cudaStream_t)cuda_stream : E->stream, out, tail_off);
+  if (E->inflate_deferred) {   // BAMGPU_DEFER_CRC: the blocks' verdict (K2 ran beside the exchange and the record kernels) comes first
+    E->inflate_deferred = false;
+    const int w = engine_inflate_finish(E, E->k3_stream);
+    if (w < 0) { E->last_valid = false; memset(out, 0, sizeof *out); return w; }
+  }
+  return rc;
 }
 
 extern "C" int bamgpu_engine_stats(const bamgpu_engine* E, bamgpu_stats* out) {

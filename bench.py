@@ -353,7 +353,7 @@ def run_b200(a, rank: int, world: int, local_rank: int, host_group=None):
             batch, tail, rc = eng.decode(d_comp, my_blocks, my_nb, my_start, True, 0, sptr)
             return batch, tail
         step_no[0] += 1
-        eng.inflate(d_comp, my_blocks, my_nb, 0, sptr)           # K1 + K2 over the shard's BGZF blocks
+        eng.inflate(d_comp, my_blocks, my_nb, bp.DEFER_CRC, sptr)   # K1 over the shard's BGZF blocks; K2 on a side stream beside what follows
         eng.edge_exchange(step_no[0], sptr)                      # my head -> left neighbour; right neighbour's head behind my bytes
         flags = bp.SPECULATIVE_START if rank > 0 else 0
         batch, tail, rc = eng.records(my_start, rank == world - 1, flags, sptr)   # K3: records that START in my bytes

@@ -138,6 +138,9 @@ enum {
   BAMGPU_COPY_OFFSETS = 64,     /* D2H only rec_off + rec_len of the columns (with BAMGPU_COPY_DATA this is all that
                                    next_rec / append_record need: the reference lends bodies, nothing else) */
   BAMGPU_SORT_EMIT_BLOCK_SIZE = 128, /* bamgpu_engine_sort: gather (u32 block_size, body)* instead of bodies (sort.rs:340-347) */
+  BAMGPU_DEFER_CRC = 256,       /* bamgpu_engine_inflate: do not wait for K1 / K2; the CRC32 pass runs on a side stream next to whatever the
+                                   caller queues behind K1 (edge exchange, record kernels) and a failed block (inflate, ISIZE, CRC) is
+                                   reported by the bamgpu_engine_records call that follows, before it hands anything out */
   BAMGPU_SPECULATIVE_START = 32 /* shard-edge mode (multi-GPU): stream_start is NOT a known record start; the chain
                                    begins at the first offset >= stream_start that looks like a run of records.
                                    The caller must confirm batch.chain_start with the left-hand shard's tail_off. */

@@ -262,7 +262,8 @@ def test_edge_exchange_in_peer_memory(oracle, shape, n, payload, n_shards):
             shard.append((e.upload(data[c0:c1]), mb, b1 - b0, u0, int(mv["isize"].sum())))
         for step in (1, 2, 3):          # three passes: the two inbox buffers and the acknowledgements are reused
             for g, e in enumerate(engines):
-                e.inflate(shard[g][0], shard[g][1], shard[g][2])
+                # step 2: BAMGPU_DEFER_CRC - K2 runs beside the exchange and the record kernels, records() delivers its verdict
+                e.inflate(shard[g][0], shard[g][1], shard[g][2], flags=bp.DEFER_CRC if step == 2 else 0)
             for g in reversed(range(n_shards)):       # one host thread: a shard's right-hand neighbour must have sent first
                 engines[g].edge_exchange(step)
             offs, lens, exits, starts, counts = [], [], [], [], []
@@ -307,6 +308,37 @@ def test_streamed_sort_over_several_gpus(oracle, sort_by):
     assert hashlib.md5(sink.getvalue()).hexdigest() == hashlib.md5(want).hexdigest()
     if ng > 1:
         assert st["p2p_bytes"] > 0            # keys really crossed GPUs
+
+
+def test_deferred_crc_verdict_comes_with_the_records(oracle):
+    """BAMGPU_DEFER_CRC: bamgpu_engine_inflate returns at once, a damaged block is reported by bamgpu_engine_records (nothing is
+    handed out), and the next inflate on the engine starts clean."""
+    data = bytearray(synth.generate("pe150", 20000, level=6).tobytes())
+    u, start, off, ln, cols = _oracle(oracle, bytes(data))
+    blocks, nb, _, _, _ = bp.scan_blocks(bytes(data))
+    e = bp.Engine()
+    try:
+        d_good = e.upload(bytes(data))
+        bad = bytearray(data)
+        bad[int(blocks[nb // 2].in_off + blocks[nb // 2].in_len)] ^= 0x21          # first CRC32 byte of a block in the middle
+        d_bad = e.upload(bytes(bad))
+        bad_blocks, _, _, _, _ = bp.scan_blocks(bytes(bad))                        # the footers travel in the block table
+        e.inflate(d_bad, bad_blocks, nb, flags=bp.DEFER_CRC)                       # no error yet
+        with pytest.raises(bp.BamGpuError) as err:
+            e.records(start, True, 0)
+        assert err.value.code == -14
+        e.inflate(d_good, blocks, nb, flags=bp.DEFER_CRC)
+        batch, tail, rc = e.records(start, True, bp.COPY_COLUMNS)
+        assert batch.n_records == off.size and np.array_equal(batch.columns["rec_off"], off)
+        e.inflate(d_bad, bad_blocks, nb, flags=bp.DEFER_CRC)                       # verdict never collected by a records call ...
+        with pytest.raises(bp.BamGpuError) as err:
+            e.inflate(d_good, blocks, nb)                                          # ... so the next inflate reports it
+        assert err.value.code == -14
+        e.inflate(d_good, blocks, nb)
+        batch, tail, rc = e.records(start, True, 0)
+        assert batch.n_records == off.size
+    finally:
+        e.close()
 
 
 def _n_sort_devices(k):
