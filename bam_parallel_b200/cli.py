@@ -4,6 +4,7 @@
     python -m bam_parallel_b200.cli -i in.bam -o out.bin      # coordinate + strand sort       (main.rs:50-79)
     python -m bam_parallel_b200.cli -n -i in.bam -o out.bin   # name sort
     python -m bam_parallel_b200.cli -n -M -i in.bam -o out.bin  # name sort, mates matched (HI, flag)
+    python -m bam_parallel_b200.cli -i in.bam -o sorted.bam --output-format bam --compress-level 2 --devices 0,1   # (not in the reference)
 
 `-h` is calc-hash like in the reference (structopt's help is shadowed there too, main.rs:36-37); `-q` is accepted and
 ignored (`_quite_mode`, main.rs:19-20).  This is the parity harness for the reference's own end-to-end suites
@@ -66,6 +67,11 @@ def parse(argv):
     ap.add_argument("-M", "--match-mates", dest="match_mates", action="store_true")
     ap.add_argument("-h", "--calc-hash", dest="calc_hash", action="store_true")
     ap.add_argument("--reference-suites", dest="suites", metavar="DIR")
+    # beyond the reference (it dumps bodies, sort.rs:643): what the sort writes, how hard it compresses, on which GPUs
+    ap.add_argument("--output-format", dest="fmt", choices=("bodies", "records", "bam"), default="bodies")
+    ap.add_argument("--compress-level", dest="level", type=int, default=0,
+                    help="with --output-format bam: 0 stored BGZF blocks, 1 fixed Huffman, 2 per-block Huffman codes (sort.rs:143 _out_compr_level)")
+    ap.add_argument("--devices", dest="devices", default="", help="comma-separated GPU ordinals: the sort runs as a sample sort over them")
     return ap.parse_args(argv)
 
 
@@ -84,7 +90,8 @@ def run(opt, out=sys.stdout) -> int:
         return 0
     sort_by = sort_by_of(opt)
     with open(opt.input, "rb") as f, open(opt.output, "wb") as o:               # main.rs:55 output.unwrap()
-        sort_bam(2000 * MEGA_BYTE_SIZE, f, o, None, 0, 5, None, None, sort_by, None)   # main.rs:66-77
+        devices = [int(x) for x in opt.devices.split(",") if x != ""] or None
+        sort_bam(2000 * MEGA_BYTE_SIZE, f, o, None, opt.level, 5, None, None, sort_by, None, output=opt.fmt, devices=devices)   # main.rs:66-77
     return 0
 
 

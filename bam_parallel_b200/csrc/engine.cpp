@@ -2103,6 +2103,13 @@ extern "C" int bamgpu_next_rec(bamgpu_reader* R, const uint8_t** body, size_t* l
   uint64_t i = R->rec_cursor++;
   *body = R->batch.h_data + R->batch.host.rec_off[i];
   *len = R->batch.host.rec_len[i];
+  // the bodies were written by the GPU's DMA, not by this core: a consumer that looks at every record (bam_binary's md5, main.rs:83-99)
+  // misses the cache on each; ask for a record a few calls ahead (its first and last line) while the caller works on this one
+  if (i + 6 < R->batch.n_records) {
+    const uint8_t* nx = R->batch.h_data + R->batch.host.rec_off[i + 6];
+    __builtin_prefetch(nx, 0, 1);
+    __builtin_prefetch(nx + R->batch.host.rec_len[i + 6] - 1, 0, 1);
+  }
   return BAMGPU_OK;
 }
 

@@ -44,3 +44,11 @@ def test_hash_and_sort_modes_match_oracle(oracle, tmp_path):
         assert cli.main(flags + ["-i", str(path), "-o", str(o)]) == 0
         perm = oracle.sort_perm(u, off, cols, mode)
         assert o.read_bytes() == b"".join(bodies[i] for i in perm.tolist()), flags
+    # beyond the reference: a complete, compressed BAM, sorted over a device list; the CLI itself (hash mode) reads it back
+    srt = tmp_path / "sorted.bam"
+    assert cli.main(["-n", "-i", str(path), "-o", str(srt), "--output-format", "bam", "--compress-level", "2", "--devices", "0,0"]) == 0
+    perm = oracle.sort_perm(u, off, cols, 1)
+    assert srt.stat().st_size < len(ub) // 2
+    out = io.StringIO()
+    assert cli.run(cli.parse(["-h", "-i", str(srt)]), out) == 0
+    assert out.getvalue().strip() == hashlib.md5(b"".join(bodies[i] for i in perm.tolist())).hexdigest()
