@@ -222,8 +222,9 @@ k6_deflate_fixed(const uint8_t* __restrict__ src, unsigned long long len, uint8_
     {
       const uint4* g = reinterpret_cast<const uint4*>(p - mis);
       uint4* d = reinterpret_cast<uint4*>(S.raw);
-      const uint32_t vecs = (mis + n + 15) / 16;
-      for (uint32_t i = tid; i < vecs; i += DF_THREADS) d[i] = g[i];
+      const uint32_t vecs = (mis + n) / 16;                      // whole vectors; the bytes behind them one by one (nothing is read
+      for (uint32_t i = tid; i < vecs; i += DF_THREADS) d[i] = g[i];   // past src + len)
+      for (uint32_t i = vecs * 16 + tid; i < mis + n; i += DF_THREADS) if (i >= mis) reinterpret_cast<uint8_t*>(S.raw)[i] = (p - mis)[i];
       for (uint32_t i = tid; i < (1u << DF_HASH_BITS); i += DF_THREADS) S.htab[i] = 0;
       if (tid == 0) S.overflow = 0;
     }
@@ -476,8 +477,9 @@ k6_deflate_dynamic(const uint8_t* __restrict__ src, unsigned long long len, uint
     {
       const uint4* g = reinterpret_cast<const uint4*>(p - mis);
       uint4* d = reinterpret_cast<uint4*>(S.raw);
-      const uint32_t vecs = (mis + n + 15) / 16;
-      for (uint32_t i = tid; i < vecs; i += DF_THREADS) d[i] = g[i];
+      const uint32_t vecs = (mis + n) / 16;                      // whole vectors; the bytes behind them one by one (nothing is read
+      for (uint32_t i = tid; i < vecs; i += DF_THREADS) d[i] = g[i];   // past src + len)
+      for (uint32_t i = vecs * 16 + tid; i < mis + n; i += DF_THREADS) if (i >= mis) reinterpret_cast<uint8_t*>(S.raw)[i] = (p - mis)[i];
       for (uint32_t i = tid; i < (1u << DF_HASH_BITS); i += DF_THREADS) S.htab[i] = 0;
       if (tid < 288) D.lfreq[tid] = tid == 256 ? 1u : 0u;     // one end-of-block symbol
       if (tid < 32) D.dfreq[tid] = 0;
