@@ -22,22 +22,33 @@
 // CRC32 comes from K2's warp CRC (crc32.cu).  Integer / byte work, HBM- and shared-memory-bound; no tensor-core content.
 #include <cub/cub.cuh>
 
+#include <cstdio>
+
 #include "kernels.h"
 
 namespace bamgpu {
 namespace {
 
+#ifndef DF_WALK
+#define DF_WALK 1
+#endif
 constexpr int DF_THREADS = 512;
 constexpr int DF_CHUNK = 2048;                 // positions per parse round
-constexpr int DF_SUB = 256;                    // positions looked up / inserted together
-constexpr int DF_HASH_BITS = 13;
+#ifndef DF_SUB_N
+#define DF_SUB_N 256
+#endif
+constexpr int DF_SUB = DF_SUB_N;            // positions looked up / inserted together
+#ifndef DF_TAB32
+#define DF_TAB32 1
+#endif
+constexpr int DF_HASH_BITS = DF_TAB32 ? 12 : 13;   // 16 KB of shared memory either way: 4096 x u32 or 8192 x u16
 constexpr int DF_ITEMS = DF_CHUNK / DF_THREADS;
 constexpr uint32_t DF_MAX_MATCH = 258, DF_MIN_MATCH = 4;
 constexpr uint32_t DF_RAW_BYTES = BGZF_STORE_PAYLOAD + 48;   // payload + alignment slack in front + zero pad behind
 
 struct DfShared {
   uint32_t raw[DF_RAW_BYTES / 4];
-  uint16_t htab[1 << DF_HASH_BITS];
+  uint16_t htab[8192];                         // DF_TAB32: used as 4096 x u32
   uint16_t mlen[DF_CHUNK];                     // phase A leaves the candidate (position + 1) here, phase B replaces it by the match length
   uint16_t mdist[DF_CHUNK];
   uint16_t jmp[2][DF_CHUNK];
@@ -102,12 +113,21 @@ __device__ __forceinline__ void token_bits(uint32_t lit, uint32_t len, uint32_t 
 // Phases A - C for the chunk [c0, c0 + clen) of an n-byte payload at raw + mis: on return mark[i] != 0 for the positions of the
 // greedy parse, mlen / mdist hold their matches (mlen 0: a literal).  `entry`: where the chain enters the chunk.
 using DfScan = cub::BlockScan<uint32_t, DF_THREADS>;
+#ifdef DF_PROFILE   // diagnostic build: cycles of CTA 0's thread 0 per phase
+__device__ unsigned long long df_prof[8];
+#define DF_TICK(k) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); df_prof[k] += (unsigned long long)(t_ - t_prof); t_prof = t_; } } while (0)
+#else
+#define DF_TICK(k) do { } while (0)
+#endif
 __device__ __forceinline__ void parse_chunk(DfShared& S, DfScan::TempStorage& scan_tmp, uint32_t mis, uint32_t c0, uint32_t clen, uint32_t n,
                                             uint32_t entry, uint32_t tid) {
   // runs: nz[i] = the first chunk position q >= i whose byte differs from the byte in front of it (clen: none), by a reverse
   // min-scan.  The distance-1 match at i is then nz[i] - i bytes long: no position of a long run (binned base qualities) loops
   // over it - with a compare loop per position a warp waited for its longest run at every one of them (6x the time).
   uint16_t* nz = S.jmp[1];
+#ifdef DF_PROFILE
+  long long t_prof = clock64();
+#endif
   {
     const uint8_t* rb = reinterpret_cast<const uint8_t*>(S.raw) + mis + c0;
     uint32_t v[DF_ITEMS];
@@ -129,6 +149,7 @@ __device__ __forceinline__ void parse_chunk(DfShared& S, DfScan::TempStorage& sc
     }
   }
   __syncthreads();
+  DF_TICK(0);
   // A. candidates
   for (uint32_t s0 = 0; s0 < clen; s0 += DF_SUB) {
     uint32_t h = 0;
@@ -137,11 +158,24 @@ __device__ __forceinline__ void parse_chunk(DfShared& S, DfScan::TempStorage& sc
     if (tid < DF_SUB && i < clen && c0 + i + DF_MIN_MATCH <= n) {
       live = true;
       h = (ld32u(S.raw, mis + c0 + i) * 2654435761u) >> (32 - DF_HASH_BITS);
-      S.mlen[i] = S.htab[h];
+      S.mlen[i] = DF_TAB32 ? (uint16_t)reinterpret_cast<const uint32_t*>(S.htab)[h] : S.htab[h];
     } else if (tid < DF_SUB && i < clen) {
       S.mlen[i] = 0;
     }
     __syncthreads();
+    // Positions inside a run (the same 4 bytes as one position earlier) are not inserted: the distance-1 probe covers them, and
+    // hundreds of equal hashes fighting for one table word made this phase 70 % of the kernel.  Among the lanes of a warp that
+    // still share a hash, only the highest position goes to the table.
+    if (live && nz[i] - i >= 4) live = false;
+#if DF_TAB32
+    // one 32-bit word per entry (position + 1, 0: empty): atomicMax lets the HIGHEST position of the sub-step win whatever the
+    // thread order - the same bytes on every run - in one instruction
+    if (live) atomicMax(reinterpret_cast<uint32_t*>(S.htab) + h, c0 + i + 1);
+#else
+    if (tid < DF_SUB) {
+      const uint32_t peers = __match_any_sync(0xffffffffu, live ? h : 0xffffffffu - (tid & 31u));
+      if (live && (peers >> (tid & 31u)) > 1u) live = false;      // a higher lane (= a higher position) has the same hash
+    }
     if (live) {
       // entry = position + 1 (0: empty); the HIGHEST position of the sub-step wins, whatever the thread order: the output
       // is the same bytes on every run.  Two entries share a 32-bit word: compare-and-swap on the word.
@@ -155,9 +189,12 @@ __device__ __forceinline__ void parse_chunk(DfShared& S, DfScan::TempStorage& sc
         old = seen;
       }
     }
+#endif
     __syncthreads();
   }
-  // B. verify + extend
+  DF_TICK(1);
+  // B. verify + extend.  (Giving a thread DF_ITEMS consecutive positions and deriving the match inside a long match from the position
+  // in front of it - no compare loop there - was measured SLOWER, 34.1 vs 32.1 ms: the loops are not what this phase waits for.)
 #pragma unroll
   for (int k = 0; k < DF_ITEMS; ++k) {
     const uint32_t i = tid + k * DF_THREADS;
@@ -181,12 +218,52 @@ __device__ __forceinline__ void parse_chunk(DfShared& S, DfScan::TempStorage& sc
       }
       S.mlen[i] = (uint16_t)best;
       S.mdist[i] = (uint16_t)bdist;
+#if DF_WALK
+      S.mark[i] = 0;
+#else
       const uint32_t nx = i + (best ? best : 1u);
       S.jmp[0][i] = (uint16_t)(nx < clen ? nx : DF_CHUNK);
       S.mark[i] = i == entry ? 1 : 0;
+#endif
     }
   }
   __syncthreads();
+  DF_TICK(2);
+#if DF_WALK
+  // C. the greedy parse  next(p) = p + max(1, len(p)): every warp walks its own 128 positions, 32 at a time - the first lane with a
+  // match decides how far the cursor jumps, the lanes in front of it are literals.  Matches are cut at the end of the warp's range
+  // (so every range, and every chunk, starts a token: no chain from range to range, no block-wide rounds); a cut shorter than 3
+  // bytes becomes a literal.  (Marking the chain of the whole chunk by pointer doubling - 11 block-wide rounds - was 24 % of the
+  // kernel's instructions and most of its barriers; -DDF_WALK=0 builds it.)
+  {
+    const uint32_t lane = tid & 31u, w0 = (tid >> 5) * (DF_CHUNK / (DF_THREADS / 32));
+    const uint32_t end = w0 + DF_CHUNK / (DF_THREADS / 32) < clen ? w0 + DF_CHUNK / (DF_THREADS / 32) : clen;
+    for (uint32_t c = w0; c < end;) {
+      const uint32_t q = c + lane;
+      const uint32_t l = q < end ? S.mlen[q] : 0u;
+      const uint32_t any = __ballot_sync(0xffffffffu, l != 0);
+      if (!any) {
+        if (q < end) S.mark[q] = 1;
+        c += 32;
+        continue;
+      }
+      const uint32_t f = (uint32_t)__ffs((int)any) - 1u;
+      uint32_t L = __shfl_sync(0xffffffffu, l, (int)f);
+      const uint32_t qf = c + f;
+      if (qf + L > end) {
+        L = end - qf;
+        if (L < 3) L = 0;
+        if (lane == f) S.mlen[qf] = (uint16_t)L;
+      }
+      if (lane <= f) S.mark[q] = 1;
+      c = qf + (L ? L : 1u);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  DF_TICK(3);
+}
+#else
   // C. mark the greedy chain by pointer doubling
   int cur = 0;
   for (uint32_t span = 1; span < clen; span <<= 1) {
@@ -203,6 +280,7 @@ __device__ __forceinline__ void parse_chunk(DfShared& S, DfScan::TempStorage& sc
     __syncthreads();
   }
 }
+#endif
 
 // One CTA per payload.  slots: n_blocks x DF_SLOT bytes; sizes[b] = DEFLATE bytes, or 0 = "store it" (no gain / overflow).
 constexpr uint32_t DF_SLOT = 1u << 16;
@@ -225,7 +303,7 @@ k6_deflate_fixed(const uint8_t* __restrict__ src, unsigned long long len, uint8_
       const uint32_t vecs = (mis + n) / 16;                      // whole vectors; the bytes behind them one by one (nothing is read
       for (uint32_t i = tid; i < vecs; i += DF_THREADS) d[i] = g[i];   // past src + len)
       for (uint32_t i = vecs * 16 + tid; i < mis + n; i += DF_THREADS) if (i >= mis) reinterpret_cast<uint8_t*>(S.raw)[i] = (p - mis)[i];
-      for (uint32_t i = tid; i < (1u << DF_HASH_BITS); i += DF_THREADS) S.htab[i] = 0;
+      for (uint32_t i = tid; i < 8192; i += DF_THREADS) S.htab[i] = 0;
       if (tid == 0) S.overflow = 0;
     }
     __syncthreads();
@@ -242,6 +320,9 @@ k6_deflate_fixed(const uint8_t* __restrict__ src, unsigned long long len, uint8_
     for (uint32_t c0 = 0; c0 < n; c0 += DF_CHUNK) {
       const uint32_t clen = n - c0 < DF_CHUNK ? n - c0 : DF_CHUNK;
       parse_chunk(S, scan_tmp, mis, c0, clen, n, entry, tid);
+#ifdef DF_PROFILE
+      long long t_prof = clock64();
+#endif
       // D. tokens -> bits
       uint32_t bits[DF_ITEMS], nb[DF_ITEMS], off[DF_ITEMS];
       const uint8_t* rb = reinterpret_cast<const uint8_t*>(S.raw) + mis + c0;
@@ -275,9 +356,10 @@ k6_deflate_fixed(const uint8_t* __restrict__ src, unsigned long long len, uint8_
       else for (uint32_t i = tid; i < full; i += DF_THREADS) gout[wpos + i] = S.outw[i];
       carry_word = S.outw[full];
       carry_bits = tb & 31u;
-      entry = S.exit_rel;
+      entry = DF_WALK ? 0u : S.exit_rel;
       __syncthreads();
       if (!S.overflow) wpos += full;
+      DF_TICK(4);
     }
     // end of block: symbol 256 = seven zero bits
     if (tid == 0) {
@@ -311,7 +393,7 @@ struct DfBuild {            // overlays DfShared::htab (dead after pass 1)
   uint32_t cfreq[20];
   uint32_t maxd, hlit, hdist, hclen, cost_dyn, cost_fix, use_fixed;
 };
-static_assert(sizeof(DfBuild) <= sizeof(uint16_t) * (1 << DF_HASH_BITS), "DfBuild must fit the hash table it overlays");
+static_assert(sizeof(DfBuild) <= sizeof(uint16_t) * 8192, "DfBuild must fit the hash table it overlays");
 struct DfDyn {
   DfShared P;
   uint32_t lfreq[288], dfreq[32];
@@ -480,7 +562,7 @@ k6_deflate_dynamic(const uint8_t* __restrict__ src, unsigned long long len, uint
       const uint32_t vecs = (mis + n) / 16;                      // whole vectors; the bytes behind them one by one (nothing is read
       for (uint32_t i = tid; i < vecs; i += DF_THREADS) d[i] = g[i];   // past src + len)
       for (uint32_t i = vecs * 16 + tid; i < mis + n; i += DF_THREADS) if (i >= mis) reinterpret_cast<uint8_t*>(S.raw)[i] = (p - mis)[i];
-      for (uint32_t i = tid; i < (1u << DF_HASH_BITS); i += DF_THREADS) S.htab[i] = 0;
+      for (uint32_t i = tid; i < 8192; i += DF_THREADS) S.htab[i] = 0;
       if (tid < 288) D.lfreq[tid] = tid == 256 ? 1u : 0u;     // one end-of-block symbol
       if (tid < 32) D.dfreq[tid] = 0;
       if (tid == 0) S.overflow = 0;
@@ -529,7 +611,7 @@ k6_deflate_dynamic(const uint8_t* __restrict__ src, unsigned long long len, uint
       __syncthreads();
       for (uint32_t i = tid; i < cnt; i += DF_THREADS) gtok[ntok + i] = stage[i];
       ntok += cnt;
-      entry = S.exit_rel;
+      entry = DF_WALK ? 0u : S.exit_rel;
       __syncthreads();
     }
     // ---- the two codes ----
@@ -738,6 +820,14 @@ cudaError_t bgzf_deflate_blocks(const uint8_t* src, uint64_t len, const uint32_t
   cudaMemcpyAsync(&total, woff + nb, 8, cudaMemcpyDeviceToHost, s);
   cudaError_t e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return e;
+#ifdef DF_PROFILE
+  {
+    unsigned long long h[8] = {0}, z[8] = {0};
+    cudaMemcpyFromSymbol(h, df_prof, sizeof h);
+    cudaMemcpyToSymbol(df_prof, z, sizeof z);
+    fprintf(stderr, "[k6 profile, CTA 0, cycles] runs %llu  candidates %llu  verify+extend %llu  parse %llu  bits %llu\n", h[0], h[1], h[2], h[3], h[4]);
+  }
+#endif
   *out_len = total + (eof_marker ? 28 : 0);
   return cudaGetLastError();
 }

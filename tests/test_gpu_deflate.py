@@ -62,7 +62,7 @@ def test_bgzf_write_round_trips(oracle, engine, name, payload, level):
     if level == 2:
         assert len(z) <= len(engine.bgzf_write(payload, level=1, eof_marker=False))   # never worse than the fixed code
         if name == "high bytes":
-            assert len(z) < len(payload) // 3                                  # four symbols: two bits each
+            assert len(z) < 0.34 * len(payload)                                 # four symbols: two bits each
 
 
 @pytest.mark.parametrize("shape,n,payload", [("pe150", 60000, 0xFF00), ("long10k", 300, 4096), ("longname", 6000, 0xFF00)])
