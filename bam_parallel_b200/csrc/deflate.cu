@@ -32,6 +32,9 @@ namespace {
 #ifndef DF_WALK
 #define DF_WALK 1
 #endif
+#ifndef DF_LAZY
+#define DF_LAZY 0
+#endif
 constexpr int DF_THREADS = 512;
 constexpr int DF_CHUNK = 2048;                 // positions per parse round
 #ifndef DF_SUB_N
@@ -193,6 +196,71 @@ __device__ __forceinline__ void parse_chunk(DfShared& S, DfScan::TempStorage& sc
     __syncthreads();
   }
   DF_TICK(1);
+#if DF_LAZY
+  // B + C in one: every warp walks its own 128 positions, 32 at a time.  The lanes only VERIFY their candidates (4 bytes) and
+  // look up their run lengths; the first lane with a match is the next token, and its match is extended by the whole warp (128
+  // bytes per round).  Positions a match jumps over are never looked at.  Same tokens as the two-phase form below.
+  {
+    const uint32_t lane = tid & 31u, per = DF_CHUNK / (DF_THREADS / 32), w0 = (tid >> 5) * per;
+    const uint32_t end = w0 + per < clen ? w0 + per : clen;
+    for (uint32_t q = w0 + lane; q < end; q += 32) S.mark[q] = 0;
+    __syncwarp();
+    for (uint32_t c = w0; c < end;) {
+      const uint32_t q = c + lane, pos = c0 + q;
+      uint32_t l1 = 0, c1 = 0, maxl = 0;
+      bool okh = false;
+      if (q < end && pos + DF_MIN_MATCH <= n) {
+        maxl = n - pos < DF_MAX_MATCH ? n - pos : DF_MAX_MATCH;
+        l1 = nz[q] - q;
+        if (l1 && q + l1 == clen && l1 < maxl) {
+          const uint8_t* rb = reinterpret_cast<const uint8_t*>(S.raw) + mis + pos;
+          while (l1 < maxl && rb[l1] == rb[l1 - 1]) ++l1;
+        }
+        l1 = l1 < maxl ? l1 : maxl;
+        c1 = S.mlen[q];
+        okh = l1 < 64 && c1 && pos - (c1 - 1) <= 32768u && ld32u(S.raw, mis + c1 - 1) == ld32u(S.raw, mis + pos);
+      }
+      const uint32_t any = __ballot_sync(0xffffffffu, okh || l1 >= DF_MIN_MATCH);
+      if (!any) {
+        if (q < end) { S.mlen[q] = 0; S.mark[q] = 1; }
+        c += 32;
+        __syncwarp();
+        continue;
+      }
+      const uint32_t f = (uint32_t)__ffs((int)any) - 1u, qf = c + f, posf = c0 + qf;
+      if (lane < f) { S.mlen[q] = 0; S.mark[q] = 1; }
+      const bool hf = __shfl_sync(0xffffffffu, (int)okh, (int)f) != 0;
+      const uint32_t l1f = __shfl_sync(0xffffffffu, l1, (int)f), c1f = __shfl_sync(0xffffffffu, c1, (int)f);
+      const uint32_t maxlf = __shfl_sync(0xffffffffu, maxl, (int)f);
+      uint32_t best = l1f >= DF_MIN_MATCH ? l1f : 0u, dist = 1;
+      if (hf) {
+        const uint32_t a = mis + c1f - 1, b = mis + posf;
+        uint32_t lh = maxlf;
+        for (uint32_t base = 0; base < maxlf; base += 128) {
+          const uint32_t off = base + 4 * lane;
+          const uint32_t x = off < maxlf ? (ld32u(S.raw, a + off) ^ ld32u(S.raw, b + off)) : 1u;
+          const uint32_t mm = __ballot_sync(0xffffffffu, x != 0);
+          if (mm) {
+            const uint32_t m = (uint32_t)__ffs((int)mm) - 1u;
+            const uint32_t xm = __shfl_sync(0xffffffffu, x, (int)m);
+            lh = base + 4 * m + ((uint32_t)(__ffs((int)xm) - 1) >> 3);
+            break;
+          }
+        }
+        lh = lh < maxlf ? lh : maxlf;
+        if (lh > best) { best = lh; dist = posf - (c1f - 1); }
+      }
+      uint32_t L = best;
+      if (qf + L > end) { L = end - qf; if (L < 3) L = 0; }
+      if (lane == f) { S.mlen[qf] = (uint16_t)L; S.mdist[qf] = (uint16_t)dist; S.mark[qf] = 1; }
+      c = qf + (L ? L : 1u);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  DF_TICK(3);
+}
+#else
   // B. verify + extend.  (Giving a thread DF_ITEMS consecutive positions and deriving the match inside a long match from the position
   // in front of it - no compare loop there - was measured SLOWER, 34.1 vs 32.1 ms: the loops are not what this phase waits for.)
 #pragma unroll
@@ -280,6 +348,7 @@ __device__ __forceinline__ void parse_chunk(DfShared& S, DfScan::TempStorage& sc
     __syncthreads();
   }
 }
+#endif
 #endif
 
 // One CTA per payload.  slots: n_blocks x DF_SLOT bytes; sizes[b] = DEFLATE bytes, or 0 = "store it" (no gain / overflow).
