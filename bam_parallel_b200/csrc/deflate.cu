@@ -279,7 +279,11 @@ __device__ __forceinline__ void parse_chunk(DfShared& S, DfScan::TempStorage& sc
         l1 = l1 < maxl ? l1 : maxl;
         const uint32_t c1 = S.mlen[i];        // candidate position + 1 (same thread overwrites it below)
         if (l1 < 64 && c1 && pos - (c1 - 1) <= 32768u && ld32u(S.raw, mis + c1 - 1) == ld32u(S.raw, mis + pos)) {   // the DEFLATE window is 32 KiB
+#ifdef DF_EXT_CAP   // experiment: how much of this phase is the tail of long compare loops?
+          best = extend_match(S.raw, mis + c1 - 1, mis + pos, maxl < DF_EXT_CAP ? maxl : DF_EXT_CAP);
+#else
           best = extend_match(S.raw, mis + c1 - 1, mis + pos, maxl);
+#endif
           bdist = pos - (c1 - 1);
         }
         if (l1 >= DF_MIN_MATCH && l1 >= best) { best = l1; bdist = 1; }
