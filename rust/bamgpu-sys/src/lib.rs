@@ -38,6 +38,7 @@ pub const BAMGPU_FIELD_CIGAR: u32 = 1;
 pub const BAMGPU_FIELD_SEQ: u32 = 2;
 pub const BAMGPU_FIELD_QUAL: u32 = 4;
 pub const BAMGPU_COPY_DATA: u32 = 1;
+pub const BAMGPU_DEFER_CRC: u32 = 256;   // bamgpu_engine_inflate: the CRC32 verdict comes with the following bamgpu_engine_records call
 pub type bamgpu_read_fn = unsafe extern "C" fn(ctx: *mut c_void, dst: *mut u8, cap: usize) -> c_long;
 pub const BAMGPU_OK: c_int = 0;
 pub const BAMGPU_EOF: c_int = 1;
@@ -176,7 +177,9 @@ pub fn sort_bam<R: Read + Send + 'static, W: Write, IndexW: Write, TmpDir>(
 }
 
 /// `sort_bam` with explicit options (bamgpu_opts.sort_output: 0 bodies = the reference's output, 1 (u32 block_size, body)*,
-/// 2 a complete BAM in stored-block BGZF; bamgpu_opts.sort_mem_limit: device bytes for record bodies, 0 = whatever fits).
+/// 2 a complete BAM in BGZF - stored blocks, or with bamgpu_opts.out_compr_level >= 1 compressed on the GPU;
+/// bamgpu_opts.sort_mem_limit: device bytes for record bodies, 0 = whatever fits; bamgpu_opts.devices (`with_devices`): the
+/// sample sort over several GPUs, same output bytes).
 pub fn sort_bam_with<R: Read + Send + 'static, W: Write>(reader: R, sorted_sink: &mut W, reader_thread_num: usize, sort_by: SortBy,
                                                        opts: &bamgpu_opts) -> io::Result<()> {
     let mut boxed: Box<Box<dyn Read + Send>> = Box::new(Box::new(reader));
