@@ -35,6 +35,9 @@ namespace {
 #ifndef DF_LAZY
 #define DF_LAZY 0
 #endif
+#ifndef DF_PREFETCH
+#define DF_PREFETCH 0
+#endif
 constexpr int DF_THREADS = 512;
 constexpr int DF_CHUNK = 2048;                 // positions per parse round
 #ifndef DF_SUB_N
@@ -263,6 +266,25 @@ __device__ __forceinline__ void parse_chunk(DfShared& S, DfScan::TempStorage& sc
 #else
   // B. verify + extend.  (Giving a thread DF_ITEMS consecutive positions and deriving the match inside a long match from the position
   // in front of it - no compare loop there - was measured SLOWER, 34.1 vs 32.1 ms: the loops are not what this phase waits for.)
+#if DF_PREFETCH
+  // the loads every position needs - run length, candidate, its four bytes and the candidate's - for all DF_ITEMS positions of the
+  // thread first: four chains of dependent shared-memory loads overlap instead of following each other (the compare loops below keep
+  // the compiler from doing it)
+  uint32_t pf_l1[DF_ITEMS], pf_c1[DF_ITEMS], pf_eq[DF_ITEMS];
+#pragma unroll
+  for (int k = 0; k < DF_ITEMS; ++k) {
+    const uint32_t i = tid + k * DF_THREADS;
+    pf_l1[k] = 0; pf_c1[k] = 0;
+    if (i < clen) { pf_l1[k] = nz[i] - i; pf_c1[k] = S.mlen[i]; }
+  }
+#pragma unroll
+  for (int k = 0; k < DF_ITEMS; ++k) {
+    const uint32_t i = tid + k * DF_THREADS, pos = c0 + i;
+    pf_eq[k] = 0;
+    if (i < clen && pos + DF_MIN_MATCH <= n && pf_c1[k] && pos - (pf_c1[k] - 1) <= 32768u)
+      pf_eq[k] = ld32u(S.raw, mis + pf_c1[k] - 1) == ld32u(S.raw, mis + pos) ? 1u : 0u;
+  }
+#endif
 #pragma unroll
   for (int k = 0; k < DF_ITEMS; ++k) {
     const uint32_t i = tid + k * DF_THREADS;
@@ -271,14 +293,23 @@ __device__ __forceinline__ void parse_chunk(DfShared& S, DfScan::TempStorage& sc
       uint32_t best = 0, bdist = 0;
       if (pos + DF_MIN_MATCH <= n) {
         const uint32_t maxl = n - pos < DF_MAX_MATCH ? n - pos : DF_MAX_MATCH;
+#if DF_PREFETCH
+        uint32_t l1 = pf_l1[k];
+#else
         uint32_t l1 = nz[i] - i;              // bytes from pos on that repeat the byte in front of them
+#endif
         if (l1 && i + l1 == clen && l1 < maxl) {   // the run reaches the end of the chunk: follow it (few positions per chunk)
           const uint8_t* rb = reinterpret_cast<const uint8_t*>(S.raw) + mis + pos;
           while (l1 < maxl && rb[l1] == rb[l1 - 1]) ++l1;
         }
         l1 = l1 < maxl ? l1 : maxl;
+#if DF_PREFETCH
+        const uint32_t c1 = pf_c1[k];
+        if (l1 < 64 && pf_eq[k]) {
+#else
         const uint32_t c1 = S.mlen[i];        // candidate position + 1 (same thread overwrites it below)
         if (l1 < 64 && c1 && pos - (c1 - 1) <= 32768u && ld32u(S.raw, mis + c1 - 1) == ld32u(S.raw, mis + pos)) {   // the DEFLATE window is 32 KiB
+#endif
 #ifdef DF_EXT_CAP   // experiment: how much of this phase is the tail of long compare loops?
           best = extend_match(S.raw, mis + c1 - 1, mis + pos, maxl < DF_EXT_CAP ? maxl : DF_EXT_CAP);
 #else
