@@ -17,6 +17,11 @@ def test_flags_follow_main_rs():
         cli.sort_by_of(cli.parse(["-M", "-i", "x"]))
     assert cli.parse(["-h", "-i", "x"]).calc_hash                                             # -h is calc-hash, not help
     assert len(cli.REFERENCE_MD5) == 7                                                        # tests_list.py:6-48
+    # beyond the reference: output format, compression level (sort.rs:143 _out_compr_level), device list
+    o = cli.parse(["-i", "x", "-o", "y"])
+    assert (o.fmt, o.level, o.devices) == ("bodies", 0, "")                                   # defaults = what bam_binary writes
+    o = cli.parse(["-n", "-i", "x", "-o", "y", "--output-format", "bam", "--compress-level", "2", "--devices", "0,1,2"])
+    assert (o.fmt, o.level, o.devices) == ("bam", 2, "0,1,2")
 
 
 def test_reference_suites_report_missing_files(tmp_path):
